@@ -1,0 +1,602 @@
+/* nrgrep_oracle.c -- TEST INFRASTRUCTURE ONLY; see nrgrep_oracle.h.
+ *
+ * Restatement of nrgrep_coords (reference: /root/reference/www/bin/nrgrep_coords,
+ * invoked by www/FlaskApp/FlaskApp/patmatch.py:733-743).  The binary has no
+ * sources; each routine cites the unstripped symbol it restates.
+ */
+#include "nrgrep_oracle.h"
+#include <stdlib.h>
+#include <string.h>
+#include <ctype.h>
+
+/* ------------------------------------------------------------------------- */
+/* letterProb @621120 (.data): per-byte text frequencies, stored in the       */
+/* binary as the doubles n/1e6 for the integers below (verified bit-exact).   */
+static const int letter_ppm[256] = {
+         0,      0,      0,      0,      0,      0,      0,      0,      0,    344,  20793,      0,      0,      0,      0,      0,
+         0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,
+    146588,     43,    460,    398,  11430,   3034,   1013,   1707,   4156,   4162,    506,    998,   8441,   3342,   9616,    903,
+      2255,   4002,   2441,   1222,    937,   1102,    874,    828,    970,   1810,    679,    168,    190,   1562,    143,     35,
+        86,   2093,   1334,   1530,    818,    981,   1181,    571,    754,   1534,    156,    228,    656,   1308,    922,   1299,
+      1202,    261,    689,   1809,   3403,    669,    340,    961,    158,    390,    234,    847,  15840,    846,   1258,   1695,
+       715,  53857,  11376,  27900,  21596,  94887,  15707,  13246,  30408,  54368,    933,   3729,  28211,  20693,  48064,  47054,
+     18812,   2436,  44806,  48118,  65831,  16154,   6572,   8692,   5656,   7099,   1124,   8146,    445,   8146,   1852,      0,
+         0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,
+         0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,
+         1,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,
+         0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,
+         0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,
+         0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,      0,
+         0,     35,      0,      0,      0,      0,      0,      0,      0,     19,      0,      0,      0,     32,      0,      0,
+         0,      9,      0,     40,      0,      0,      0,      0,      0,      0,     27,      0,      0,      0,      0,      0,
+};
+
+static inline int cls_has(const nro_pattern *P, int j, unsigned c)
+{
+    return (int)((P->cls[j][c >> 6] >> (c & 63)) & 1);
+}
+static inline void cls_add(nro_pattern *P, int j, unsigned c, int icase)
+{
+    P->cls[j][c >> 6] |= 1ULL << (c & 63);
+    if (icase && isalpha((int)c)) {
+        unsigned d = isupper((int)c) ? (unsigned)tolower((int)c) : (unsigned)toupper((int)c);
+        P->cls[j][d >> 6] |= 1ULL << (d & 63);
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* Pattern syntax: main @400e00 strips a leading '^' / trailing '$'; parse    */
+/* @41ae90 (parseOr/parseConc/parseLiteral/getAclass) builds the tree and     */
+/* simplify @41a170 flattens plain groups.  Only the SIMPLE sub-language      */
+/* (letters, classes, '.', plain grouping) is on this path; operators make    */
+/* the reference take its EXTENDED/REGULAR engines and are reported as        */
+/* NRO_ERR_UNSUPPORTED.                                                       */
+static int parse_class(const char *s, int *ip, int n, nro_pattern *P, int j, int icase)
+{
+    int i = *ip;                 /* s[i-1] == '[' */
+    int neg = 0;
+    if (i < n && s[i] == '^') { neg = 1; i++; }
+    memset(P->cls[j], 0, sizeof P->cls[j]);
+    int first = 1;
+    while (i < n && (s[i] != ']' || first)) {
+        unsigned c = (unsigned char)s[i];
+        if (c == '\\') return NRO_ERR_UNSUPPORTED;
+        first = 0;
+        if (i + 2 < n && s[i + 1] == '-' && s[i + 2] != ']') {
+            unsigned d = (unsigned char)s[i + 2];
+            if (d == '\\') return NRO_ERR_UNSUPPORTED;
+            for (unsigned x = c; x <= d; x++) cls_add(P, j, x, icase);
+            i += 3;
+        } else {
+            cls_add(P, j, c, icase);
+            i++;
+        }
+    }
+    if (i >= n) return NRO_ERR_SYNTAX;
+    i++;                         /* ']' */
+    if (neg)
+        for (int w = 0; w < 4; w++) P->cls[j][w] = ~P->cls[j][w];
+    *ip = i;
+    return NRO_OK;
+}
+
+int nro_parse(const char *pattern, int icase, nro_pattern *P)
+{
+    memset(P, 0, sizeof *P);
+    int n = (int)strlen(pattern);
+    const char *s = pattern;
+    if (n > 0 && s[0] == '^') { P->start_line = 1; s++; n--; }
+    if (n > 0 && s[n - 1] == '$') { P->end_line = 1; n--; }
+    int depth = 0, i = 0, m = 0;
+    while (i < n) {
+        unsigned c = (unsigned char)s[i++];
+        switch (c) {
+        case '(': depth++; break;
+        case ')':
+            if (--depth < 0) return NRO_ERR_SYNTAX;
+            /* a group followed by an operator is EXTENDED/REGULAR */
+            break;
+        case '?': case '*': case '+': case '|': case '\\': case '#':
+            return NRO_ERR_UNSUPPORTED;
+        case '[': {
+            if (m >= NRO_MAXM) return NRO_ERR_TOOLONG;
+            int rc = parse_class(s, &i, n, P, m, icase);
+            if (rc) return rc;
+            m++;
+            break;
+        }
+        case '.':
+            if (m >= NRO_MAXM) return NRO_ERR_TOOLONG;
+            memset(P->cls[m], 0xff, sizeof P->cls[m]);
+            m++;
+            break;
+        default:
+            if (m >= NRO_MAXM) return NRO_ERR_TOOLONG;
+            memset(P->cls[m], 0, sizeof P->cls[m]);
+            cls_add(P, m, c, icase);
+            m++;
+        }
+    }
+    if (depth != 0 || m == 0) return NRO_ERR_SYNTAX;
+    P->m = m;
+    return NRO_OK;
+}
+
+/* ------------------------------------------------------------------------- */
+/* prob[i] = sum of letterProb over the class of position i, bytes ascending  */
+/* (esimplePreproc @415696-4156f5, simpleFindBest @416a5c-416aab).            */
+static void class_probs(const nro_pattern *P, double *prob)
+{
+    for (int i = 0; i < P->m; i++) {
+        double p = 0.0;
+        for (unsigned c = 0; c < 256; c++)
+            if (cls_has(P, i, c)) p += (double)letter_ppm[c] / 1000000.0;
+        prob[i] = p;
+    }
+}
+
+/* simpleFindBest @416a10: best BNDM sub-pattern [beg,end) under the cost     */
+/* model, for a search with k errors; returns its cost (1.0 if >= 0.8).       */
+static double simple_find_best(const nro_pattern *P, int k, int *flag, int *beg, int *end)
+{
+    int m = P->m, S = m + 1;
+    double *prob = malloc(sizeof(double) * (size_t)(m ? m : 1));
+    class_probs(P, prob);
+    double *pp = calloc((size_t)S * (size_t)S, sizeof(double));   /* pp[i*S + l] */
+    pp[m * S + 0] = 1.0;
+    for (int i = m - 1; i >= 0; i--) {
+        pp[i * S + 0] = 1.0;
+        for (int l = 1; l <= m; l++) pp[i * S + l] = pp[(i + 1) * S + (l - 1)] * prob[i];
+    }
+    free(prob);
+    *end = 0; *beg = 0;
+    double *mprob = malloc(sizeof(double) * (size_t)(m ? m : 1));
+    int *last = malloc(sizeof(int) * (size_t)(m ? m : 1));
+    const int K1 = k + 1;
+    const double dK1 = (double)K1;
+    double best = 0.8;
+    for (int i = 0; i < m; i++) {
+        for (int x = 0; x < m; x++) { mprob[x] = 0.0; last[x] = i - 1 + x; }
+        int j = K1 + i;
+        if (m < j) continue;
+        int len = j - i;
+        if ((unsigned)len > 64u) continue;
+        int lk = len - k;                      /* r14d */
+        for (;;) {
+            int lk1 = lk + 1;                  /* r15d */
+            double dlk1 = (double)lk1;         /* xmm4 */
+            double sum;                        /* xmm3 */
+            if (len <= 0 || dK1 >= dlk1) {
+                sum = dK1;
+            } else {
+                double dlk = (double)lk;       /* xmm13 */
+                double c0 = dK1 / ((dlk - dK1) + 1.0);
+                sum = dK1;
+                if (!(c0 >= best)) {
+                    int l = 1;                 /* rsi == r9d */
+                    for (;;) {
+                        int e = last[l - 1];
+                        double v = mprob[l - 1];
+                        e++;
+                        if (e <= j) {
+                            int row = e - l + 1;
+                            do {
+                                double a = 1.0 - pp[row * S + l];
+                                double b = 1.0 - v;
+                                v = 1.0 - b * a;
+                                mprob[l - 1] = v;
+                                row++;
+                                e++;
+                            } while (e != j + 1);
+                        }
+                        last[l - 1] = j;
+                        sum += v;
+                        if (l + 1 > len) break;
+                        if (sum >= dlk1) break;
+                        double c = sum / ((dlk - sum) + 1.0);
+                        l++;
+                        if (!(c < best)) break;
+                    }
+                }
+            }
+            if (dlk1 > sum) {
+                double c = sum / (((double)lk - sum) + 1.0);
+                if (best > c) { best = c; *beg = i; *end = j; }
+            }
+            j = j + 1;
+            if (m < j) break;
+            len++;
+            lk = lk1;
+            if ((unsigned)(j - i) > 64u) break;
+        }
+    }
+    free(pp); free(mprob); free(last);
+    if (*end - *beg <= K1) { *end = 0; *beg = 0; }
+    *flag = (*end != 0);
+    if (!*flag) *end = m >= 65 ? 64 : m;
+    return best < 0.8 ? best : 1.0;
+}
+
+/* esimplePreproc @415540: choose between k+1 exact pieces (SPLIT), backward  */
+/* (BWD) and forward (FWD) filtering, and fix the split points V[].           */
+int nro_plan_make(const nro_pattern *P, int k, int ins, int del, int subs, nro_plan *plan)
+{
+    memset(plan, 0, sizeof *plan);
+    plan->k = k; plan->ins = ins; plan->del = del; plan->subs = subs;
+    const int m = P->m;
+    if (k == 0) { plan->type = NRO_SIMPLE; plan->L = m; plan->npieces = 1; return NRO_OK; }
+    if (k > NRO_MAXK) return NRO_ERR_TOOLONG;
+    const int K1 = k + 1, K2 = k + 2, transp = 0;
+
+    plan->fb_cost = simple_find_best(P, k, &plan->fb_flag, &plan->fb_beg, &plan->fb_end);
+
+    int mm = m - k * transp;
+    if (mm > 64) mm = 64;
+    const int Lmax = mm / K1;
+    const int S = Lmax + 1;
+
+    double *prob = malloc(sizeof(double) * (size_t)m);
+    class_probs(P, prob);
+    double *pp = calloc((size_t)(m + 1) * (size_t)S, sizeof(double));    /* pp[i*S + l] */
+    pp[m * S + 0] = 1.0;
+    for (int i = m - 1; i >= 0; i--) {
+        pp[i * S + 0] = 1.0;
+        for (int l = 1; l <= Lmax; l++) pp[i * S + l] = pp[(i + 1) * S + (l - 1)] * prob[i];
+    }
+    free(prob);
+
+    /* Bm[i*Lmax + (l-1)]: expected characters inspected per BNDM window for
+     * the piece P[i..i+l) (415a02-415ac5).  The reference reads one never-
+     * written cell A[l-1][l-1] of its scratch rows here (fresh heap memory,
+     * i.e. +0.0, in the CLI process); calloc reproduces that. */
+    double *A = calloc((size_t)(Lmax + 1) * (size_t)(Lmax ? Lmax : 1), sizeof(double));
+    double *Bm = calloc((size_t)m * (size_t)(Lmax ? Lmax : 1), sizeof(double));
+    for (int i = 0; i < m && Lmax > 0; i++) {
+        memset(A, 0, sizeof(double) * (size_t)Lmax);
+        double *prev = A;
+        for (int l = 1; l <= Lmax; l++) {
+            double *cur = prev + Lmax;
+            double sum = 1.0;
+            for (int r = 0; r < l; r++) {
+                int row = i + l - 1 - r;
+                double pv = row <= m ? pp[row * S + (1 + r)] : 0.0;
+                double a = 1.0 - prev[r];
+                double b = 1.0 - pv;
+                double v = 1.0 - b * a;
+                cur[r] = v;
+                sum += v;
+            }
+            Bm[i * Lmax + (l - 1)] = sum;
+            prev = cur;
+        }
+    }
+
+    double best = 0.97;
+    int bestL = 0;
+    int V[NRO_MAXK + 1];
+    if (Lmax > 1 && !(1.0 / (double)Lmax > 0.97)) {
+        double *cost = calloc((size_t)(m + 1) * (size_t)K2, sizeof(double));
+        int *choice = calloc((size_t)(m + 1) * (size_t)K2, sizeof(int));
+        int Lc = Lmax;
+        for (;;) {
+            for (int i = 0; i <= m; i++) cost[i * K2 + 0] = 0.0;
+            for (int j = 1; j <= K1; j++) cost[m * K2 + j] = 1.0;
+            const double dL = (double)Lc, dL1 = (double)(Lc + 1);
+            for (int j = 1; j <= K1; j++) {
+                int istart = m - j * Lc - (j - 1) * transp;
+                for (int i = istart; i >= 0; i--) {
+                    double x = Bm[i * Lmax + (Lc - 1)];
+                    double c;
+                    if (dL1 > x) {
+                        c = x / ((dL - x) + 1.0);
+                        if (c > 1.0) c = 0.0; else c = 1.0 - c;
+                    } else c = 0.0;
+                    double val = 1.0 - c * (1.0 - cost[(i + Lc + transp) * K2 + (j - 1)]);
+                    choice[i * K2 + j] = i;
+                    if (i < istart) {
+                        double nx = cost[(i + 1) * K2 + j];
+                        if (val > nx) { val = nx; choice[i * K2 + j] = choice[(i + 1) * K2 + j]; }
+                    }
+                    cost[i * K2 + j] = val;
+                }
+            }
+            double total = cost[0 * K2 + K1];
+            if (best > total) {
+                int i = 0, n = 0;
+                for (int j = K1; j >= 1; j--) {
+                    int s = choice[i * K2 + j];
+                    V[n++] = s;
+                    i = s + Lc + transp;
+                }
+                best = total;
+                bestL = Lc;
+            }
+            Lc--;
+            if (Lc <= 1) break;
+            if (1.0 / (double)Lc > best) break;
+        }
+        free(cost); free(choice);
+    }
+    free(pp); free(A); free(Bm);
+
+    plan->split_cost = best;
+    int split = 0;
+    if (0.97 > best && !(best >= (double)K1 * plan->fb_cost) && bestL != 0) split = 1;
+    if (split) {
+        plan->type = NRO_SPLIT; plan->L = bestL; plan->npieces = K1;
+        for (int i = 0; i < K1; i++) plan->V[i] = V[i];
+    } else {
+        plan->npieces = 1;
+        plan->L = plan->fb_end - plan->fb_beg;
+        if (plan->fb_flag) { plan->type = NRO_BWD; plan->V[0] = plan->fb_beg; }
+        else { plan->type = NRO_FWD; plan->V[0] = plan->fb_end; }
+    }
+    return NRO_OK;
+}
+
+/* ------------------------------------------------------------------------- */
+/* recCheckLeftContext @402170 / recCheckRightContext @4021e0 with           */
+/* OptWholeWord = OptWholeRecord = 0 (patmatch.py never passes -w/-x).        */
+static inline int leftctx(const nro_pattern *P, const uint8_t *t, int64_t ptr, int64_t rbeg)
+{
+    if (P->start_line && ptr > rbeg && t[ptr - 1] != '\n') return 0;
+    return 1;
+}
+static inline int rightctx(const nro_pattern *P, const uint8_t *t, int64_t ptr, int64_t rend)
+{
+    if (P->end_line && ptr < rend && t[ptr] != '\n') return 0;
+    return 1;
+}
+
+/* multi-word state vectors (createMask @41b430) */
+typedef struct { uint64_t w[NRO_WORDS]; } mask_t;
+
+static inline void m_lowbits(mask_t *r, int e)          /* bits [0,e) set */
+{
+    for (int w = 0; w < NRO_WORDS; w++) {
+        int lo = w * 64;
+        if (e >= lo + 64) r->w[w] = ~0ULL;
+        else if (e > lo) r->w[w] = ~(~0ULL << (e - lo));
+        else r->w[w] = 0;
+    }
+}
+static inline mask_t m_shl1(const mask_t *a, uint64_t carry, int nw)
+{
+    mask_t r; memset(&r, 0, sizeof r);
+    for (int w = 0; w < nw; w++) { r.w[w] = (a->w[w] << 1) | carry; carry = a->w[w] >> 63; }
+    return r;
+}
+
+/* One direction of checkMatch1 @414190: anchored k-row NFA over a pattern part
+ * of length plen whose position j (0-based, counted from the anchor) accepts
+ * the bytes of P->cls[map(j)].  dir = -1 walks text leftwards from pos
+ * (first byte read is t[pos-1]) down to lim = rbeg; dir = +1 walks rightwards
+ * from pos (first byte t[pos]) up to lim = rend.
+ * Returns 1 and (*ext, *err) on success: *ext = number of text bytes consumed,
+ * *err = the error row that matched (only meaningful for the caller's budget
+ * when dir = -1).                                                            */
+static int nfa_side(const nro_pattern *P, const nro_plan *pl, const uint8_t *t,
+                    int dir, int pbase, int plen, int kmax,
+                    int64_t pos, int64_t lim, int64_t *ext, int *err)
+{
+    const int nw = (plen + 63) / 64;
+    const uint64_t fin = 1ULL << ((plen - 1) & 63);
+    const int fw = nw - 1;
+    mask_t R[NRO_MAXK + 1];
+    int kb = kmax;
+    int64_t best_ext = -1; int best_err = kmax;
+
+    if (kmax < 0) {
+        /* 415115 / 41515a: no rows are initialised; the reference then runs the
+         * scan with an empty row set.  With kmax < 0 nothing can match. */
+        return 0;
+    }
+    for (int e = 0; e <= kb; e++) {
+        if (pl->del) m_lowbits(&R[e], e); else memset(&R[e], 0, sizeof R[e]);
+        if ((R[e].w[fw] & fin) &&
+            (dir < 0 ? leftctx(P, t, pos, lim) : rightctx(P, t, pos, lim))) {
+            best_err = e; kb = e - 1; best_ext = 0;
+        }
+    }
+    int64_t avail = dir < 0 ? pos - lim : lim - pos;
+    uint64_t first = 1;
+    for (int64_t step = 1; step <= avail; step++) {
+        int64_t tp = dir < 0 ? pos - step : pos + step - 1;   /* byte consumed */
+        int64_t edge = dir < 0 ? tp : tp + 1;                 /* match boundary after it */
+        unsigned c = t[tp];
+        /* T[c]: bit j set iff part position j accepts c */
+        mask_t T; memset(&T, 0, sizeof T);
+        for (int j = 0; j < plen; j++) {
+            int pj = dir < 0 ? pbase - 1 - j : pbase + j;
+            if (cls_has(P, pj, c)) T.w[j >> 6] |= 1ULL << (j & 63);
+        }
+        mask_t oldp = R[0];
+        mask_t sh = m_shl1(&R[0], first, nw);
+        for (int w = 0; w < nw; w++) R[0].w[w] = sh.w[w] & T.w[w];
+        mask_t newp = R[0];
+        if ((R[0].w[fw] & fin) &&
+            (dir < 0 ? leftctx(P, t, edge, lim) : rightctx(P, t, edge, lim))) {
+            *ext = step; *err = 0;
+            return 1;                                /* 415194 / 414bd3->414f86 */
+        }
+        for (int e = 1; e <= kb; e++) {
+            mask_t x; memset(&x, 0, sizeof x);
+            if (pl->del) { mask_t d = m_shl1(&newp, 0, nw); x = d; }
+            if (pl->ins) for (int w = 0; w < nw; w++) x.w[w] |= oldp.w[w];
+            if (pl->subs) { mask_t s = m_shl1(&oldp, first, nw); for (int w = 0; w < nw; w++) x.w[w] |= s.w[w]; }
+            mask_t y = m_shl1(&R[e], first, nw);
+            mask_t nw_row;  memset(&nw_row, 0, sizeof nw_row);
+            for (int w = 0; w < nw; w++) nw_row.w[w] = (y.w[w] & T.w[w]) | x.w[w];
+            oldp = R[e];
+            R[e] = nw_row;
+            newp = nw_row;
+            if ((nw_row.w[fw] & fin) &&
+                (dir < 0 ? leftctx(P, t, edge, lim) : rightctx(P, t, edge, lim))) {
+                /* 4147fa-41483c / 414f51-414f84: walk down while lower rows also accept */
+                int ec = e, ed;
+                for (;;) {
+                    ed = ec - 1;
+                    if (ed == -1) break;
+                    if (!(R[ed].w[fw] & fin)) break;
+                    ec = ed;
+                }
+                if (ed == -1) {
+                    if (dir > 0) { *ext = step; *err = 0; return 1; }     /* 414f86 */
+                    *ext = step; *err = 0; return 1;                       /* 41483c, e = 0 */
+                }
+                kb = ed; best_err = ec; best_ext = step;                   /* 414da8 / 414fae */
+                break;                                                     /* e = ed+1 > kb */
+            }
+        }
+        /* 414de3 / 414fe3: is any state of row kb still alive? */
+        int alive = 0;
+        for (int w = 0; w < nw; w++) {
+            uint64_t v = R[kb].w[w];
+            if (w == fw) v &= (fin << 1) - 1;
+            if (v) { alive = 1; break; }
+        }
+        if (!alive) break;
+        first = 0;
+    }
+    if (best_ext < 0) return 0;
+    *ext = best_ext; *err = best_err;
+    return 1;
+}
+
+/* checkMatch1 @414190 (OptTransp = 0).                                       */
+static int check_match1(const nro_pattern *P, const nro_plan *pl, int i, const uint8_t *t,
+                        int64_t pos, int64_t rbeg, int64_t rend, int64_t *beg, int64_t *end)
+{
+    const int k = pl->k;
+    const int lb = pl->V[i], rl = P->m - pl->V[i];
+    int64_t bext; int berr;
+    if (lb == 0) {
+        /* 4141ef-414236: only insertions may precede an empty left part */
+        int e = 0; int64_t ptr = pos;
+        if (k < 0) return 0;
+        for (;;) {
+            if (leftctx(P, t, ptr, rbeg)) break;
+            if (ptr == rbeg) return 0;
+            if (!pl->ins) return 0;
+            ptr--; e++;
+            if (e > k) return 0;
+        }
+        bext = pos - ptr; berr = e;
+    } else {
+        if (!nfa_side(P, pl, t, -1, lb, lb, k, pos, rbeg, &bext, &berr)) return 0;
+    }
+    const int kf = k - berr;
+    int64_t fext; int ferr;
+    if (rl == 0) {
+        /* 414eae-414f19 */
+        if (kf < 0) return 0;
+        int n = 0; int64_t p = pos;
+        for (;;) {
+            if (rightctx(P, t, p, rend)) break;
+            if (p - pos == rend - pos) return 0;
+            if (!pl->ins) return 0;
+            n++; p++;
+            if (kf < n) return 0;
+        }
+        fext = p - pos;
+    } else {
+        if (!nfa_side(P, pl, t, +1, lb, rl, kf, pos, rend, &fext, &ferr)) return 0;
+    }
+    *beg = pos - bext;
+    *end = pos + fext;
+    return 1;
+}
+
+/* esimple checkMatch @4151d0 with recGetRecord @402030 ('\n' records clipped  */
+/* to the current scan range [tbeg, tend)).                                    */
+int nro_check_match(const nro_pattern *P, const nro_plan *pl, int i, const uint8_t *t,
+                    int64_t pos, int64_t tbeg, int64_t tend, int64_t *beg, int64_t *end)
+{
+    int64_t p = pl->type == NRO_FWD ? pos - 1 : pos;
+    int64_t rbeg = tbeg, rend = tend;
+    for (int64_t q = p - 1; q >= tbeg; q--) if (t[q] == '\n') { rbeg = q + 1; break; }
+    for (int64_t q = p; q < tend; q++) if (t[q] == '\n') { rend = q; break; }
+    if (p < rbeg || p >= rend) return 0;
+    return check_match1(P, pl, i, t, pos, rbeg, rend, beg, end);
+}
+
+/* ------------------------------------------------------------------------- */
+/* simple checkMatch @416790 in coordinate mode ([P+0x1028] != 0): the whole  */
+/* pattern must lie inside the scan range; no record logic.                   */
+static int simple_at(const nro_pattern *P, const uint8_t *t, int64_t s, int64_t tbeg, int64_t tend)
+{
+    if (s < tbeg || s + P->m > tend) return 0;
+    for (int j = 0; j < P->m; j++) if (!cls_has(P, j, t[s + j])) return 0;
+    if (P->start_line || P->end_line) {
+        if (!leftctx(P, t, s, tbeg)) return 0;
+        if (!rightctx(P, t, s + P->m, tend)) return 0;
+    }
+    return 1;
+}
+
+/* first match in [tbeg, tend): simpleScan @416600 / esimpleScan @4136d0       */
+static int scan_first(const nro_pattern *P, const nro_plan *pl, const uint8_t *t,
+                      int64_t tbeg, int64_t tend, int64_t *beg, int64_t *end)
+{
+    const int m = P->m;
+    switch (pl->type) {
+    case NRO_SIMPLE:
+        for (int64_t s = tbeg; s + m <= tend; s++)
+            if (simple_at(P, t, s, tbeg, tend)) { *beg = s; *end = s + m; return 1; }
+        return 0;
+    case NRO_SPLIT: {
+        /* 413725-4138a2: multi-pattern BNDM over the k+1 superimposed pieces.
+         * After a full window the state D holds bit b_j = L-1 + j*L for every
+         * piece j that matches the window exactly.  Piece i is then tested with
+         * the C expression D & (1 << b_i) evaluated in 32-bit int arithmetic
+         * (41384b: shl eax,cl ; cdqe): for b_i >= 32 the shift count wraps
+         * modulo 32 and bit 31 sign-extends.  The quirk is part of the
+         * reference's observable behaviour and is restated here. */
+        const int L = pl->L;
+        for (int64_t w = tbeg; w + L <= tend; w++) {
+            uint64_t D = 0;
+            for (int i = 0; i < pl->npieces; i++) {
+                int ok = 1;
+                for (int j = 0; j < L && ok; j++) ok = cls_has(P, pl->V[i] + j, t[w + j]);
+                if (ok) D |= 1ULL << (L - 1 + i * L);
+            }
+            if (!D) continue;
+            for (int i = 0; i < pl->npieces; i++) {
+                uint64_t mask = (uint64_t)(int64_t)(int32_t)(1u << ((L - 1 + i * L) & 31));
+                if ((D & mask) && nro_check_match(P, pl, i, t, w, tbeg, tend, beg, end)) return 1;
+            }
+        }
+        return 0;
+    }
+    case NRO_FWD:
+        /* 4138a7-4139e6 / 413d44 / 413f8c: candidate = text position just
+         * after an approximate occurrence of the scanned prefix */
+        for (int64_t pos = tbeg + 1; pos <= tend; pos++)
+            if (nro_check_match(P, pl, 0, t, pos, tbeg, tend, beg, end)) return 1;
+        return 0;
+    case NRO_BWD:
+        /* 4139eb-413d0c / 413e58 / 41404c: candidate = start of a window of
+         * L-k bytes */
+        for (int64_t w = tbeg; w + (pl->L - pl->k) <= tend; w++)
+            if (nro_check_match(P, pl, 0, t, w, tbeg, tend, beg, end)) return 1;
+        return 0;
+    }
+    return 0;
+}
+
+/* recSearchFile @402250 (whole file in one buffer).                          */
+int64_t nro_search(const nro_pattern *P, const nro_plan *pl, const uint8_t *t, int64_t n,
+                   nro_hit *hits, int64_t cap)
+{
+    int64_t count = 0, pos = 0;
+    if (n <= 0) return 0;
+    for (;;) {
+        int64_t b, e;
+        if (!scan_first(P, pl, t, pos, n, &b, &e)) break;
+        if (count < cap) { hits[count].beg = b; hits[count].end = e; }
+        count++;
+        if (e == n) break;
+        pos = e;
+    }
+    return count;
+}

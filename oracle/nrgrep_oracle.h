@@ -1,0 +1,79 @@
+/* nrgrep_oracle.h -- TEST INFRASTRUCTURE ONLY (CPU oracle, never shipped).
+ *
+ * Plain-C restatement of the search semantics of the reference's search
+ * engine, /root/reference/www/bin/nrgrep_coords (nrgrep 1.1 patched by the
+ * PatMatch authors to print match coordinates; shipped as an unstripped
+ * x86-64 binary WITHOUT sources).  Because there is no source, every
+ * function below cites the symbol + address range of the routine in that
+ * binary whose behaviour it restates (see `nm nrgrep_coords`), and the call
+ * site in the reference's Python that invokes it
+ * (www/FlaskApp/FlaskApp/patmatch.py:733-743).
+ *
+ * Parity pinning: oracle/ref/difftest.c maps the reference binary into the
+ * test process (oracle/ref/refload.c) and compares this restatement against
+ * the reference's own searchPreproc/searchScan on millions of random
+ * (pattern, options, text) cases; tests/golden/ holds vectors produced by
+ * running the reference binary itself (tests/golden/make_golden.py).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
+ * use this code.  The product path (patmatchdocker_b200/csrc) never does.
+ */
+#ifndef NRGREP_ORACLE_H
+#define NRGREP_ORACLE_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRO_MAXM 256            /* max pattern positions handled by the oracle */
+#define NRO_MAXK 15
+#define NRO_WORDS (NRO_MAXM / 64)
+
+enum { NRO_SIMPLE = 0, NRO_SPLIT = 1, NRO_BWD = 2, NRO_FWD = 3 };
+
+enum {
+    NRO_OK = 0,
+    NRO_ERR_SYNTAX = -1,        /* malformed pattern */
+    NRO_ERR_UNSUPPORTED = -2,   /* extended / regular pattern (?, *, +, |): not this path */
+    NRO_ERR_TOOLONG = -3
+};
+
+typedef struct {
+    int m;                       /* number of pattern positions */
+    int start_line, end_line;    /* leading '^' / trailing '$' (main @400e00: 40164d, 40162a) */
+    uint64_t cls[NRO_MAXM][4];   /* 256-bit byte class per position */
+} nro_pattern;
+
+typedef struct {
+    int k, ins, del, subs;       /* -k <k>[ids] */
+    int type;                    /* NRO_SIMPLE (k == 0) / NRO_SPLIT / NRO_BWD / NRO_FWD */
+    int L;                       /* SPLIT: piece length; BWD/FWD: sub-pattern length */
+    int npieces;                 /* SPLIT: k+1 ; BWD/FWD: 1 */
+    int V[NRO_MAXK + 1];         /* split points: left part = P[0..V[i]), right part = P[V[i]..m) */
+    double split_cost, fb_cost;  /* cost-model values (exact doubles of the reference) */
+    int fb_flag, fb_beg, fb_end; /* simpleFindBest outputs */
+} nro_plan;
+
+typedef struct { int64_t beg, end; } nro_hit;
+
+int nro_parse(const char *pattern, int icase, nro_pattern *P);
+int nro_plan_make(const nro_pattern *P, int k, int ins, int del, int subs, nro_plan *plan);
+
+/* Whole-file search exactly as recSearchFile @402250 drives searchScan: returns the
+ * number of hits (may exceed cap; only the first cap are stored). Offsets are
+ * byte offsets into text, [beg, end). */
+int64_t nro_search(const nro_pattern *P, const nro_plan *plan,
+                   const uint8_t *text, int64_t n, nro_hit *hits, int64_t cap);
+
+/* One verification call: esimple checkMatch @4151d0 (+ checkMatch1 @414190) for
+ * candidate (piece i, position pos) with the scan range [tbeg, tend). */
+int nro_check_match(const nro_pattern *P, const nro_plan *plan, int i,
+                    const uint8_t *text, int64_t pos, int64_t tbeg, int64_t tend,
+                    int64_t *beg, int64_t *end);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
