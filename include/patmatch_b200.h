@@ -1,0 +1,110 @@
+/* patmatch_b200.h -- C ABI of the B200-native PatMatch search engine.
+ *
+ * Drop-in boundary.  The reference Flask app (www/FlaskApp/FlaskApp/patmatch.py)
+ * reaches its search engine through two shell-outs:
+ *
+ *   patmatch.py:733-735   output  = os.popen(nrgrep_coords -i -b 1600000
+ *                                       -k <k><ids> '<pattern>' '<datafile>').read()
+ *   patmatch.py:739-743   output2 = the same for the reverse-complement pattern
+ *
+ * and then parses the "[beg, end]: text" lines (patmatch.py:505-516).  Every
+ * entry point below replaces one of those interfaces; the ctypes stub a
+ * maintainer adds is shown in INTEGRATION.md.  Plain pointers and sizes only.
+ *
+ * All functions return 0 on success, a negative PM_ERR_* code otherwise;
+ * pm_last_error() gives the message for the calling thread.  There is no CPU
+ * fallback: without a CUDA device pm_engine_create fails.
+ */
+#ifndef PATMATCH_B200_H
+#define PATMATCH_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PM_OK               0
+#define PM_ERR_CUDA        -1   /* CUDA runtime failure (message has the cudaError) */
+#define PM_ERR_SYNTAX      -2   /* malformed nrgrep pattern / -k option */
+#define PM_ERR_UNSUPPORTED -3   /* pattern needs nrgrep's EXTENDED/REGULAR engines (?,*,+,|), anchors, or m > 64 */
+#define PM_ERR_ARG         -4
+#define PM_ERR_OVERFLOW    -5   /* caller's hit buffer too small; *nhits holds the required size */
+
+#define PM_MAX_PIECES 16
+
+/* search plan types = nrgrep's esimple scan types (esimpleScan @4136d0) */
+#define PM_PLAN_SIMPLE 0        /* k = 0: exact scan (simpleScan @416600) */
+#define PM_PLAN_SPLIT  1        /* k+1 exact pieces + verification */
+#define PM_PLAN_BWD    2        /* backward approximate filter */
+#define PM_PLAN_FWD    3        /* forward approximate filter */
+
+typedef struct pm_engine pm_engine;
+typedef struct pm_dataset pm_dataset;
+
+/* one output line of nrgrep_coords: "[beg, end]: <bytes beg..end-1>" (recSearchFile @402250) */
+typedef struct { int64_t beg, end; } pm_hit;
+
+/* what esimplePreproc @415540 decides for (pattern, k); host-only introspection */
+typedef struct {
+    int m, k, ins, del, subs;
+    int type, L, npieces;
+    int V[PM_MAX_PIECES];
+    double split_cost, fb_cost;
+} pm_plan_info;
+
+/* per-search device timings (ms, CUDA events on the engine's stream) and counters */
+typedef struct {
+    float scan_ms, sort_ms, verify_ms, chain_ms, total_ms;
+    int64_t candidates, verified, hits;
+    int64_t scan_bytes;          /* text bytes the scan kernel covered */
+    int launches;                /* kernels launched by the last search */
+} pm_stats;
+
+const char *pm_last_error(void);
+const char *pm_version(void);
+
+/* host-only: parse `pattern` (nrgrep syntax as written by patmatch_to_nrgrep.pl) and the
+ * -k argument ("2ids", "1s", "0ids", ...) and report the plan the reference would choose. */
+int pm_plan(const char *pattern, const char *kopt, pm_plan_info *info);
+
+int pm_engine_create(int device, pm_engine **out);
+void pm_engine_destroy(pm_engine *e);
+/* launch on this cudaStream_t instead of the engine's own stream (0 = back to own) */
+int pm_engine_set_stream(pm_engine *e, void *cuda_stream);
+int pm_engine_synchronize(pm_engine *e);
+
+/* Replaces '<datafile>': the bytes of a .seq FASTA file (one sequence per line,
+ * patmatch.py:700) are copied to HBM once and stay resident across searches. */
+int pm_dataset_create(pm_engine *e, const uint8_t *host_bytes, int64_t n, pm_dataset **out);
+/* same, bytes already on the device (pointer stays owned by the caller) */
+int pm_dataset_wrap_device(pm_engine *e, const uint8_t *device_bytes, int64_t n, pm_dataset **out);
+void pm_dataset_destroy(pm_dataset *d);
+int64_t pm_dataset_size(const pm_dataset *d);
+
+/* Replaces one nrgrep_coords run (patmatch.py:733-735): all hits, in output order.
+ * hits may be NULL to only count.  *nhits receives the number of hits found. */
+int pm_search(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt,
+              pm_hit *hits, int64_t cap, int64_t *nhits);
+
+/* Batched motifs (same -k for all): hit lists are concatenated, offsets[i]..offsets[i+1]
+ * delimit pattern i.  offsets has npat+1 entries. */
+int pm_search_batch(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns,
+                    const char *kopt, pm_hit *hits, int64_t cap, int64_t *offsets);
+
+/* Sharded search for multi-GPU runs: only candidates whose anchor position lies in
+ * [pos_beg, pos_end) are produced; they are verified but NOT chained.  The caller
+ * gathers the per-rank lists (already sorted) and calls pm_resolve on one rank. */
+typedef struct { int64_t key, beg, end, reach; } pm_candidate;
+int pm_candidates(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt,
+                  int64_t pos_beg, int64_t pos_end,
+                  pm_candidate *cands, int64_t cap, int64_t *ncands);
+int pm_resolve(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt,
+               const pm_candidate *cands, int64_t ncands,
+               pm_hit *hits, int64_t cap, int64_t *nhits);
+
+int pm_get_stats(pm_engine *e, pm_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,216 @@
+"""ctypes binding of lib/libpatmatch_b200.so (C ABI: include/patmatch_b200.h)."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PM_MAX_PIECES = 16
+PLAN_NAMES = {0: "SIMPLE", 1: "SPLIT", 2: "BWD", 3: "FWD"}
+PM_ERR_OVERFLOW = -5
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("patmatch_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class PmHit(ctypes.Structure):
+    _fields_ = [("beg", ctypes.c_int64), ("end", ctypes.c_int64)]
+
+
+class PmCandidate(ctypes.Structure):
+    _fields_ = [("key", ctypes.c_int64), ("beg", ctypes.c_int64), ("end", ctypes.c_int64), ("reach", ctypes.c_int64)]
+
+
+class PmPlanInfo(ctypes.Structure):
+    _fields_ = [("m", ctypes.c_int), ("k", ctypes.c_int), ("ins", ctypes.c_int), ("del_", ctypes.c_int),
+                ("subs", ctypes.c_int), ("type", ctypes.c_int), ("L", ctypes.c_int), ("npieces", ctypes.c_int),
+                ("V", ctypes.c_int * PM_MAX_PIECES), ("split_cost", ctypes.c_double), ("fb_cost", ctypes.c_double)]
+
+
+class PmStats(ctypes.Structure):
+    _fields_ = [("scan_ms", ctypes.c_float), ("sort_ms", ctypes.c_float), ("verify_ms", ctypes.c_float),
+                ("chain_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
+                ("candidates", ctypes.c_int64), ("verified", ctypes.c_int64), ("hits", ctypes.c_int64),
+                ("scan_bytes", ctypes.c_int64), ("launches", ctypes.c_int)]
+
+
+HIT_DTYPE = np.dtype([("beg", "<i8"), ("end", "<i8")])
+CAND_DTYPE = np.dtype([("key", "<i8"), ("beg", "<i8"), ("end", "<i8"), ("reach", "<i8")])
+
+_lib = None
+
+
+def lib_path():
+    return os.path.join(_HERE, "lib", "libpatmatch_b200.so")
+
+
+def load():
+    """Load the native library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise NativeError(-1, "%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`" % path)
+    L = ctypes.CDLL(path)
+    vp, cp, i64 = ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64
+    L.pm_last_error.restype = cp
+    L.pm_version.restype = cp
+    L.pm_plan.argtypes = [cp, cp, ctypes.POINTER(PmPlanInfo)]
+    L.pm_engine_create.argtypes = [ctypes.c_int, ctypes.POINTER(vp)]
+    L.pm_engine_destroy.argtypes = [vp]
+    L.pm_engine_destroy.restype = None
+    L.pm_engine_set_stream.argtypes = [vp, vp]
+    L.pm_engine_synchronize.argtypes = [vp]
+    L.pm_dataset_create.argtypes = [vp, vp, i64, ctypes.POINTER(vp)]
+    L.pm_dataset_wrap_device.argtypes = [vp, vp, i64, ctypes.POINTER(vp)]
+    L.pm_dataset_destroy.argtypes = [vp]
+    L.pm_dataset_destroy.restype = None
+    L.pm_dataset_size.argtypes = [vp]
+    L.pm_dataset_size.restype = i64
+    L.pm_search.argtypes = [vp, vp, cp, cp, vp, i64, ctypes.POINTER(i64)]
+    L.pm_search_batch.argtypes = [vp, vp, ctypes.c_int, ctypes.POINTER(cp), cp, vp, i64, ctypes.POINTER(i64)]
+    L.pm_candidates.argtypes = [vp, vp, cp, cp, i64, i64, vp, i64, ctypes.POINTER(i64)]
+    L.pm_resolve.argtypes = [vp, vp, cp, cp, vp, i64, vp, i64, ctypes.POINTER(i64)]
+    L.pm_get_stats.argtypes = [vp, ctypes.POINTER(PmStats)]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise NativeError(rc, load().pm_last_error().decode("utf-8", "replace"))
+
+
+def _b(s):
+    return s if isinstance(s, bytes) else s.encode("latin-1")
+
+
+def plan(pattern, kopt):
+    """Host-only: the search plan the reference's esimplePreproc picks for (pattern, -k kopt)."""
+    info = PmPlanInfo()
+    _check(load().pm_plan(_b(pattern), _b(kopt), ctypes.byref(info)))
+    return {"m": info.m, "k": info.k, "ins": info.ins, "del": info.del_, "subs": info.subs,
+            "type": PLAN_NAMES[info.type], "L": info.L, "V": list(info.V)[:info.npieces],
+            "split_cost": info.split_cost, "fb_cost": info.fb_cost}
+
+
+class Dataset:
+    """A .seq file resident in HBM (replaces the '<datafile>' argument of nrgrep_coords)."""
+
+    def __init__(self, engine, handle, host_bytes=None):
+        self.engine, self._h, self.host_bytes = engine, handle, host_bytes
+
+    def __len__(self):
+        return load().pm_dataset_size(self._h)
+
+    def close(self):
+        if self._h:
+            load().pm_dataset_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One engine per GPU (one process per GPU in multi-GPU runs)."""
+
+    def __init__(self, device=0):
+        self._h = ctypes.c_void_p()
+        _check(load().pm_engine_create(int(device), ctypes.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            load().pm_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_handle):
+        _check(load().pm_engine_set_stream(self._h, ctypes.c_void_p(cuda_stream_handle or 0)))
+
+    def synchronize(self):
+        _check(load().pm_engine_synchronize(self._h))
+
+    def load_dataset(self, data):
+        """data: bytes / bytearray / numpy uint8 array with the .seq file contents (host memory)."""
+        arr = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
+        h = ctypes.c_void_p()
+        _check(load().pm_dataset_create(self._h, ctypes.c_void_p(arr.ctypes.data), arr.size, ctypes.byref(h)))
+        return Dataset(self, h, arr)
+
+    def wrap_device(self, device_ptr, nbytes):
+        h = ctypes.c_void_p()
+        _check(load().pm_dataset_wrap_device(self._h, ctypes.c_void_p(device_ptr), nbytes, ctypes.byref(h)))
+        return Dataset(self, h)
+
+    def search(self, dataset, pattern, kopt="0ids", cap=1 << 16):
+        """-> numpy structured array (beg, end): the '[beg, end]' pairs nrgrep_coords prints, in order."""
+        L = load()
+        n = ctypes.c_int64()
+        while True:
+            hits = np.empty(cap, dtype=HIT_DTYPE)
+            rc = L.pm_search(self._h, dataset._h, _b(pattern), _b(kopt), ctypes.c_void_p(hits.ctypes.data), cap, ctypes.byref(n))
+            if rc == PM_ERR_OVERFLOW:
+                cap = int(n.value)
+                continue
+            _check(rc)
+            return hits[: n.value]
+
+    def count(self, dataset, pattern, kopt="0ids"):
+        n = ctypes.c_int64()
+        _check(load().pm_search(self._h, dataset._h, _b(pattern), _b(kopt), None, 0, ctypes.byref(n)))
+        return n.value
+
+    def search_batch(self, dataset, patterns, kopt="0ids", cap=1 << 20):
+        L = load()
+        arr = (ctypes.c_char_p * len(patterns))(*[_b(p) for p in patterns])
+        offsets = (ctypes.c_int64 * (len(patterns) + 1))()
+        while True:
+            hits = np.empty(cap, dtype=HIT_DTYPE)
+            rc = L.pm_search_batch(self._h, dataset._h, len(patterns), arr, _b(kopt), ctypes.c_void_p(hits.ctypes.data), cap, offsets)
+            if rc == PM_ERR_OVERFLOW:
+                cap *= 4
+                continue
+            _check(rc)
+            off = np.array(list(offsets), dtype=np.int64)
+            return hits[: off[-1]], off
+
+    def candidates(self, dataset, pattern, kopt, pos_beg, pos_end, cap=1 << 16):
+        L = load()
+        n = ctypes.c_int64()
+        while True:
+            c = np.empty(cap, dtype=CAND_DTYPE)
+            rc = L.pm_candidates(self._h, dataset._h, _b(pattern), _b(kopt), pos_beg, pos_end, ctypes.c_void_p(c.ctypes.data), cap, ctypes.byref(n))
+            if rc == PM_ERR_OVERFLOW:
+                cap = int(n.value)
+                continue
+            _check(rc)
+            return c[: n.value]
+
+    def resolve(self, dataset, pattern, kopt, cands, cap=None):
+        L = load()
+        cands = np.ascontiguousarray(cands, dtype=CAND_DTYPE)
+        cap = max(len(cands), 1) if cap is None else cap
+        hits = np.empty(cap, dtype=HIT_DTYPE)
+        n = ctypes.c_int64()
+        _check(L.pm_resolve(self._h, dataset._h, _b(pattern), _b(kopt), ctypes.c_void_p(cands.ctypes.data), len(cands),
+                            ctypes.c_void_p(hits.ctypes.data), cap, ctypes.byref(n)))
+        return hits[: n.value]
+
+    def stats(self):
+        s = PmStats()
+        _check(load().pm_get_stats(self._h, ctypes.byref(s)))
+        return {f: getattr(s, f) for f, _ in PmStats._fields_}

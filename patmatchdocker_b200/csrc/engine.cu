@@ -1,0 +1,771 @@
+// engine.cu -- CUDA kernels (sm_100a) and the C ABI of the B200-native PatMatch engine.
+//
+// Replaces the reference's search engine process (nrgrep_coords, spawned by
+// www/FlaskApp/FlaskApp/patmatch.py:733-743).  Pipeline of one search:
+//
+//   scan    k_scan_bytes    bit-parallel Shift-And over the resident text; emits one
+//                           candidate (anchor position, piece) per exact piece hit
+//                           [esimpleScan @4136d0 type 1 / simpleScan @416600]
+//           k_scan_dense    BWD / FWD plans: every anchor whose verification succeeds
+//   sort    cub radix sort  candidate keys -> the order the reference meets them
+//   verify  k_verify        anchored k-error NFA left and right of the anchor
+//                           [esimple checkMatch @4151d0, checkMatch1 @414190]
+//   chain   k_chain         the reference restarts its scan at the end of every reported
+//                           hit (recSearchFile @402250); resolved per dependency cluster
+//   select  cub select      compacts the chosen hits in output order
+//
+// No CPU fallback anywhere: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "../../include/patmatch_b200.h"
+#include "plan.hpp"
+
+#define PM_MAXK 15
+
+static thread_local std::string g_err;
+const char *pm_last_error(void) { return g_err.c_str(); }
+const char *pm_version(void) { return "patmatch_b200 0.1 (sm_100a)"; }
+
+#define CK(call)                                                                       \
+    do {                                                                               \
+        cudaError_t _e = (call);                                                       \
+        if (_e != cudaSuccess) {                                                       \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(_e);                \
+            return PM_ERR_CUDA;                                                        \
+        }                                                                              \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------
+// device-side plan description (passed by value)
+struct DevPlan {
+    int type, m, k, L, npieces;
+    int ins, del, subs;
+    int V[PM_MAX_PIECES];
+    unsigned long long trig[PM_MAX_PIECES];
+    unsigned long long init, fin;
+};
+
+struct Cand { long long key, beg, end, reach; };   // == pm_candidate
+struct H16 { long long a, b; };                     // == pm_hit
+
+// ---------------------------------------------------------------------------------------
+// Anchored k-error NFA on one side of the anchor (checkMatch1 @414190, one direction).
+// dir < 0: consumes text[pos-1], text[pos-2], ... down to `lim` (record start / scan start);
+// dir > 0: consumes text[pos], text[pos+1], ... up to `lim` (record end).  The record
+// delimiter '\n' also stops the walk (recGetRecord @402030).
+// Returns 1 with *ext = bytes consumed by the chosen match, *err = its error row and
+// *steps = bytes examined (for the dependency test of the chain stage).
+__device__ __forceinline__ int nfa_side(const unsigned char *__restrict__ text, const unsigned long long *__restrict__ T,
+                                        int dir, int plen, int kmax, int ins, int del, int subs,
+                                        long long pos, long long lim, long long *ext, int *err, long long *steps)
+{
+    const unsigned long long fin = 1ULL << (plen - 1);
+    const unsigned long long live = (fin << 1) - 1ULL;      // plen == 64 -> all ones
+    unsigned long long R[PM_MAXK + 1];
+    int kb = kmax;
+    long long best_ext = -1;
+    int best_err = kmax;
+    *steps = 0;
+    for (int e = 0; e <= kb; e++) {
+        R[e] = del ? (e >= 64 ? ~0ULL : ((1ULL << e) - 1ULL)) : 0ULL;
+        if (R[e] & fin) { best_err = e; kb = e - 1; best_ext = 0; }
+    }
+    unsigned long long first = 1;
+    long long step = 0;
+    for (;;) {
+        long long tp = dir < 0 ? pos - step - 1 : pos + step;
+        if (dir < 0 ? (tp < lim) : (tp >= lim)) break;
+        unsigned c = text[tp];
+        if (c == '\n') break;
+        step++;
+        *steps = step;
+        const unsigned long long Tc = T[c];
+        unsigned long long oldp = R[0];
+        R[0] = ((R[0] << 1) | first) & Tc;
+        unsigned long long newp = R[0];
+        if (R[0] & fin) { *ext = step; *err = 0; return 1; }
+        for (int e = 1; e <= kb; e++) {
+            unsigned long long x = 0;
+            if (del) x = newp << 1;
+            if (ins) x |= oldp;
+            if (subs) x |= (oldp << 1) | first;
+            const unsigned long long nr = (((R[e] << 1) | first) & Tc) | x;
+            oldp = R[e];
+            R[e] = nr;
+            newp = nr;
+            if (nr & fin) {
+                int ec = e, ed;
+                for (;;) {
+                    ed = ec - 1;
+                    if (ed < 0) break;
+                    if (!(R[ed] & fin)) break;
+                    ec = ed;
+                }
+                if (ed < 0) { *ext = step; *err = 0; return 1; }
+                kb = ed; best_err = ec; best_ext = step;
+                break;
+            }
+        }
+        if (!(R[kb] & live)) break;
+        first = 0;
+    }
+    if (best_ext < 0) return 0;
+    *ext = best_ext;
+    *err = best_err;
+    return 1;
+}
+
+// esimple checkMatch @4151d0 for candidate (piece i, anchor pos) with scan range [tbeg, n).
+__device__ int check_match(const DevPlan &pl, const unsigned char *__restrict__ text, long long n,
+                           const unsigned long long *__restrict__ TL, const unsigned long long *__restrict__ TR,
+                           int i, long long pos, long long tbeg, long long *beg, long long *end, long long *reach)
+{
+    const long long p = pl.type == PM_PLAN_FWD ? pos - 1 : pos;
+    *reach = pos;
+    if (p < tbeg || p >= n) return 0;
+    if (text[p] == '\n') return 0;
+    const int lb = pl.V[i], rl = pl.m - lb;
+    long long bext = 0, fext = 0, steps = 0;
+    int berr = 0, ferr = 0;
+    if (lb > 0) {
+        int ok = nfa_side(text, TL + (size_t)i * 256, -1, lb, pl.k, pl.ins, pl.del, pl.subs, pos, tbeg, &bext, &berr, &steps);
+        *reach = pos - steps;
+        if (!ok) return 0;
+    }
+    if (rl > 0) {
+        if (!nfa_side(text, TR + (size_t)i * 256, +1, rl, pl.k - berr, pl.ins, pl.del, pl.subs, pos, n, &fext, &ferr, &steps)) return 0;
+    }
+    *beg = pos - bext;
+    *end = pos + fext;
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------
+// Scan kernel: byte-level Shift-And over superimposed pieces.
+//   D = ((D << 1) | init) & B[text[p]] ;  piece i ends at p  <=>  D bit i*L+L-1
+// One block stages TILE bytes (+64 bytes of left halo) into shared memory with coalesced
+// 128-bit loads; every thread then walks its own SEG-byte run.  Rows are padded by 16
+// bytes so that the per-thread 128-bit shared loads of a quarter-warp hit distinct banks.
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_SEG = 128;                              // bytes per thread per tile
+constexpr int SCAN_ROW = SCAN_SEG + 16;                    // padded row
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_SEG;         // 32 KiB
+constexpr int SCAN_HALO = 64;
+
+template <typename T>
+struct ScanArgs {
+    const unsigned char *text;
+    long long n;
+    long long p0, p1;            // end positions p handled: p0 <= p < p1
+    long long tile0;             // first tile index (tile = p / SCAN_TILE)
+    long long ntiles;
+    const unsigned long long *B; // 256 masks
+    T init, fin;
+    T trig[PM_MAX_PIECES];
+    int L, npieces;
+    unsigned long long *keys;
+    unsigned long long *count;   // [0] = candidates produced
+    long long cap;
+};
+
+template <typename T>
+__device__ __forceinline__ void scan_emit(const ScanArgs<T> &a, T hit, long long p)
+{
+    if (p < a.p0 || p >= a.p1 || p >= a.n) return;
+    const long long w = p - a.L + 1;
+    for (int i = 0; i < a.npieces; i++) {
+        if (hit & a.trig[i]) {
+            unsigned long long idx = atomicAdd(a.count, 1ULL);
+            if ((long long)idx < a.cap) a.keys[idx] = ((unsigned long long)w << 4) | (unsigned)i;
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_bytes(const ScanArgs<T> a)
+{
+    __shared__ T sB[256];
+    __shared__ __align__(16) unsigned char srow[SCAN_THREADS * SCAN_ROW];
+    __shared__ __align__(16) unsigned char shalo[SCAN_HALO];
+    const int tid = threadIdx.x;
+    sB[tid] = (T)a.B[tid];
+    const bool aligned = ((size_t)a.text & 15) == 0;
+
+    for (long long t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+        const long long tstart = (a.tile0 + t) * SCAN_TILE;
+        __syncthreads();
+        // ---- stage tile ----
+#pragma unroll
+        for (int it = 0; it < SCAN_TILE / 16 / SCAN_THREADS; it++) {
+            const int c = it * SCAN_THREADS + tid;              // 16-byte chunk in tile
+            const long long g = tstart + (long long)c * 16;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (aligned && g + 16 <= a.n) v = __ldg(reinterpret_cast<const uint4 *>(a.text + g));
+            else if (g < a.n) {
+                unsigned char tmp[16];
+#pragma unroll
+                for (int b = 0; b < 16; b++) tmp[b] = (g + b < a.n) ? a.text[g + b] : 0;
+                v = *reinterpret_cast<uint4 *>(tmp);
+            }
+            const int row = c / (SCAN_SEG / 16), col = c % (SCAN_SEG / 16);
+            *reinterpret_cast<uint4 *>(srow + row * SCAN_ROW + col * 16) = v;
+        }
+        if (tid < SCAN_HALO) {
+            const long long g = tstart - SCAN_HALO + tid;
+            shalo[tid] = (g >= 0 && g < a.n) ? a.text[g] : 0;
+        }
+        __syncthreads();
+        // ---- per-thread run ----
+        const long long seg = tstart + (long long)tid * SCAN_SEG;
+        if (seg >= a.p1 || seg >= a.n) continue;
+        if (seg + SCAN_SEG <= a.p0) continue;
+        T D = 0;
+        // warm-up over the L-1 bytes before the run (no emission)
+        {
+            int o = tid * SCAN_SEG - (a.L - 1);                 // offset relative to tile start
+            if (tstart + o < 0) o = (int)(-tstart);
+            for (; o < tid * SCAN_SEG; o++) {
+                unsigned c = o < 0 ? shalo[SCAN_HALO + o] : srow[(o / SCAN_SEG) * SCAN_ROW + (o % SCAN_SEG)];
+                D = ((D << 1) | a.init) & sB[c];
+            }
+        }
+        const unsigned char *my = srow + tid * SCAN_ROW;
+#pragma unroll 2
+        for (int v4 = 0; v4 < SCAN_SEG / 16; v4++) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(my + v4 * 16);
+            const unsigned ww[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int wi = 0; wi < 4; wi++) {
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const unsigned c = (ww[wi] >> (8 * b)) & 0xffu;
+                    D = ((D << 1) | a.init) & sB[c];
+                    const T hit = D & a.fin;
+                    if (hit) scan_emit(a, hit, seg + v4 * 16 + wi * 4 + b);
+                }
+            }
+        }
+    }
+}
+
+// BWD / FWD plans: the reference's approximate filters only propose anchors; the hit list is
+// decided by checkMatch alone (validated against the reference), so every anchor is verified.
+struct DenseArgs {
+    DevPlan pl;
+    const unsigned char *text;
+    long long n, a0, a1;         // anchors a0 <= a < a1
+    const unsigned long long *TL, *TR;
+    unsigned long long *keys, *count;
+    long long cap;
+};
+
+__global__ void __launch_bounds__(256) k_scan_dense(const DenseArgs a)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long pos = a.a0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; pos < a.a1; pos += stride) {
+        long long b, e, r;
+        if (check_match(a.pl, a.text, a.n, a.TL, a.TR, 0, pos, 0, &b, &e, &r)) {
+            unsigned long long idx = atomicAdd(a.count, 1ULL);
+            if ((long long)idx < a.cap) a.keys[idx] = (unsigned long long)pos << 4;
+        }
+    }
+}
+
+// verification of sorted candidates, unclipped (scan start = 0)
+__global__ void __launch_bounds__(128) k_verify(const DevPlan pl, const unsigned char *__restrict__ text, long long n,
+                                                const unsigned long long *__restrict__ TL, const unsigned long long *__restrict__ TR,
+                                                const unsigned long long *__restrict__ keys, long long ncand, Cand *__restrict__ out)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncand) return;
+    const unsigned long long key = keys[j];
+    const long long pos = (long long)(key >> 4);
+    const int i = (int)(key & 15);
+    Cand c;
+    c.key = (long long)key;
+    if (pl.type == PM_PLAN_SIMPLE) {
+        c.beg = pos; c.end = pos + pl.m; c.reach = pos;
+    } else {
+        long long b = -1, e = -1, r = pos;
+        if (!check_match(pl, text, n, TL, TR, i, pos, 0, &b, &e, &r)) { b = -1; e = -1; }
+        c.beg = b; c.end = e; c.reach = r;
+    }
+    out[j] = c;
+}
+
+// Chain stage.  The reference reports the first verified candidate at or after its scan
+// start, then restarts the scan at the end of that hit; verification never looks left of
+// the scan start.  Candidate j opens an independent cluster when no earlier candidate can
+// produce a hit that ends right of everything j depends on.
+__device__ __forceinline__ long long dep_lo(const DevPlan &pl, const Cand &c)
+{
+    long long a = c.key >> 4;
+    if (pl.type == PM_PLAN_FWD) a -= 1;
+    return c.reach < a ? c.reach : a;
+}
+
+__global__ void __launch_bounds__(128) k_chain(const DevPlan pl, const unsigned char *__restrict__ text, long long n,
+                                               const unsigned long long *__restrict__ TL, const unsigned long long *__restrict__ TR,
+                                               const Cand *__restrict__ cands, long long ncand,
+                                               pm_hit *__restrict__ hits, unsigned char *__restrict__ sel)
+{
+    const long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j0 >= ncand) return;
+    const long long span = pl.m + pl.k;
+    auto independent = [&](long long j) -> bool {
+        if (j == 0) return true;
+        return (cands[j - 1].key >> 4) + span <= dep_lo(pl, cands[j]);
+    };
+    if (!independent(j0)) return;
+    long long pos = 0;
+    for (long long t = j0; t < ncand; t++) {
+        if (t > j0 && independent(t)) break;
+        sel[t] = 0;
+        const Cand c = cands[t];
+        if (c.beg < 0) continue;
+        const long long anchor = c.key >> 4;
+        const long long p = pl.type == PM_PLAN_FWD ? anchor - 1 : anchor;
+        if (p < pos) continue;
+        long long b = c.beg, e = c.end;
+        if (pl.type != PM_PLAN_SIMPLE && dep_lo(pl, c) < pos) {
+            // the unclipped verification looked left of the new scan start: redo it clipped
+            long long r;
+            if (!check_match(pl, text, n, TL, TR, (int)(c.key & 15), anchor, pos, &b, &e, &r)) continue;
+        }
+        hits[t].beg = b;
+        hits[t].end = e;
+        sel[t] = 1;
+        if (e <= pos && b == e) break;                      // zero-length hit: the reference would not advance either
+        pos = e;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return PM_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max(bytes, (size_t)1 << 16);
+        CK(cudaMalloc(&p, want));
+        cap = want;
+        return PM_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct pm_engine {
+    int device = 0;
+    int sms = 148;
+    cudaStream_t own = nullptr, stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    DevBuf keys, keys2, cands, hits, hits2, sel, tables, counters, cubtmp;
+    unsigned long long *h_count = nullptr;          // pinned
+    pm_stats stats{};
+};
+
+struct pm_dataset {
+    pm_engine *e = nullptr;
+    const unsigned char *d_text = nullptr;
+    void *owned = nullptr;
+    long long n = 0;
+};
+
+int pm_engine_create(int device, pm_engine **out)
+{
+    if (!out) { g_err = "out is NULL"; return PM_ERR_ARG; }
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { g_err = "no such CUDA device (this engine has no CPU fallback)"; return PM_ERR_CUDA; }
+    CK(cudaSetDevice(device));
+    pm_engine *e = new pm_engine();
+    e->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    e->sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&e->own, cudaStreamNonBlocking));
+    e->stream = e->own;
+    for (auto &ev : e->ev) CK(cudaEventCreate(&ev));
+    CK(cudaMallocHost((void **)&e->h_count, 64));
+    *out = e;
+    return PM_OK;
+}
+
+void pm_engine_destroy(pm_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    for (DevBuf *b : {&e->keys, &e->keys2, &e->cands, &e->hits, &e->hits2, &e->sel, &e->tables, &e->counters, &e->cubtmp}) b->release();
+    for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
+    if (e->h_count) cudaFreeHost(e->h_count);
+    if (e->own) cudaStreamDestroy(e->own);
+    delete e;
+}
+
+int pm_engine_set_stream(pm_engine *e, void *s)
+{
+    if (!e) { g_err = "engine is NULL"; return PM_ERR_ARG; }
+    e->stream = s ? (cudaStream_t)s : e->own;
+    return PM_OK;
+}
+
+int pm_engine_synchronize(pm_engine *e)
+{
+    if (!e) { g_err = "engine is NULL"; return PM_ERR_ARG; }
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    return PM_OK;
+}
+
+int pm_dataset_create(pm_engine *e, const uint8_t *host, int64_t n, pm_dataset **out)
+{
+    if (!e || !out || n < 0 || (!host && n > 0)) { g_err = "bad argument"; return PM_ERR_ARG; }
+    CK(cudaSetDevice(e->device));
+    pm_dataset *d = new pm_dataset();
+    d->e = e; d->n = n;
+    void *p = nullptr;
+    cudaError_t rc = cudaMalloc(&p, (size_t)n + 256);
+    if (rc != cudaSuccess) { delete d; g_err = std::string("cudaMalloc dataset: ") + cudaGetErrorString(rc); return PM_ERR_CUDA; }
+    d->owned = p; d->d_text = (const unsigned char *)p;
+    if (n > 0) {
+        rc = cudaMemcpyAsync(p, host, (size_t)n, cudaMemcpyHostToDevice, e->stream);
+        if (rc == cudaSuccess) rc = cudaMemsetAsync((char *)p + n, 0, 256, e->stream);
+        if (rc == cudaSuccess) rc = cudaStreamSynchronize(e->stream);
+        if (rc != cudaSuccess) { cudaFree(p); delete d; g_err = std::string("dataset upload: ") + cudaGetErrorString(rc); return PM_ERR_CUDA; }
+    }
+    *out = d;
+    return PM_OK;
+}
+
+int pm_dataset_wrap_device(pm_engine *e, const uint8_t *dev, int64_t n, pm_dataset **out)
+{
+    if (!e || !out || n < 0 || (!dev && n > 0)) { g_err = "bad argument"; return PM_ERR_ARG; }
+    pm_dataset *d = new pm_dataset();
+    d->e = e; d->n = n; d->d_text = dev; d->owned = nullptr;
+    *out = d;
+    return PM_OK;
+}
+
+void pm_dataset_destroy(pm_dataset *d)
+{
+    if (!d) return;
+    if (d->owned) { cudaSetDevice(d->e->device); cudaFree(d->owned); }
+    delete d;
+}
+
+int64_t pm_dataset_size(const pm_dataset *d) { return d ? d->n : 0; }
+
+int pm_get_stats(pm_engine *e, pm_stats *out)
+{
+    if (!e || !out) { g_err = "bad argument"; return PM_ERR_ARG; }
+    *out = e->stats;
+    return PM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+struct Compiled {
+    pm::Pattern P;
+    pm::Options o;
+    pm::Plan plan;
+    DevPlan dp;
+    pm::FilterTables ft;
+    pm::VerifyTables vt;
+};
+
+static int compile(const char *pattern, const char *kopt, Compiled &c, bool need_tables)
+{
+    std::string err;
+    int rc = pm::parse_kopt(kopt, c.o, err);
+    if (rc) { g_err = err; return rc; }
+    rc = pm::parse_pattern(pattern, /*icase: patmatch.py always passes -i*/ true, c.P, err);
+    if (rc) { g_err = err; return rc; }
+    if (c.P.start_line || c.P.end_line) { g_err = "line anchors (^ $) are not supported on the GPU path yet"; return PM_ERR_UNSUPPORTED; }
+    rc = pm::make_plan(c.P, c.o, c.plan, err);
+    if (rc) { g_err = err; return rc; }
+    if (!need_tables) return PM_OK;
+    if (c.P.m() > 64) { g_err = "patterns longer than 64 positions are not supported on the GPU path yet"; return PM_ERR_UNSUPPORTED; }
+    DevPlan &d = c.dp;
+    memset(&d, 0, sizeof d);
+    d.type = c.plan.type; d.m = c.plan.m; d.k = c.plan.k; d.L = c.plan.L; d.npieces = c.plan.npieces;
+    d.ins = c.plan.ins; d.del = c.plan.del; d.subs = c.plan.subs;
+    for (int i = 0; i < PM_MAX_PIECES; i++) { d.V[i] = c.plan.V[i]; d.trig[i] = c.plan.trig[i]; }
+    if (c.plan.type == pm::SIMPLE || c.plan.type == pm::SPLIT) {
+        pm::build_filter(c.P, c.plan, c.ft);
+        d.init = c.ft.init; d.fin = c.ft.fin;
+        if (c.plan.type == pm::SIMPLE) d.trig[0] = c.ft.fin;
+    }
+    if (c.plan.type != pm::SIMPLE) pm::build_verify(c.P, c.plan, c.vt);
+    return PM_OK;
+}
+
+int pm_plan(const char *pattern, const char *kopt, pm_plan_info *info)
+{
+    if (!pattern || !kopt || !info) { g_err = "bad argument"; return PM_ERR_ARG; }
+    Compiled c;
+    int rc = compile(pattern, kopt, c, false);
+    if (rc) return rc;
+    memset(info, 0, sizeof *info);
+    info->m = c.plan.m; info->k = c.plan.k; info->ins = c.plan.ins; info->del = c.plan.del; info->subs = c.plan.subs;
+    info->type = c.plan.type; info->L = c.plan.L; info->npieces = c.plan.npieces;
+    for (int i = 0; i < PM_MAX_PIECES; i++) info->V[i] = c.plan.V[i];
+    info->split_cost = c.plan.split_cost; info->fb_cost = c.plan.fb_cost;
+    return PM_OK;
+}
+
+// upload B / TL / TR into e->tables; returns device pointers
+static int upload_tables(pm_engine *e, const Compiled &c, const unsigned long long **dB, const unsigned long long **dTL,
+                         const unsigned long long **dTR)
+{
+    const size_t nb = 256, nv = c.vt.TL.size();
+    int rc = e->tables.reserve((nb + 2 * nv) * 8 + 64);
+    if (rc) return rc;
+    unsigned long long *base = (unsigned long long *)e->tables.p;
+    CK(cudaMemcpyAsync(base, c.ft.B, nb * 8, cudaMemcpyHostToDevice, e->stream));
+    if (nv) {
+        CK(cudaMemcpyAsync(base + nb, c.vt.TL.data(), nv * 8, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(base + nb + nv, c.vt.TR.data(), nv * 8, cudaMemcpyHostToDevice, e->stream));
+    }
+    *dB = base; *dTL = base + nb; *dTR = base + nb + nv;
+    return PM_OK;
+}
+
+// scan + sort + verify: leaves ncand verified candidates (sorted) in e->cands
+static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, long long a0, long long a1,
+                              const unsigned long long *dB, const unsigned long long *dTL, const unsigned long long *dTR,
+                              long long *ncand_out)
+{
+    const DevPlan &dp = c.dp;
+    const long long n = d->n;
+    int rc;
+    if ((rc = e->counters.reserve(64))) return rc;
+    unsigned long long *d_count = (unsigned long long *)e->counters.p;
+    long long cap = std::max<long long>((long long)(e->keys.cap / 8), 1 << 16);
+    long long ncand = 0;
+    for (int attempt = 0; attempt < 3; attempt++) {
+        if ((rc = e->keys.reserve((size_t)cap * 8))) return rc;
+        CK(cudaMemsetAsync(d_count, 0, 8, e->stream));
+        CK(cudaEventRecord(e->ev[0], e->stream));
+        if (dp.type == PM_PLAN_SIMPLE || dp.type == PM_PLAN_SPLIT) {
+            // window starts w in [a0, a1) <=> end positions p = w + L - 1
+            long long p0 = a0 + dp.L - 1, p1 = std::min(a1 + dp.L - 1, n);
+            if (p1 > p0) {
+                const long long tile0 = p0 / SCAN_TILE, tile1 = (p1 - 1) / SCAN_TILE + 1;
+                const long long ntiles = tile1 - tile0;
+                const int grid = (int)std::min<long long>(ntiles, (long long)e->sms * 8);
+                if (dp.npieces * dp.L <= 32) {
+                    ScanArgs<unsigned> a;
+                    a.text = d->d_text; a.n = n; a.p0 = p0; a.p1 = p1; a.tile0 = tile0; a.ntiles = ntiles; a.B = dB;
+                    a.init = (unsigned)dp.init; a.fin = (unsigned)dp.fin;
+                    for (int i = 0; i < PM_MAX_PIECES; i++) a.trig[i] = (unsigned)dp.trig[i];
+                    a.L = dp.L; a.npieces = dp.npieces; a.keys = (unsigned long long *)e->keys.p; a.count = d_count; a.cap = cap;
+                    k_scan_bytes<unsigned><<<grid, SCAN_THREADS, 0, e->stream>>>(a);
+                } else {
+                    ScanArgs<unsigned long long> a;
+                    a.text = d->d_text; a.n = n; a.p0 = p0; a.p1 = p1; a.tile0 = tile0; a.ntiles = ntiles; a.B = dB;
+                    a.init = dp.init; a.fin = dp.fin;
+                    for (int i = 0; i < PM_MAX_PIECES; i++) a.trig[i] = dp.trig[i];
+                    a.L = dp.L; a.npieces = dp.npieces; a.keys = (unsigned long long *)e->keys.p; a.count = d_count; a.cap = cap;
+                    k_scan_bytes<unsigned long long><<<grid, SCAN_THREADS, 0, e->stream>>>(a);
+                }
+                e->stats.launches++;
+                e->stats.scan_bytes = p1 - p0;
+            }
+        } else {
+            // BWD: anchors w with w + (L - k) <= n ; FWD: anchors pos in [1, n]
+            long long lo = a0, hi = a1;
+            if (dp.type == PM_PLAN_BWD) { hi = std::min(hi, n - (dp.L - dp.k) + 1); }
+            else { lo = std::max<long long>(lo, 1); hi = std::min(hi, n + 1); }
+            if (hi > lo) {
+                DenseArgs a;
+                a.pl = dp; a.text = d->d_text; a.n = n; a.a0 = lo; a.a1 = hi; a.TL = dTL; a.TR = dTR;
+                a.keys = (unsigned long long *)e->keys.p; a.count = d_count; a.cap = cap;
+                const long long want = (hi - lo + 255) / 256;
+                const int grid = (int)std::min<long long>(want, (long long)e->sms * 16);
+                k_scan_dense<<<grid, 256, 0, e->stream>>>(a);
+                e->stats.launches++;
+                e->stats.scan_bytes = hi - lo;
+            }
+        }
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e->ev[1], e->stream));
+        CK(cudaMemcpyAsync(e->h_count, d_count, 8, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        ncand = (long long)e->h_count[0];
+        if (ncand <= cap) break;
+        cap = ncand + 1024;                                    // grow and rescan
+    }
+    e->stats.candidates = ncand;
+    // ---- sort ----
+    unsigned long long *keys = (unsigned long long *)e->keys.p;
+    if (ncand > 1) {
+        if ((rc = e->keys2.reserve((size_t)ncand * 8))) return rc;
+        size_t tmp = 0;
+        int end_bit = 64;
+        {
+            unsigned long long maxkey = ((unsigned long long)n << 4) | 15ULL;
+            end_bit = 1;
+            while (end_bit < 64 && (maxkey >> end_bit)) end_bit++;
+        }
+        CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp, keys, (unsigned long long *)e->keys2.p, (int)ncand, 0, end_bit, e->stream));
+        if ((rc = e->cubtmp.reserve(tmp))) return rc;
+        CK(cub::DeviceRadixSort::SortKeys(e->cubtmp.p, tmp, keys, (unsigned long long *)e->keys2.p, (int)ncand, 0, end_bit, e->stream));
+        keys = (unsigned long long *)e->keys2.p;
+        e->stats.launches += 3;
+    }
+    CK(cudaEventRecord(e->ev[2], e->stream));
+    // ---- verify ----
+    if (ncand > 0) {
+        if ((rc = e->cands.reserve((size_t)ncand * sizeof(Cand)))) return rc;
+        k_verify<<<(unsigned)((ncand + 127) / 128), 128, 0, e->stream>>>(dp, d->d_text, n, dTL, dTR, keys, ncand, (Cand *)e->cands.p);
+        CK(cudaGetLastError());
+        e->stats.launches++;
+    }
+    CK(cudaEventRecord(e->ev[3], e->stream));
+    *ncand_out = ncand;
+    return PM_OK;
+}
+
+// chain + select over ncand candidates in d_cands; hits copied to the host
+static int resolve_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, const Cand *d_cands, long long ncand,
+                              const unsigned long long *dTL, const unsigned long long *dTR,
+                              pm_hit *hits, int64_t cap, int64_t *nhits)
+{
+    int rc;
+    long long nh = 0;
+    if (ncand > 0) {
+        if ((rc = e->hits.reserve((size_t)ncand * sizeof(pm_hit)))) return rc;
+        if ((rc = e->hits2.reserve((size_t)ncand * sizeof(pm_hit)))) return rc;
+        if ((rc = e->sel.reserve((size_t)ncand))) return rc;
+        if ((rc = e->counters.reserve(64))) return rc;
+        CK(cudaMemsetAsync(e->sel.p, 0, (size_t)ncand, e->stream));
+        k_chain<<<(unsigned)((ncand + 127) / 128), 128, 0, e->stream>>>(c.dp, d->d_text, d->n, dTL, dTR, d_cands, ncand,
+                                                                       (pm_hit *)e->hits.p, (unsigned char *)e->sel.p);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e->ev[4], e->stream));
+        size_t tmp = 0;
+        long long *d_nsel = (long long *)((char *)e->counters.p + 16);
+        // select on 16-byte hit records
+        CK(cub::DeviceSelect::Flagged(nullptr, tmp, (H16 *)e->hits.p, (unsigned char *)e->sel.p, (H16 *)e->hits2.p, d_nsel, (int)ncand, e->stream));
+        if ((rc = e->cubtmp.reserve(tmp))) return rc;
+        CK(cub::DeviceSelect::Flagged(e->cubtmp.p, tmp, (H16 *)e->hits.p, (unsigned char *)e->sel.p, (H16 *)e->hits2.p, d_nsel, (int)ncand, e->stream));
+        CK(cudaMemcpyAsync(e->h_count + 2, d_nsel, 8, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        e->stats.launches += 3;
+        nh = (long long)e->h_count[2];
+    } else {
+        CK(cudaEventRecord(e->ev[4], e->stream));
+    }
+    *nhits = nh;
+    e->stats.hits = nh;
+    if (hits && nh > 0) {
+        if (nh > cap) { g_err = "hit buffer too small"; return PM_ERR_OVERFLOW; }
+        CK(cudaMemcpyAsync(hits, e->hits2.p, (size_t)nh * sizeof(pm_hit), cudaMemcpyDeviceToHost, e->stream));
+    }
+    CK(cudaEventRecord(e->ev[5], e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return PM_OK;
+}
+
+static void finish_stats(pm_engine *e)
+{
+    cudaEventElapsedTime(&e->stats.scan_ms, e->ev[0], e->ev[1]);
+    cudaEventElapsedTime(&e->stats.sort_ms, e->ev[1], e->ev[2]);
+    cudaEventElapsedTime(&e->stats.verify_ms, e->ev[2], e->ev[3]);
+    cudaEventElapsedTime(&e->stats.chain_ms, e->ev[3], e->ev[5]);
+    cudaEventElapsedTime(&e->stats.total_ms, e->ev[0], e->ev[5]);
+}
+
+int pm_search(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt, pm_hit *hits, int64_t cap, int64_t *nhits)
+{
+    if (!e || !d || !pattern || !kopt || !nhits || d->e != e) { g_err = "bad argument"; return PM_ERR_ARG; }
+    CK(cudaSetDevice(e->device));
+    Compiled c;
+    int rc = compile(pattern, kopt, c, true);
+    if (rc) return rc;
+    e->stats = pm_stats{};
+    *nhits = 0;
+    const unsigned long long *dB, *dTL, *dTR;
+    if ((rc = upload_tables(e, c, &dB, &dTL, &dTR))) return rc;
+    long long ncand = 0;
+    if ((rc = produce_candidates(e, d, c, 0, d->n + 1, dB, dTL, dTR, &ncand))) return rc;
+    e->stats.verified = ncand;
+    rc = resolve_candidates(e, d, c, (const Cand *)e->cands.p, ncand, dTL, dTR, hits, cap, nhits);
+    finish_stats(e);
+    return rc;
+}
+
+int pm_search_batch(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
+                    pm_hit *hits, int64_t cap, int64_t *offsets)
+{
+    if (!e || !d || npat < 0 || !patterns || !offsets) { g_err = "bad argument"; return PM_ERR_ARG; }
+    int64_t total = 0;
+    offsets[0] = 0;
+    pm_stats acc{};
+    for (int i = 0; i < npat; i++) {
+        int64_t nh = 0;
+        int rc = pm_search(e, d, patterns[i], kopt, hits ? hits + total : nullptr, hits ? cap - total : 0, &nh);
+        if (rc) return rc;
+        total += nh;
+        offsets[i + 1] = total;
+        acc.scan_ms += e->stats.scan_ms; acc.sort_ms += e->stats.sort_ms; acc.verify_ms += e->stats.verify_ms;
+        acc.chain_ms += e->stats.chain_ms; acc.total_ms += e->stats.total_ms;
+        acc.candidates += e->stats.candidates; acc.verified += e->stats.verified; acc.hits += e->stats.hits;
+        acc.scan_bytes += e->stats.scan_bytes; acc.launches += e->stats.launches;
+    }
+    e->stats = acc;
+    return PM_OK;
+}
+
+int pm_candidates(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt, int64_t pos_beg, int64_t pos_end,
+                  pm_candidate *cands, int64_t cap, int64_t *ncands)
+{
+    if (!e || !d || !pattern || !kopt || !ncands || d->e != e) { g_err = "bad argument"; return PM_ERR_ARG; }
+    CK(cudaSetDevice(e->device));
+    Compiled c;
+    int rc = compile(pattern, kopt, c, true);
+    if (rc) return rc;
+    e->stats = pm_stats{};
+    const unsigned long long *dB, *dTL, *dTR;
+    if ((rc = upload_tables(e, c, &dB, &dTL, &dTR))) return rc;
+    long long ncand = 0;
+    if ((rc = produce_candidates(e, d, c, std::max<int64_t>(pos_beg, 0), std::min<int64_t>(pos_end, d->n + 1), dB, dTL, dTR, &ncand))) return rc;
+    *ncands = ncand;
+    if (cands && ncand > 0) {
+        if (ncand > cap) { g_err = "candidate buffer too small"; return PM_ERR_OVERFLOW; }
+        CK(cudaMemcpyAsync(cands, e->cands.p, (size_t)ncand * sizeof(Cand), cudaMemcpyDeviceToHost, e->stream));
+    }
+    CK(cudaEventRecord(e->ev[4], e->stream));
+    CK(cudaEventRecord(e->ev[5], e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    finish_stats(e);
+    return PM_OK;
+}
+
+int pm_resolve(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt, const pm_candidate *cands, int64_t ncands,
+               pm_hit *hits, int64_t cap, int64_t *nhits)
+{
+    if (!e || !d || !pattern || !kopt || !nhits || ncands < 0 || (ncands && !cands) || d->e != e) { g_err = "bad argument"; return PM_ERR_ARG; }
+    CK(cudaSetDevice(e->device));
+    Compiled c;
+    int rc = compile(pattern, kopt, c, true);
+    if (rc) return rc;
+    e->stats = pm_stats{};
+    const unsigned long long *dB, *dTL, *dTR;
+    if ((rc = upload_tables(e, c, &dB, &dTL, &dTR))) return rc;
+    if ((rc = e->cands.reserve((size_t)std::max<int64_t>(ncands, 1) * sizeof(Cand)))) return rc;
+    for (auto &ev : e->ev) CK(cudaEventRecord(ev, e->stream));
+    if (ncands) CK(cudaMemcpyAsync(e->cands.p, cands, (size_t)ncands * sizeof(Cand), cudaMemcpyHostToDevice, e->stream));
+    rc = resolve_candidates(e, d, c, (const Cand *)e->cands.p, ncands, dTL, dTR, hits, cap, nhits);
+    finish_stats(e);
+    return rc;
+}

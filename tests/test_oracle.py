@@ -1,0 +1,43 @@
+"""CPU: the oracle against vectors produced by the reference itself (no GPU needed)."""
+import oracle_lib as O
+
+
+def test_oracle_matches_reference_golden(search_golden):
+    bad = []
+    for c in search_golden:
+        got = [list(h) for h in O.search(c["pattern"], c["text"], c["kopt"])]
+        if got != c["hits"]:
+            bad.append((c["pattern"], c["kopt"], got[:4], c["hits"][:4]))
+    assert not bad, bad[:5]
+
+
+def test_golden_covers_every_plan_type(search_golden):
+    seen = set()
+    for c in search_golden:
+        _, pl = O.plan(c["pattern"], c["kopt"])
+        seen.add(O.TYPE_NAMES[pl.type])
+    assert seen == {"SIMPLE", "SPLIT", "BWD", "FWD"}
+
+
+def test_banner(search_golden):
+    for c in search_golden:
+        k = O.parse_kopt(c["kopt"])[0]
+        assert c["banner"] == ("SIMPLE search" if k == 0 else "ESIMPLE search")
+
+
+def test_known_answers():
+    # hand-checked behaviours of the reference (see DESIGN.md "semantics")
+    assert O.search("(AAA)", ">s1\nAAAAAAA\n", "0ids") == [(4, 7), (7, 10)]                  # restart at hit end
+    assert O.search("(AC..)", ">ab AC\nGTNN\n", "0ids") == [(4, 8)]                           # '.' crosses '\n' when k = 0
+    assert O.search("(ACGT)", ">s\nAAGT\n", "1ids") == [(4, 7)]                               # shortest left extension
+    assert O.search("(ACGA)", ">s\nACGACGA\n", "1ids") == [(3, 7), (7, 10)]                   # never left of the scan start
+
+
+def test_32bit_piece_test_quirk():
+    # k+1 pieces of length 11 occupy 44 state bits; the reference tests piece i with a 32-bit
+    # `1 << bit`, so pieces 2 and 3 can never start a verification (esimpleScan @41384b)
+    pat = "([ACT]GCGGCT[^TG]TA[AG]TTCCCCC[AG]A[ATG]GT[^GAT]TA.CGGGAA[AC].TGGTCCA[AC][AT]CC)"
+    _, pl = O.plan(pat, "3id")
+    assert (pl.type, pl.L, list(pl.V)[:4]) == (1, 11, [1, 12, 23, 35])
+    text = ">s\nCTCCCTACCCGTGCGGCTACTAATTCCCCCAAAGGTCTAGCGGGAACTGGTCCAAACCGAGTGCG\n"
+    assert O.search(pat, text, "3id") == []
