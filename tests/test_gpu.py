@@ -182,16 +182,16 @@ def test_config2_20nt_two_errors_with_indels(engine):
 
 
 def test_large_genome_properties(engine):
-    # size-independent properties at 256 Mb (oracle too slow to run whole): ordering,
-    # no overlap, every hit is a genuine <= k-error occurrence, planted copies are found,
-    # and the hit list equals the oracle on sampled windows around the hits.
+    # 256 Mb (the oracle is too slow to run whole): ordering, no overlap, determinism, every
+    # planted copy is covered by a hit, and the hit list equals the oracle's inside sampled
+    # windows (compared away from the window edges, where the oracle's scan start differs).
     n = 256_000_000
     text = bytearray(genome(9, 8, n))
     motif = b"GATTACAGATTACA"
     rng = random.Random(10)
     planted_at = []
     for _ in range(200):
-        p = rng.randrange(1000, len(text) - 1000)
+        p = rng.randrange(5000, len(text) - 5000)
         if b"\n" in text[p - 40:p + 40]:
             continue
         text[p:p + len(motif)] = motif
@@ -200,16 +200,20 @@ def test_large_genome_properties(engine):
     ds = engine.load_dataset(text)
     hits = engine.search(ds, "(GATTACAGATTACA)", "2ids")
     b, e = hits["beg"], hits["end"]
+    assert len(hits) > len(planted_at)
     assert np.all(b[1:] >= e[:-1]) and np.all(e > b)
-    starts = set(b.tolist())
-    assert all(p in starts for p in planted_at)
     again = engine.search(ds, "(GATTACAGATTACA)", "2ids")
     assert np.array_equal(hits, again)                         # deterministic
-    for i in rng.sample(range(len(hits)), min(40, len(hits))):  # local oracle check
-        lo = text.rfind(b"\n", 0, int(b[i])) + 1
-        hi = text.find(b"\n", int(e[i]))
-        lo2, hi2 = max(lo, int(b[i]) - 3000), min(hi, int(e[i]) + 3000)
-        window = text[lo2:hi2]
-        local = O.search("(GATTACAGATTACA)", window, "2ids")
-        assert (int(b[i]) - lo2, int(e[i]) - lo2) in local or lo2 != lo
+    for p in planted_at:
+        j = np.searchsorted(e, p, side="right")
+        assert j < len(hits) and b[j] < p + len(motif), p      # some hit overlaps the planted copy
+    centers = planted_at[:30] + [int(b[i]) for i in rng.sample(range(len(hits)), 30)]
+    for c in centers:
+        lo = max(text.rfind(b"\n", 0, c) + 1, c - 3000)
+        hi = text.find(b"\n", c)
+        hi = min(hi if hi >= 0 else len(text), c + 3000)
+        local = [(x + lo, y + lo) for x, y in O.search("(GATTACAGATTACA)", text[lo:hi], "2ids")]
+        inner = lambda hs: [h for h in hs if h[0] >= lo + 200 and h[1] <= hi - 200]
+        mine = [(int(x), int(y)) for x, y in zip(b, e) if x >= lo and y <= hi]
+        assert inner(mine) == inner(local), c
     ds.close()
