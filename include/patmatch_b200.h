@@ -56,8 +56,10 @@ typedef struct {
 typedef struct {
     float scan_ms, sort_ms, verify_ms, chain_ms, total_ms;
     int64_t candidates, verified, hits;
-    int64_t scan_bytes;          /* text bytes the scan kernel covered */
+    int64_t scan_bytes;          /* HBM bytes the scan kernel had to read (its algorithmic bytes) */
+    int64_t scan_bases;          /* text positions the scan kernel covered */
     int launches;                /* kernels launched by the last search */
+    int packed;                  /* 1: 2-bit packed bit-sliced scan, 0: byte Shift-And / dense */
 } pm_stats;
 
 const char *pm_last_error(void);
@@ -72,6 +74,11 @@ void pm_engine_destroy(pm_engine *e);
 /* launch on this cudaStream_t instead of the engine's own stream (0 = back to own) */
 int pm_engine_set_stream(pm_engine *e, void *cuda_stream);
 int pm_engine_synchronize(pm_engine *e);
+/* scan kernel selection: 0 = auto (packed for DNA-like datasets), 1 = byte Shift-And, 2 = packed */
+int pm_engine_set_scan_mode(pm_engine *e, int mode);
+/* the reference's -b buffer size in BYTES (patmatch.py:37,733 pass 1600000, the default here):
+ * nrgrep_coords scans the file one buffer fill at a time and no hit crosses a fill. 0 = one fill. */
+int pm_engine_set_buffer_size(pm_engine *e, int64_t bytes);
 
 /* Replaces '<datafile>': the bytes of a .seq FASTA file (one sequence per line,
  * patmatch.py:700) are copied to HBM once and stay resident across searches. */

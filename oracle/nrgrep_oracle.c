@@ -584,19 +584,77 @@ static int scan_first(const nro_pattern *P, const nro_plan *pl, const uint8_t *t
     return 0;
 }
 
-/* recSearchFile @402250 (whole file in one buffer).                          */
+/* recSearchFile @402250 over the text of one buffer fill [s, e).                */
+static int64_t search_range(const nro_pattern *P, const nro_plan *pl, const uint8_t *t, int64_t s, int64_t e,
+                            nro_hit *hits, int64_t cap, int64_t count)
+{
+    int64_t pos = s;
+    for (;;) {
+        int64_t b, en;
+        if (!scan_first(P, pl, t, pos, e, &b, &en)) break;
+        if (count < cap) { hits[count].beg = b; hits[count].end = en; }
+        count++;
+        if (en == e) break;
+        if (en <= pos && b == en) break;          /* zero-length hit: the reference would spin here */
+        pos = en;
+    }
+    return count;
+}
+
+/* Buffer fills (bufCreate @41bb60, bufSetFile @41bbc0, bufLoad @41bbf0 and the top of
+ * recSearchFile @402298-4024f0).  The buffer holds `bufsize` BYTES (main @401150 stores
+ * atoi(-b) unscaled; patmatch.py passes 1600000).  A fill that does not reach EOF is
+ * scanned up to and including its last '\n'; the next fill starts AT that '\n'.  A fill
+ * without a usable '\n' ("Record longer than buffer size ... has been split") is scanned
+ * whole and the next fill starts right after it.  Returns the number of fills written to
+ * seg (pairs start,end).                                                               */
+int64_t nro_buffer_fills(const uint8_t *t, int64_t n, int64_t bufsize, int64_t *seg, int64_t segcap)
+{
+    int64_t k = 0, S = 0;
+    if (bufsize <= 0) bufsize = n + 1;
+    while (n - S > 0) {
+        int64_t dsize = n - S < bufsize ? n - S : bufsize;
+        int64_t E, next;
+        if (dsize < bufsize) { E = S + dsize; next = n; }
+        else {
+            int64_t p = S + dsize - 1;
+            while (p > S && t[p] != '\n') p--;
+            if (p > S) { E = p + 1; next = p; }
+            else { E = S + dsize; next = S + dsize; }
+        }
+        if (k < segcap) { seg[2 * k] = S; seg[2 * k + 1] = E; }
+        k++;
+        S = next;
+    }
+    return k;
+}
+
+int64_t nro_search_buffered(const nro_pattern *P, const nro_plan *pl, const uint8_t *t, int64_t n, int64_t bufsize,
+                            nro_hit *hits, int64_t cap)
+{
+    int64_t count = 0, S = 0;
+    if (bufsize <= 0) bufsize = n + 1;
+    while (n - S > 0) {
+        int64_t seg[2];
+        /* one fill at a time, same rule as nro_buffer_fills */
+        int64_t dsize = n - S < bufsize ? n - S : bufsize, next;
+        if (dsize < bufsize) { seg[0] = S; seg[1] = S + dsize; next = n; }
+        else {
+            int64_t p = S + dsize - 1;
+            while (p > S && t[p] != '\n') p--;
+            if (p > S) { seg[0] = S; seg[1] = p + 1; next = p; }
+            else { seg[0] = S; seg[1] = S + dsize; next = S + dsize; }
+        }
+        count = search_range(P, pl, t, seg[0], seg[1], hits, cap, count);
+        S = next;
+    }
+    return count;
+}
+
+/* whole file in one buffer fill */
 int64_t nro_search(const nro_pattern *P, const nro_plan *pl, const uint8_t *t, int64_t n,
                    nro_hit *hits, int64_t cap)
 {
-    int64_t count = 0, pos = 0;
     if (n <= 0) return 0;
-    for (;;) {
-        int64_t b, e;
-        if (!scan_first(P, pl, t, pos, n, &b, &e)) break;
-        if (count < cap) { hits[count].beg = b; hits[count].end = e; }
-        count++;
-        if (e == n) break;
-        pos = e;
-    }
-    return count;
+    return search_range(P, pl, t, 0, n, hits, cap, 0);
 }

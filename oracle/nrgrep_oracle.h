@@ -67,6 +67,12 @@ int nro_plan_make(const nro_pattern *P, int k, int ins, int del, int subs, nro_p
 int64_t nro_search(const nro_pattern *P, const nro_plan *plan,
                    const uint8_t *text, int64_t n, nro_hit *hits, int64_t cap);
 
+/* The same with the reference's buffer fills of `bufsize` bytes (-b; patmatch.py:731 passes
+ * 1600000): recSearchFile scans one fill at a time and a hit never crosses a fill. */
+int64_t nro_search_buffered(const nro_pattern *P, const nro_plan *plan, const uint8_t *text, int64_t n,
+                            int64_t bufsize, nro_hit *hits, int64_t cap);
+int64_t nro_buffer_fills(const uint8_t *text, int64_t n, int64_t bufsize, int64_t *seg, int64_t segcap);
+
 /* One verification call: esimple checkMatch @4151d0 (+ checkMatch1 @414190) for
  * candidate (piece i, position pos) with the scan range [tbeg, tend). */
 int nro_check_match(const nro_pattern *P, const nro_plan *plan, int i,

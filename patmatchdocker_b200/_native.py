@@ -34,7 +34,8 @@ class PmStats(ctypes.Structure):
     _fields_ = [("scan_ms", ctypes.c_float), ("sort_ms", ctypes.c_float), ("verify_ms", ctypes.c_float),
                 ("chain_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
                 ("candidates", ctypes.c_int64), ("verified", ctypes.c_int64), ("hits", ctypes.c_int64),
-                ("scan_bytes", ctypes.c_int64), ("launches", ctypes.c_int)]
+                ("scan_bytes", ctypes.c_int64), ("scan_bases", ctypes.c_int64), ("launches", ctypes.c_int),
+                ("packed", ctypes.c_int)]
 
 
 HIT_DTYPE = np.dtype([("beg", "<i8"), ("end", "<i8")])
@@ -65,6 +66,8 @@ def load():
     L.pm_engine_destroy.restype = None
     L.pm_engine_set_stream.argtypes = [vp, vp]
     L.pm_engine_synchronize.argtypes = [vp]
+    L.pm_engine_set_scan_mode.argtypes = [vp, ctypes.c_int]
+    L.pm_engine_set_buffer_size.argtypes = [vp, i64]
     L.pm_dataset_create.argtypes = [vp, vp, i64, ctypes.POINTER(vp)]
     L.pm_dataset_wrap_device.argtypes = [vp, vp, i64, ctypes.POINTER(vp)]
     L.pm_dataset_destroy.argtypes = [vp]
@@ -140,6 +143,14 @@ class Engine:
 
     def set_stream(self, cuda_stream_handle):
         _check(load().pm_engine_set_stream(self._h, ctypes.c_void_p(cuda_stream_handle or 0)))
+
+    def set_scan_mode(self, mode):
+        """'auto' | 'bytes' | 'packed' -- which scan kernel SIMPLE/SPLIT plans use."""
+        _check(load().pm_engine_set_scan_mode(self._h, {"auto": 0, "bytes": 1, "packed": 2}[mode]))
+
+    def set_buffer_size(self, nbytes):
+        """the reference's -b (bytes); patmatch.py uses 1600000, the default"""
+        _check(load().pm_engine_set_buffer_size(self._h, int(nbytes)))
 
     def synchronize(self):
         _check(load().pm_engine_synchronize(self._h))

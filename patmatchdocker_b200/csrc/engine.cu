@@ -36,7 +36,7 @@ const char *pm_version(void) { return "patmatch_b200 0.1 (sm_100a)"; }
     do {                                                                               \
         cudaError_t _e = (call);                                                       \
         if (_e != cudaSuccess) {                                                       \
-            g_err = std::string(#call) + ": " + cudaGetErrorString(_e);                \
+            g_err = std::string(#call) + " (engine.cu:" + std::to_string(__LINE__) + "): " + cudaGetErrorString(_e); \
             return PM_ERR_CUDA;                                                        \
         }                                                                              \
     } while (0)
@@ -53,6 +53,8 @@ struct DevPlan {
 
 struct Cand { long long key, beg, end, reach; };   // == pm_candidate
 struct H16 { long long a, b; };                     // == pm_hit
+
+#include "packed.cuh"
 
 // ---------------------------------------------------------------------------------------
 // Anchored k-error NFA on one side of the anchor (checkMatch1 @414190, one direction).
@@ -119,6 +121,20 @@ __device__ __forceinline__ int nfa_side(const unsigned char *__restrict__ text, 
     *ext = best_ext;
     *err = best_err;
     return 1;
+}
+
+// Buffer fills of the reference (bufLoad @41bbf0, recSearchFile @402298): the file is scanned one
+// fill [S_k, E_k) at a time; fills are computed on the host (compute_fills) and looked up here.
+struct Fills { const long long *S, *E; int n; };
+
+__device__ __forceinline__ int fill_of(const Fills &f, long long x)      // last k with S[k] <= x
+{
+    int lo = 0, hi = f.n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (f.S[mid] <= x) lo = mid; else hi = mid - 1;
+    }
+    return lo;
 }
 
 // esimple checkMatch @4151d0 for candidate (piece i, anchor pos) with scan range [tbeg, n).
@@ -263,6 +279,7 @@ struct DenseArgs {
     const unsigned long long *TL, *TR;
     unsigned long long *keys, *count;
     long long cap;
+    Fills fills;
 };
 
 __global__ void __launch_bounds__(256) k_scan_dense(const DenseArgs a)
@@ -270,17 +287,37 @@ __global__ void __launch_bounds__(256) k_scan_dense(const DenseArgs a)
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long pos = a.a0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; pos < a.a1; pos += stride) {
         long long b, e, r;
-        if (check_match(a.pl, a.text, a.n, a.TL, a.TR, 0, pos, 0, &b, &e, &r)) {
+        const long long p = a.pl.type == PM_PLAN_FWD ? pos - 1 : pos;
+        const int f = fill_of(a.fills, p);
+        const long long S = a.fills.S[f], E = a.fills.E[f];
+        if (a.pl.type == PM_PLAN_BWD && pos + (a.pl.L - a.pl.k) > E) continue;
+        if (check_match(a.pl, a.text, E, a.TL, a.TR, 0, pos, S, &b, &e, &r)) {
             unsigned long long idx = atomicAdd(a.count, 1ULL);
             if ((long long)idx < a.cap) a.keys[idx] = (unsigned long long)pos << 4;
         }
     }
 }
 
+// Exact re-check of a packed-scan candidate on the raw bytes: which pieces match the window
+// at w, and does that set fire piece i (same rule as scan_emit).
+__device__ __forceinline__ bool raw_trigger(const DevPlan &pl, const unsigned long long *__restrict__ B,
+                                            const unsigned char *__restrict__ text, long long n, long long w, int i)
+{
+    if (w < 0 || w + pl.L > n) return false;
+    unsigned long long D = ~0ULL;
+    for (int j = 0; j < pl.L; j++) D &= B[text[w + j]] >> j;      // bit i*L set <=> piece i accepts all L bytes
+    unsigned long long top = 0;
+    for (int q = 0; q < pl.npieces; q++)
+        if ((D >> (q * pl.L)) & 1ULL) top |= 1ULL << (q * pl.L + pl.L - 1);
+    return (top & pl.trig[i]) != 0;
+}
+
 // verification of sorted candidates, unclipped (scan start = 0)
 __global__ void __launch_bounds__(128) k_verify(const DevPlan pl, const unsigned char *__restrict__ text, long long n,
+                                                const unsigned long long *__restrict__ B,
                                                 const unsigned long long *__restrict__ TL, const unsigned long long *__restrict__ TR,
-                                                const unsigned long long *__restrict__ keys, long long ncand, Cand *__restrict__ out)
+                                                const unsigned long long *__restrict__ keys, long long ncand, Cand *__restrict__ out,
+                                                int recheck, const Fills fills)
 {
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= ncand) return;
@@ -289,11 +326,18 @@ __global__ void __launch_bounds__(128) k_verify(const DevPlan pl, const unsigned
     const int i = (int)(key & 15);
     Cand c;
     c.key = (long long)key;
-    if (pl.type == PM_PLAN_SIMPLE) {
+    const long long p = pl.type == PM_PLAN_FWD ? pos - 1 : pos;
+    const int f = fill_of(fills, p);
+    const long long S = fills.S[f], E = fills.E[f];
+    // the scanned window of the candidate must lie inside its fill
+    const long long wlen = pl.type == PM_PLAN_SIMPLE ? pl.m : pl.type == PM_PLAN_SPLIT ? pl.L : pl.type == PM_PLAN_BWD ? pl.L - pl.k : 0;
+    if (pos + wlen > E || (recheck && !raw_trigger(pl, B, text, n, pos, i))) {
+        c.beg = -1; c.end = -1; c.reach = pos;
+    } else if (pl.type == PM_PLAN_SIMPLE) {
         c.beg = pos; c.end = pos + pl.m; c.reach = pos;
     } else {
         long long b = -1, e = -1, r = pos;
-        if (!check_match(pl, text, n, TL, TR, i, pos, 0, &b, &e, &r)) { b = -1; e = -1; }
+        if (!check_match(pl, text, E, TL, TR, i, pos, S, &b, &e, &r)) { b = -1; e = -1; }
         c.beg = b; c.end = e; c.reach = r;
     }
     out[j] = c;
@@ -313,17 +357,23 @@ __device__ __forceinline__ long long dep_lo(const DevPlan &pl, const Cand &c)
 __global__ void __launch_bounds__(128) k_chain(const DevPlan pl, const unsigned char *__restrict__ text, long long n,
                                                const unsigned long long *__restrict__ TL, const unsigned long long *__restrict__ TR,
                                                const Cand *__restrict__ cands, long long ncand,
-                                               pm_hit *__restrict__ hits, unsigned char *__restrict__ sel)
+                                               pm_hit *__restrict__ hits, unsigned char *__restrict__ sel, const Fills fills)
 {
     const long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j0 >= ncand) return;
     const long long span = pl.m + pl.k;
+    auto fill_at = [&](long long j) -> int {
+        const long long a = cands[j].key >> 4;
+        return fill_of(fills, pl.type == PM_PLAN_FWD ? a - 1 : a);
+    };
     auto independent = [&](long long j) -> bool {
         if (j == 0) return true;
-        return (cands[j - 1].key >> 4) + span <= dep_lo(pl, cands[j]);
+        if ((cands[j - 1].key >> 4) + span <= dep_lo(pl, cands[j])) return true;
+        return fill_at(j) != fill_at(j - 1);               // a new fill restarts the scan
     };
     if (!independent(j0)) return;
-    long long pos = 0;
+    int cur = fill_at(j0);
+    long long pos = fills.S[cur];
     for (long long t = j0; t < ncand; t++) {
         if (t > j0 && independent(t)) break;
         sel[t] = 0;
@@ -332,11 +382,12 @@ __global__ void __launch_bounds__(128) k_chain(const DevPlan pl, const unsigned 
         const long long anchor = c.key >> 4;
         const long long p = pl.type == PM_PLAN_FWD ? anchor - 1 : anchor;
         if (p < pos) continue;
+        const long long n_fill = fills.E[cur];
         long long b = c.beg, e = c.end;
         if (pl.type != PM_PLAN_SIMPLE && dep_lo(pl, c) < pos) {
             // the unclipped verification looked left of the new scan start: redo it clipped
             long long r;
-            if (!check_match(pl, text, n, TL, TR, (int)(c.key & 15), anchor, pos, &b, &e, &r)) continue;
+            if (!check_match(pl, text, n_fill, TL, TR, (int)(c.key & 15), anchor, pos, &b, &e, &r)) continue;
         }
         hits[t].beg = b;
         hits[t].end = e;
@@ -370,6 +421,8 @@ struct pm_engine {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     DevBuf keys, keys2, cands, hits, hits2, sel, tables, counters, cubtmp;
     unsigned long long *h_count = nullptr;          // pinned
+    int scan_mode = 0;                              // 0 auto, 1 byte Shift-And, 2 packed bit-sliced
+    long long bufsize = 1600000;                    // patmatch.py:37 MAX_BUFFER_SIZE (-b, in bytes)
     pm_stats stats{};
 };
 
@@ -378,7 +431,96 @@ struct pm_dataset {
     const unsigned char *d_text = nullptr;
     void *owned = nullptr;
     long long n = 0;
+    // 2-bit packed planes (packed.cuh)
+    unsigned *hi = nullptr, *lo = nullptr, *xx = nullptr;
+    long long nwords = 0;
+    long long nexc = 0;            // bytes that are not ACGTacgt
+    bool dna_like = false;         // few enough exceptions for the packed scan to pay off
+    // buffer fills of the reference for the engine's buffer size
+    std::vector<long long> newlines;   // sorted positions of '\n'
+    long long fills_bufsize = -1;
+    long long *d_fills = nullptr;      // S[0..nfills) then E[0..nfills)
+    int nfills = 0;
 };
+
+static int pack_dataset(pm_engine *e, pm_dataset *d)
+{
+    const long long n = d->n;
+    long long nw = (n + 31) / 32;
+    nw = (nw + 127) / 128 * 128 + 128;
+    d->nwords = nw;
+    void *p = nullptr;
+    CK(cudaMalloc(&p, (size_t)nw * 4 * 3));
+    d->hi = (unsigned *)p; d->lo = d->hi + nw; d->xx = d->lo + nw;
+    int rc;
+    if ((rc = e->counters.reserve(64))) return rc;
+    unsigned long long *d_exc = (unsigned long long *)((char *)e->counters.p + 32);
+    CK(cudaMemsetAsync(d_exc, 0, 24, e->stream));
+    const long long groups = nw / 32;
+    const int grid = (int)std::min<long long>((groups + 7) / 8, (long long)e->sms * 16);
+    k_pack<<<std::max(grid, 1), 256, 0, e->stream>>>(d->d_text, n, nw, d->hi, d->lo, d->xx, d_exc);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(e->h_count + 4, d_exc, 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpyAsync(e->h_count + 5, d_exc + 1, 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    d->nexc = (long long)e->h_count[4];
+    d->dna_like = n > 0 && d->nexc * 8 <= n;
+    // newline positions for the buffer-fill table
+    const long long nnl = (long long)e->h_count[5];
+    d->newlines.resize((size_t)nnl);
+    if (nnl > 0) {
+        void *dn = nullptr;
+        CK(cudaMalloc(&dn, (size_t)nnl * 8));
+        const int g2 = (int)std::min<long long>((n / 16 + 255) / 256 + 1, (long long)e->sms * 16);
+        k_newlines<<<g2, 256, 0, e->stream>>>(d->d_text, n, (unsigned long long *)dn, d_exc + 2);
+        cudaError_t rc2 = cudaGetLastError();
+        if (rc2 == cudaSuccess) rc2 = cudaMemcpyAsync(d->newlines.data(), dn, (size_t)nnl * 8, cudaMemcpyDeviceToHost, e->stream);
+        if (rc2 == cudaSuccess) rc2 = cudaStreamSynchronize(e->stream);
+        cudaFree(dn);
+        if (rc2 != cudaSuccess) { g_err = std::string("newline index: ") + cudaGetErrorString(rc2); return PM_ERR_CUDA; }
+        std::sort(d->newlines.begin(), d->newlines.end());
+    }
+    return PM_OK;
+}
+
+// Buffer fills [S_k, E_k) exactly as the reference produces them (bufSetFile @41bbc0, bufLoad @41bbf0,
+// recSearchFile @402298-4024f0): a fill of `bufsize` bytes that does not reach EOF is scanned up to and
+// including its last '\n' and the next fill starts AT that '\n'; without a usable '\n' the fill is scanned
+// whole ("Record longer than buffer size ... has been split") and the next one starts right after it.
+static int ensure_fills(pm_engine *e, pm_dataset *d, Fills *out)
+{
+    if (d->fills_bufsize != e->bufsize) {
+        std::vector<long long> S, E;
+        const long long n = d->n, bs = e->bufsize > 0 ? e->bufsize : n + 1;
+        long long s0 = 0;
+        while (n - s0 > 0) {
+            const long long dsize = std::min(bs, n - s0);
+            long long en, next;
+            if (dsize < bs) { en = s0 + dsize; next = n; }
+            else {
+                // last newline p with s0 < p <= s0 + dsize - 1
+                auto it = std::upper_bound(d->newlines.begin(), d->newlines.end(), s0 + dsize - 1);
+                long long p = -1;
+                if (it != d->newlines.begin()) p = *(it - 1);
+                if (p > s0) { en = p + 1; next = p; }
+                else { en = s0 + dsize; next = s0 + dsize; }
+            }
+            S.push_back(s0); E.push_back(en);
+            s0 = next;
+        }
+        if (S.empty()) { S.push_back(0); E.push_back(0); }
+        if (d->d_fills) { cudaFree(d->d_fills); d->d_fills = nullptr; }
+        CK(cudaMalloc((void **)&d->d_fills, S.size() * 16));
+        CK(cudaMemcpyAsync(d->d_fills, S.data(), S.size() * 8, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(d->d_fills + S.size(), E.data(), S.size() * 8, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        d->nfills = (int)S.size();
+        d->fills_bufsize = e->bufsize;
+    }
+    out->S = d->d_fills; out->E = d->d_fills + d->nfills; out->n = d->nfills;
+    return PM_OK;
+}
 
 int pm_engine_create(int device, pm_engine **out)
 {
@@ -419,6 +561,20 @@ int pm_engine_set_stream(pm_engine *e, void *s)
     return PM_OK;
 }
 
+int pm_engine_set_scan_mode(pm_engine *e, int mode)
+{
+    if (!e || mode < 0 || mode > 2) { g_err = "bad argument"; return PM_ERR_ARG; }
+    e->scan_mode = mode;
+    return PM_OK;
+}
+
+int pm_engine_set_buffer_size(pm_engine *e, int64_t bytes)
+{
+    if (!e || bytes < 0) { g_err = "bad argument"; return PM_ERR_ARG; }
+    e->bufsize = bytes;
+    return PM_OK;
+}
+
 int pm_engine_synchronize(pm_engine *e)
 {
     if (!e) { g_err = "engine is NULL"; return PM_ERR_ARG; }
@@ -443,6 +599,8 @@ int pm_dataset_create(pm_engine *e, const uint8_t *host, int64_t n, pm_dataset *
         if (rc == cudaSuccess) rc = cudaStreamSynchronize(e->stream);
         if (rc != cudaSuccess) { cudaFree(p); delete d; g_err = std::string("dataset upload: ") + cudaGetErrorString(rc); return PM_ERR_CUDA; }
     }
+    int prc = pack_dataset(e, d);
+    if (prc) { pm_dataset_destroy(d); return prc; }
     *out = d;
     return PM_OK;
 }
@@ -452,6 +610,9 @@ int pm_dataset_wrap_device(pm_engine *e, const uint8_t *dev, int64_t n, pm_datas
     if (!e || !out || n < 0 || (!dev && n > 0)) { g_err = "bad argument"; return PM_ERR_ARG; }
     pm_dataset *d = new pm_dataset();
     d->e = e; d->n = n; d->d_text = dev; d->owned = nullptr;
+    CK(cudaSetDevice(e->device));
+    int prc = pack_dataset(e, d);
+    if (prc) { pm_dataset_destroy(d); return prc; }
     *out = d;
     return PM_OK;
 }
@@ -459,7 +620,10 @@ int pm_dataset_wrap_device(pm_engine *e, const uint8_t *dev, int64_t n, pm_datas
 void pm_dataset_destroy(pm_dataset *d)
 {
     if (!d) return;
-    if (d->owned) { cudaSetDevice(d->e->device); cudaFree(d->owned); }
+    cudaSetDevice(d->e->device);
+    if (d->owned) cudaFree(d->owned);
+    if (d->hi) cudaFree(d->hi);
+    if (d->d_fills) cudaFree(d->d_fills);
     delete d;
 }
 
@@ -547,6 +711,10 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
     const DevPlan &dp = c.dp;
     const long long n = d->n;
     int rc;
+    Fills fills;
+    if ((rc = ensure_fills(e, d, &fills))) return rc;
+    const bool packable = (dp.type == PM_PLAN_SIMPLE || dp.type == PM_PLAN_SPLIT) && dp.npieces <= 4 && d->hi != nullptr;
+    const bool use_packed = packable && (e->scan_mode == 2 || (e->scan_mode == 0 && d->dna_like));
     if ((rc = e->counters.reserve(64))) return rc;
     unsigned long long *d_count = (unsigned long long *)e->counters.p;
     long long cap = std::max<long long>((long long)(e->keys.cap / 8), 1 << 16);
@@ -555,7 +723,45 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
         if ((rc = e->keys.reserve((size_t)cap * 8))) return rc;
         CK(cudaMemsetAsync(d_count, 0, 8, e->stream));
         CK(cudaEventRecord(e->ev[0], e->stream));
-        if (dp.type == PM_PLAN_SIMPLE || dp.type == PM_PLAN_SPLIT) {
+        if (use_packed) {
+            const long long wend = std::min(a1, n - dp.L + 1);
+            if (wend > a0) {
+                PackedArgs<4> a;
+                memset(&a, 0, sizeof a);
+                a.hi = d->hi; a.lo = d->lo; a.xx = d->xx; a.nwords = d->nwords; a.n = n; a.a0 = a0; a.a1 = wend;
+                a.tile0 = (a0 / 32) / 128;
+                a.ntiles = ((wend - 1) / 32) / 128 + 1 - a.tile0;
+                a.L = dp.L; a.npieces = dp.npieces;
+                for (int i = 0; i < dp.npieces; i++) {
+                    for (int j = 0; j < dp.npieces; j++)
+                        if (dp.trig[i] & (1ULL << (j * dp.L + dp.L - 1))) a.trigsets[i] |= 1u << j;
+                    const int base = dp.type == PM_PLAN_SPLIT ? dp.V[i] : 0;
+                    for (int j = 0; j < dp.L; j++) {
+                        const pm::ByteSet &bs = c.P.pos[base + j];
+                        unsigned cls = (bs.has('A') ? 1u : 0u) | (bs.has('C') ? 2u : 0u) | (bs.has('G') ? 4u : 0u) | (bs.has('T') ? 8u : 0u);
+                        int other = 0;
+                        for (unsigned ch = 0; ch < 256; ch++) {
+                            const unsigned f = ch | 0x20u;
+                            if (f == 'a' || f == 'c' || f == 'g' || f == 't') continue;
+                            other += bs.has(ch);
+                        }
+                        if (other) cls |= 16u;             // some non-ACGT bytes accepted: superset, re-checked on raw bytes
+                        PackedPos pp;
+                        pp.cls = (unsigned char)cls;
+                        pp.sel = cls == 1 ? 0 : cls == 2 ? 1 : cls == 4 ? 2 : cls == 8 ? 3 : cls == 16 ? 4 : 5;
+                        a.pos[i][j] = pp;
+                    }
+                }
+                a.keys = (unsigned long long *)e->keys.p; a.count = d_count; a.cap = cap;
+                const long long warps_needed = a.ntiles;
+                const int grid = (int)std::min<long long>((warps_needed + 7) / 8, (long long)e->sms * 8);
+                k_scan_packed<4><<<std::max(grid, 1), 256, 0, e->stream>>>(a);
+                e->stats.launches++;
+                e->stats.scan_bytes = a.ntiles * 128 * 4 * 3;
+                e->stats.scan_bases = wend - a0;
+                e->stats.packed = 1;
+            }
+        } else if (dp.type == PM_PLAN_SIMPLE || dp.type == PM_PLAN_SPLIT) {
             // window starts w in [a0, a1) <=> end positions p = w + L - 1
             long long p0 = a0 + dp.L - 1, p1 = std::min(a1 + dp.L - 1, n);
             if (p1 > p0) {
@@ -579,6 +785,7 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
                 }
                 e->stats.launches++;
                 e->stats.scan_bytes = p1 - p0;
+                e->stats.scan_bases = p1 - p0;
             }
         } else {
             // BWD: anchors w with w + (L - k) <= n ; FWD: anchors pos in [1, n]
@@ -588,12 +795,13 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
             if (hi > lo) {
                 DenseArgs a;
                 a.pl = dp; a.text = d->d_text; a.n = n; a.a0 = lo; a.a1 = hi; a.TL = dTL; a.TR = dTR;
-                a.keys = (unsigned long long *)e->keys.p; a.count = d_count; a.cap = cap;
+                a.keys = (unsigned long long *)e->keys.p; a.count = d_count; a.cap = cap; a.fills = fills;
                 const long long want = (hi - lo + 255) / 256;
                 const int grid = (int)std::min<long long>(want, (long long)e->sms * 16);
                 k_scan_dense<<<grid, 256, 0, e->stream>>>(a);
                 e->stats.launches++;
                 e->stats.scan_bytes = hi - lo;
+                e->stats.scan_bases = hi - lo;
             }
         }
         CK(cudaGetLastError());
@@ -626,7 +834,8 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
     // ---- verify ----
     if (ncand > 0) {
         if ((rc = e->cands.reserve((size_t)ncand * sizeof(Cand)))) return rc;
-        k_verify<<<(unsigned)((ncand + 127) / 128), 128, 0, e->stream>>>(dp, d->d_text, n, dTL, dTR, keys, ncand, (Cand *)e->cands.p);
+        k_verify<<<(unsigned)((ncand + 127) / 128), 128, 0, e->stream>>>(dp, d->d_text, n, dB, dTL, dTR, keys, ncand, (Cand *)e->cands.p,
+                                                                        use_packed ? 1 : 0, fills);
         CK(cudaGetLastError());
         e->stats.launches++;
     }
@@ -642,6 +851,8 @@ static int resolve_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, co
 {
     int rc;
     long long nh = 0;
+    Fills fills;
+    if ((rc = ensure_fills(e, d, &fills))) return rc;
     if (ncand > 0) {
         if ((rc = e->hits.reserve((size_t)ncand * sizeof(pm_hit)))) return rc;
         if ((rc = e->hits2.reserve((size_t)ncand * sizeof(pm_hit)))) return rc;
@@ -649,7 +860,7 @@ static int resolve_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, co
         if ((rc = e->counters.reserve(64))) return rc;
         CK(cudaMemsetAsync(e->sel.p, 0, (size_t)ncand, e->stream));
         k_chain<<<(unsigned)((ncand + 127) / 128), 128, 0, e->stream>>>(c.dp, d->d_text, d->n, dTL, dTR, d_cands, ncand,
-                                                                       (pm_hit *)e->hits.p, (unsigned char *)e->sel.p);
+                                                                       (pm_hit *)e->hits.p, (unsigned char *)e->sel.p, fills);
         CK(cudaGetLastError());
         CK(cudaEventRecord(e->ev[4], e->stream));
         size_t tmp = 0;
@@ -689,6 +900,7 @@ int pm_search(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt
 {
     if (!e || !d || !pattern || !kopt || !nhits || d->e != e) { g_err = "bad argument"; return PM_ERR_ARG; }
     CK(cudaSetDevice(e->device));
+    (void)cudaGetLastError();
     Compiled c;
     int rc = compile(pattern, kopt, c, true);
     if (rc) return rc;
@@ -720,7 +932,8 @@ int pm_search_batch(pm_engine *e, pm_dataset *d, int npat, const char *const *pa
         acc.scan_ms += e->stats.scan_ms; acc.sort_ms += e->stats.sort_ms; acc.verify_ms += e->stats.verify_ms;
         acc.chain_ms += e->stats.chain_ms; acc.total_ms += e->stats.total_ms;
         acc.candidates += e->stats.candidates; acc.verified += e->stats.verified; acc.hits += e->stats.hits;
-        acc.scan_bytes += e->stats.scan_bytes; acc.launches += e->stats.launches;
+        acc.scan_bytes += e->stats.scan_bytes; acc.scan_bases += e->stats.scan_bases; acc.launches += e->stats.launches;
+        acc.packed = e->stats.packed;
     }
     e->stats = acc;
     return PM_OK;

@@ -32,8 +32,8 @@ ZERO_ENV = dict(os.environ, GLIBC_TUNABLES="glibc.malloc.tcache_count=0:glibc.ma
 DNA, PEP = "ACGT", "ACDEFGHIKLMNPQRSTVWY"
 
 
-def run_engine(pattern, kopt, path, env):
-    out = subprocess.run([BIN, "-i", "-b", "1600000", "-k", kopt, pattern, path], capture_output=True, env=env).stdout
+def run_engine(pattern, kopt, path, env, bufsize=1600000):
+    out = subprocess.run([BIN, "-i", "-b", str(bufsize), "-k", kopt, pattern, path], capture_output=True, env=env).stdout
     out = out.decode("latin-1")
     return out.split("\n")[0], [[int(a), int(b)] for a, b in re.findall(r"^\[(\d+), (\d+)\]: ", out, re.M)]
 
@@ -118,15 +118,27 @@ def search_fixture():
             k = min(k, m - 1)
             ids = rng.choice(["ids", "ids", "s", "id", "is", "ds", "i", "d"])
             cases.append(random_case(rng, alpha, m, k, ids))
+    cases = [(p, k, t, 1600000) for p, k, t in cases]
+    # small -b values: buffer fills (bufLoad @41bbf0) cut the file; hits never cross a fill
+    for _ in range(80):
+        m = rng.randint(3, 12)
+        k = min(rng.choice([0, 0, 1, 2]), m - 1)
+        pat, kopt, text = random_case(rng, DNA, m, k, rng.choice(["ids", "s", "id"]))
+        if k == 0:
+            pat = pat.replace(rng.choice("ACGT"), ".", 1)
+        lines = text.split("\n")
+        text = "\n".join(l if rng.random() < 0.7 else l[: rng.choice([0, 1, 7, 40])] for l in lines)
+        cases.append((pat, kopt, text, rng.choice([16, 33, 64, 100, 128, 257, 1000])))
+    cases.append(("(A.C)", "0ids", ">s\nGGA\nCGG\nA\nC\n", 6))
     out = []
     with tempfile.TemporaryDirectory() as td:
         path = os.path.join(td, "t.seq")
-        for pat, kopt, text in cases:
+        for pat, kopt, text, bufsize in cases:
             with open(path, "w") as f:
                 f.write(text)
-            banner, hits = run_engine(pat, kopt, path, ZERO_ENV)
-            _, dep = run_engine(pat, kopt, path, os.environ)
-            out.append({"pattern": pat, "kopt": kopt, "text": text, "banner": banner, "hits": hits,
+            banner, hits = run_engine(pat, kopt, path, ZERO_ENV, bufsize)
+            _, dep = run_engine(pat, kopt, path, os.environ, bufsize)
+            out.append({"pattern": pat, "kopt": kopt, "text": text, "bufsize": bufsize, "banner": banner, "hits": hits,
                         "deployed_agrees": dep == hits})
     json.dump(out, open(os.path.join(HERE, "search_golden.json"), "w"), indent=0)
     agree = sum(c["deployed_agrees"] for c in out)

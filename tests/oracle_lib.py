@@ -56,6 +56,9 @@ def lib():
         L.nro_search.argtypes = [ctypes.POINTER(NroPattern), ctypes.POINTER(NroPlan), ctypes.c_char_p,
                                  ctypes.c_int64, ctypes.POINTER(NroHit), ctypes.c_int64]
         L.nro_search.restype = ctypes.c_int64
+        L.nro_search_buffered.argtypes = [ctypes.POINTER(NroPattern), ctypes.POINTER(NroPlan), ctypes.c_char_p,
+                                          ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(NroHit), ctypes.c_int64]
+        L.nro_search_buffered.restype = ctypes.c_int64
         _lib = L
     return _lib
 
@@ -84,24 +87,27 @@ def plan(pattern, kopt="0ids", icase=True):
     return P, pl
 
 
-def search(pattern, text, kopt="0ids", icase=True, cap=1 << 20):
-    """-> list of (beg, end) byte offsets, the hit list nrgrep_coords prints."""
+BUFSIZE = 1600000          # patmatch.py:37 MAX_BUFFER_SIZE, passed as -b
+
+
+def search(pattern, text, kopt="0ids", icase=True, cap=1 << 20, bufsize=BUFSIZE):
+    """-> list of (beg, end) byte offsets, the hit list `nrgrep_coords -b bufsize` prints."""
     L = lib()
     P, pl = plan(pattern, kopt, icase)
     if isinstance(text, str):
         text = text.encode("latin-1")
     hits = (NroHit * cap)()
-    n = L.nro_search(ctypes.byref(P), ctypes.byref(pl), text, len(text), hits, cap)
+    n = L.nro_search_buffered(ctypes.byref(P), ctypes.byref(pl), text, len(text), bufsize, hits, cap)
     if n > cap:
         raise OverflowError("oracle hit buffer too small: %d" % n)
     return [(hits[i].beg, hits[i].end) for i in range(n)]
 
 
-def run_reference(pattern, path, kopt="0ids", binary=None):
+def run_reference(pattern, path, kopt="0ids", binary=None, bufsize=BUFSIZE):
     """Run the reference engine itself exactly as patmatch.py:733 does; -> (banner, [(beg, end, text)])."""
     import re
     binary = binary or REF_BIN
-    out = subprocess.run([binary, "-i", "-b", "1600000", "-k", kopt, pattern, path],
+    out = subprocess.run([binary, "-i", "-b", str(bufsize), "-k", kopt, pattern, path],
                          capture_output=True, env=ENV).stdout.decode("latin-1")
     hits = []
     lines = out.split("\n")

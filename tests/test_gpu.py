@@ -14,6 +14,14 @@ from test_host import check_requests
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["bytes", "packed"])
+def scan_mode(request, engine):
+    """run the parity tests through both scan kernels (byte Shift-And and 2-bit packed bit-sliced)"""
+    engine.set_scan_mode(request.param)
+    yield request.param
+    engine.set_scan_mode("auto")
+
+
 def gpu_hits(engine, text, pattern, kopt):
     raw = text.encode("latin-1") if isinstance(text, str) else text
     ds = engine.load_dataset(raw)
@@ -23,17 +31,38 @@ def gpu_hits(engine, text, pattern, kopt):
         ds.close()
 
 
-def test_reference_golden_vectors(engine, search_golden):
+def test_reference_golden_vectors(engine, search_golden, scan_mode):
     bad = []
-    for c in search_golden:
-        got = [list(h) for h in gpu_hits(engine, c["text"], c["pattern"], c["kopt"])]
-        if got != c["hits"]:
-            bad.append((c["pattern"], c["kopt"], got[:4], c["hits"][:4]))
+    try:
+        for c in search_golden:
+            engine.set_buffer_size(c["bufsize"])
+            got = [list(h) for h in gpu_hits(engine, c["text"], c["pattern"], c["kopt"])]
+            if got != c["hits"]:
+                bad.append((c["pattern"], c["kopt"], c["bufsize"], got[:4], c["hits"][:4]))
+    finally:
+        engine.set_buffer_size(1600000)
     assert not bad, bad[:5]
 
 
+def test_buffer_fills_against_oracle(engine, scan_mode):
+    # the reference cuts the file into -b sized fills; exercise many fills per file
+    rng = random.Random(2718)
+    try:
+        for it in range(150):
+            m = rng.randint(3, 14)
+            k = min(rng.choice([0, 0, 1, 2, 3]), m - 1)
+            kopt = "%d%s" % (k, rng.choice(["ids", "s", "id"]))
+            pat, members = random_pattern(rng, DNA, m, dot_pct=0.2 if k == 0 else 0.05, neg_pct=0.3)
+            text = random_text(rng, members, DNA, k, nrec=rng.randint(1, 6), lo=20, hi=1500)
+            bs = rng.choice([16, 33, 64, 100, 257, 1000, 4096])
+            engine.set_buffer_size(bs)
+            assert gpu_hits(engine, text, pat, kopt) == O.search(pat, text, kopt, bufsize=bs), (pat, kopt, bs)
+    finally:
+        engine.set_buffer_size(1600000)
+
+
 @pytest.mark.parametrize("alpha", [DNA, PEP])
-def test_random_cases_against_oracle(engine, alpha):
+def test_random_cases_against_oracle(engine, alpha, scan_mode):
     rng = random.Random(1234 if alpha == DNA else 4321)
     types = set()
     for it in range(250):
@@ -49,7 +78,7 @@ def test_random_cases_against_oracle(engine, alpha):
     assert types == {"SIMPLE", "SPLIT", "BWD", "FWD"}
 
 
-def test_multi_tile_texts(engine):
+def test_multi_tile_texts(engine, scan_mode):
     # texts several scan tiles long, planted hits straddling tile and thread-run borders
     rng = random.Random(5)
     for it in range(12):
@@ -62,7 +91,7 @@ def test_multi_tile_texts(engine):
         assert gpu_hits(engine, text, pat, kopt) == O.search(pat, text, kopt), (pat, kopt)
 
 
-def test_edge_cases(engine):
+def test_edge_cases(engine, scan_mode):
     cases = [
         ("(GATAAG)", "0ids", ""),
         ("(GATAAG)", "1ids", ""),
@@ -93,7 +122,7 @@ def test_small_hit_buffer_is_regrown(engine):
     ds.close()
 
 
-def test_sharded_candidates_then_resolve_equals_search(engine):
+def test_sharded_candidates_then_resolve_equals_search(engine, scan_mode):
     rng = random.Random(77)
     for it in range(20):
         m = rng.randint(5, 22)
@@ -130,7 +159,7 @@ def test_request_level_parity_with_reference_python(engine, request_golden):
 
 
 # ---- BASELINE.json configurations at (or near) full size -------------------------------
-def test_config0_exact_motif_both_strands_yeast_size(engine):
+def test_config0_exact_motif_both_strands_yeast_size(engine, scan_mode):
     text = genome(0, 16, 12_000_000)
     ds = engine.load_dataset(text)
     conv, comp, opt = host.process_pattern("GATAAG", "dna", "Both strands", None, None, None, 0)
@@ -149,7 +178,7 @@ def test_config1_peptide_one_substitution(engine):
     ds.close()
 
 
-def test_config2_20nt_two_errors_with_indels(engine):
+def test_config2_20nt_two_errors_with_indels(engine, scan_mode):
     text = bytearray(genome(2, 16, 12_000_000))
     motif = b"TGACGTCAGATAAGCCGATT"
     rng = random.Random(8)
@@ -199,11 +228,15 @@ def test_large_genome_properties(engine):
     text = bytes(text)
     ds = engine.load_dataset(text)
     hits = engine.search(ds, "(GATTACAGATTACA)", "2ids")
+    assert engine.stats()["packed"] == 1                       # auto mode picks the packed scan for DNA
     b, e = hits["beg"], hits["end"]
     assert len(hits) > len(planted_at)
     assert np.all(b[1:] >= e[:-1]) and np.all(e > b)
+    engine.set_scan_mode("bytes")
     again = engine.search(ds, "(GATTACAGATTACA)", "2ids")
-    assert np.array_equal(hits, again)                         # deterministic
+    engine.set_scan_mode("auto")
+    assert engine.stats()["packed"] == 0
+    assert np.array_equal(hits, again)                         # both scan kernels, same hit list
     for p in planted_at:
         j = np.searchsorted(e, p, side="right")
         assert j < len(hits) and b[j] < p + len(motif), p      # some hit overlaps the planted copy

@@ -5,7 +5,7 @@ import oracle_lib as O
 def test_oracle_matches_reference_golden(search_golden):
     bad = []
     for c in search_golden:
-        got = [list(h) for h in O.search(c["pattern"], c["text"], c["kopt"])]
+        got = [list(h) for h in O.search(c["pattern"], c["text"], c["kopt"], bufsize=c["bufsize"])]
         if got != c["hits"]:
             bad.append((c["pattern"], c["kopt"], got[:4], c["hits"][:4]))
     assert not bad, bad[:5]
@@ -31,6 +31,13 @@ def test_known_answers():
     assert O.search("(AC..)", ">ab AC\nGTNN\n", "0ids") == [(4, 8)]                           # '.' crosses '\n' when k = 0
     assert O.search("(ACGT)", ">s\nAAGT\n", "1ids") == [(4, 7)]                               # shortest left extension
     assert O.search("(ACGA)", ">s\nACGACGA\n", "1ids") == [(3, 7), (7, 10)]                   # never left of the scan start
+
+
+def test_buffer_fills_cut_hits():
+    # nrgrep scans one -b sized fill at a time (bufLoad @41bbf0): with -b 6 the file ">s\nGGA\nCGG\n"
+    # is cut after the first '\n' inside each fill, so the k=0 hit "A\nC" that crosses a cut is lost
+    assert O.search("(A.C)", ">s\nGGA\nCGG\n", "0ids") == [(5, 8)]
+    assert O.search("(A.C)", ">s\nGGA\nCGG\n", "0ids", bufsize=6) == []
 
 
 def test_32bit_piece_test_quirk():
