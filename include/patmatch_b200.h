@@ -76,6 +76,9 @@ int pm_engine_set_stream(pm_engine *e, void *cuda_stream);
 int pm_engine_synchronize(pm_engine *e);
 /* scan kernel selection: 0 = auto (packed for DNA-like datasets), 1 = byte Shift-And, 2 = packed */
 int pm_engine_set_scan_mode(pm_engine *e, int mode);
+/* packed scan only: verify candidates inside the scan kernel on the packed planes and drop the ones
+ * that surely fail (default on); off = every exact piece hit goes through k_verify */
+int pm_engine_set_fused_filter(pm_engine *e, int on);
 /* the reference's -b buffer size in BYTES (patmatch.py:37,733 pass 1600000, the default here):
  * nrgrep_coords scans the file one buffer fill at a time and no hit crosses a fill. 0 = one fill. */
 int pm_engine_set_buffer_size(pm_engine *e, int64_t bytes);

@@ -68,6 +68,7 @@ def load():
     L.pm_engine_synchronize.argtypes = [vp]
     L.pm_engine_set_scan_mode.argtypes = [vp, ctypes.c_int]
     L.pm_engine_set_buffer_size.argtypes = [vp, i64]
+    L.pm_engine_set_fused_filter.argtypes = [vp, ctypes.c_int]
     L.pm_dataset_create.argtypes = [vp, vp, i64, ctypes.POINTER(vp)]
     L.pm_dataset_wrap_device.argtypes = [vp, vp, i64, ctypes.POINTER(vp)]
     L.pm_dataset_destroy.argtypes = [vp]
@@ -147,6 +148,9 @@ class Engine:
     def set_scan_mode(self, mode):
         """'auto' | 'bytes' | 'packed' -- which scan kernel SIMPLE/SPLIT plans use."""
         _check(load().pm_engine_set_scan_mode(self._h, {"auto": 0, "bytes": 1, "packed": 2}[mode]))
+
+    def set_fused_filter(self, on):
+        _check(load().pm_engine_set_fused_filter(self._h, int(bool(on))))
 
     def set_buffer_size(self, nbytes):
         """the reference's -b (bytes); patmatch.py uses 1600000, the default"""

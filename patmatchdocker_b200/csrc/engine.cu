@@ -423,6 +423,7 @@ struct pm_engine {
     unsigned long long *h_count = nullptr;          // pinned
     int scan_mode = 0;                              // 0 auto, 1 byte Shift-And, 2 packed bit-sliced
     long long bufsize = 1600000;                    // patmatch.py:37 MAX_BUFFER_SIZE (-b, in bytes)
+    int fused_filter = 1;                           // packed scan drops candidates whose verification surely fails
     pm_stats stats{};
 };
 
@@ -439,8 +440,10 @@ struct pm_dataset {
     // buffer fills of the reference for the engine's buffer size
     std::vector<long long> newlines;   // sorted positions of '\n'
     long long fills_bufsize = -1;
-    long long *d_fills = nullptr;      // S[0..nfills) then E[0..nfills)
+    long long *d_fills = nullptr;      // S[0..nfills) then E[0..nfills), then the forced cuts
     int nfills = 0;
+    int ncuts = 0;                     // fill boundaries that do not fall on a '\n'
+
 };
 
 static int pack_dataset(pm_engine *e, pm_dataset *d)
@@ -491,7 +494,7 @@ static int pack_dataset(pm_engine *e, pm_dataset *d)
 static int ensure_fills(pm_engine *e, pm_dataset *d, Fills *out)
 {
     if (d->fills_bufsize != e->bufsize) {
-        std::vector<long long> S, E;
+        std::vector<long long> S, E, cuts;
         const long long n = d->n, bs = e->bufsize > 0 ? e->bufsize : n + 1;
         long long s0 = 0;
         while (n - s0 > 0) {
@@ -504,18 +507,21 @@ static int ensure_fills(pm_engine *e, pm_dataset *d, Fills *out)
                 long long p = -1;
                 if (it != d->newlines.begin()) p = *(it - 1);
                 if (p > s0) { en = p + 1; next = p; }
-                else { en = s0 + dsize; next = s0 + dsize; }
+                else { en = s0 + dsize; next = s0 + dsize; if (next < n) cuts.push_back(next); }
             }
             S.push_back(s0); E.push_back(en);
             s0 = next;
         }
         if (S.empty()) { S.push_back(0); E.push_back(0); }
         if (d->d_fills) { cudaFree(d->d_fills); d->d_fills = nullptr; }
-        CK(cudaMalloc((void **)&d->d_fills, S.size() * 16));
+        CK(cudaMalloc((void **)&d->d_fills, (S.size() * 2 + cuts.size() + 1) * 8));
         CK(cudaMemcpyAsync(d->d_fills, S.data(), S.size() * 8, cudaMemcpyHostToDevice, e->stream));
         CK(cudaMemcpyAsync(d->d_fills + S.size(), E.data(), S.size() * 8, cudaMemcpyHostToDevice, e->stream));
+        if (!cuts.empty())
+            CK(cudaMemcpyAsync(d->d_fills + 2 * S.size(), cuts.data(), cuts.size() * 8, cudaMemcpyHostToDevice, e->stream));
         CK(cudaStreamSynchronize(e->stream));
         d->nfills = (int)S.size();
+        d->ncuts = (int)cuts.size();
         d->fills_bufsize = e->bufsize;
     }
     out->S = d->d_fills; out->E = d->d_fills + d->nfills; out->n = d->nfills;
@@ -565,6 +571,13 @@ int pm_engine_set_scan_mode(pm_engine *e, int mode)
 {
     if (!e || mode < 0 || mode > 2) { g_err = "bad argument"; return PM_ERR_ARG; }
     e->scan_mode = mode;
+    return PM_OK;
+}
+
+int pm_engine_set_fused_filter(pm_engine *e, int on)
+{
+    if (!e) { g_err = "bad argument"; return PM_ERR_ARG; }
+    e->fused_filter = on ? 1 : 0;
     return PM_OK;
 }
 
@@ -753,9 +766,24 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
                     }
                 }
                 a.keys = (unsigned long long *)e->keys.p; a.count = d_count; a.cap = cap;
+                PackedVerify<4> pv;
+                memset(&pv, 0, sizeof pv);
+                pv.enabled = (dp.type == PM_PLAN_SPLIT && dp.k <= 3 && e->fused_filter) ? 1 : 0;
+                pv.m = dp.m; pv.k = dp.k; pv.ins = dp.ins; pv.del = dp.del; pv.subs = dp.subs;
+                pv.cuts = d->d_fills + 2 * (size_t)d->nfills; pv.ncuts = d->ncuts;
+                if (pv.enabled) {
+                    static const unsigned char code_byte[4] = {'A', 'C', 'T', 'G'};   // code = hi<<1 | lo
+                    for (int i = 0; i < dp.npieces; i++) {
+                        pv.V[i] = dp.V[i];
+                        for (int q = 0; q < 4; q++) {
+                            pv.TL[i][q] = c.vt.TL[(size_t)i * 256 + code_byte[q]];
+                            pv.TR[i][q] = c.vt.TR[(size_t)i * 256 + code_byte[q]];
+                        }
+                    }
+                }
                 const long long warps_needed = a.ntiles;
                 const int grid = (int)std::min<long long>((warps_needed + 7) / 8, (long long)e->sms * 8);
-                k_scan_packed<4><<<std::max(grid, 1), 256, 0, e->stream>>>(a);
+                k_scan_packed<4><<<std::max(grid, 1), 256, 0, e->stream>>>(a, pv);
                 e->stats.launches++;
                 e->stats.scan_bytes = a.ntiles * 128 * 4 * 3;
                 e->stats.scan_bases = wend - a0;

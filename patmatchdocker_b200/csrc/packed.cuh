@@ -86,32 +86,125 @@ __device__ __forceinline__ void packed_apply(unsigned (&M)[4], const unsigned (&
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Fused candidate filter.  For SPLIT plans every exact piece hit is a candidate the reference
+// verifies (checkMatch1 @414190); with short pieces that is one candidate per ~40-100 bases
+// and almost all of them fail.  The scan kernel therefore runs the same anchored k-error NFA
+// right away, reading the text from the packed planes staged in shared memory, and drops a
+// candidate only when that verification fails for certain.  Whenever the walk meets a
+// non-ACGT byte (X plane: '\n', N, header text ...) or the tile is near a forced buffer cut,
+// the candidate is kept and decided later on the raw bytes by k_verify.  Dropping is safe for
+// the chain stage as well: a scan start that clips the verification can only remove matches.
+#define PK_HALO 4                       // words of halo on each side of a 128-word warp tile
+#define PK_ROW (128 + 2 * PK_HALO)
+
 template <int NP>
-__global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a)
+struct PackedVerify {
+    unsigned long long TL[NP][4], TR[NP][4];     // NFA masks per nucleotide code (hi<<1 | lo)
+    int V[NP];
+    int m, k, ins, del, subs, enabled;
+    const long long *cuts;                       // forced buffer cuts (fill starts not at a '\n'), sorted
+    int ncuts;
+};
+
+// one side of checkMatch1 on packed symbols; *bail is set when the outcome needs the raw bytes
+template <int DIR>
+__device__ __forceinline__ int nfa_packed(const unsigned *__restrict__ sh, long long base, const unsigned long long (&T)[4],
+                                          int plen, int kmax, int ins, int del, int subs, long long pos, int *err, bool *bail)
 {
+    const unsigned long long fin = 1ULL << (plen - 1);
+    const unsigned long long live = (fin << 1) - 1ULL;
+    unsigned long long R[4];                      // k <= 3 on this path
+    int kb = kmax;
+    int best_err = -1;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        R[e] = del ? ((1ULL << e) - 1ULL) : 0ULL;
+        if (e <= kb && (R[e] & fin)) { best_err = e; kb = e - 1; }
+    }
+    unsigned long long first = 1;
+    for (int step = 0; step < 96; step++) {
+        const long long tp = DIR < 0 ? pos - step - 1 : pos + step;
+        const long long rel = tp - base;           // bit index inside the staged row
+        const int wi = (int)(rel >> 5), bi = (int)(rel & 31);
+        if (wi < 0 || wi >= PK_ROW) { *bail = true; return 0; }
+        if ((sh[2 * PK_ROW + wi] >> bi) & 1u) { *bail = true; return 0; }
+        const unsigned code = (((sh[wi] >> bi) & 1u) << 1) | ((sh[PK_ROW + wi] >> bi) & 1u);
+        const unsigned long long Tc = T[code];
+        unsigned long long oldp = R[0];
+        R[0] = ((R[0] << 1) | first) & Tc;
+        unsigned long long newp = R[0];
+        if (R[0] & fin) { *err = 0; return 1; }
+        bool lowered = false;
+#pragma unroll
+        for (int e = 1; e < 4; e++) {
+            if (e <= kb && !lowered) {
+                unsigned long long x = 0;
+                if (del) x = newp << 1;
+                if (ins) x |= oldp;
+                if (subs) x |= (oldp << 1) | first;
+                const unsigned long long nr = (((R[e] << 1) | first) & Tc) | x;
+                oldp = R[e];
+                R[e] = nr;
+                newp = nr;
+                if (nr & fin) {
+                    // rows below e were tested (and lacked the final bit) earlier in this step
+                    best_err = e; kb = e - 1; lowered = true;
+                }
+            }
+        }
+        if (kb < 0) break;
+        const unsigned long long alive = kb == 0 ? R[0] : kb == 1 ? R[1] : kb == 2 ? R[2] : R[3];
+        if (!(alive & live)) break;
+        first = 0;
+    }
+    if (best_err < 0) return 0;
+    *err = best_err;
+    return 1;
+}
+
+template <int NP>
+__global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, const PackedVerify<NP> v)
+{
+    __shared__ unsigned sh_all[8][3 * PK_ROW];
     const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    unsigned *sh = sh_all[wib];
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long t = warp; t < a.ntiles; t += nwarps) {
-        const long long q0 = (a.tile0 + t) * 128 + 4 * lane;          // first of this lane's 4 words
-        // ---- load 4 words + 2 halo words of each plane ----
-        const uint4 h4 = __ldg(reinterpret_cast<const uint4 *>(a.hi + q0));
-        const uint4 l4 = __ldg(reinterpret_cast<const uint4 *>(a.lo + q0));
-        const uint4 x4 = __ldg(reinterpret_cast<const uint4 *>(a.xx + q0));
-        const uint2 h2 = __ldg(reinterpret_cast<const uint2 *>(a.hi + q0 + 4));
-        const uint2 l2 = __ldg(reinterpret_cast<const uint2 *>(a.lo + q0 + 4));
-        const uint2 x2 = __ldg(reinterpret_cast<const uint2 *>(a.xx + q0 + 4));
-        const unsigned H[6] = {h4.x, h4.y, h4.z, h4.w, h2.x, h2.y};
-        const unsigned Lw[6] = {l4.x, l4.y, l4.z, l4.w, l2.x, l2.y};
+        const long long qt = (a.tile0 + t) * 128;                       // first word of the tile
+        const long long q0 = qt + 4 * lane;                             // first of this lane's 4 words
+        // ---- stage the tile (+ halos) of the three planes in shared memory ----
+        __syncwarp();
+        {
+            const uint4 h4 = __ldg(reinterpret_cast<const uint4 *>(a.hi + q0));
+            const uint4 l4 = __ldg(reinterpret_cast<const uint4 *>(a.lo + q0));
+            const uint4 x4 = __ldg(reinterpret_cast<const uint4 *>(a.xx + q0));
+            *reinterpret_cast<uint4 *>(sh + PK_HALO + 4 * lane) = h4;
+            *reinterpret_cast<uint4 *>(sh + PK_ROW + PK_HALO + 4 * lane) = l4;
+            *reinterpret_cast<uint4 *>(sh + 2 * PK_ROW + PK_HALO + 4 * lane) = x4;
+            if (lane < 2 * PK_HALO) {
+                const bool left = lane < PK_HALO;
+                const long long q = left ? qt - PK_HALO + lane : qt + 128 + (lane - PK_HALO);
+                const int si = left ? lane : PK_HALO + 128 + (lane - PK_HALO);
+                const bool ok = q >= 0 && q < a.nwords;
+                sh[si] = ok ? __ldg(a.hi + q) : 0u;
+                sh[PK_ROW + si] = ok ? __ldg(a.lo + q) : 0u;
+                sh[2 * PK_ROW + si] = ok ? __ldg(a.xx + q) : 0xffffffffu;
+            }
+        }
+        __syncwarp();
         unsigned PA[6], PC[6], PG[6], PT[6], PX[6];
 #pragma unroll
         for (int w = 0; w < 6; w++) {
-            const unsigned x = w < 4 ? (&x4.x)[w] : (&x2.x)[w - 4];
+            const unsigned h = sh[PK_HALO + 4 * lane + w], l = sh[PK_ROW + PK_HALO + 4 * lane + w],
+                           x = sh[2 * PK_ROW + PK_HALO + 4 * lane + w];
             PX[w] = x;
-            PA[w] = ~(H[w] | Lw[w] | x);
-            PC[w] = Lw[w] & ~H[w];
-            PG[w] = H[w] & Lw[w];
-            PT[w] = H[w] & ~Lw[w];
+            PA[w] = ~(h | l | x);
+            PC[w] = l & ~h;
+            PG[w] = h & l;
+            PT[w] = h & ~l;
         }
         // ---- pieces ----
         unsigned M[NP][4];
@@ -144,6 +237,15 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a)
                 for (int w = 0; w < 4; w++) M[i][w] = 0;
             }
         }
+        // tiles next to a forced buffer cut are decided on the raw bytes
+        bool fused = v.enabled != 0;
+        if (fused && v.ncuts > 0) {
+            const long long lo = (qt - PK_HALO) * 32, hi = (qt + 128 + PK_HALO) * 32;
+            int l = 0, r = v.ncuts;
+            while (l < r) { const int mid = (l + r) >> 1; if (v.cuts[mid] < lo) l = mid + 1; else r = mid; }
+            if (l < v.ncuts && v.cuts[l] < hi) fused = false;
+        }
+        const long long base = (qt - PK_HALO) * 32;                      // text position of bit 0 of the staged row
         // ---- candidates: piece i fires when any piece of trigsets[i] matched at the same start ----
 #pragma unroll
         for (int i = 0; i < NP; i++) {
@@ -162,7 +264,17 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a)
                     const int b = __ffs(c) - 1;
                     c &= c - 1;
                     const long long p = (q0 + w) * 32 + b;
-                    if (p >= a.a0 && p < a.a1 && p + a.L <= a.n) {
+                    if (p < a.a0 || p >= a.a1 || p + a.L > a.n) continue;
+                    bool keep = true;
+                    if (fused) {
+                        bool bail = false;
+                        int berr = 0, ferr = 0;
+                        const int lb = v.V[i], rl = v.m - lb;
+                        if (lb > 0 && !nfa_packed<-1>(sh, base, v.TL[i], lb, v.k, v.ins, v.del, v.subs, p, &berr, &bail) && !bail) keep = false;
+                        if (keep && !bail && rl > 0 &&
+                            !nfa_packed<+1>(sh, base, v.TR[i], rl, v.k - berr, v.ins, v.del, v.subs, p, &ferr, &bail) && !bail) keep = false;
+                    }
+                    if (keep) {
                         const unsigned long long idx = atomicAdd(a.count, 1ULL);
                         if ((long long)idx < a.cap) a.keys[idx] = ((unsigned long long)p << 4) | (unsigned)i;
                     }
