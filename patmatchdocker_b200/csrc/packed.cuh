@@ -97,6 +97,7 @@ __device__ __forceinline__ void packed_apply(unsigned (&M)[4], const unsigned (&
 // the chain stage as well: a scan start that clips the verification can only remove matches.
 #define PK_HALO 4                       // words of halo on each side of a 128-word warp tile
 #define PK_ROW (128 + 2 * PK_HALO)
+#define PK_QUEUE 512                    // per-warp candidate queue (entries beyond it go to k_verify unfiltered)
 
 template <int NP>
 struct PackedVerify {
@@ -167,9 +168,13 @@ template <int NP>
 __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, const PackedVerify<NP> v)
 {
     __shared__ unsigned sh_all[8][3 * PK_ROW];
+    __shared__ unsigned queue_all[8][PK_QUEUE];
+    __shared__ unsigned qcount_all[8];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     unsigned *sh = sh_all[wib];
+    unsigned *queue = queue_all[wib];
+    unsigned *qcount = &qcount_all[wib];
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long t = warp; t < a.ntiles; t += nwarps) {
@@ -246,7 +251,10 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
             if (l < v.ncuts && v.cuts[l] < hi) fused = false;
         }
         const long long base = (qt - PK_HALO) * 32;                      // text position of bit 0 of the staged row
-        // ---- candidates: piece i fires when any piece of trigsets[i] matched at the same start ----
+        // ---- candidates: piece i fires when any piece of trigsets[i] matched at the same start.
+        // They are first queued per warp in shared memory, then verified with all lanes busy.
+        if (lane == 0) *qcount = 0;
+        __syncwarp();
 #pragma unroll
         for (int i = 0; i < NP; i++) {
             if (i >= a.npieces) break;
@@ -263,23 +271,35 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
                 while (c) {
                     const int b = __ffs(c) - 1;
                     c &= c - 1;
-                    const long long p = (q0 + w) * 32 + b;
+                    const unsigned rel = (unsigned)((4 * lane + w) * 32 + b);      // window start inside the tile
+                    const long long p = qt * 32 + rel;
                     if (p < a.a0 || p >= a.a1 || p + a.L > a.n) continue;
-                    bool keep = true;
-                    if (fused) {
-                        bool bail = false;
-                        int berr = 0, ferr = 0;
-                        const int lb = v.V[i], rl = v.m - lb;
-                        if (lb > 0 && !nfa_packed<-1>(sh, base, v.TL[i], lb, v.k, v.ins, v.del, v.subs, p, &berr, &bail) && !bail) keep = false;
-                        if (keep && !bail && rl > 0 &&
-                            !nfa_packed<+1>(sh, base, v.TR[i], rl, v.k - berr, v.ins, v.del, v.subs, p, &ferr, &bail) && !bail) keep = false;
-                    }
-                    if (keep) {
+                    const unsigned slot = fused ? atomicAdd(qcount, 1u) : PK_QUEUE;
+                    if (slot < PK_QUEUE) queue[slot] = (rel << 2) | (unsigned)i;
+                    else {                                                          // not filtered: decided by k_verify
                         const unsigned long long idx = atomicAdd(a.count, 1ULL);
                         if ((long long)idx < a.cap) a.keys[idx] = ((unsigned long long)p << 4) | (unsigned)i;
                     }
                 }
             }
         }
+        __syncwarp();
+        const unsigned nq = min(*qcount, (unsigned)PK_QUEUE);
+        for (unsigned e = lane; e < nq; e += 32) {
+            const unsigned ent = queue[e];
+            const int i = (int)(ent & 3u);
+            const long long p = qt * 32 + (ent >> 2);
+            bool keep = true, bail = false;
+            int berr = 0, ferr = 0;
+            const int lb = v.V[i], rl = v.m - lb;
+            if (lb > 0 && !nfa_packed<-1>(sh, base, v.TL[i], lb, v.k, v.ins, v.del, v.subs, p, &berr, &bail) && !bail) keep = false;
+            if (keep && !bail && rl > 0 &&
+                !nfa_packed<+1>(sh, base, v.TR[i], rl, v.k - berr, v.ins, v.del, v.subs, p, &ferr, &bail) && !bail) keep = false;
+            if (keep) {
+                const unsigned long long idx = atomicAdd(a.count, 1ULL);
+                if ((long long)idx < a.cap) a.keys[idx] = ((unsigned long long)p << 4) | (unsigned)i;
+            }
+        }
+        __syncwarp();
     }
 }
