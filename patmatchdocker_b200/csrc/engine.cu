@@ -739,53 +739,75 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
         if (use_packed) {
             const long long wend = std::min(a1, n - dp.L + 1);
             if (wend > a0) {
-                PackedArgs<4> a;
-                memset(&a, 0, sizeof a);
-                a.hi = d->hi; a.lo = d->lo; a.xx = d->xx; a.nwords = d->nwords; a.n = n; a.a0 = a0; a.a1 = wend;
-                a.tile0 = (a0 / 32) / 128;
-                a.ntiles = ((wend - 1) / 32) / 128 + 1 - a.tile0;
-                a.L = dp.L; a.npieces = dp.npieces;
-                for (int i = 0; i < dp.npieces; i++) {
-                    for (int j = 0; j < dp.npieces; j++)
-                        if (dp.trig[i] & (1ULL << (j * dp.L + dp.L - 1))) a.trigsets[i] |= 1u << j;
-                    const int base = dp.type == PM_PLAN_SPLIT ? dp.V[i] : 0;
-                    for (int j = 0; j < dp.L; j++) {
-                        const pm::ByteSet &bs = c.P.pos[base + j];
-                        unsigned cls = (bs.has('A') ? 1u : 0u) | (bs.has('C') ? 2u : 0u) | (bs.has('G') ? 4u : 0u) | (bs.has('T') ? 8u : 0u);
-                        int other = 0;
-                        for (unsigned ch = 0; ch < 256; ch++) {
-                            const unsigned f = ch | 0x20u;
-                            if (f == 'a' || f == 'c' || f == 'g' || f == 't') continue;
-                            other += bs.has(ch);
-                        }
-                        if (other) cls |= 16u;             // some non-ACGT bytes accepted: superset, re-checked on raw bytes
-                        PackedPos pp;
-                        pp.cls = (unsigned char)cls;
-                        pp.sel = cls == 1 ? 0 : cls == 2 ? 1 : cls == 4 ? 2 : cls == 8 ? 3 : cls == 16 ? 4 : 5;
-                        a.pos[i][j] = pp;
+                const long long tile0 = (a0 / 32) / 128;
+                const long long ntiles = ((wend - 1) / 32) / 128 + 1 - tile0;
+                const long long warps_needed = ntiles;
+                const int grid = std::max((int)std::min<long long>((warps_needed + 7) / 8, (long long)e->sms * 8), 1);
+                // class of one pattern position over the packed alphabet: bits A,C,G,T and X (= any non-ACGT byte)
+                auto packed_class = [&](const pm::ByteSet &bs) -> unsigned {
+                    unsigned cls = (bs.has('A') ? 1u : 0u) | (bs.has('C') ? 2u : 0u) | (bs.has('G') ? 4u : 0u) | (bs.has('T') ? 8u : 0u);
+                    for (unsigned ch = 0; ch < 256; ch++) {
+                        const unsigned f = ch | 0x20u;
+                        if (f == 'a' || f == 'c' || f == 'g' || f == 't') continue;
+                        if (bs.has(ch)) { cls |= 16u; break; }   // some non-ACGT byte accepted: superset, re-checked on raw bytes
                     }
-                }
-                a.keys = (unsigned long long *)e->keys.p; a.count = d_count; a.cap = cap;
-                PackedVerify<4> pv;
-                memset(&pv, 0, sizeof pv);
-                pv.enabled = (dp.type == PM_PLAN_SPLIT && dp.k <= 3 && e->fused_filter) ? 1 : 0;
-                pv.m = dp.m; pv.k = dp.k; pv.ins = dp.ins; pv.del = dp.del; pv.subs = dp.subs;
-                pv.cuts = d->d_fills + 2 * (size_t)d->nfills; pv.ncuts = d->ncuts;
-                if (pv.enabled) {
+                    return cls;
+                };
+                auto plane_of = [](unsigned cls) -> int { return cls == 1 ? 0 : cls == 2 ? 1 : cls == 4 ? 2 : cls == 8 ? 3 : cls == 16 ? 4 : 5; };
+                if (dp.type == PM_PLAN_SIMPLE) {
+                    ExactArgs a;
+                    memset(&a, 0, sizeof a);
+                    a.hi = d->hi; a.lo = d->lo; a.xx = d->xx; a.nwords = d->nwords; a.n = n; a.a0 = a0; a.a1 = wend;
+                    a.tile0 = tile0; a.ntiles = ntiles; a.L = dp.L;
+                    for (int j = 0; j < dp.L; j++) {
+                        const unsigned cls = packed_class(c.P.pos[j]);
+                        const int s = plane_of(cls);
+                        if (s == 5) a.cls[a.npos[5]] = (unsigned char)cls;
+                        a.shift[s][a.npos[s]++] = (unsigned char)j;
+                    }
+                    a.keys = (unsigned long long *)e->keys.p; a.count = d_count; a.cap = cap;
+                    k_scan_packed_exact<<<grid, 256, 0, e->stream>>>(a);
+                } else {
+                    PackedArgs<4> a;
+                    memset(&a, 0, sizeof a);
+                    a.hi = d->hi; a.lo = d->lo; a.xx = d->xx; a.nwords = d->nwords; a.n = n; a.a0 = a0; a.a1 = wend;
+                    a.tile0 = tile0; a.ntiles = ntiles;
+                    a.L = dp.L; a.npieces = dp.npieces;
+                    for (int i = 0; i < dp.npieces; i++) {
+                        for (int j = 0; j < dp.npieces; j++)
+                            if (dp.trig[i] & (1ULL << (j * dp.L + dp.L - 1))) a.trigsets[i] |= 1u << j;
+                        for (int j = 0; j < dp.L; j++) {
+                            const unsigned cls = packed_class(c.P.pos[dp.V[i] + j]);
+                            PackedPos pp;
+                            pp.cls = (unsigned char)cls;
+                            pp.sel = (unsigned char)plane_of(cls);
+                            a.pos[i][j] = pp;
+                        }
+                    }
+                    a.keys = (unsigned long long *)e->keys.p; a.count = d_count; a.cap = cap;
+                    PackedVerify<4> pv;
+                    memset(&pv, 0, sizeof pv);
+                    pv.enabled = (dp.k <= 3 && e->fused_filter) ? 1 : 0;
+                    pv.m = dp.m; pv.k = dp.k; pv.ins = dp.ins; pv.del = dp.del; pv.subs = dp.subs;
+                    pv.cuts = d->d_fills + 2 * (size_t)d->nfills; pv.ncuts = d->ncuts;
+                    bool narrow = true;                                   // every pattern part fits a 32-bit state word
                     static const unsigned char code_byte[4] = {'A', 'C', 'T', 'G'};   // code = hi<<1 | lo
                     for (int i = 0; i < dp.npieces; i++) {
                         pv.V[i] = dp.V[i];
+                        if (dp.V[i] > 32 || dp.m - dp.V[i] > 32) narrow = false;
                         for (int q = 0; q < 4; q++) {
                             pv.TL[i][q] = c.vt.TL[(size_t)i * 256 + code_byte[q]];
                             pv.TR[i][q] = c.vt.TR[(size_t)i * 256 + code_byte[q]];
                         }
                     }
+                    const int rows = std::min(std::max(dp.k, 1), 3) + 1;
+#define PM_LAUNCH(W, R) k_scan_packed<4, W, R><<<grid, 256, 0, e->stream>>>(a, pv)
+                    if (narrow) { if (rows == 2) PM_LAUNCH(unsigned, 2); else if (rows == 3) PM_LAUNCH(unsigned, 3); else PM_LAUNCH(unsigned, 4); }
+                    else { if (rows == 2) PM_LAUNCH(unsigned long long, 2); else if (rows == 3) PM_LAUNCH(unsigned long long, 3); else PM_LAUNCH(unsigned long long, 4); }
+#undef PM_LAUNCH
                 }
-                const long long warps_needed = a.ntiles;
-                const int grid = (int)std::min<long long>((warps_needed + 7) / 8, (long long)e->sms * 8);
-                k_scan_packed<4><<<std::max(grid, 1), 256, 0, e->stream>>>(a, pv);
                 e->stats.launches++;
-                e->stats.scan_bytes = a.ntiles * 128 * 4 * 3;
+                e->stats.scan_bytes = ntiles * 128 * 4 * 3;
                 e->stats.scan_bases = wend - a0;
                 e->stats.packed = 1;
             }

@@ -108,54 +108,54 @@ struct PackedVerify {
     int ncuts;
 };
 
-// one side of checkMatch1 on packed symbols; *bail is set when the outcome needs the raw bytes
-template <int DIR>
-__device__ __forceinline__ int nfa_packed(const unsigned *__restrict__ sh, long long base, const unsigned long long (&T)[4],
+// one side of checkMatch1 on packed symbols; *bail is set when the outcome needs the raw bytes.
+// W = state word (uint32 when the pattern part fits 32 bits), ROWS = k+1 error rows.
+template <int DIR, typename W, int ROWS>
+__device__ __forceinline__ int nfa_packed(const unsigned *__restrict__ sh, long long base, const unsigned long long (&T64)[4],
                                           int plen, int kmax, int ins, int del, int subs, long long pos, int *err, bool *bail)
 {
-    const unsigned long long fin = 1ULL << (plen - 1);
-    const unsigned long long live = (fin << 1) - 1ULL;
-    unsigned long long R[4];                      // k <= 3 on this path
+    const W fin = (W)1 << (plen - 1);
+    const W live = (W)((fin << 1) - 1);
+    const W T[4] = {(W)T64[0], (W)T64[1], (W)T64[2], (W)T64[3]};
+    W R[ROWS];
     int kb = kmax;
     int best_err = -1;
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-        R[e] = del ? ((1ULL << e) - 1ULL) : 0ULL;
+    for (int e = 0; e < ROWS; e++) {
+        R[e] = del ? (W)(((W)1 << e) - 1) : (W)0;
         if (e <= kb && (R[e] & fin)) { best_err = e; kb = e - 1; }
     }
-    unsigned long long first = 1;
-    for (int step = 0; step < 96; step++) {
-        const long long tp = DIR < 0 ? pos - step - 1 : pos + step;
-        const long long rel = tp - base;           // bit index inside the staged row
-        const int wi = (int)(rel >> 5), bi = (int)(rel & 31);
+    W first = 1;
+    int rel = (int)(pos - base) + (DIR < 0 ? -1 : 0);          // bit index of the next symbol in the staged row
+    for (int step = 0; step < 96; step++, rel += DIR) {
+        const int wi = rel >> 5, bi = rel & 31;
         if (wi < 0 || wi >= PK_ROW) { *bail = true; return 0; }
         if ((sh[2 * PK_ROW + wi] >> bi) & 1u) { *bail = true; return 0; }
         const unsigned code = (((sh[wi] >> bi) & 1u) << 1) | ((sh[PK_ROW + wi] >> bi) & 1u);
-        const unsigned long long Tc = T[code];
-        unsigned long long oldp = R[0];
-        R[0] = ((R[0] << 1) | first) & Tc;
-        unsigned long long newp = R[0];
+        const W Tc = code == 0 ? T[0] : code == 1 ? T[1] : code == 2 ? T[2] : T[3];
+        W oldp = R[0];
+        R[0] = (W)(((R[0] << 1) | first) & Tc);
+        W newp = R[0];
         if (R[0] & fin) { *err = 0; return 1; }
         bool lowered = false;
 #pragma unroll
-        for (int e = 1; e < 4; e++) {
+        for (int e = 1; e < ROWS; e++) {
             if (e <= kb && !lowered) {
-                unsigned long long x = 0;
-                if (del) x = newp << 1;
+                W x = 0;
+                if (del) x = (W)(newp << 1);
                 if (ins) x |= oldp;
-                if (subs) x |= (oldp << 1) | first;
-                const unsigned long long nr = (((R[e] << 1) | first) & Tc) | x;
+                if (subs) x |= (W)((oldp << 1) | first);
+                const W nr = (W)((((R[e] << 1) | first) & Tc) | x);
                 oldp = R[e];
                 R[e] = nr;
                 newp = nr;
-                if (nr & fin) {
-                    // rows below e were tested (and lacked the final bit) earlier in this step
-                    best_err = e; kb = e - 1; lowered = true;
-                }
+                if (nr & fin) { best_err = e; kb = e - 1; lowered = true; }   // rows below e lacked the final bit in this step
             }
         }
         if (kb < 0) break;
-        const unsigned long long alive = kb == 0 ? R[0] : kb == 1 ? R[1] : kb == 2 ? R[2] : R[3];
+        W alive = R[0];
+#pragma unroll
+        for (int e = 1; e < ROWS; e++) if (kb == e) alive = R[e];
         if (!(alive & live)) break;
         first = 0;
     }
@@ -164,7 +164,98 @@ __device__ __forceinline__ int nfa_packed(const unsigned *__restrict__ sh, long 
     return 1;
 }
 
-template <int NP>
+// ---------------------------------------------------------------------------------------
+// Exact (k = 0, SIMPLE) scan: one piece, registers only, next tile prefetched while the current
+// one is evaluated.  Positions are grouped by the plane they read so that no per-position
+// dispatch is needed.
+struct ExactArgs {
+    const unsigned *hi, *lo, *xx;
+    long long nwords, n, a0, a1, tile0, ntiles;
+    int L;
+    unsigned char npos[6];                // positions reading plane A,C,G,T,X and general classes
+    unsigned char shift[6][64];
+    unsigned char cls[64];                // general classes: bits A,C,G,T,X (parallel to shift[5])
+    unsigned long long *keys, *count;
+    long long cap;
+};
+
+__global__ void __launch_bounds__(256, 4) k_scan_packed_exact(const ExactArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    long long t = warp;
+    if (t >= a.ntiles) return;
+    long long q0 = (a.tile0 + t) * 128 + 4 * lane;
+    uint4 h4 = __ldg(reinterpret_cast<const uint4 *>(a.hi + q0)), l4 = __ldg(reinterpret_cast<const uint4 *>(a.lo + q0)),
+          x4 = __ldg(reinterpret_cast<const uint4 *>(a.xx + q0));
+    uint2 h2 = __ldg(reinterpret_cast<const uint2 *>(a.hi + q0 + 4)), l2 = __ldg(reinterpret_cast<const uint2 *>(a.lo + q0 + 4)),
+          x2 = __ldg(reinterpret_cast<const uint2 *>(a.xx + q0 + 4));
+    for (; t < a.ntiles; t += nwarps) {
+        const unsigned H[6] = {h4.x, h4.y, h4.z, h4.w, h2.x, h2.y};
+        const unsigned Lw[6] = {l4.x, l4.y, l4.z, l4.w, l2.x, l2.y};
+        const unsigned X[6] = {x4.x, x4.y, x4.z, x4.w, x2.x, x2.y};
+        const long long qcur = q0;
+        // prefetch the next tile of this warp
+        const long long tn = t + nwarps;
+        if (tn < a.ntiles) {
+            q0 = (a.tile0 + tn) * 128 + 4 * lane;
+            h4 = __ldg(reinterpret_cast<const uint4 *>(a.hi + q0)); l4 = __ldg(reinterpret_cast<const uint4 *>(a.lo + q0));
+            x4 = __ldg(reinterpret_cast<const uint4 *>(a.xx + q0));
+            h2 = __ldg(reinterpret_cast<const uint2 *>(a.hi + q0 + 4)); l2 = __ldg(reinterpret_cast<const uint2 *>(a.lo + q0 + 4));
+            x2 = __ldg(reinterpret_cast<const uint2 *>(a.xx + q0 + 4));
+        }
+        unsigned M[4] = {~0u, ~0u, ~0u, ~0u};
+        unsigned P[6];
+        if (a.npos[0]) {
+#pragma unroll
+            for (int w = 0; w < 6; w++) P[w] = ~(H[w] | Lw[w] | X[w]);
+            for (int e = 0; e < a.npos[0]; e++) packed_apply(M, P, a.shift[0][e]);
+        }
+        if (a.npos[1]) {
+#pragma unroll
+            for (int w = 0; w < 6; w++) P[w] = Lw[w] & ~H[w];
+            for (int e = 0; e < a.npos[1]; e++) packed_apply(M, P, a.shift[1][e]);
+        }
+        if (a.npos[2]) {
+#pragma unroll
+            for (int w = 0; w < 6; w++) P[w] = H[w] & Lw[w];
+            for (int e = 0; e < a.npos[2]; e++) packed_apply(M, P, a.shift[2][e]);
+        }
+        if (a.npos[3]) {
+#pragma unroll
+            for (int w = 0; w < 6; w++) P[w] = H[w] & ~Lw[w];
+            for (int e = 0; e < a.npos[3]; e++) packed_apply(M, P, a.shift[3][e]);
+        }
+        if (a.npos[4]) {
+            for (int e = 0; e < a.npos[4]; e++) packed_apply(M, X, a.shift[4][e]);
+        }
+        for (int e = 0; e < a.npos[5]; e++) {
+            const unsigned c = a.cls[e];
+            const unsigned sA = (c & 1) ? ~0u : 0u, sC = (c & 2) ? ~0u : 0u, sG = (c & 4) ? ~0u : 0u, sT = (c & 8) ? ~0u : 0u,
+                           sX = (c & 16) ? ~0u : 0u;
+#pragma unroll
+            for (int w = 0; w < 6; w++)
+                P[w] = (~(H[w] | Lw[w] | X[w]) & sA) | (Lw[w] & ~H[w] & sC) | (H[w] & Lw[w] & sG) | (H[w] & ~Lw[w] & sT) | (X[w] & sX);
+            packed_apply(M, P, a.shift[5][e]);
+        }
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            unsigned c = M[w];
+            while (c) {
+                const int b = __ffs(c) - 1;
+                c &= c - 1;
+                const long long p = (qcur + w) * 32 + b;
+                if (p >= a.a0 && p < a.a1 && p + a.L <= a.n) {
+                    const unsigned long long idx = atomicAdd(a.count, 1ULL);
+                    if ((long long)idx < a.cap) a.keys[idx] = (unsigned long long)p << 4;
+                }
+            }
+        }
+    }
+}
+
+template <int NP, typename W, int ROWS>
 __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, const PackedVerify<NP> v)
 {
     __shared__ unsigned sh_all[8][3 * PK_ROW];
@@ -292,9 +383,9 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
             bool keep = true, bail = false;
             int berr = 0, ferr = 0;
             const int lb = v.V[i], rl = v.m - lb;
-            if (lb > 0 && !nfa_packed<-1>(sh, base, v.TL[i], lb, v.k, v.ins, v.del, v.subs, p, &berr, &bail) && !bail) keep = false;
+            if (lb > 0 && !nfa_packed<-1, W, ROWS>(sh, base, v.TL[i], lb, v.k, v.ins, v.del, v.subs, p, &berr, &bail) && !bail) keep = false;
             if (keep && !bail && rl > 0 &&
-                !nfa_packed<+1>(sh, base, v.TR[i], rl, v.k - berr, v.ins, v.del, v.subs, p, &ferr, &bail) && !bail) keep = false;
+                !nfa_packed<+1, W, ROWS>(sh, base, v.TR[i], rl, v.k - berr, v.ins, v.del, v.subs, p, &ferr, &bail) && !bail) keep = false;
             if (keep) {
                 const unsigned long long idx = atomicAdd(a.count, 1ULL);
                 if ((long long)idx < a.cap) a.keys[idx] = ((unsigned long long)p << 4) | (unsigned)i;
