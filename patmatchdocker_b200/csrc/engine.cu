@@ -450,7 +450,7 @@ static int pack_dataset(pm_engine *e, pm_dataset *d)
 {
     const long long n = d->n;
     long long nw = (n + 31) / 32;
-    nw = (nw + 127) / 128 * 128 + 128;
+    nw = (nw + 1023) / 1024 * 1024 + 1024;          // whole block tiles of the TMA-staged scan + halo
     d->nwords = nw;
     void *p = nullptr;
     CK(cudaMalloc(&p, (size_t)nw * 4 * 3));
@@ -766,7 +766,15 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
                         a.shift[s][a.npos[s]++] = (unsigned char)j;
                     }
                     a.keys = (unsigned long long *)e->keys.p; a.count = d_count; a.cap = cap;
-                    k_scan_packed_exact<<<grid, 256, 0, e->stream>>>(a);
+                    const size_t smem = EX_STAGES * EX_STAGE_BYTES + 2 * EX_STAGES * 8;
+                    static bool attr_set = false;
+                    if (!attr_set) {
+                        CK(cudaFuncSetAttribute(k_scan_packed_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        attr_set = true;
+                    }
+                    const long long nbt = (ntiles + 7) / 8;
+                    const int grid_ex = std::max((int)std::min<long long>(nbt, (long long)e->sms * 4), 1);
+                    k_scan_packed_exact<<<grid_ex, 256, smem, e->stream>>>(a);
                 } else {
                     PackedArgs<4> a;
                     memset(&a, 0, sizeof a);

@@ -179,32 +179,97 @@ struct ExactArgs {
     long long cap;
 };
 
-__global__ void __launch_bounds__(256, 4) k_scan_packed_exact(const ExactArgs a)
+// --- TMA (bulk async copy) + mbarrier helpers -------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
 {
-    const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    long long t = warp;
-    if (t >= a.ntiles) return;
-    long long q0 = (a.tile0 + t) * 128 + 4 * lane;
-    uint4 h4 = __ldg(reinterpret_cast<const uint4 *>(a.hi + q0)), l4 = __ldg(reinterpret_cast<const uint4 *>(a.lo + q0)),
-          x4 = __ldg(reinterpret_cast<const uint4 *>(a.xx + q0));
-    uint2 h2 = __ldg(reinterpret_cast<const uint2 *>(a.hi + q0 + 4)), l2 = __ldg(reinterpret_cast<const uint2 *>(a.lo + q0 + 4)),
-          x2 = __ldg(reinterpret_cast<const uint2 *>(a.xx + q0 + 4));
-    for (; t < a.ntiles; t += nwarps) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Block tile of the exact scan: 8 warp tiles = 1024 words (32768 bases) per plane plus 4 halo
+// words, staged by TMA bulk copies into a ring of EX_STAGES shared-memory buffers.
+#define EX_WORDS 1024
+#define EX_ROW (EX_WORDS + 4)
+#define EX_STAGES 4
+#define EX_STAGE_BYTES (3 * EX_ROW * 4)
+
+__global__ void __launch_bounds__(256) k_scan_packed_exact(const ExactArgs a)
+{
+    extern __shared__ __align__(128) unsigned char ex_smem[];
+    unsigned *stage_base = reinterpret_cast<unsigned *>(ex_smem);
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(ex_smem + EX_STAGES * EX_STAGE_BYTES);
+    unsigned long long *empty = full + EX_STAGES;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    // block tiles handled by this CTA: bt = blockIdx.x, blockIdx.x + gridDim.x, ...
+    const long long nbt = (a.ntiles + 7) / 8;
+    const long long my = blockIdx.x < nbt ? (nbt - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < EX_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](long long it) {                       // thread 0 only
+        const int s = (int)(it % EX_STAGES);
+        const long long bt = blockIdx.x + it * gridDim.x;
+        const long long q = (a.tile0 * 128) + bt * EX_WORDS;
+        unsigned *dst = stage_base + (size_t)s * (3 * EX_ROW);
+        mbar_expect_tx(&full[s], EX_STAGE_BYTES);
+        tma_load_1d(dst, a.hi + q, EX_ROW * 4, &full[s]);
+        tma_load_1d(dst + EX_ROW, a.lo + q, EX_ROW * 4, &full[s]);
+        tma_load_1d(dst + 2 * EX_ROW, a.xx + q, EX_ROW * 4, &full[s]);
+    };
+    if (threadIdx.x == 0)
+        for (long long it = 0; it < my && it < EX_STAGES - 1; it++) issue(it);
+
+    for (long long it = 0; it < my; it++) {
+        const int s = (int)(it % EX_STAGES);
+        const unsigned ph = (unsigned)((it / EX_STAGES) & 1);
+        // refill the stage that the previous iteration released
+        if (threadIdx.x == 0) {
+            const long long nx = it + EX_STAGES - 1;
+            if (nx < my) {
+                if (nx >= EX_STAGES) mbar_wait(&empty[nx % EX_STAGES], (unsigned)(((nx / EX_STAGES) - 1) & 1));
+                issue(nx);
+            }
+        }
+        mbar_wait(&full[s], ph);
+        const unsigned *sp = stage_base + (size_t)s * (3 * EX_ROW) + wib * 128 + 4 * lane;
+        const uint4 h4 = *reinterpret_cast<const uint4 *>(sp), l4 = *reinterpret_cast<const uint4 *>(sp + EX_ROW),
+                    x4 = *reinterpret_cast<const uint4 *>(sp + 2 * EX_ROW);
+        const uint2 h2 = *reinterpret_cast<const uint2 *>(sp + 4), l2 = *reinterpret_cast<const uint2 *>(sp + EX_ROW + 4),
+                    x2 = *reinterpret_cast<const uint2 *>(sp + 2 * EX_ROW + 4);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);            // this warp's slice is in registers
         const unsigned H[6] = {h4.x, h4.y, h4.z, h4.w, h2.x, h2.y};
         const unsigned Lw[6] = {l4.x, l4.y, l4.z, l4.w, l2.x, l2.y};
         const unsigned X[6] = {x4.x, x4.y, x4.z, x4.w, x2.x, x2.y};
-        const long long qcur = q0;
-        // prefetch the next tile of this warp
-        const long long tn = t + nwarps;
-        if (tn < a.ntiles) {
-            q0 = (a.tile0 + tn) * 128 + 4 * lane;
-            h4 = __ldg(reinterpret_cast<const uint4 *>(a.hi + q0)); l4 = __ldg(reinterpret_cast<const uint4 *>(a.lo + q0));
-            x4 = __ldg(reinterpret_cast<const uint4 *>(a.xx + q0));
-            h2 = __ldg(reinterpret_cast<const uint2 *>(a.hi + q0 + 4)); l2 = __ldg(reinterpret_cast<const uint2 *>(a.lo + q0 + 4));
-            x2 = __ldg(reinterpret_cast<const uint2 *>(a.xx + q0 + 4));
-        }
+        const long long bt = blockIdx.x + it * gridDim.x;
+        const long long qcur = (a.tile0 * 128) + bt * EX_WORDS + wib * 128 + 4 * lane;
         unsigned M[4] = {~0u, ~0u, ~0u, ~0u};
         unsigned P[6];
         if (a.npos[0]) {
