@@ -769,12 +769,14 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
                     const size_t smem = EX_STAGES * EX_STAGE_BYTES + 2 * EX_STAGES * 8;
                     static bool attr_set = false;
                     if (!attr_set) {
-                        CK(cudaFuncSetAttribute(k_scan_packed_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        CK(cudaFuncSetAttribute(k_scan_packed_exact<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        CK(cudaFuncSetAttribute(k_scan_packed_exact<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                         attr_set = true;
                     }
                     const long long nbt = (ntiles + 7) / 8;
                     const int grid_ex = std::max((int)std::min<long long>(nbt, (long long)e->sms * 4), 1);
-                    k_scan_packed_exact<<<grid_ex, 256, smem, e->stream>>>(a);
+                    if (dp.L > 32) k_scan_packed_exact<true><<<grid_ex, 256, smem, e->stream>>>(a);
+                    else k_scan_packed_exact<false><<<grid_ex, 256, smem, e->stream>>>(a);
                 } else {
                     PackedArgs<4> a;
                     memset(&a, 0, sizeof a);
@@ -878,7 +880,7 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
         size_t tmp = 0;
         int end_bit = 64;
         {
-            unsigned long long maxkey = ((unsigned long long)n << 4) | 15ULL;
+            unsigned long long maxkey = ((unsigned long long)(n + 2) << 4) | 15ULL;
             end_bit = 1;
             while (end_bit < 64 && (maxkey >> end_bit)) end_bit++;
         }

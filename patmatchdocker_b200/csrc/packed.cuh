@@ -75,9 +75,10 @@ __global__ void __launch_bounds__(256) k_newlines(const unsigned char *__restric
     }
 }
 
+template <bool LONG = true>
 __device__ __forceinline__ void packed_apply(unsigned (&M)[4], const unsigned (&P)[6], int sh)
 {
-    if (sh < 32) {
+    if (!LONG || sh < 32) {
 #pragma unroll
         for (int w = 0; w < 4; w++) M[w] &= __funnelshift_r(P[w], P[w + 1], sh);
     } else {
@@ -218,9 +219,25 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
 #define EX_STAGES 4
 #define EX_STAGE_BYTES (3 * EX_ROW * 4)
 
+#define EX_HITBUF 128                    // per-warp hit buffer (keys), flushed with one global atomic
+
+template <bool LONG>
 __global__ void __launch_bounds__(256) k_scan_packed_exact(const ExactArgs a)
 {
     extern __shared__ __align__(128) unsigned char ex_smem[];
+    __shared__ unsigned long long hitbuf_all[8][EX_HITBUF];
+    unsigned long long *hitbuf = hitbuf_all[threadIdx.x >> 5];
+    unsigned nbuf = 0;                                      // warp-uniform fill of hitbuf
+    auto flush = [&]() {
+        if (nbuf == 0) return;
+        unsigned long long basei = 0;
+        if ((threadIdx.x & 31) == 0) basei = atomicAdd(a.count, (unsigned long long)nbuf);
+        basei = __shfl_sync(0xffffffffu, basei, 0);
+        for (unsigned e = threadIdx.x & 31; e < nbuf; e += 32)
+            if ((long long)(basei + e) < a.cap) a.keys[basei + e] = hitbuf[e];
+        __syncwarp();
+        nbuf = 0;
+    };
     unsigned *stage_base = reinterpret_cast<unsigned *>(ex_smem);
     unsigned long long *full = reinterpret_cast<unsigned long long *>(ex_smem + EX_STAGES * EX_STAGE_BYTES);
     unsigned long long *empty = full + EX_STAGES;
@@ -275,25 +292,25 @@ __global__ void __launch_bounds__(256) k_scan_packed_exact(const ExactArgs a)
         if (a.npos[0]) {
 #pragma unroll
             for (int w = 0; w < 6; w++) P[w] = ~(H[w] | Lw[w] | X[w]);
-            for (int e = 0; e < a.npos[0]; e++) packed_apply(M, P, a.shift[0][e]);
+            for (int e = 0; e < a.npos[0]; e++) packed_apply<LONG>(M, P, a.shift[0][e]);
         }
         if (a.npos[1]) {
 #pragma unroll
             for (int w = 0; w < 6; w++) P[w] = Lw[w] & ~H[w];
-            for (int e = 0; e < a.npos[1]; e++) packed_apply(M, P, a.shift[1][e]);
+            for (int e = 0; e < a.npos[1]; e++) packed_apply<LONG>(M, P, a.shift[1][e]);
         }
         if (a.npos[2]) {
 #pragma unroll
             for (int w = 0; w < 6; w++) P[w] = H[w] & Lw[w];
-            for (int e = 0; e < a.npos[2]; e++) packed_apply(M, P, a.shift[2][e]);
+            for (int e = 0; e < a.npos[2]; e++) packed_apply<LONG>(M, P, a.shift[2][e]);
         }
         if (a.npos[3]) {
 #pragma unroll
             for (int w = 0; w < 6; w++) P[w] = H[w] & ~Lw[w];
-            for (int e = 0; e < a.npos[3]; e++) packed_apply(M, P, a.shift[3][e]);
+            for (int e = 0; e < a.npos[3]; e++) packed_apply<LONG>(M, P, a.shift[3][e]);
         }
         if (a.npos[4]) {
-            for (int e = 0; e < a.npos[4]; e++) packed_apply(M, X, a.shift[4][e]);
+            for (int e = 0; e < a.npos[4]; e++) packed_apply<LONG>(M, X, a.shift[4][e]);
         }
         for (int e = 0; e < a.npos[5]; e++) {
             const unsigned c = a.cls[e];
@@ -302,8 +319,40 @@ __global__ void __launch_bounds__(256) k_scan_packed_exact(const ExactArgs a)
 #pragma unroll
             for (int w = 0; w < 6; w++)
                 P[w] = (~(H[w] | Lw[w] | X[w]) & sA) | (Lw[w] & ~H[w] & sC) | (H[w] & Lw[w] & sG) | (H[w] & ~Lw[w] & sT) | (X[w] & sX);
-            packed_apply(M, P, a.shift[5][e]);
+            packed_apply<LONG>(M, P, a.shift[5][e]);
         }
+        // ---- hits of this warp tile: buffered in shared memory, no per-hit global atomics ----
+        const unsigned mine = __popc(M[0]) + __popc(M[1]) + __popc(M[2]) + __popc(M[3]);
+        if (!__any_sync(0xffffffffu, mine != 0)) continue;
+        unsigned incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total > EX_HITBUF) {
+            // dense tile: straight to global memory
+            flush();
+            unsigned long long basei = 0;
+            if (lane == 0) basei = atomicAdd(a.count, (unsigned long long)total);
+            basei = __shfl_sync(0xffffffffu, basei, 0) + (incl - mine);
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                unsigned c = M[w];
+                while (c) {
+                    const int b = __ffs(c) - 1;
+                    c &= c - 1;
+                    const long long p = (qcur + w) * 32 + b;
+                    const bool ok = p >= a.a0 && p < a.a1 && p + a.L <= a.n;
+                    if ((long long)basei < a.cap) a.keys[basei] = ok ? (unsigned long long)p << 4 : (((unsigned long long)(a.n + 1) << 4) | 15ULL);
+                    basei++;
+                }
+            }
+            continue;
+        }
+        if (nbuf + total > EX_HITBUF) flush();
+        unsigned slot = nbuf + (incl - mine);
 #pragma unroll
         for (int w = 0; w < 4; w++) {
             unsigned c = M[w];
@@ -311,13 +360,14 @@ __global__ void __launch_bounds__(256) k_scan_packed_exact(const ExactArgs a)
                 const int b = __ffs(c) - 1;
                 c &= c - 1;
                 const long long p = (qcur + w) * 32 + b;
-                if (p >= a.a0 && p < a.a1 && p + a.L <= a.n) {
-                    const unsigned long long idx = atomicAdd(a.count, 1ULL);
-                    if ((long long)idx < a.cap) a.keys[idx] = (unsigned long long)p << 4;
-                }
+                const bool ok = p >= a.a0 && p < a.a1 && p + a.L <= a.n;
+                hitbuf[slot++] = ok ? (unsigned long long)p << 4 : (((unsigned long long)(a.n + 1) << 4) | 15ULL);
             }
         }
+        nbuf += total;
+        __syncwarp();
     }
+    flush();
 }
 
 template <int NP, typename W, int ROWS>
