@@ -734,7 +734,7 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
     long long ncand = 0;
     for (int attempt = 0; attempt < 3; attempt++) {
         if ((rc = e->keys.reserve((size_t)cap * 8))) return rc;
-        CK(cudaMemsetAsync(d_count, 0, 8, e->stream));
+        CK(cudaMemsetAsync(d_count, 0, 16, e->stream));
         CK(cudaEventRecord(e->ev[0], e->stream));
         if (use_packed) {
             const long long wend = std::min(a1, n - dp.L + 1);
@@ -866,13 +866,14 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(e->ev[1], e->stream));
-        CK(cudaMemcpyAsync(e->h_count, d_count, 8, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(e->h_count, d_count, 16, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
         ncand = (long long)e->h_count[0];
         if (ncand <= cap) break;
         cap = ncand + 1024;                                    // grow and rescan
     }
-    e->stats.candidates = ncand;
+    const long long nplaceholders = (long long)e->h_count[1];  // out-of-range slots written by k_scan_packed_exact
+    e->stats.candidates = ncand - nplaceholders;
     // ---- sort ----
     unsigned long long *keys = (unsigned long long *)e->keys.p;
     if (ncand > 1) {
@@ -890,6 +891,7 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
         keys = (unsigned long long *)e->keys2.p;
         e->stats.launches += 3;
     }
+    ncand -= nplaceholders;                                   // they carry the largest key and sit at the end
     CK(cudaEventRecord(e->ev[2], e->stream));
     // ---- verify ----
     if (ncand > 0) {

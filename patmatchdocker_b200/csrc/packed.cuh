@@ -346,6 +346,7 @@ __global__ void __launch_bounds__(256) k_scan_packed_exact(const ExactArgs a)
                     const long long p = (qcur + w) * 32 + b;
                     const bool ok = p >= a.a0 && p < a.a1 && p + a.L <= a.n;
                     if ((long long)basei < a.cap) a.keys[basei] = ok ? (unsigned long long)p << 4 : (((unsigned long long)(a.n + 1) << 4) | 15ULL);
+                    if (!ok) atomicAdd(a.count + 1, 1ULL);          // placeholders sort last and are cut off by the host
                     basei++;
                 }
             }
@@ -362,6 +363,7 @@ __global__ void __launch_bounds__(256) k_scan_packed_exact(const ExactArgs a)
                 const long long p = (qcur + w) * 32 + b;
                 const bool ok = p >= a.a0 && p < a.a1 && p + a.L <= a.n;
                 hitbuf[slot++] = ok ? (unsigned long long)p << 4 : (((unsigned long long)(a.n + 1) << 4) | 15ULL);
+                if (!ok) atomicAdd(a.count + 1, 1ULL);              // placeholders sort last and are cut off by the host
             }
         }
         nbuf += total;
