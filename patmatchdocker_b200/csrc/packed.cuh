@@ -216,10 +216,10 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
 // words, staged by TMA bulk copies into a ring of EX_STAGES shared-memory buffers.
 #define EX_WORDS 1024
 #define EX_ROW (EX_WORDS + 4)
-#define EX_STAGES 4
+#define EX_STAGES 3
 #define EX_STAGE_BYTES (3 * EX_ROW * 4)
 
-#define EX_HITBUF 128                    // per-warp hit buffer (keys), flushed with one global atomic
+#define EX_HITBUF 64                     // per-warp hit buffer (keys), flushed with one global atomic
 
 template <bool LONG>
 __global__ void __launch_bounds__(256) k_scan_packed_exact(const ExactArgs a)
@@ -331,6 +331,11 @@ __global__ void __launch_bounds__(256) k_scan_packed_exact(const ExactArgs a)
             if (lane >= o) incl += v;
         }
         const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        const long long wbase = ((a.tile0 * 128) + bt * EX_WORDS + wib * 128) * 32;   // text position of the warp tile
+        // only the first / last tiles of the scanned range need the per-hit range test
+        const bool inside = wbase >= a.a0 && wbase + 4096 <= (a.a1 < a.n - a.L + 1 ? a.a1 : a.n - a.L + 1);
+        const unsigned long long bad = ((unsigned long long)(a.n + 1) << 4) | 15ULL;
+        const unsigned lrel = (unsigned)(4 * lane) * 32;
         if (total > EX_HITBUF) {
             // dense tile: straight to global memory
             flush();
@@ -343,9 +348,9 @@ __global__ void __launch_bounds__(256) k_scan_packed_exact(const ExactArgs a)
                 while (c) {
                     const int b = __ffs(c) - 1;
                     c &= c - 1;
-                    const long long p = (qcur + w) * 32 + b;
-                    const bool ok = p >= a.a0 && p < a.a1 && p + a.L <= a.n;
-                    if ((long long)basei < a.cap) a.keys[basei] = ok ? (unsigned long long)p << 4 : (((unsigned long long)(a.n + 1) << 4) | 15ULL);
+                    const long long p = wbase + (lrel + w * 32 + b);
+                    const bool ok = inside || (p >= a.a0 && p < a.a1 && p + a.L <= a.n);
+                    if ((long long)basei < a.cap) a.keys[basei] = ok ? (unsigned long long)p << 4 : bad;
                     if (!ok) atomicAdd(a.count + 1, 1ULL);          // placeholders sort last and are cut off by the host
                     basei++;
                 }
@@ -360,9 +365,9 @@ __global__ void __launch_bounds__(256) k_scan_packed_exact(const ExactArgs a)
             while (c) {
                 const int b = __ffs(c) - 1;
                 c &= c - 1;
-                const long long p = (qcur + w) * 32 + b;
-                const bool ok = p >= a.a0 && p < a.a1 && p + a.L <= a.n;
-                hitbuf[slot++] = ok ? (unsigned long long)p << 4 : (((unsigned long long)(a.n + 1) << 4) | 15ULL);
+                const long long p = wbase + (lrel + w * 32 + b);
+                const bool ok = inside || (p >= a.a0 && p < a.a1 && p + a.L <= a.n);
+                hitbuf[slot++] = ok ? (unsigned long long)p << 4 : bad;
                 if (!ok) atomicAdd(a.count + 1, 1ULL);              // placeholders sort last and are cut off by the host
             }
         }
