@@ -193,16 +193,16 @@ __device__ __forceinline__ void nfa_init(NfaState<W, ROWS> &s, int plen, int kma
 }
 
 // returns 0 = keep walking, 1 = matched (err in s.best_err), 2 = failed, 3 = needs the raw bytes
-template <int DIR, typename W, int ROWS>
-__device__ __forceinline__ int nfa_step(NfaState<W, ROWS> &s, const unsigned *__restrict__ sh, const unsigned long long (&T64)[4],
+template <typename W, int ROWS>
+__device__ __forceinline__ int nfa_step(NfaState<W, ROWS> &s, const unsigned *__restrict__ sh, const W (&T)[4], int dir,
                                         int ins, int del, int subs)
 {
     const int wi = s.rel >> 5, bi = s.rel & 31;
     if (wi < 0 || wi >= PK_ROW || s.steps >= 96) return 3;
     if ((sh[2 * PK_ROW + wi] >> bi) & 1u) return 3;
     const unsigned code = (((sh[wi] >> bi) & 1u) << 1) | ((sh[PK_ROW + wi] >> bi) & 1u);
-    const W Tc = (W)(code == 0 ? T64[0] : code == 1 ? T64[1] : code == 2 ? T64[2] : T64[3]);
-    s.rel += DIR;
+    const W Tc = code == 0 ? T[0] : code == 1 ? T[1] : code == 2 ? T[2] : T[3];
+    s.rel += dir;
     s.steps++;
     W oldp = s.R[0];
     s.R[0] = (W)(((s.R[0] << 1) | s.first) & Tc);
@@ -570,7 +570,8 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
         {
             NfaState<W, ROWS> st;
             bool active = false;
-            int ci = 0, side = 0, berr = 0;
+            int ci = 0, dir = 0, berr = 0;
+            W T[4] = {0, 0, 0, 0};
             long long cp = 0;
             for (;;) {
                 if (!active) {
@@ -582,20 +583,28 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
                         const int rel0 = (int)(cp - base);
                         active = true;
                         berr = 0;
-                        if (v.V[ci] > 0) { side = 0; nfa_init<W, ROWS>(st, v.V[ci], v.k, v.del, rel0 - 1); }
-                        else { side = 1; nfa_init<W, ROWS>(st, v.m, v.k, v.del, rel0); }
+                        if (v.V[ci] > 0) {
+                            dir = -1;
+                            nfa_init<W, ROWS>(st, v.V[ci], v.k, v.del, rel0 - 1);
+#pragma unroll
+                            for (int c4 = 0; c4 < 4; c4++) T[c4] = (W)v.TL[ci][c4];
+                        } else {
+                            dir = +1;
+                            nfa_init<W, ROWS>(st, v.m, v.k, v.del, rel0);
+#pragma unroll
+                            for (int c4 = 0; c4 < 4; c4++) T[c4] = (W)v.TR[ci][c4];
+                        }
                     }
                 }
                 if (!__any_sync(0xffffffffu, active)) break;
                 if (active) {
-                    // a part shorter than the error budget can be matched by deletions alone (nfa_init found it);
-                    // the walk still continues for a lower error count, exactly like the reference
-                    int r = side == 0 ? nfa_step<-1, W, ROWS>(st, sh, v.TL[ci], v.ins, v.del, v.subs)
-                                      : nfa_step<+1, W, ROWS>(st, sh, v.TR[ci], v.ins, v.del, v.subs);
-                    if (r == 1 && side == 0 && v.m - v.V[ci] > 0) {
+                    int r = nfa_step<W, ROWS>(st, sh, T, dir, v.ins, v.del, v.subs);
+                    if (r == 1 && dir < 0 && v.m - v.V[ci] > 0) {
                         berr = st.best_err;
-                        side = 1;
+                        dir = +1;
                         nfa_init<W, ROWS>(st, v.m - v.V[ci], v.k - berr, v.del, (int)(cp - base));
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; c4++) T[c4] = (W)v.TR[ci][c4];
                         r = 0;
                     }
                     if (r != 0) {
