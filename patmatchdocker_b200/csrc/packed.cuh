@@ -165,72 +165,6 @@ __device__ __forceinline__ int nfa_packed(const unsigned *__restrict__ sh, long 
     return 1;
 }
 
-// The same NFA as nfa_packed, cut into init + single steps, so that the lanes of a warp can each
-// run their own candidate and fetch the next one the moment theirs is decided (lane-persistent
-// verification: cost follows the average walk length instead of the longest one in the warp).
-template <typename W, int ROWS>
-struct NfaState {
-    W R[ROWS];
-    W first, fin, live;
-    int kb, best_err, rel, steps;
-};
-
-template <typename W, int ROWS>
-__device__ __forceinline__ void nfa_init(NfaState<W, ROWS> &s, int plen, int kmax, int del, int rel0)
-{
-    s.fin = (W)1 << (plen - 1);
-    s.live = (W)((s.fin << 1) - 1);
-    s.kb = kmax;
-    s.best_err = -1;
-#pragma unroll
-    for (int e = 0; e < ROWS; e++) {
-        s.R[e] = del ? (W)(((W)1 << e) - 1) : (W)0;
-        if (e <= s.kb && (s.R[e] & s.fin)) { s.best_err = e; s.kb = e - 1; }
-    }
-    s.first = 1;
-    s.rel = rel0;
-    s.steps = 0;
-}
-
-// returns 0 = keep walking, 1 = matched (err in s.best_err), 2 = failed, 3 = needs the raw bytes
-template <typename W, int ROWS>
-__device__ __forceinline__ int nfa_step(NfaState<W, ROWS> &s, const unsigned *__restrict__ sh, const W (&T)[4], int dir,
-                                        int ins, int del, int subs)
-{
-    const int wi = s.rel >> 5, bi = s.rel & 31;
-    if (wi < 0 || wi >= PK_ROW || s.steps >= 96) return 3;
-    if ((sh[2 * PK_ROW + wi] >> bi) & 1u) return 3;
-    const unsigned code = (((sh[wi] >> bi) & 1u) << 1) | ((sh[PK_ROW + wi] >> bi) & 1u);
-    const W Tc = code == 0 ? T[0] : code == 1 ? T[1] : code == 2 ? T[2] : T[3];
-    s.rel += dir;
-    s.steps++;
-    W oldp = s.R[0];
-    s.R[0] = (W)(((s.R[0] << 1) | s.first) & Tc);
-    W newp = s.R[0];
-    if (s.R[0] & s.fin) { s.best_err = 0; return 1; }
-    bool lowered = false;
-#pragma unroll
-    for (int e = 1; e < ROWS; e++) {
-        if (e <= s.kb && !lowered) {
-            W x = 0;
-            if (del) x = (W)(newp << 1);
-            if (ins) x |= oldp;
-            if (subs) x |= (W)((oldp << 1) | s.first);
-            const W nr = (W)((((s.R[e] << 1) | s.first) & Tc) | x);
-            oldp = s.R[e];
-            s.R[e] = nr;
-            newp = nr;
-            if (nr & s.fin) { s.best_err = e; s.kb = e - 1; lowered = true; }
-        }
-    }
-    W alive = s.R[0];
-#pragma unroll
-    for (int e = 1; e < ROWS; e++) if (s.kb == e) alive = s.R[e];
-    if (s.kb < 0 || !(alive & s.live)) return s.best_err >= 0 ? 1 : 2;
-    s.first = 0;
-    return 0;
-}
-
 // ---------------------------------------------------------------------------------------
 // Exact (k = 0, SIMPLE) scan: one piece, registers only, next tile prefetched while the current
 // one is evaluated.  Positions are grouped by the plane they read so that no per-position
@@ -564,57 +498,19 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
         }
         __syncwarp();
         const unsigned nq = min(*qcount, (unsigned)PK_QUEUE);
-        __syncwarp();
-        if (lane == 0) *qcount = 0;                        // reused as the queue head
-        __syncwarp();
-        {
-            NfaState<W, ROWS> st;
-            bool active = false;
-            int ci = 0, dir = 0, berr = 0;
-            W T[4] = {0, 0, 0, 0};
-            long long cp = 0;
-            for (;;) {
-                if (!active) {
-                    const unsigned idx = atomicAdd(qcount, 1u);
-                    if (idx < nq) {
-                        const unsigned ent = queue[idx];
-                        ci = (int)(ent & 3u);
-                        cp = qt * 32 + (ent >> 2);
-                        const int rel0 = (int)(cp - base);
-                        active = true;
-                        berr = 0;
-                        if (v.V[ci] > 0) {
-                            dir = -1;
-                            nfa_init<W, ROWS>(st, v.V[ci], v.k, v.del, rel0 - 1);
-#pragma unroll
-                            for (int c4 = 0; c4 < 4; c4++) T[c4] = (W)v.TL[ci][c4];
-                        } else {
-                            dir = +1;
-                            nfa_init<W, ROWS>(st, v.m, v.k, v.del, rel0);
-#pragma unroll
-                            for (int c4 = 0; c4 < 4; c4++) T[c4] = (W)v.TR[ci][c4];
-                        }
-                    }
-                }
-                if (!__any_sync(0xffffffffu, active)) break;
-                if (active) {
-                    int r = nfa_step<W, ROWS>(st, sh, T, dir, v.ins, v.del, v.subs);
-                    if (r == 1 && dir < 0 && v.m - v.V[ci] > 0) {
-                        berr = st.best_err;
-                        dir = +1;
-                        nfa_init<W, ROWS>(st, v.m - v.V[ci], v.k - berr, v.del, (int)(cp - base));
-#pragma unroll
-                        for (int c4 = 0; c4 < 4; c4++) T[c4] = (W)v.TR[ci][c4];
-                        r = 0;
-                    }
-                    if (r != 0) {
-                        if (r != 2) {                      // matched, or undecidable on packed data: keep
-                            const unsigned long long idx = atomicAdd(a.count, 1ULL);
-                            if ((long long)idx < a.cap) a.keys[idx] = ((unsigned long long)cp << 4) | (unsigned)ci;
-                        }
-                        active = false;
-                    }
-                }
+        for (unsigned e = lane; e < nq; e += 32) {
+            const unsigned ent = queue[e];
+            const int i = (int)(ent & 3u);
+            const long long p = qt * 32 + (ent >> 2);
+            bool keep = true, bail = false;
+            int berr = 0, ferr = 0;
+            const int lb = v.V[i], rl = v.m - lb;
+            if (lb > 0 && !nfa_packed<-1, W, ROWS>(sh, base, v.TL[i], lb, v.k, v.ins, v.del, v.subs, p, &berr, &bail) && !bail) keep = false;
+            if (keep && !bail && rl > 0 &&
+                !nfa_packed<+1, W, ROWS>(sh, base, v.TR[i], rl, v.k - berr, v.ins, v.del, v.subs, p, &ferr, &bail) && !bail) keep = false;
+            if (keep) {
+                const unsigned long long idx = atomicAdd(a.count, 1ULL);
+                if ((long long)idx < a.cap) a.keys[idx] = ((unsigned long long)p << 4) | (unsigned)i;
             }
         }
         __syncwarp();
