@@ -762,8 +762,8 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
                     for (int j = 0; j < dp.L; j++) {
                         const unsigned cls = packed_class(c.P.pos[j]);
                         const int s = plane_of(cls);
-                        if (s == 5) { a.cls[a.npos[5]] = (unsigned char)cls; a.shift[5][a.npos[5]++] = (unsigned char)j; }
-                        else a.pmask[s] |= 1ULL << j;
+                        if (s == 5) a.cls[a.npos[5]] = (unsigned char)cls;
+                        a.shift[s][a.npos[s]++] = (unsigned char)j;
                     }
                     a.keys = (unsigned long long *)e->keys.p; a.count = d_count; a.cap = cap;
                     const size_t smem = EX_STAGES * EX_STAGE_BYTES + 2 * EX_STAGES * 8;

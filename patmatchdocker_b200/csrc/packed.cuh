@@ -173,8 +173,7 @@ struct ExactArgs {
     const unsigned *hi, *lo, *xx;
     long long nwords, n, a0, a1, tile0, ntiles;
     int L;
-    unsigned long long pmask[5];          // bit j set: position j reads plane A,C,G,T,X directly
-    unsigned char npos[6];                // [5] = number of general-class positions
+    unsigned char npos[6];                // positions reading plane A,C,G,T,X and general classes
     unsigned char shift[6][64];
     unsigned char cls[64];                // general classes: bits A,C,G,T,X (parallel to shift[5])
     unsigned long long *keys, *count;
@@ -290,35 +289,36 @@ __global__ void __launch_bounds__(256) k_scan_packed_exact(const ExactArgs a)
         const long long qcur = (a.tile0 * 128) + bt * EX_WORDS + wib * 128 + 4 * lane;
         unsigned M[4] = {~0u, ~0u, ~0u, ~0u};
         unsigned P[6];
-        // positions grouped by plane; each group is a 64-bit set of shifts walked with ffs (no table loads)
-#define EX_GROUP(MASK, EXPR)                                                          \
-        if (MASK) {                                                                   \
-            _Pragma("unroll") for (int w = 0; w < 6; w++) P[w] = (EXPR);              \
-            unsigned long long mm = (MASK);                                           \
-            do {                                                                      \
-                const int sh = __ffsll((long long)mm) - 1;                            \
-                mm &= mm - 1;                                                         \
-                packed_apply<LONG>(M, P, sh);                                         \
-            } while (mm);                                                             \
+        if (a.npos[0]) {
+#pragma unroll
+            for (int w = 0; w < 6; w++) P[w] = ~(H[w] | Lw[w] | X[w]);
+            for (int e = 0; e < a.npos[0]; e++) packed_apply<LONG>(M, P, a.shift[0][e]);
         }
-        EX_GROUP(a.pmask[0], ~(H[w] | Lw[w] | X[w]))
-        EX_GROUP(a.pmask[1], Lw[w] & ~H[w])
-        EX_GROUP(a.pmask[2], H[w] & Lw[w])
-        EX_GROUP(a.pmask[3], H[w] & ~Lw[w])
-        EX_GROUP(a.pmask[4], X[w])
-#undef EX_GROUP
+        if (a.npos[1]) {
+#pragma unroll
+            for (int w = 0; w < 6; w++) P[w] = Lw[w] & ~H[w];
+            for (int e = 0; e < a.npos[1]; e++) packed_apply<LONG>(M, P, a.shift[1][e]);
+        }
+        if (a.npos[2]) {
+#pragma unroll
+            for (int w = 0; w < 6; w++) P[w] = H[w] & Lw[w];
+            for (int e = 0; e < a.npos[2]; e++) packed_apply<LONG>(M, P, a.shift[2][e]);
+        }
+        if (a.npos[3]) {
+#pragma unroll
+            for (int w = 0; w < 6; w++) P[w] = H[w] & ~Lw[w];
+            for (int e = 0; e < a.npos[3]; e++) packed_apply<LONG>(M, P, a.shift[3][e]);
+        }
+        if (a.npos[4]) {
+            for (int e = 0; e < a.npos[4]; e++) packed_apply<LONG>(M, X, a.shift[4][e]);
+        }
         for (int e = 0; e < a.npos[5]; e++) {
-            // general class as a 3-level select on (X, H, L): 4 logic ops per word
             const unsigned c = a.cls[e];
             const unsigned sA = (c & 1) ? ~0u : 0u, sC = (c & 2) ? ~0u : 0u, sG = (c & 4) ? ~0u : 0u, sT = (c & 8) ? ~0u : 0u,
                            sX = (c & 16) ? ~0u : 0u;
 #pragma unroll
-            for (int w = 0; w < 6; w++) {
-                const unsigned lo0 = (Lw[w] & sC) | (~Lw[w] & sA);       // H = 0: C or A
-                const unsigned lo1 = (Lw[w] & sG) | (~Lw[w] & sT);       // H = 1: G or T
-                const unsigned nuc = (H[w] & lo1) | (~H[w] & lo0);
-                P[w] = (X[w] & sX) | (~X[w] & nuc);
-            }
+            for (int w = 0; w < 6; w++)
+                P[w] = (~(H[w] | Lw[w] | X[w]) & sA) | (Lw[w] & ~H[w] & sC) | (H[w] & Lw[w] & sG) | (H[w] & ~Lw[w] & sT) | (X[w] & sX);
             packed_apply<LONG>(M, P, a.shift[5][e]);
         }
         // ---- hits of this warp tile: buffered in shared memory, no per-hit global atomics ----
