@@ -96,6 +96,10 @@ int64_t pm_dataset_size(const pm_dataset *d);
 int pm_search(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt,
               pm_hit *hits, int64_t cap, int64_t *nhits);
 
+/* After pm_search returned PM_ERR_OVERFLOW (or was called with hits = NULL): copy the hit list of that
+ * search, which is still on the device, without searching again. */
+int pm_last_hits(pm_engine *e, pm_hit *hits, int64_t cap, int64_t *nhits);
+
 /* Batched motifs (same -k for all): hit lists are concatenated, offsets[i]..offsets[i+1]
  * delimit pattern i.  offsets has npat+1 entries. */
 int pm_search_batch(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns,

@@ -76,6 +76,7 @@ def load():
     L.pm_dataset_size.argtypes = [vp]
     L.pm_dataset_size.restype = i64
     L.pm_search.argtypes = [vp, vp, cp, cp, vp, i64, ctypes.POINTER(i64)]
+    L.pm_last_hits.argtypes = [vp, vp, i64, ctypes.POINTER(i64)]
     L.pm_search_batch.argtypes = [vp, vp, ctypes.c_int, ctypes.POINTER(cp), cp, vp, i64, ctypes.POINTER(i64)]
     L.pm_candidates.argtypes = [vp, vp, cp, cp, i64, i64, vp, i64, ctypes.POINTER(i64)]
     L.pm_resolve.argtypes = [vp, vp, cp, cp, vp, i64, vp, i64, ctypes.POINTER(i64)]
@@ -175,14 +176,13 @@ class Engine:
         """-> numpy structured array (beg, end): the '[beg, end]' pairs nrgrep_coords prints, in order."""
         L = load()
         n = ctypes.c_int64()
-        while True:
-            hits = np.empty(cap, dtype=HIT_DTYPE)
-            rc = L.pm_search(self._h, dataset._h, _b(pattern), _b(kopt), ctypes.c_void_p(hits.ctypes.data), cap, ctypes.byref(n))
-            if rc == PM_ERR_OVERFLOW:
-                cap = int(n.value)
-                continue
-            _check(rc)
-            return hits[: n.value]
+        hits = np.empty(cap, dtype=HIT_DTYPE)
+        rc = L.pm_search(self._h, dataset._h, _b(pattern), _b(kopt), ctypes.c_void_p(hits.ctypes.data), cap, ctypes.byref(n))
+        if rc == PM_ERR_OVERFLOW:                      # the hit list is still on the device: fetch it, do not search again
+            hits = np.empty(int(n.value), dtype=HIT_DTYPE)
+            rc = L.pm_last_hits(self._h, ctypes.c_void_p(hits.ctypes.data), len(hits), ctypes.byref(n))
+        _check(rc)
+        return hits[: n.value]
 
     def count(self, dataset, pattern, kopt="0ids"):
         n = ctypes.c_int64()

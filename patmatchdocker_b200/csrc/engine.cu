@@ -978,6 +978,20 @@ int pm_search(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt
     return rc;
 }
 
+int pm_last_hits(pm_engine *e, pm_hit *hits, int64_t cap, int64_t *nhits)
+{
+    if (!e || !nhits) { g_err = "bad argument"; return PM_ERR_ARG; }
+    CK(cudaSetDevice(e->device));
+    const long long nh = e->stats.hits;
+    *nhits = nh;
+    if (hits && nh > 0) {
+        if (nh > cap) { g_err = "hit buffer too small"; return PM_ERR_OVERFLOW; }
+        CK(cudaMemcpyAsync(hits, e->hits2.p, (size_t)nh * sizeof(pm_hit), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    return PM_OK;
+}
+
 int pm_search_batch(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
                     pm_hit *hits, int64_t cap, int64_t *offsets)
 {

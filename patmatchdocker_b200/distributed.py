@@ -1,0 +1,54 @@
+"""Multi-GPU search: one process per GPU (torch.distributed), no data-path collective.
+
+Every rank holds the dataset and scans only its share of the file positions
+(`Engine.candidates`, i.e. pm_candidates): the reference's scan is embarrassingly parallel up
+to the point where it restarts after each reported hit, and that sequential rule is applied
+once, on rank 0, to the gathered list of verified candidates (`Engine.resolve`, pm_resolve).
+The only communication is the final gather of the (sparse) candidate records over NCCL.
+Because candidates do not depend on where the file is cut, the result is bit-identical to the
+single-GPU search for any number of ranks (tests/test_gpu.py::test_sharded_candidates_...).
+"""
+import numpy as np
+
+from ._native import CAND_DTYPE
+
+
+def shard_ranges(n, world):
+    """Position ranges [beg, end) of the `world` ranks over a file of n bytes (anchors 0..n)."""
+    edges = [(n + 1) * r // world for r in range(world + 1)]
+    return [(edges[r], edges[r + 1]) for r in range(world)]
+
+
+def gather_candidates(cands, rank, world, device=None, group=None):
+    """Gather per-rank candidate arrays on rank 0 in rank (= file) order. Returns the merged array on
+    rank 0 and None elsewhere.  Works with the nccl (device tensors) and gloo (CPU tensors) backends."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return cands
+    flat = torch.from_numpy(np.ascontiguousarray(cands).view(np.int64).reshape(-1, 4))
+    if device is not None:
+        flat = flat.to(device)
+    count = torch.tensor([flat.shape[0]], dtype=torch.int64, device=flat.device)
+    counts = [torch.zeros_like(count) for _ in range(world)]
+    dist.all_gather(counts, count, group=group)
+    mx = max(int(c) for c in counts)
+    pad = torch.zeros((mx, 4), dtype=torch.int64, device=flat.device)
+    pad[: flat.shape[0]] = flat
+    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+    dist.gather(pad, bufs, dst=0, group=group)
+    if rank != 0:
+        return None
+    parts = [bufs[r][: int(counts[r])].cpu().numpy() for r in range(world)]
+    merged = np.concatenate(parts) if parts else np.zeros((0, 4), np.int64)
+    return np.ascontiguousarray(merged).view(CAND_DTYPE).reshape(-1)
+
+
+def search_sharded(engine, dataset, pattern, kopt, rank, world, device=None, group=None):
+    """The hit list of Engine.search, computed by `world` ranks; returned on rank 0 (None elsewhere)."""
+    beg, end = shard_ranges(len(dataset), world)[rank]
+    cands = engine.candidates(dataset, pattern, kopt, beg, end)
+    merged = gather_candidates(cands, rank, world, device=device, group=group)
+    if rank != 0:
+        return None
+    return engine.resolve(dataset, pattern, kopt, merged)

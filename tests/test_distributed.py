@@ -1,0 +1,64 @@
+"""CPU: the N>1 host logic over gloo with world_size 2 (no GPU needed)."""
+import os
+import socket
+
+import numpy as np
+import torch.multiprocessing as mp
+
+from patmatchdocker_b200 import distributed as D
+from patmatchdocker_b200._native import CAND_DTYPE
+
+
+def test_shard_ranges_cover_every_anchor_once():
+    for n in (0, 1, 17, 1000, 12_000_037):
+        for world in (1, 2, 3, 4, 8):
+            r = D.shard_ranges(n, world)
+            assert r[0][0] == 0 and r[-1][1] == n + 1
+            assert all(a[1] == b[0] for a, b in zip(r[:-1], r[1:]))
+            assert all(e >= b for b, e in r)
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(100)
+    # one global candidate list, cut at the rank boundary of shard_ranges
+    n = 100000
+    keys = np.sort(rng.choice(n * 16, size=5000, replace=False)).astype(np.int64)
+    allc = np.zeros(len(keys), dtype=CAND_DTYPE)
+    allc["key"] = keys
+    allc["beg"] = keys >> 4
+    allc["end"] = (keys >> 4) + 7
+    allc["reach"] = (keys >> 4) - 3
+    beg, end = D.shard_ranges(n, world)[rank]
+    mine = allc[((allc["key"] >> 4) >= beg) & ((allc["key"] >> 4) < end)]
+    merged = D.gather_candidates(mine, rank, world)
+    if rank == 0:
+        q.put(bool(np.array_equal(merged, allc)))
+    else:
+        q.put(merged is None)
+    # an empty shard must not break the gather
+    merged = D.gather_candidates(mine if rank == 0 else mine[:0], rank, world)
+    if rank == 0:
+        q.put(len(merged) == len(mine))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_over_gloo_world_size_2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(3)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(results)
