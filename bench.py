@@ -139,10 +139,12 @@ def run_ours(args):
 
     stats_acc = {"scan_ms": 0.0, "scan_bytes": 0, "launches": 0, "searches": 0, "total_ms": 0.0, "packed": 0}
 
+    sharded = pmd.DeviceShardedSearch(eng, rank, world, dev, cap=1 << 19) if world > 1 else None
+
     def run_search(d, p):
         if world == 1:
             return eng.search(d, p, kopt)
-        return pmd.search_sharded(eng, d, p, kopt, rank, world, device=dev)   # hits on rank 0, None elsewhere
+        return sharded.search(d, p, kopt)                  # hits on rank 0, None elsewhere
 
     def step_resident():
         hits = []

@@ -116,6 +116,15 @@ int pm_resolve(pm_engine *e, pm_dataset *d, const char *pattern, const char *kop
                const pm_candidate *cands, int64_t ncands,
                pm_hit *hits, int64_t cap, int64_t *nhits);
 
+/* the same two calls with the candidate array in DEVICE memory of e's device (e.g. a torch tensor
+ * that NCCL gathers into): nothing but the final hit list crosses PCIe */
+int pm_candidates_device(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt,
+                         int64_t pos_beg, int64_t pos_end,
+                         pm_candidate *dev_cands, int64_t cap, int64_t *ncands);
+int pm_resolve_device(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt,
+                      const pm_candidate *dev_cands, int64_t ncands,
+                      pm_hit *hits, int64_t cap, int64_t *nhits);
+
 int pm_get_stats(pm_engine *e, pm_stats *out);
 
 #ifdef __cplusplus

@@ -80,6 +80,8 @@ def load():
     L.pm_search_batch.argtypes = [vp, vp, ctypes.c_int, ctypes.POINTER(cp), cp, vp, i64, ctypes.POINTER(i64)]
     L.pm_candidates.argtypes = [vp, vp, cp, cp, i64, i64, vp, i64, ctypes.POINTER(i64)]
     L.pm_resolve.argtypes = [vp, vp, cp, cp, vp, i64, vp, i64, ctypes.POINTER(i64)]
+    L.pm_candidates_device.argtypes = [vp, vp, cp, cp, i64, i64, vp, i64, ctypes.POINTER(i64)]
+    L.pm_resolve_device.argtypes = [vp, vp, cp, cp, vp, i64, vp, i64, ctypes.POINTER(i64)]
     L.pm_get_stats.argtypes = [vp, ctypes.POINTER(PmStats)]
     _lib = L
     return L
@@ -214,6 +216,28 @@ class Engine:
                 continue
             _check(rc)
             return c[: n.value]
+
+    def candidates_device(self, dataset, pattern, kopt, pos_beg, pos_end, dev_ptr, cap):
+        """candidates written to device memory at dev_ptr (cap records of 32 bytes); -> count (may exceed cap: overflow)"""
+        n = ctypes.c_int64()
+        rc = load().pm_candidates_device(self._h, dataset._h, _b(pattern), _b(kopt), pos_beg, pos_end,
+                                         ctypes.c_void_p(dev_ptr), cap, ctypes.byref(n))
+        if rc == PM_ERR_OVERFLOW:
+            return -int(n.value)
+        _check(rc)
+        return int(n.value)
+
+    def resolve_device(self, dataset, pattern, kopt, dev_ptr, ncands, cap=1 << 16):
+        L = load()
+        n = ctypes.c_int64()
+        hits = np.empty(cap, dtype=HIT_DTYPE)
+        rc = L.pm_resolve_device(self._h, dataset._h, _b(pattern), _b(kopt), ctypes.c_void_p(dev_ptr), ncands,
+                                 ctypes.c_void_p(hits.ctypes.data), cap, ctypes.byref(n))
+        if rc == PM_ERR_OVERFLOW:
+            hits = np.empty(int(n.value), dtype=HIT_DTYPE)
+            rc = L.pm_last_hits(self._h, ctypes.c_void_p(hits.ctypes.data), len(hits), ctypes.byref(n))
+        _check(rc)
+        return hits[: n.value]
 
     def resolve(self, dataset, pattern, kopt, cands, cap=None):
         L = load()

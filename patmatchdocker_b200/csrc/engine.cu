@@ -940,12 +940,14 @@ static int resolve_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, co
     }
     *nhits = nh;
     e->stats.hits = nh;
+    bool overflow = false;
     if (hits && nh > 0) {
-        if (nh > cap) { g_err = "hit buffer too small"; return PM_ERR_OVERFLOW; }
-        CK(cudaMemcpyAsync(hits, e->hits2.p, (size_t)nh * sizeof(pm_hit), cudaMemcpyDeviceToHost, e->stream));
+        if (nh > cap) overflow = true;                   // the list stays on the device for pm_last_hits
+        else CK(cudaMemcpyAsync(hits, e->hits2.p, (size_t)nh * sizeof(pm_hit), cudaMemcpyDeviceToHost, e->stream));
     }
     CK(cudaEventRecord(e->ev[5], e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    if (overflow) { g_err = "hit buffer too small"; return PM_ERR_OVERFLOW; }
     return PM_OK;
 }
 
@@ -956,6 +958,7 @@ static void finish_stats(pm_engine *e)
     cudaEventElapsedTime(&e->stats.verify_ms, e->ev[2], e->ev[3]);
     cudaEventElapsedTime(&e->stats.chain_ms, e->ev[3], e->ev[5]);
     cudaEventElapsedTime(&e->stats.total_ms, e->ev[0], e->ev[5]);
+    (void)cudaGetLastError();                            // an unrecorded event must not poison later calls
 }
 
 int pm_search(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt, pm_hit *hits, int64_t cap, int64_t *nhits)
@@ -1015,8 +1018,23 @@ int pm_search_batch(pm_engine *e, pm_dataset *d, int npat, const char *const *pa
     return PM_OK;
 }
 
+static int candidates_impl(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt, int64_t pos_beg, int64_t pos_end,
+                           pm_candidate *cands, int64_t cap, int64_t *ncands, cudaMemcpyKind kind);
+
 int pm_candidates(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt, int64_t pos_beg, int64_t pos_end,
                   pm_candidate *cands, int64_t cap, int64_t *ncands)
+{
+    return candidates_impl(e, d, pattern, kopt, pos_beg, pos_end, cands, cap, ncands, cudaMemcpyDeviceToHost);
+}
+
+int pm_candidates_device(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt, int64_t pos_beg, int64_t pos_end,
+                         pm_candidate *dev_cands, int64_t cap, int64_t *ncands)
+{
+    return candidates_impl(e, d, pattern, kopt, pos_beg, pos_end, dev_cands, cap, ncands, cudaMemcpyDeviceToDevice);
+}
+
+static int candidates_impl(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt, int64_t pos_beg, int64_t pos_end,
+                           pm_candidate *cands, int64_t cap, int64_t *ncands, cudaMemcpyKind kind)
 {
     if (!e || !d || !pattern || !kopt || !ncands || d->e != e) { g_err = "bad argument"; return PM_ERR_ARG; }
     CK(cudaSetDevice(e->device));
@@ -1031,7 +1049,7 @@ int pm_candidates(pm_engine *e, pm_dataset *d, const char *pattern, const char *
     *ncands = ncand;
     if (cands && ncand > 0) {
         if (ncand > cap) { g_err = "candidate buffer too small"; return PM_ERR_OVERFLOW; }
-        CK(cudaMemcpyAsync(cands, e->cands.p, (size_t)ncand * sizeof(Cand), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(cands, e->cands.p, (size_t)ncand * sizeof(Cand), kind, e->stream));
     }
     CK(cudaEventRecord(e->ev[4], e->stream));
     CK(cudaEventRecord(e->ev[5], e->stream));
@@ -1040,21 +1058,44 @@ int pm_candidates(pm_engine *e, pm_dataset *d, const char *pattern, const char *
     return PM_OK;
 }
 
+static int resolve_impl(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt, const pm_candidate *cands, int64_t ncands,
+                        pm_hit *hits, int64_t cap, int64_t *nhits, cudaMemcpyKind kind);
+
 int pm_resolve(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt, const pm_candidate *cands, int64_t ncands,
                pm_hit *hits, int64_t cap, int64_t *nhits)
+{
+    return resolve_impl(e, d, pattern, kopt, cands, ncands, hits, cap, nhits, cudaMemcpyHostToDevice);
+}
+
+int pm_resolve_device(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt, const pm_candidate *dev_cands, int64_t ncands,
+                      pm_hit *hits, int64_t cap, int64_t *nhits)
+{
+    return resolve_impl(e, d, pattern, kopt, dev_cands, ncands, hits, cap, nhits, cudaMemcpyDeviceToDevice);
+}
+
+static int resolve_impl(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt, const pm_candidate *cands, int64_t ncands,
+                        pm_hit *hits, int64_t cap, int64_t *nhits, cudaMemcpyKind kind)
 {
     if (!e || !d || !pattern || !kopt || !nhits || ncands < 0 || (ncands && !cands) || d->e != e) { g_err = "bad argument"; return PM_ERR_ARG; }
     CK(cudaSetDevice(e->device));
     Compiled c;
     int rc = compile(pattern, kopt, c, true);
     if (rc) return rc;
-    e->stats = pm_stats{};
+    const pm_stats before = e->stats;                    // keep the scan figures of the preceding pm_candidates
     const unsigned long long *dB, *dTL, *dTR;
     if ((rc = upload_tables(e, c, &dB, &dTL, &dTR))) return rc;
     if ((rc = e->cands.reserve((size_t)std::max<int64_t>(ncands, 1) * sizeof(Cand)))) return rc;
-    for (auto &ev : e->ev) CK(cudaEventRecord(ev, e->stream));
-    if (ncands) CK(cudaMemcpyAsync(e->cands.p, cands, (size_t)ncands * sizeof(Cand), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaEventRecord(e->ev[3], e->stream));
+    if (ncands) CK(cudaMemcpyAsync(e->cands.p, cands, (size_t)ncands * sizeof(Cand), kind, e->stream));
     rc = resolve_candidates(e, d, c, (const Cand *)e->cands.p, ncands, dTL, dTR, hits, cap, nhits);
-    finish_stats(e);
+    float chain_ms = 0;
+    cudaEventElapsedTime(&chain_ms, e->ev[3], e->ev[5]);
+    (void)cudaGetLastError();
+    const long long nh = e->stats.hits;
+    const int launches = e->stats.launches;
+    e->stats = before;
+    e->stats.chain_ms = chain_ms;
+    e->stats.hits = nh;
+    e->stats.launches = launches;                        // resolve_candidates added its launches to the kept count
     return rc;
 }

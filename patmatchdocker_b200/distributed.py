@@ -52,3 +52,43 @@ def search_sharded(engine, dataset, pattern, kopt, rank, world, device=None, gro
     if rank != 0:
         return None
     return engine.resolve(dataset, pattern, kopt, merged)
+
+
+class DeviceShardedSearch:
+    """search_sharded with the candidates kept in device memory end to end (nccl backend):
+    pm_candidates_device -> dist.gather of device tensors -> pm_resolve_device on rank 0."""
+
+    def __init__(self, engine, rank, world, device, cap=1 << 16, group=None):
+        import torch
+        self.engine, self.rank, self.world, self.device, self.group = engine, rank, world, device, group
+        self.torch = torch
+        self._alloc(cap)
+
+    def _alloc(self, cap):
+        torch = self.torch
+        self.cap = cap
+        self.mine = torch.empty((cap, 4), dtype=torch.int64, device=self.device)
+        self.bufs = [torch.empty((cap, 4), dtype=torch.int64, device=self.device) for _ in range(self.world)] if self.rank == 0 else None
+        self.merged = torch.empty((cap * self.world, 4), dtype=torch.int64, device=self.device) if self.rank == 0 else None
+
+    def search(self, dataset, pattern, kopt):
+        import torch.distributed as dist
+        torch = self.torch
+        beg, end = shard_ranges(len(dataset), self.world)[self.rank]
+        while True:
+            n = self.engine.candidates_device(dataset, pattern, kopt, beg, end, self.mine.data_ptr(), self.cap)
+            count = torch.tensor([abs(n)], dtype=torch.int64, device=self.device)
+            counts = [torch.zeros_like(count) for _ in range(self.world)]
+            dist.all_gather(counts, count, group=self.group)
+            counts = [int(c) for c in counts]
+            if max(counts) <= self.cap:
+                break
+            self._alloc(max(counts) + 1024)                    # some rank overflowed: everybody grows and rescans
+        dist.gather(self.mine, self.bufs, dst=0, group=self.group)
+        if self.rank != 0:
+            return None
+        off = 0
+        for r in range(self.world):
+            self.merged[off:off + counts[r]] = self.bufs[r][: counts[r]]
+            off += counts[r]
+        return self.engine.resolve_device(dataset, pattern, kopt, self.merged.data_ptr(), off)
