@@ -99,6 +99,7 @@ __device__ __forceinline__ void packed_apply(unsigned (&M)[4], const unsigned (&
 #define PK_HALO 4                       // words of halo on each side of a 128-word warp tile
 #define PK_ROW (128 + 2 * PK_HALO)
 #define PK_QUEUE 512                    // per-warp candidate queue (entries beyond it go to k_verify unfiltered)
+#define PK_PRE 5                        // steps of the lock-step pre-check of round A
 
 template <int NP>
 struct PackedVerify {
@@ -113,7 +114,8 @@ struct PackedVerify {
 // W = state word (uint32 when the pattern part fits 32 bits), ROWS = k+1 error rows.
 template <int DIR, typename W, int ROWS>
 __device__ __forceinline__ int nfa_packed(const unsigned *__restrict__ sh, long long base, const unsigned long long (&T64)[4],
-                                          int plen, int kmax, int ins, int del, int subs, long long pos, int *err, bool *bail)
+                                          int plen, int kmax, int ins, int del, int subs, long long pos, int *err, bool *bail,
+                                          int maxsteps = 96, bool *undecided = nullptr)
 {
     const W fin = (W)1 << (plen - 1);
     const W live = (W)((fin << 1) - 1);
@@ -128,7 +130,11 @@ __device__ __forceinline__ int nfa_packed(const unsigned *__restrict__ sh, long 
     }
     W first = 1;
     int rel = (int)(pos - base) + (DIR < 0 ? -1 : 0);          // bit index of the next symbol in the staged row
-    for (int step = 0; step < 96; step++, rel += DIR) {
+    for (int step = 0;; step++, rel += DIR) {
+        if (step >= maxsteps) {                              // capped pre-check: still alive, decide later
+            if (undecided) *undecided = true; else *bail = true;
+            return 0;
+        }
         const int wi = rel >> 5, bi = rel & 31;
         if (wi < 0 || wi >= PK_ROW) { *bail = true; return 0; }
         if ((sh[2 * PK_ROW + wi] >> bi) & 1u) { *bail = true; return 0; }
@@ -382,11 +388,13 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
 {
     __shared__ unsigned sh_all[8][3 * PK_ROW];
     __shared__ unsigned queue_all[8][PK_QUEUE];
+    __shared__ unsigned queue2_all[8][PK_QUEUE];
     __shared__ unsigned qcount_all[8];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     unsigned *sh = sh_all[wib];
     unsigned *queue = queue_all[wib];
+    unsigned *queue2 = queue2_all[wib];
     unsigned *qcount = &qcount_all[wib];
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -498,8 +506,40 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
         }
         __syncwarp();
         const unsigned nq = min(*qcount, (unsigned)PK_QUEUE);
-        for (unsigned e = lane; e < nq; e += 32) {
-            const unsigned ent = queue[e];
+        // Round A: every queued candidate gets a short, equally long look at its first side (PK_PRE
+        // steps), so the lanes stay in lock step; most candidates die here.  Survivors are compacted
+        // into queue2 and only they pay for the full, divergent walk of round B.
+        __syncwarp();
+        if (lane == 0) *qcount = 0;                        // now counts queue2
+        __syncwarp();
+        for (unsigned e0 = 0; e0 < nq; e0 += 32) {
+            const unsigned e = e0 + lane;
+            bool survive = false;
+            unsigned ent = 0;
+            if (e < nq) {
+                ent = queue[e];
+                const int i = (int)(ent & 3u);
+                const long long p = qt * 32 + (ent >> 2);
+                bool bail = false, und = false;
+                int err = 0;
+                const int lb = v.V[i];
+                int ok;
+                if (lb > 0) ok = nfa_packed<-1, W, ROWS>(sh, base, v.TL[i], lb, v.k, v.ins, v.del, v.subs, p, &err, &bail, PK_PRE, &und);
+                else ok = nfa_packed<+1, W, ROWS>(sh, base, v.TR[i], v.m, v.k, v.ins, v.del, v.subs, p, &err, &bail, a.L + PK_PRE, &und);
+                survive = ok || bail || und;
+            }
+            const unsigned ball = __ballot_sync(0xffffffffu, survive);
+            if (ball) {
+                unsigned b0 = 0;
+                if (lane == 0) b0 = atomicAdd(qcount, (unsigned)__popc(ball));
+                b0 = __shfl_sync(0xffffffffu, b0, 0);
+                if (survive) queue2[b0 + __popc(ball & ((1u << lane) - 1u))] = ent;
+            }
+        }
+        __syncwarp();
+        const unsigned nq2 = *qcount;
+        for (unsigned e = lane; e < nq2; e += 32) {
+            const unsigned ent = queue2[e];
             const int i = (int)(ent & 3u);
             const long long p = qt * 32 + (ent >> 2);
             bool keep = true, bail = false;
