@@ -805,6 +805,10 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
                     for (int i = 0; i < dp.npieces; i++) {
                         pv.V[i] = dp.V[i];
                         if (dp.V[i] > 32 || dp.m - dp.V[i] > 32) narrow = false;
+                        const int lbp = dp.V[i], rlp = dp.m - dp.V[i];
+                        pv.itmax = std::max(pv.itmax, (lbp > 0 ? lbp + dp.k : 0) + (rlp > 0 ? rlp + dp.k : 0));
+                        for (int j = 0; j < lbp; j++) if (packed_class(c.P.pos[lbp - 1 - j]) & 16u) pv.TLX[i] |= 1ULL << j;
+                        for (int j = 0; j < rlp; j++) if (packed_class(c.P.pos[lbp + j]) & 16u) pv.TRX[i] |= 1ULL << j;
                         for (int q = 0; q < 4; q++) {
                             pv.TL[i][q] = c.vt.TL[(size_t)i * 256 + code_byte[q]];
                             pv.TR[i][q] = c.vt.TR[(size_t)i * 256 + code_byte[q]];

@@ -103,7 +103,9 @@ __device__ __forceinline__ void packed_apply(unsigned (&M)[4], const unsigned (&
 
 template <int NP>
 struct PackedVerify {
-    unsigned long long TL[NP][4], TR[NP][4];     // NFA masks per nucleotide code (hi<<1 | lo)
+    unsigned long long TL[NP][4], TR[NP][4];     // match masks per nucleotide code (hi<<1 | lo)
+    unsigned long long TLX[NP], TRX[NP];         // positions accepting some non-ACGT byte (X symbols)
+    int itmax;                                   // max over pieces of the filter's step count
     int V[NP];
     int m, k, ins, del, subs, enabled;
     const long long *cuts;                       // forced buffer cuts (fill starts not at a '\n'), sorted
@@ -388,13 +390,11 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
 {
     __shared__ unsigned sh_all[8][3 * PK_ROW];
     __shared__ unsigned queue_all[8][PK_QUEUE];
-    __shared__ unsigned queue2_all[8][PK_QUEUE];
     __shared__ unsigned qcount_all[8];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     unsigned *sh = sh_all[wib];
     unsigned *queue = queue_all[wib];
-    unsigned *queue2 = queue2_all[wib];
     unsigned *qcount = &qcount_all[wib];
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -506,49 +506,59 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
         }
         __syncwarp();
         const unsigned nq = min(*qcount, (unsigned)PK_QUEUE);
-        // Round A: every queued candidate gets a short, equally long look at its first side (PK_PRE
-        // steps), so the lanes stay in lock step; most candidates die here.  Survivors are compacted
-        // into queue2 and only they pay for the full, divergent walk of round B.
-        __syncwarp();
-        if (lane == 0) *qcount = 0;                        // now counts queue2
-        __syncwarp();
+        // Lock-step filter: Myers' bit-vector edit distance of the pattern part left of the anchor
+        // against the text read leftwards, then of the right part against the text read rightwards.
+        // The reference's NFA accepts a subset of the edit-distance alignments and spends at most k
+        // errors over both sides, so  min_left + min_right <= k  is necessary for its verification to
+        // succeed; X symbols count as matching every position that accepts any non-ACGT byte.  Every
+        // lane runs exactly (lb + k) + (rl + k) steps: no divergence.  Survivors go to k_verify.
         for (unsigned e0 = 0; e0 < nq; e0 += 32) {
             const unsigned e = e0 + lane;
-            bool survive = false;
-            unsigned ent = 0;
-            if (e < nq) {
-                ent = queue[e];
-                const int i = (int)(ent & 3u);
-                const long long p = qt * 32 + (ent >> 2);
-                bool bail = false, und = false;
-                int err = 0;
-                const int lb = v.V[i];
-                int ok;
-                if (lb > 0) ok = nfa_packed<-1, W, ROWS>(sh, base, v.TL[i], lb, v.k, v.ins, v.del, v.subs, p, &err, &bail, PK_PRE, &und);
-                else ok = nfa_packed<+1, W, ROWS>(sh, base, v.TR[i], v.m, v.k, v.ins, v.del, v.subs, p, &err, &bail, a.L + PK_PRE, &und);
-                survive = ok || bail || und;
-            }
-            const unsigned ball = __ballot_sync(0xffffffffu, survive);
-            if (ball) {
-                unsigned b0 = 0;
-                if (lane == 0) b0 = atomicAdd(qcount, (unsigned)__popc(ball));
-                b0 = __shfl_sync(0xffffffffu, b0, 0);
-                if (survive) queue2[b0 + __popc(ball & ((1u << lane) - 1u))] = ent;
-            }
-        }
-        __syncwarp();
-        const unsigned nq2 = *qcount;
-        for (unsigned e = lane; e < nq2; e += 32) {
-            const unsigned ent = queue2[e];
+            const bool valid = e < nq;
+            const unsigned ent = valid ? queue[e] : queue[0];
             const int i = (int)(ent & 3u);
             const long long p = qt * 32 + (ent >> 2);
-            bool keep = true, bail = false;
-            int berr = 0, ferr = 0;
             const int lb = v.V[i], rl = v.m - lb;
-            if (lb > 0 && !nfa_packed<-1, W, ROWS>(sh, base, v.TL[i], lb, v.k, v.ins, v.del, v.subs, p, &berr, &bail) && !bail) keep = false;
-            if (keep && !bail && rl > 0 &&
-                !nfa_packed<+1, W, ROWS>(sh, base, v.TR[i], rl, v.k - berr, v.ins, v.del, v.subs, p, &ferr, &bail) && !bail) keep = false;
-            if (keep) {
+            const int nL = lb > 0 ? lb + v.k : 0, nR = rl > 0 ? rl + v.k : 0;
+            int minL = 0, best = lb, score = lb;
+            W Pv = (W)~(W)0, Mv = 0;
+            W top = lb > 0 ? (W)((W)1 << (lb - 1)) : (W)0;
+            W T0 = (W)v.TL[i][0], T1 = (W)v.TL[i][1], T2 = (W)v.TL[i][2], T3 = (W)v.TL[i][3], TXm = (W)v.TLX[i];
+            int rel = (int)(p - base) - 1, dir = -1;
+            const int iters = v.itmax;                      // max over pieces of nL + nR (warp-uniform)
+            for (int it = 0; it < iters; it++) {
+                if (it == nL) {                             // switch to the right side
+                    minL = best;
+                    Pv = (W)~(W)0; Mv = 0; score = rl; best = rl;
+                    top = rl > 0 ? (W)((W)1 << (rl - 1)) : (W)0;
+                    T0 = (W)v.TR[i][0]; T1 = (W)v.TR[i][1]; T2 = (W)v.TR[i][2]; T3 = (W)v.TR[i][3]; TXm = (W)v.TRX[i];
+                    rel = (int)(p - base); dir = +1;
+                }
+                if (it < nL + nR) {
+                    int wi = rel >> 5;
+                    const int bi = rel & 31;
+                    wi = wi < 0 ? 0 : (wi >= PK_ROW ? PK_ROW - 1 : wi);
+                    const unsigned xb = (sh[2 * PK_ROW + wi] >> bi) & 1u;
+                    const unsigned hb = (sh[wi] >> bi) & 1u, lbit = (sh[PK_ROW + wi] >> bi) & 1u;
+                    const W Eq = xb ? TXm : (hb ? (lbit ? T3 : T2) : (lbit ? T1 : T0));
+                    const W Xv = Eq | Mv;
+                    const W Xh = (W)((((Eq & Pv) + Pv) ^ Pv) | Eq);
+                    W Ph = (W)(Mv | ~(Xh | Pv));
+                    W Mh = (W)(Pv & Xh);
+                    score += (Ph & top) ? 1 : 0;
+                    score -= (Mh & top) ? 1 : 0;
+                    Ph = (W)((Ph << 1) | 1);
+                    Mh = (W)(Mh << 1);
+                    Pv = (W)(Mh | ~(Xv | Ph));
+                    Mv = (W)(Ph & Xv);
+                    best = score < best ? score : best;
+                    rel += dir;
+                }
+            }
+            int minR;
+            if (nR > 0) { minR = best; if (nL == 0) minL = 0; }
+            else { minR = 0; minL = best; }
+            if (valid && minL + minR <= v.k) {
                 const unsigned long long idx = atomicAdd(a.count, 1ULL);
                 if ((long long)idx < a.cap) a.keys[idx] = ((unsigned long long)p << 4) | (unsigned)i;
             }
