@@ -98,7 +98,7 @@ __device__ __forceinline__ void packed_apply(unsigned (&M)[4], const unsigned (&
 // the chain stage as well: a scan start that clips the verification can only remove matches.
 #define PK_HALO 4                       // words of halo on each side of a 128-word warp tile
 #define PK_ROW (128 + 2 * PK_HALO)
-#define PK_QUEUE 512                    // per-warp candidate queue (entries beyond it go to k_verify unfiltered)
+#define PK_QUEUE 192                    // per-warp, per-piece candidate queue (entries beyond it go to k_verify unfiltered)
 #define PK_PRE 5                        // steps of the lock-step pre-check of round A
 
 template <int NP>
@@ -389,13 +389,13 @@ template <int NP, typename W, int ROWS>
 __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, const PackedVerify<NP> v)
 {
     __shared__ unsigned sh_all[8][3 * PK_ROW];
-    __shared__ unsigned queue_all[8][PK_QUEUE];
-    __shared__ unsigned qcount_all[8];
+    __shared__ unsigned queue_all[8][NP][PK_QUEUE];      // one queue per piece: a round of 32 candidates shares all parameters
+    __shared__ unsigned qcount_all[8][NP];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     unsigned *sh = sh_all[wib];
-    unsigned *queue = queue_all[wib];
-    unsigned *qcount = &qcount_all[wib];
+    unsigned (*queue)[PK_QUEUE] = queue_all[wib];
+    unsigned *qcount = qcount_all[wib];
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long t = warp; t < a.ntiles; t += nwarps) {
@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
         const long long base = (qt - PK_HALO) * 32;                      // text position of bit 0 of the staged row
         // ---- candidates: piece i fires when any piece of trigsets[i] matched at the same start.
         // They are first queued per warp in shared memory, then verified with all lanes busy.
-        if (lane == 0) *qcount = 0;
+        if (lane < NP) qcount[lane] = 0;
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < NP; i++) {
@@ -495,8 +495,8 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
                     const unsigned rel = (unsigned)((4 * lane + w) * 32 + b);      // window start inside the tile
                     const long long p = qt * 32 + rel;
                     if (p < a.a0 || p >= a.a1 || p + a.L > a.n) continue;
-                    const unsigned slot = fused ? atomicAdd(qcount, 1u) : PK_QUEUE;
-                    if (slot < PK_QUEUE) queue[slot] = (rel << 2) | (unsigned)i;
+                    const unsigned slot = fused ? atomicAdd(&qcount[i], 1u) : PK_QUEUE;
+                    if (slot < PK_QUEUE) queue[i][slot] = rel;
                     else {                                                          // not filtered: decided by k_verify
                         const unsigned long long idx = atomicAdd(a.count, 1ULL);
                         if ((long long)idx < a.cap) a.keys[idx] = ((unsigned long long)p << 4) | (unsigned)i;
@@ -505,62 +505,71 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
             }
         }
         __syncwarp();
-        const unsigned nq = min(*qcount, (unsigned)PK_QUEUE);
         // Lock-step filter: Myers' bit-vector edit distance of the pattern part left of the anchor
         // against the text read leftwards, then of the right part against the text read rightwards.
         // The reference's NFA accepts a subset of the edit-distance alignments and spends at most k
         // errors over both sides, so  min_left + min_right <= k  is necessary for its verification to
-        // succeed; X symbols count as matching every position that accepts any non-ACGT byte.  Every
-        // lane runs exactly (lb + k) + (rl + k) steps: no divergence.  Survivors go to k_verify.
-        for (unsigned e0 = 0; e0 < nq; e0 += 32) {
-            const unsigned e = e0 + lane;
-            const bool valid = e < nq;
-            const unsigned ent = valid ? queue[e] : queue[0];
-            const int i = (int)(ent & 3u);
-            const long long p = qt * 32 + (ent >> 2);
+        // succeed; X symbols count as matching every position that accepts any non-ACGT byte.  A round
+        // of 32 candidates belongs to one piece, so part lengths, masks and trip counts are uniform.
+#pragma unroll
+        for (int i = 0; i < NP; i++) {
+            if (i >= a.npieces) break;
+            const unsigned nq = min(qcount[i], (unsigned)PK_QUEUE);
             const int lb = v.V[i], rl = v.m - lb;
+            const W L0 = (W)v.TL[i][0], L1 = (W)v.TL[i][1], L2 = (W)v.TL[i][2], L3 = (W)v.TL[i][3], LX = (W)v.TLX[i];
+            const W R0 = (W)v.TR[i][0], R1 = (W)v.TR[i][1], R2 = (W)v.TR[i][2], R3 = (W)v.TR[i][3], RX = (W)v.TRX[i];
+            const W topL = lb > 0 ? (W)((W)1 << (lb - 1)) : (W)0, topR = rl > 0 ? (W)((W)1 << (rl - 1)) : (W)0;
             const int nL = lb > 0 ? lb + v.k : 0, nR = rl > 0 ? rl + v.k : 0;
-            int minL = 0, best = lb, score = lb;
-            W Pv = (W)~(W)0, Mv = 0;
-            W top = lb > 0 ? (W)((W)1 << (lb - 1)) : (W)0;
-            W T0 = (W)v.TL[i][0], T1 = (W)v.TL[i][1], T2 = (W)v.TL[i][2], T3 = (W)v.TL[i][3], TXm = (W)v.TLX[i];
-            int rel = (int)(p - base) - 1, dir = -1;
-            const int iters = v.itmax;                      // max over pieces of nL + nR (warp-uniform)
-            for (int it = 0; it < iters; it++) {
-                if (it == nL) {                             // switch to the right side
+            for (unsigned e0 = 0; e0 < nq; e0 += 32) {
+                const unsigned e = e0 + lane;
+                const bool valid = e < nq;
+                const int rel0 = (int)(valid ? queue[i][e] : queue[i][0]) + PK_HALO * 32;   // bit index in the staged row
+                int minL = 0, minR = 0;
+                if (nL > 0) {
+                    W Pv = (W)~(W)0, Mv = 0;
+                    int score = lb, best = lb, rel = rel0 - 1;
+                    for (int it = 0; it < nL; it++, rel--) {
+                        const int wi = rel >> 5, bi = rel & 31;
+                        const unsigned xb = (sh[2 * PK_ROW + wi] >> bi) & 1u, hb = (sh[wi] >> bi) & 1u, lo1 = (sh[PK_ROW + wi] >> bi) & 1u;
+                        const W Eq = xb ? LX : (hb ? (lo1 ? L3 : L2) : (lo1 ? L1 : L0));
+                        const W Xv = Eq | Mv;
+                        const W Xh = (W)((((Eq & Pv) + Pv) ^ Pv) | Eq);
+                        W Ph = (W)(Mv | ~(Xh | Pv));
+                        W Mh = (W)(Pv & Xh);
+                        score += ((Ph & topL) != 0) - ((Mh & topL) != 0);
+                        Ph = (W)((Ph << 1) | 1);
+                        Mh = (W)(Mh << 1);
+                        Pv = (W)(Mh | ~(Xv | Ph));
+                        Mv = (W)(Ph & Xv);
+                        best = min(best, score);
+                    }
                     minL = best;
-                    Pv = (W)~(W)0; Mv = 0; score = rl; best = rl;
-                    top = rl > 0 ? (W)((W)1 << (rl - 1)) : (W)0;
-                    T0 = (W)v.TR[i][0]; T1 = (W)v.TR[i][1]; T2 = (W)v.TR[i][2]; T3 = (W)v.TR[i][3]; TXm = (W)v.TRX[i];
-                    rel = (int)(p - base); dir = +1;
                 }
-                if (it < nL + nR) {
-                    int wi = rel >> 5;
-                    const int bi = rel & 31;
-                    wi = wi < 0 ? 0 : (wi >= PK_ROW ? PK_ROW - 1 : wi);
-                    const unsigned xb = (sh[2 * PK_ROW + wi] >> bi) & 1u;
-                    const unsigned hb = (sh[wi] >> bi) & 1u, lbit = (sh[PK_ROW + wi] >> bi) & 1u;
-                    const W Eq = xb ? TXm : (hb ? (lbit ? T3 : T2) : (lbit ? T1 : T0));
-                    const W Xv = Eq | Mv;
-                    const W Xh = (W)((((Eq & Pv) + Pv) ^ Pv) | Eq);
-                    W Ph = (W)(Mv | ~(Xh | Pv));
-                    W Mh = (W)(Pv & Xh);
-                    score += (Ph & top) ? 1 : 0;
-                    score -= (Mh & top) ? 1 : 0;
-                    Ph = (W)((Ph << 1) | 1);
-                    Mh = (W)(Mh << 1);
-                    Pv = (W)(Mh | ~(Xv | Ph));
-                    Mv = (W)(Ph & Xv);
-                    best = score < best ? score : best;
-                    rel += dir;
+                if (nR > 0) {
+                    W Pv = (W)~(W)0, Mv = 0;
+                    int score = rl, best = rl, rel = rel0;
+                    for (int it = 0; it < nR; it++, rel++) {
+                        const int wi = rel >> 5, bi = rel & 31;
+                        const unsigned xb = (sh[2 * PK_ROW + wi] >> bi) & 1u, hb = (sh[wi] >> bi) & 1u, lo1 = (sh[PK_ROW + wi] >> bi) & 1u;
+                        const W Eq = xb ? RX : (hb ? (lo1 ? R3 : R2) : (lo1 ? R1 : R0));
+                        const W Xv = Eq | Mv;
+                        const W Xh = (W)((((Eq & Pv) + Pv) ^ Pv) | Eq);
+                        W Ph = (W)(Mv | ~(Xh | Pv));
+                        W Mh = (W)(Pv & Xh);
+                        score += ((Ph & topR) != 0) - ((Mh & topR) != 0);
+                        Ph = (W)((Ph << 1) | 1);
+                        Mh = (W)(Mh << 1);
+                        Pv = (W)(Mh | ~(Xv | Ph));
+                        Mv = (W)(Ph & Xv);
+                        best = min(best, score);
+                    }
+                    minR = best;
                 }
-            }
-            int minR;
-            if (nR > 0) { minR = best; if (nL == 0) minL = 0; }
-            else { minR = 0; minL = best; }
-            if (valid && minL + minR <= v.k) {
-                const unsigned long long idx = atomicAdd(a.count, 1ULL);
-                if ((long long)idx < a.cap) a.keys[idx] = ((unsigned long long)p << 4) | (unsigned)i;
+                if (valid && minL + minR <= v.k) {
+                    const long long p = qt * 32 + (rel0 - PK_HALO * 32);
+                    const unsigned long long idx = atomicAdd(a.count, 1ULL);
+                    if ((long long)idx < a.cap) a.keys[idx] = ((unsigned long long)p << 4) | (unsigned)i;
+                }
             }
         }
         __syncwarp();
