@@ -815,7 +815,8 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
                         }
                     }
                     const int rows = std::min(std::max(dp.k, 1), 3) + 1;
-#define PM_LAUNCH(W, R) k_scan_packed<4, W, R><<<grid, 256, 0, e->stream>>>(a, pv)
+                    const int grid_bk = std::max((int)std::min<long long>((ntiles + 7) / 8, (long long)e->sms * 6), 1);
+#define PM_LAUNCH(W, R) k_scan_packed<4, W, R><<<grid_bk, 256, 0, e->stream>>>(a, pv)
                     if (narrow) { if (rows == 2) PM_LAUNCH(unsigned, 2); else if (rows == 3) PM_LAUNCH(unsigned, 3); else PM_LAUNCH(unsigned, 4); }
                     else { if (rows == 2) PM_LAUNCH(unsigned long long, 2); else if (rows == 3) PM_LAUNCH(unsigned long long, 3); else PM_LAUNCH(unsigned long long, 4); }
 #undef PM_LAUNCH

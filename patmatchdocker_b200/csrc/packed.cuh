@@ -385,47 +385,47 @@ __global__ void __launch_bounds__(256) k_scan_packed_exact(const ExactArgs a)
     flush();
 }
 
+#define BK_WORDS 1024                   // block tile: 8 warp tiles of 128 words (32768 bases) per plane
+#define BK_ROW (BK_WORDS + 2 * PK_HALO)
+#define BK_QUEUE 1024                   // per-block, per-piece candidate queue (overflow goes to k_verify unfiltered)
+
 template <int NP, typename W, int ROWS>
 __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, const PackedVerify<NP> v)
 {
-    __shared__ unsigned sh_all[8][3 * PK_ROW];
-    __shared__ unsigned queue_all[8][NP][PK_QUEUE];      // one queue per piece: a round of 32 candidates shares all parameters
-    __shared__ unsigned qcount_all[8][NP];
-    const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    unsigned *sh = sh_all[wib];
-    unsigned (*queue)[PK_QUEUE] = queue_all[wib];
-    unsigned *qcount = qcount_all[wib];
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long t = warp; t < a.ntiles; t += nwarps) {
-        const long long qt = (a.tile0 + t) * 128;                       // first word of the tile
-        const long long q0 = qt + 4 * lane;                             // first of this lane's 4 words
-        // ---- stage the tile (+ halos) of the three planes in shared memory ----
-        __syncwarp();
+    __shared__ unsigned sh[3 * BK_ROW];                 // hi | lo | x rows of the block tile, with halos
+    __shared__ unsigned queue[NP][BK_QUEUE];            // one queue per piece: a round of candidates shares all parameters
+    __shared__ unsigned qcount[NP];
+    const int tid = threadIdx.x;
+    const long long nbt = (a.ntiles + 7) / 8;
+    for (long long bt = blockIdx.x; bt < nbt; bt += gridDim.x) {
+        const long long qb = a.tile0 * 128 + bt * BK_WORDS;             // first word of the block tile
+        const long long q0 = qb + 4 * tid;                              // first of this thread's 4 words
+        __syncthreads();
+        // ---- stage the block tile (+ halos) of the three planes in shared memory ----
         {
             const uint4 h4 = __ldg(reinterpret_cast<const uint4 *>(a.hi + q0));
             const uint4 l4 = __ldg(reinterpret_cast<const uint4 *>(a.lo + q0));
             const uint4 x4 = __ldg(reinterpret_cast<const uint4 *>(a.xx + q0));
-            *reinterpret_cast<uint4 *>(sh + PK_HALO + 4 * lane) = h4;
-            *reinterpret_cast<uint4 *>(sh + PK_ROW + PK_HALO + 4 * lane) = l4;
-            *reinterpret_cast<uint4 *>(sh + 2 * PK_ROW + PK_HALO + 4 * lane) = x4;
-            if (lane < 2 * PK_HALO) {
-                const bool left = lane < PK_HALO;
-                const long long q = left ? qt - PK_HALO + lane : qt + 128 + (lane - PK_HALO);
-                const int si = left ? lane : PK_HALO + 128 + (lane - PK_HALO);
+            *reinterpret_cast<uint4 *>(sh + PK_HALO + 4 * tid) = h4;
+            *reinterpret_cast<uint4 *>(sh + BK_ROW + PK_HALO + 4 * tid) = l4;
+            *reinterpret_cast<uint4 *>(sh + 2 * BK_ROW + PK_HALO + 4 * tid) = x4;
+            if (tid < 2 * PK_HALO) {
+                const bool left = tid < PK_HALO;
+                const long long q = left ? qb - PK_HALO + tid : qb + BK_WORDS + (tid - PK_HALO);
+                const int si = left ? tid : PK_HALO + BK_WORDS + (tid - PK_HALO);
                 const bool ok = q >= 0 && q < a.nwords;
                 sh[si] = ok ? __ldg(a.hi + q) : 0u;
-                sh[PK_ROW + si] = ok ? __ldg(a.lo + q) : 0u;
-                sh[2 * PK_ROW + si] = ok ? __ldg(a.xx + q) : 0xffffffffu;
+                sh[BK_ROW + si] = ok ? __ldg(a.lo + q) : 0u;
+                sh[2 * BK_ROW + si] = ok ? __ldg(a.xx + q) : 0xffffffffu;
             }
+            if (tid < NP) qcount[tid] = 0;
         }
-        __syncwarp();
+        __syncthreads();
         unsigned PA[6], PC[6], PG[6], PT[6], PX[6];
 #pragma unroll
         for (int w = 0; w < 6; w++) {
-            const unsigned h = sh[PK_HALO + 4 * lane + w], l = sh[PK_ROW + PK_HALO + 4 * lane + w],
-                           x = sh[2 * PK_ROW + PK_HALO + 4 * lane + w];
+            const unsigned h = sh[PK_HALO + 4 * tid + w], l = sh[BK_ROW + PK_HALO + 4 * tid + w],
+                           x = sh[2 * BK_ROW + PK_HALO + 4 * tid + w];
             PX[w] = x;
             PA[w] = ~(h | l | x);
             PC[w] = l & ~h;
@@ -466,16 +466,13 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
         // tiles next to a forced buffer cut are decided on the raw bytes
         bool fused = v.enabled != 0;
         if (fused && v.ncuts > 0) {
-            const long long lo = (qt - PK_HALO) * 32, hi = (qt + 128 + PK_HALO) * 32;
+            const long long lo = (qb - PK_HALO) * 32, hi = (qb + BK_WORDS + PK_HALO) * 32;
             int l = 0, r = v.ncuts;
             while (l < r) { const int mid = (l + r) >> 1; if (v.cuts[mid] < lo) l = mid + 1; else r = mid; }
             if (l < v.ncuts && v.cuts[l] < hi) fused = false;
         }
-        const long long base = (qt - PK_HALO) * 32;                      // text position of bit 0 of the staged row
         // ---- candidates: piece i fires when any piece of trigsets[i] matched at the same start.
-        // They are first queued per warp in shared memory, then verified with all lanes busy.
-        if (lane < NP) qcount[lane] = 0;
-        __syncwarp();
+        // They are queued per block and per piece in shared memory, then filtered by all threads.
 #pragma unroll
         for (int i = 0; i < NP; i++) {
             if (i >= a.npieces) break;
@@ -492,11 +489,11 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
                 while (c) {
                     const int b = __ffs(c) - 1;
                     c &= c - 1;
-                    const unsigned rel = (unsigned)((4 * lane + w) * 32 + b);      // window start inside the tile
-                    const long long p = qt * 32 + rel;
+                    const unsigned rel = (unsigned)((4 * tid + w) * 32 + b);       // window start inside the block tile
+                    const long long p = qb * 32 + rel;
                     if (p < a.a0 || p >= a.a1 || p + a.L > a.n) continue;
-                    const unsigned slot = fused ? atomicAdd(&qcount[i], 1u) : PK_QUEUE;
-                    if (slot < PK_QUEUE) queue[i][slot] = rel;
+                    const unsigned slot = fused ? atomicAdd(&qcount[i], 1u) : BK_QUEUE;
+                    if (slot < BK_QUEUE) queue[i][slot] = rel;
                     else {                                                          // not filtered: decided by k_verify
                         const unsigned long long idx = atomicAdd(a.count, 1ULL);
                         if ((long long)idx < a.cap) a.keys[idx] = ((unsigned long long)p << 4) | (unsigned)i;
@@ -504,33 +501,31 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
                 }
             }
         }
-        __syncwarp();
+        __syncthreads();
         // Lock-step filter: Myers' bit-vector edit distance of the pattern part left of the anchor
         // against the text read leftwards, then of the right part against the text read rightwards.
         // The reference's NFA accepts a subset of the edit-distance alignments and spends at most k
         // errors over both sides, so  min_left + min_right <= k  is necessary for its verification to
-        // succeed; X symbols count as matching every position that accepts any non-ACGT byte.  A round
-        // of 32 candidates belongs to one piece, so part lengths, masks and trip counts are uniform.
+        // succeed; X symbols count as matching every position that accepts any non-ACGT byte.  All
+        // candidates of a round belong to one piece: part lengths, masks and trip counts are uniform.
 #pragma unroll
         for (int i = 0; i < NP; i++) {
             if (i >= a.npieces) break;
-            const unsigned nq = min(qcount[i], (unsigned)PK_QUEUE);
+            const unsigned nq = min(qcount[i], (unsigned)BK_QUEUE);
             const int lb = v.V[i], rl = v.m - lb;
             const W L0 = (W)v.TL[i][0], L1 = (W)v.TL[i][1], L2 = (W)v.TL[i][2], L3 = (W)v.TL[i][3], LX = (W)v.TLX[i];
             const W R0 = (W)v.TR[i][0], R1 = (W)v.TR[i][1], R2 = (W)v.TR[i][2], R3 = (W)v.TR[i][3], RX = (W)v.TRX[i];
             const W topL = lb > 0 ? (W)((W)1 << (lb - 1)) : (W)0, topR = rl > 0 ? (W)((W)1 << (rl - 1)) : (W)0;
             const int nL = lb > 0 ? lb + v.k : 0, nR = rl > 0 ? rl + v.k : 0;
-            for (unsigned e0 = 0; e0 < nq; e0 += 32) {
-                const unsigned e = e0 + lane;
-                const bool valid = e < nq;
-                const int rel0 = (int)(valid ? queue[i][e] : queue[i][0]) + PK_HALO * 32;   // bit index in the staged row
+            for (unsigned e = tid; e < nq; e += 256) {
+                const int rel0 = (int)queue[i][e] + PK_HALO * 32;                   // bit index in the staged rows
                 int minL = 0, minR = 0;
                 if (nL > 0) {
                     W Pv = (W)~(W)0, Mv = 0;
                     int score = lb, best = lb, rel = rel0 - 1;
                     for (int it = 0; it < nL; it++, rel--) {
                         const int wi = rel >> 5, bi = rel & 31;
-                        const unsigned xb = (sh[2 * PK_ROW + wi] >> bi) & 1u, hb = (sh[wi] >> bi) & 1u, lo1 = (sh[PK_ROW + wi] >> bi) & 1u;
+                        const unsigned xb = (sh[2 * BK_ROW + wi] >> bi) & 1u, hb = (sh[wi] >> bi) & 1u, lo1 = (sh[BK_ROW + wi] >> bi) & 1u;
                         const W Eq = xb ? LX : (hb ? (lo1 ? L3 : L2) : (lo1 ? L1 : L0));
                         const W Xv = Eq | Mv;
                         const W Xh = (W)((((Eq & Pv) + Pv) ^ Pv) | Eq);
@@ -550,7 +545,7 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
                     int score = rl, best = rl, rel = rel0;
                     for (int it = 0; it < nR; it++, rel++) {
                         const int wi = rel >> 5, bi = rel & 31;
-                        const unsigned xb = (sh[2 * PK_ROW + wi] >> bi) & 1u, hb = (sh[wi] >> bi) & 1u, lo1 = (sh[PK_ROW + wi] >> bi) & 1u;
+                        const unsigned xb = (sh[2 * BK_ROW + wi] >> bi) & 1u, hb = (sh[wi] >> bi) & 1u, lo1 = (sh[BK_ROW + wi] >> bi) & 1u;
                         const W Eq = xb ? RX : (hb ? (lo1 ? R3 : R2) : (lo1 ? R1 : R0));
                         const W Xv = Eq | Mv;
                         const W Xh = (W)((((Eq & Pv) + Pv) ^ Pv) | Eq);
@@ -565,13 +560,12 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
                     }
                     minR = best;
                 }
-                if (valid && minL + minR <= v.k) {
-                    const long long p = qt * 32 + (rel0 - PK_HALO * 32);
+                if (minL + minR <= v.k) {
+                    const long long p = qb * 32 + (rel0 - PK_HALO * 32);
                     const unsigned long long idx = atomicAdd(a.count, 1ULL);
                     if ((long long)idx < a.cap) a.keys[idx] = ((unsigned long long)p << 4) | (unsigned)i;
                 }
             }
         }
-        __syncwarp();
     }
 }
