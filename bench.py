@@ -204,6 +204,13 @@ def run_ours(args):
     value = 2 * total_bases / (ms_step / 1e3) / 1e9
     e2e = 2 * total_bases / (ms_e2e / 1e3) / 1e9
     peak, peak_src = peaks()
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp) and stats_acc["packed"]:
+        tr = json.load(open(tp)).get("k_scan_packed")
+        if tr:                                             # DRAM bytes of one launch from the committed ncu capture,
+            per_base = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["scan_bases"]   # scaled to this launch's bases
+            traffic = int(per_base * total_bases / world)
     achieved = (scan_bytes / nsearch) / (scan_ms / nsearch / 1e3) / 1e9 if scan_ms > 0 else 0.0
     line = {
         "metric": "pattern.Gbases/s scanned (2-error degenerate motif, both strands)",
@@ -219,7 +226,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "hits_per_step": int(nhits),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": None, "kernel": "k_scan_packed<4,u32,3> (2-bit planes, fused NFA filter)" if stats_acc["packed"] else "k_scan_bytes",
+                     "traffic": traffic, "kernel": "k_scan_packed<4,u32,3> (2-bit planes, fused edit-distance filter; integer-pipe bound, see profiles/r01_scan_packed_approx.txt)" if stats_acc["packed"] else "k_scan_bytes",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(scan_bytes / max(nsearch, 1)),
                      "kernel_ms": round(scan_ms / max(nsearch, 1), 4),
