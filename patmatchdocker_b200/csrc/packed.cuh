@@ -395,7 +395,13 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
     __shared__ unsigned sh[3 * BK_ROW];                 // hi | lo | x rows of the block tile, with halos
     __shared__ unsigned queue[NP][BK_QUEUE];            // one queue per piece: a round of candidates shares all parameters
     __shared__ unsigned qcount[NP];
+    __shared__ W sT[NP][2][8];                          // match masks by symbol (A,C,T,G,X) for the left / right part of each piece
+    __shared__ int s_fused;
     const int tid = threadIdx.x;
+    if (tid < NP * 2 * 5) {
+        const int i = tid / 10, side = (tid / 5) & 1, c = tid % 5;
+        sT[i][side][c] = (W)(c < 4 ? (side ? v.TR[i][c] : v.TL[i][c]) : (side ? v.TRX[i] : v.TLX[i]));
+    }
     const long long nbt = (a.ntiles + 7) / 8;
     for (long long bt = blockIdx.x; bt < nbt; bt += gridDim.x) {
         const long long qb = a.tile0 * 128 + bt * BK_WORDS;             // first word of the block tile
@@ -419,6 +425,16 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
                 sh[2 * BK_ROW + si] = ok ? __ldg(a.xx + q) : 0xffffffffu;
             }
             if (tid < NP) qcount[tid] = 0;
+            if (tid == 0) {
+                int f = v.enabled != 0;
+                if (f && v.ncuts > 0) {
+                    const long long lo = (qb - PK_HALO) * 32, hi = (qb + BK_WORDS + PK_HALO) * 32;
+                    int l = 0, r = v.ncuts;
+                    while (l < r) { const int mid = (l + r) >> 1; if (v.cuts[mid] < lo) l = mid + 1; else r = mid; }
+                    if (l < v.ncuts && v.cuts[l] < hi) f = 0;
+                }
+                s_fused = f;
+            }
         }
         __syncthreads();
         unsigned PA[6], PC[6], PG[6], PT[6], PX[6];
@@ -463,14 +479,8 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
                 for (int w = 0; w < 4; w++) M[i][w] = 0;
             }
         }
-        // tiles next to a forced buffer cut are decided on the raw bytes
-        bool fused = v.enabled != 0;
-        if (fused && v.ncuts > 0) {
-            const long long lo = (qb - PK_HALO) * 32, hi = (qb + BK_WORDS + PK_HALO) * 32;
-            int l = 0, r = v.ncuts;
-            while (l < r) { const int mid = (l + r) >> 1; if (v.cuts[mid] < lo) l = mid + 1; else r = mid; }
-            if (l < v.ncuts && v.cuts[l] < hi) fused = false;
-        }
+        // tiles next to a forced buffer cut are decided on the raw bytes (s_fused set by thread 0 during staging)
+        const bool fused = s_fused != 0;
         // ---- candidates: piece i fires when any piece of trigsets[i] matched at the same start.
         // They are queued per block and per piece in shared memory, then filtered by all threads.
 #pragma unroll
@@ -513,25 +523,35 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
             if (i >= a.npieces) break;
             const unsigned nq = min(qcount[i], (unsigned)BK_QUEUE);
             const int lb = v.V[i], rl = v.m - lb;
-            const W L0 = (W)v.TL[i][0], L1 = (W)v.TL[i][1], L2 = (W)v.TL[i][2], L3 = (W)v.TL[i][3], LX = (W)v.TLX[i];
-            const W R0 = (W)v.TR[i][0], R1 = (W)v.TR[i][1], R2 = (W)v.TR[i][2], R3 = (W)v.TR[i][3], RX = (W)v.TRX[i];
             const W topL = lb > 0 ? (W)((W)1 << (lb - 1)) : (W)0, topR = rl > 0 ? (W)((W)1 << (rl - 1)) : (W)0;
             const int nL = lb > 0 ? lb + v.k : 0, nR = rl > 0 ? rl + v.k : 0;
+            const W *tl = sT[i][0], *tr = sT[i][1];
             for (unsigned e = tid; e < nq; e += 256) {
                 const int rel0 = (int)queue[i][e] + PK_HALO * 32;                   // bit index in the staged rows
                 int minL = 0, minR = 0;
                 if (nL > 0) {
+                    // symbols rel0-1, rel0-2, ... : 32 at a time, bit-reversed so that bit 0 is the next one
                     W Pv = (W)~(W)0, Mv = 0;
-                    int score = lb, best = lb, rel = rel0 - 1;
-                    for (int it = 0; it < nL; it++, rel--) {
-                        const int wi = rel >> 5, bi = rel & 31;
-                        const unsigned xb = (sh[2 * BK_ROW + wi] >> bi) & 1u, hb = (sh[wi] >> bi) & 1u, lo1 = (sh[BK_ROW + wi] >> bi) & 1u;
-                        const W Eq = xb ? LX : (hb ? (lo1 ? L3 : L2) : (lo1 ? L1 : L0));
+                    int score = lb, best = lb;
+                    unsigned hw = 0, lw = 0, xw = 0;
+#pragma unroll 1
+                    for (int it = 0; it < nL; it++) {
+                        if ((it & 31) == 0) {
+                            const int hi_bit = rel0 - 1 - it;                       // window = bits [hi_bit-31, hi_bit]
+                            const int lo_bit = hi_bit - 31;
+                            const int wi = lo_bit >> 5, bi = lo_bit & 31;
+                            hw = __brev(__funnelshift_r(sh[wi], sh[wi + 1], bi));
+                            lw = __brev(__funnelshift_r(sh[BK_ROW + wi], sh[BK_ROW + wi + 1], bi));
+                            xw = __brev(__funnelshift_r(sh[2 * BK_ROW + wi], sh[2 * BK_ROW + wi + 1], bi));
+                        }
+                        const W Eq = tl[((xw & 1u) << 2) | ((hw & 1u) << 1) | (lw & 1u)];
+                        hw >>= 1; lw >>= 1; xw >>= 1;
                         const W Xv = Eq | Mv;
                         const W Xh = (W)((((Eq & Pv) + Pv) ^ Pv) | Eq);
                         W Ph = (W)(Mv | ~(Xh | Pv));
                         W Mh = (W)(Pv & Xh);
-                        score += ((Ph & topL) != 0) - ((Mh & topL) != 0);
+                        score += (Ph & topL) ? 1 : 0;
+                        score -= (Mh & topL) ? 1 : 0;
                         Ph = (W)((Ph << 1) | 1);
                         Mh = (W)(Mh << 1);
                         Pv = (W)(Mh | ~(Xv | Ph));
@@ -542,16 +562,25 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
                 }
                 if (nR > 0) {
                     W Pv = (W)~(W)0, Mv = 0;
-                    int score = rl, best = rl, rel = rel0;
-                    for (int it = 0; it < nR; it++, rel++) {
-                        const int wi = rel >> 5, bi = rel & 31;
-                        const unsigned xb = (sh[2 * BK_ROW + wi] >> bi) & 1u, hb = (sh[wi] >> bi) & 1u, lo1 = (sh[BK_ROW + wi] >> bi) & 1u;
-                        const W Eq = xb ? RX : (hb ? (lo1 ? R3 : R2) : (lo1 ? R1 : R0));
+                    int score = rl, best = rl;
+                    unsigned hw = 0, lw = 0, xw = 0;
+#pragma unroll 1
+                    for (int it = 0; it < nR; it++) {
+                        if ((it & 31) == 0) {
+                            const int lo_bit = rel0 + it;
+                            const int wi = lo_bit >> 5, bi = lo_bit & 31;
+                            hw = __funnelshift_r(sh[wi], sh[wi + 1], bi);
+                            lw = __funnelshift_r(sh[BK_ROW + wi], sh[BK_ROW + wi + 1], bi);
+                            xw = __funnelshift_r(sh[2 * BK_ROW + wi], sh[2 * BK_ROW + wi + 1], bi);
+                        }
+                        const W Eq = tr[((xw & 1u) << 2) | ((hw & 1u) << 1) | (lw & 1u)];
+                        hw >>= 1; lw >>= 1; xw >>= 1;
                         const W Xv = Eq | Mv;
                         const W Xh = (W)((((Eq & Pv) + Pv) ^ Pv) | Eq);
                         W Ph = (W)(Mv | ~(Xh | Pv));
                         W Mh = (W)(Pv & Xh);
-                        score += ((Ph & topR) != 0) - ((Mh & topR) != 0);
+                        score += (Ph & topR) ? 1 : 0;
+                        score -= (Mh & topR) ? 1 : 0;
                         Ph = (W)((Ph << 1) | 1);
                         Mh = (W)(Mh << 1);
                         Pv = (W)(Mh | ~(Xv | Ph));
