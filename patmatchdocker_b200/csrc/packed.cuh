@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(256) k_scan_packed_exact(const ExactArgs a)
 
 #define BK_WORDS 1024                   // block tile: 8 warp tiles of 128 words (32768 bases) per plane
 #define BK_ROW (BK_WORDS + 2 * PK_HALO)
-#define BK_QUEUE 1024                   // per-block, per-piece candidate queue (overflow goes to k_verify unfiltered)
+#define BK_QUEUE 2048                   // per-block, per-piece candidate queue (overflow goes to k_verify unfiltered)
 
 template <int NP, typename W, int ROWS>
 __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, const PackedVerify<NP> v)
