@@ -716,6 +716,8 @@ static int upload_tables(pm_engine *e, const Compiled &c, const unsigned long lo
     return PM_OK;
 }
 
+static unsigned packed_class_of(const pm::ByteSet &bs, bool *mixed);
+
 // scan + sort + verify: leaves ncand verified candidates (sorted) in e->cands
 static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, long long a0, long long a1,
                               const unsigned long long *dB, const unsigned long long *dTL, const unsigned long long *dTR,
@@ -744,15 +746,7 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
                 const long long warps_needed = ntiles;
                 const int grid = std::max((int)std::min<long long>((warps_needed + 7) / 8, (long long)e->sms * 8), 1);
                 // class of one pattern position over the packed alphabet: bits A,C,G,T and X (= any non-ACGT byte)
-                auto packed_class = [&](const pm::ByteSet &bs) -> unsigned {
-                    unsigned cls = (bs.has('A') ? 1u : 0u) | (bs.has('C') ? 2u : 0u) | (bs.has('G') ? 4u : 0u) | (bs.has('T') ? 8u : 0u);
-                    for (unsigned ch = 0; ch < 256; ch++) {
-                        const unsigned f = ch | 0x20u;
-                        if (f == 'a' || f == 'c' || f == 'g' || f == 't') continue;
-                        if (bs.has(ch)) { cls |= 16u; break; }   // some non-ACGT byte accepted: superset, re-checked on raw bytes
-                    }
-                    return cls;
-                };
+                auto packed_class = [&](const pm::ByteSet &bs) -> unsigned { return packed_class_of(bs, nullptr); };
                 auto plane_of = [](unsigned cls) -> int { return cls == 1 ? 0 : cls == 2 ? 1 : cls == 4 ? 2 : cls == 8 ? 3 : cls == 16 ? 4 : 5; };
                 if (dp.type == PM_PLAN_SIMPLE) {
                     ExactArgs a;
@@ -1000,10 +994,156 @@ int pm_last_hits(pm_engine *e, pm_hit *hits, int64_t cap, int64_t *nhits)
     return PM_OK;
 }
 
+// class of one pattern position over the packed alphabet: bits A,C,G,T and X (= non-ACGT bytes);
+// *mixed is set when the class accepts some but not all non-ACGT bytes (then X is an over-approximation)
+static unsigned packed_class_of(const pm::ByteSet &bs, bool *mixed)
+{
+    unsigned cls = (bs.has('A') ? 1u : 0u) | (bs.has('C') ? 2u : 0u) | (bs.has('G') ? 4u : 0u) | (bs.has('T') ? 8u : 0u);
+    int other = 0;
+    for (unsigned ch = 0; ch < 256; ch++) {
+        const unsigned f = ch | 0x20u;
+        if (f == 'a' || f == 'c' || f == 'g' || f == 't') continue;
+        other += bs.has(ch) ? 1 : 0;
+    }
+    if (other) cls |= 16u;
+    if (mixed) *mixed = other != 0 && other != 248;
+    return cls;
+}
+
+// Batched exact motifs on a packed dataset: one scan launch evaluates every pattern on each staged tile.
+// Returns 1 when the fast path does not apply (caller falls back to one search per pattern).
+static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
+                              pm_hit *hits, int64_t cap, int64_t *offsets)
+{
+    pm::Options o;
+    std::string err;
+    if (pm::parse_kopt(kopt, o, err) || o.k != 0) return 1;
+    if (!d->hi || e->scan_mode == 1 || (e->scan_mode == 0 && !d->dna_like) || npat < 2 || npat >= (1 << 20) || d->n >= (1LL << 36)) return 1;
+    std::vector<MultiPat> mp((size_t)npat);
+    std::vector<unsigned short> mlen((size_t)npat);
+    for (int b = 0; b < npat; b++) {
+        pm::Pattern P;
+        if (pm::parse_pattern(patterns[b], true, P, err)) return 1;
+        if (P.start_line || P.end_line || P.m() > 32 || P.m() < 1) return 1;
+        MultiPat &m = mp[b];
+        memset(&m, 0, sizeof m);
+        m.m = (unsigned short)P.m();
+        mlen[b] = m.m;
+        // entries grouped by plane so that consecutive entries tend to take the same branch
+        for (int s = 0; s < 6; s++)
+            for (int j = 0; j < P.m(); j++) {
+                bool mixed = false;
+                const unsigned cls = packed_class_of(P.pos[j], &mixed);
+                if (mixed) return 1;
+                const int sel = cls == 1 ? 0 : cls == 2 ? 1 : cls == 4 ? 2 : cls == 8 ? 3 : cls == 16 ? 4 : 5;
+                if (sel != s) continue;
+                if (cls == 31) continue;                     // accepts everything: no constraint (window validity is checked separately)
+                m.ent[m.nent++] = (unsigned short)(sel | (j << 3) | (cls << 8));
+            }
+    }
+    CK(cudaSetDevice(e->device));
+    (void)cudaGetLastError();
+    e->stats = pm_stats{};
+    int rc;
+    Fills fills;
+    if ((rc = ensure_fills(e, d, &fills))) return rc;
+    if ((rc = e->tables.reserve((size_t)npat * (sizeof(MultiPat) + 2 + 8) + 256))) return rc;
+    MultiPat *d_pats = (MultiPat *)e->tables.p;
+    unsigned short *d_mlen = (unsigned short *)((char *)e->tables.p + (((size_t)npat * sizeof(MultiPat) + 15) & ~(size_t)15));
+    unsigned long long *d_perpat = (unsigned long long *)((char *)d_mlen + (((size_t)npat * 2 + 15) & ~(size_t)15));
+    CK(cudaMemcpyAsync(d_pats, mp.data(), (size_t)npat * sizeof(MultiPat), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(d_mlen, mlen.data(), (size_t)npat * 2, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemsetAsync(d_perpat, 0, (size_t)npat * 8, e->stream));
+    if ((rc = e->counters.reserve(64))) return rc;
+    unsigned long long *d_count = (unsigned long long *)e->counters.p;
+    const long long n = d->n;
+    long long capk = std::max<long long>((long long)(e->keys.cap / 8), 1 << 20);
+    long long nkeys = 0;
+    const long long ntiles = ((n > 0 ? n - 1 : 0) / 32) / 128 + 1;
+    for (int attempt = 0; attempt < 3; attempt++) {
+        if ((rc = e->keys.reserve((size_t)capk * 8))) return rc;
+        CK(cudaMemsetAsync(d_count, 0, 16, e->stream));
+        CK(cudaEventRecord(e->ev[0], e->stream));
+        MultiArgs a;
+        a.hi = d->hi; a.lo = d->lo; a.xx = d->xx; a.nwords = d->nwords; a.n = n; a.a0 = 0; a.a1 = n + 1; a.tile0 = 0; a.ntiles = ntiles;
+        a.pats = d_pats; a.npat = npat; a.keys = (unsigned long long *)e->keys.p; a.count = d_count; a.cap = capk;
+        const int grid = std::max((int)std::min<long long>((ntiles + 7) / 8, (long long)e->sms * 4), 1);
+        k_scan_packed_multi<<<grid, 256, 0, e->stream>>>(a);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e->ev[1], e->stream));
+        CK(cudaMemcpyAsync(e->h_count, d_count, 16, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        e->stats.launches++;
+        nkeys = (long long)e->h_count[0];
+        if (nkeys <= capk) break;
+        capk = nkeys + 4096;
+    }
+    const long long nplace = (long long)e->h_count[1];
+    e->stats.scan_bytes = ntiles * 128 * 4 * 3;
+    e->stats.scan_bases = n * (long long)npat;
+    e->stats.packed = 1;
+    unsigned long long *keys = (unsigned long long *)e->keys.p;
+    if (nkeys > 1) {
+        if ((rc = e->keys2.reserve((size_t)nkeys * 8))) return rc;
+        size_t tmp = 0;
+        int end_bit = 41;
+        while (end_bit < 64 && ((unsigned long long)npat >> (end_bit - 40))) end_bit++;
+        CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp, keys, (unsigned long long *)e->keys2.p, (int)nkeys, 0, end_bit, e->stream));
+        if ((rc = e->cubtmp.reserve(tmp))) return rc;
+        CK(cub::DeviceRadixSort::SortKeys(e->cubtmp.p, tmp, keys, (unsigned long long *)e->keys2.p, (int)nkeys, 0, end_bit, e->stream));
+        keys = (unsigned long long *)e->keys2.p;
+        e->stats.launches += 3;
+    }
+    nkeys -= nplace;
+    CK(cudaEventRecord(e->ev[2], e->stream));
+    CK(cudaEventRecord(e->ev[3], e->stream));
+    e->stats.candidates = nkeys;
+    e->stats.verified = nkeys;
+    long long nh = 0;
+    std::vector<unsigned long long> perpat((size_t)npat, 0);
+    if (nkeys > 0) {
+        if ((rc = e->hits.reserve((size_t)nkeys * sizeof(pm_hit)))) return rc;
+        if ((rc = e->hits2.reserve((size_t)nkeys * sizeof(pm_hit)))) return rc;
+        if ((rc = e->sel.reserve((size_t)nkeys))) return rc;
+        CK(cudaMemsetAsync(e->sel.p, 0, (size_t)nkeys, e->stream));
+        k_chain_multi<<<(unsigned)((nkeys + 127) / 128), 128, 0, e->stream>>>(keys, nkeys, d_mlen, fills.S, fills.E, fills.n,
+                                                                             (long long *)e->hits.p, (unsigned char *)e->sel.p, d_perpat);
+        CK(cudaGetLastError());
+        size_t tmp = 0;
+        long long *d_nsel = (long long *)((char *)e->counters.p + 16);
+        CK(cub::DeviceSelect::Flagged(nullptr, tmp, (H16 *)e->hits.p, (unsigned char *)e->sel.p, (H16 *)e->hits2.p, d_nsel, (int)nkeys, e->stream));
+        if ((rc = e->cubtmp.reserve(tmp))) return rc;
+        CK(cub::DeviceSelect::Flagged(e->cubtmp.p, tmp, (H16 *)e->hits.p, (unsigned char *)e->sel.p, (H16 *)e->hits2.p, d_nsel, (int)nkeys, e->stream));
+        CK(cudaMemcpyAsync(e->h_count + 2, d_nsel, 8, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(perpat.data(), d_perpat, (size_t)npat * 8, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        e->stats.launches += 3;
+        nh = (long long)e->h_count[2];
+    }
+    CK(cudaEventRecord(e->ev[4], e->stream));
+    offsets[0] = 0;
+    for (int b = 0; b < npat; b++) offsets[b + 1] = offsets[b] + (int64_t)perpat[b];
+    e->stats.hits = nh;
+    bool overflow = false;
+    if (hits && nh > 0) {
+        if (nh > cap) overflow = true;
+        else CK(cudaMemcpyAsync(hits, e->hits2.p, (size_t)nh * sizeof(pm_hit), cudaMemcpyDeviceToHost, e->stream));
+    }
+    CK(cudaEventRecord(e->ev[5], e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    finish_stats(e);
+    if (overflow) { g_err = "hit buffer too small"; return PM_ERR_OVERFLOW; }
+    return PM_OK;
+}
+
 int pm_search_batch(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
                     pm_hit *hits, int64_t cap, int64_t *offsets)
 {
-    if (!e || !d || npat < 0 || !patterns || !offsets) { g_err = "bad argument"; return PM_ERR_ARG; }
+    if (!e || !d || npat < 0 || !patterns || !offsets || !kopt) { g_err = "bad argument"; return PM_ERR_ARG; }
+    {
+        const int frc = search_batch_fused(e, d, npat, patterns, kopt, hits, cap, offsets);
+        if (frc != 1) return frc;
+    }
     int64_t total = 0;
     offsets[0] = 0;
     pm_stats acc{};

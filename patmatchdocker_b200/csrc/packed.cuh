@@ -598,3 +598,215 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------
+// Multi-pattern exact scan (batched motifs): the block tile is staged once and every pattern of
+// the batch is evaluated on it from registers, so HBM traffic is paid once per batch and the
+// kernel is bound by the integer pipe.  Patterns are k = 0, at most 32 positions, with classes
+// that are exact over the packed alphabet (A,C,G,T,X).  Keys carry the pattern id:
+//     key = pid << 40 | window start << 4
+struct MultiPat {
+    unsigned short m, nent;
+    unsigned short ent[32];              // sel (bits 0-2) | shift (bits 3-7) | class A,C,G,T,X (bits 8-12)
+};
+
+struct MultiArgs {
+    const unsigned *hi, *lo, *xx;
+    long long nwords, n, a0, a1, tile0, ntiles;
+    const MultiPat *pats;
+    int npat;
+    unsigned long long *keys, *count;
+    long long cap;
+};
+
+#define MP_CHUNK 32                      // pattern descriptors staged in shared memory at a time
+#define MP_HITBUF 96
+
+__global__ void __launch_bounds__(256) k_scan_packed_multi(const MultiArgs a)
+{
+    __shared__ unsigned sh[3 * BK_ROW];
+    __shared__ MultiPat spat[MP_CHUNK];
+    __shared__ unsigned long long hitbuf_all[8][MP_HITBUF];
+    const int tid = threadIdx.x, lane = tid & 31;
+    unsigned long long *hitbuf = hitbuf_all[tid >> 5];
+    unsigned nbuf = 0;
+    auto flush = [&]() {
+        if (nbuf == 0) return;
+        unsigned long long basei = 0;
+        if (lane == 0) basei = atomicAdd(a.count, (unsigned long long)nbuf);
+        basei = __shfl_sync(0xffffffffu, basei, 0);
+        for (unsigned e = lane; e < nbuf; e += 32)
+            if ((long long)(basei + e) < a.cap) a.keys[basei + e] = hitbuf[e];
+        __syncwarp();
+        nbuf = 0;
+    };
+    const long long nbt = (a.ntiles + 7) / 8;
+    for (long long bt = blockIdx.x; bt < nbt; bt += gridDim.x) {
+        const long long qb = a.tile0 * 128 + bt * BK_WORDS;
+        const long long q0 = qb + 4 * tid;
+        __syncthreads();
+        {
+            const uint4 h4 = __ldg(reinterpret_cast<const uint4 *>(a.hi + q0));
+            const uint4 l4 = __ldg(reinterpret_cast<const uint4 *>(a.lo + q0));
+            const uint4 x4 = __ldg(reinterpret_cast<const uint4 *>(a.xx + q0));
+            *reinterpret_cast<uint4 *>(sh + PK_HALO + 4 * tid) = h4;
+            *reinterpret_cast<uint4 *>(sh + BK_ROW + PK_HALO + 4 * tid) = l4;
+            *reinterpret_cast<uint4 *>(sh + 2 * BK_ROW + PK_HALO + 4 * tid) = x4;
+            if (tid < PK_HALO) {
+                const long long q = qb + BK_WORDS + tid;
+                const bool ok = q < a.nwords;
+                sh[PK_HALO + BK_WORDS + tid] = ok ? __ldg(a.hi + q) : 0u;
+                sh[BK_ROW + PK_HALO + BK_WORDS + tid] = ok ? __ldg(a.lo + q) : 0u;
+                sh[2 * BK_ROW + PK_HALO + BK_WORDS + tid] = ok ? __ldg(a.xx + q) : 0xffffffffu;
+            }
+        }
+        __syncthreads();
+        unsigned PA[5], PC[5], PG[5], PT[5], PX[5];        // 4 words + 1 halo word: patterns are at most 32 long
+#pragma unroll
+        for (int w = 0; w < 5; w++) {
+            const unsigned h = sh[PK_HALO + 4 * tid + w], l = sh[BK_ROW + PK_HALO + 4 * tid + w],
+                           x = sh[2 * BK_ROW + PK_HALO + 4 * tid + w];
+            PX[w] = x;
+            PA[w] = ~(h | l | x);
+            PC[w] = l & ~h;
+            PG[w] = h & l;
+            PT[w] = h & ~l;
+        }
+        const long long tbase = (qb + 4 * tid) * 32;        // text position of this thread's first window start
+        const long long wend = a.a1 < a.n + 1 ? a.a1 : a.n + 1;
+        for (int c0 = 0; c0 < a.npat; c0 += MP_CHUNK) {
+            __syncthreads();
+            {
+                // stage the next chunk of descriptors (68 bytes each) as 32-bit words
+                const int nc = min(MP_CHUNK, a.npat - c0);
+                const unsigned *src = reinterpret_cast<const unsigned *>(a.pats + c0);
+                unsigned *dst = reinterpret_cast<unsigned *>(spat);
+                for (int x = tid; x < nc * (int)(sizeof(MultiPat) / 4); x += 256) dst[x] = __ldg(src + x);
+            }
+            __syncthreads();
+            const int nc = min(MP_CHUNK, a.npat - c0);
+            for (int pb = 0; pb < nc; pb++) {
+                const int nent = spat[pb].nent, m = spat[pb].m;
+                unsigned M0 = ~0u, M1 = ~0u, M2 = ~0u, M3 = ~0u;
+                for (int e = 0; e < nent; e++) {
+                    const unsigned ent = spat[pb].ent[e];
+                    const int sel = ent & 7, shf = (ent >> 3) & 31;
+                    unsigned E0, E1, E2, E3, E4;
+                    switch (sel) {
+                    case 0: E0 = PA[0]; E1 = PA[1]; E2 = PA[2]; E3 = PA[3]; E4 = PA[4]; break;
+                    case 1: E0 = PC[0]; E1 = PC[1]; E2 = PC[2]; E3 = PC[3]; E4 = PC[4]; break;
+                    case 2: E0 = PG[0]; E1 = PG[1]; E2 = PG[2]; E3 = PG[3]; E4 = PG[4]; break;
+                    case 3: E0 = PT[0]; E1 = PT[1]; E2 = PT[2]; E3 = PT[3]; E4 = PT[4]; break;
+                    case 4: E0 = PX[0]; E1 = PX[1]; E2 = PX[2]; E3 = PX[3]; E4 = PX[4]; break;
+                    default: {
+                        const unsigned c = ent >> 8;
+                        const unsigned sA = (c & 1) ? ~0u : 0u, sC = (c & 2) ? ~0u : 0u, sG = (c & 4) ? ~0u : 0u, sT = (c & 8) ? ~0u : 0u,
+                                       sX = (c & 16) ? ~0u : 0u;
+                        E0 = (PA[0] & sA) | (PC[0] & sC) | (PG[0] & sG) | (PT[0] & sT) | (PX[0] & sX);
+                        E1 = (PA[1] & sA) | (PC[1] & sC) | (PG[1] & sG) | (PT[1] & sT) | (PX[1] & sX);
+                        E2 = (PA[2] & sA) | (PC[2] & sC) | (PG[2] & sG) | (PT[2] & sT) | (PX[2] & sX);
+                        E3 = (PA[3] & sA) | (PC[3] & sC) | (PG[3] & sG) | (PT[3] & sT) | (PX[3] & sX);
+                        E4 = (PA[4] & sA) | (PC[4] & sC) | (PG[4] & sG) | (PT[4] & sT) | (PX[4] & sX);
+                    }
+                    }
+                    M0 &= __funnelshift_r(E0, E1, shf);
+                    M1 &= __funnelshift_r(E1, E2, shf);
+                    M2 &= __funnelshift_r(E2, E3, shf);
+                    M3 &= __funnelshift_r(E3, E4, shf);
+                }
+                const unsigned mine = __popc(M0) + __popc(M1) + __popc(M2) + __popc(M3);
+                if (!__any_sync(0xffffffffu, mine != 0)) continue;
+                unsigned incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned vv = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += vv;
+                }
+                const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+                const unsigned long long pidbits = (unsigned long long)(c0 + pb) << 40;
+                const unsigned long long bad = (unsigned long long)a.npat << 40;   // sorts after every real key, cut off by the host
+                const unsigned Mw[4] = {M0, M1, M2, M3};
+                if (total > MP_HITBUF) {
+                    flush();
+                    unsigned long long basei = 0;
+                    if (lane == 0) basei = atomicAdd(a.count, (unsigned long long)total);
+                    basei = __shfl_sync(0xffffffffu, basei, 0) + (incl - mine);
+#pragma unroll
+                    for (int w = 0; w < 4; w++) {
+                        unsigned c = Mw[w];
+                        while (c) {
+                            const int b = __ffs(c) - 1;
+                            c &= c - 1;
+                            const long long p = tbase + w * 32 + b;
+                            const bool ok = p >= a.a0 && p < wend && p + m <= a.n;
+                            if ((long long)basei < a.cap) a.keys[basei] = ok ? (pidbits | ((unsigned long long)p << 4)) : bad;
+                            if (!ok) atomicAdd(a.count + 1, 1ULL);
+                            basei++;
+                        }
+                    }
+                    continue;
+                }
+                if (nbuf + total > MP_HITBUF) flush();
+                unsigned slot = nbuf + (incl - mine);
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    unsigned c = Mw[w];
+                    while (c) {
+                        const int b = __ffs(c) - 1;
+                        c &= c - 1;
+                        const long long p = tbase + w * 32 + b;
+                        const bool ok = p >= a.a0 && p < wend && p + m <= a.n;
+                        hitbuf[slot++] = ok ? (pidbits | ((unsigned long long)p << 4)) : bad;
+                        if (!ok) atomicAdd(a.count + 1, 1ULL);
+                    }
+                }
+                nbuf += total;
+                __syncwarp();
+            }
+        }
+    }
+    flush();
+}
+
+// chain stage for batched exact patterns: keys sorted by (pattern, position)
+__global__ void __launch_bounds__(128) k_chain_multi(const unsigned long long *__restrict__ keys, long long nkeys,
+                                                     const unsigned short *__restrict__ mlen, const long long *__restrict__ fillS,
+                                                     const long long *__restrict__ fillE, int nfills,
+                                                     long long *__restrict__ hits /* beg,end pairs */, unsigned char *__restrict__ sel,
+                                                     unsigned long long *__restrict__ per_pattern)
+{
+    const long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j0 >= nkeys) return;
+    const unsigned long long POSMASK = (1ULL << 36) - 1;
+    auto fill_idx = [&](long long x) -> int {
+        int lo = 0, hi = nfills - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (fillS[mid] <= x) lo = mid; else hi = mid - 1; }
+        return lo;
+    };
+    auto independent = [&](long long j) -> bool {
+        if (j == 0) return true;
+        const unsigned long long a = keys[j - 1], b = keys[j];
+        if ((a >> 40) != (b >> 40)) return true;
+        const long long pa = (long long)((a >> 4) & POSMASK), pb = (long long)((b >> 4) & POSMASK);
+        if (pa + mlen[b >> 40] <= pb) return true;
+        return fill_idx(pa) != fill_idx(pb);
+    };
+    if (!independent(j0)) return;
+    long long pos = -1;
+    for (long long t = j0; t < nkeys; t++) {
+        if (t > j0 && independent(t)) break;
+        const unsigned long long key = keys[t];
+        const int pid = (int)(key >> 40);
+        const long long p = (long long)((key >> 4) & POSMASK);
+        const int m = mlen[pid];
+        const int f = fill_idx(p);
+        sel[t] = 0;
+        if (p + m > fillE[f]) continue;                      // the window must lie inside its buffer fill
+        if (p < pos) continue;
+        hits[2 * t] = p;
+        hits[2 * t + 1] = p + m;
+        sel[t] = 1;
+        atomicAdd(&per_pattern[pid], 1ULL);
+        pos = p + m;
+    }
+}

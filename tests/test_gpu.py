@@ -154,6 +154,32 @@ def test_batch_equals_single(engine):
     ds.close()
 
 
+def test_batch_of_iupac_motifs_against_oracle(engine):
+    # BASELINE configs[3] in small: many IUPAC motifs (with N and negated classes) over several
+    # genomes in one fused multi-pattern launch, small buffer fills included
+    rng = random.Random(31)
+    iupac = {"R": "[AG]", "Y": "[CT]", "S": "[GC]", "W": "[AT]", "M": "[AC]", "K": "[GT]", "N": ".", "B": "[CGT]", "V": "[^T]"}
+    pats = []
+    for _ in range(300):
+        m = rng.randint(5, 14)
+        pats.append("(" + "".join(rng.choice("ACGT") if rng.random() < 0.7 else iupac[rng.choice(list(iupac))] for _ in range(m)) + ")")
+    text = genome(17, 12, 600_000)
+    ds = engine.load_dataset(text)
+    try:
+        for bs in (1600000, 70000):
+            engine.set_buffer_size(bs)
+            hits, off = engine.search_batch(ds, pats, "0ids")
+            assert engine.stats()["launches"] < 20                 # one fused scan, not 300 searches
+            assert off[-1] == len(hits)
+            for i in rng.sample(range(len(pats)), 40):
+                want = O.search(pats[i], text, "0ids", bufsize=bs)
+                got = [(int(b), int(e)) for b, e in hits[off[i]:off[i + 1]]]
+                assert got == want, (pats[i], bs)
+    finally:
+        engine.set_buffer_size(1600000)
+        ds.close()
+
+
 def test_request_level_parity_with_reference_python(engine, request_golden):
     check_requests(engine, request_golden)
 
