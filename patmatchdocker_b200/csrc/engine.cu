@@ -424,6 +424,10 @@ struct pm_engine {
     int scan_mode = 0;                              // 0 auto, 1 byte Shift-And, 2 packed bit-sliced
     long long bufsize = 1600000;                    // patmatch.py:37 MAX_BUFFER_SIZE (-b, in bytes)
     int fused_filter = 1;                           // packed scan drops candidates whose verification surely fails
+    // one spare text buffer and one spare plane buffer, so that re-creating a dataset of the same size
+    // (a request that uploads its file every time) does not pay cudaMalloc/cudaFree of gigabytes
+    void *pool_text = nullptr; size_t pool_text_cap = 0;
+    void *pool_planes = nullptr; size_t pool_planes_cap = 0;
     pm_stats stats{};
 };
 
@@ -431,6 +435,7 @@ struct pm_dataset {
     pm_engine *e = nullptr;
     const unsigned char *d_text = nullptr;
     void *owned = nullptr;
+    size_t owned_cap = 0, planes_cap = 0;
     long long n = 0;
     // 2-bit packed planes (packed.cuh)
     unsigned *hi = nullptr, *lo = nullptr, *xx = nullptr;
@@ -453,7 +458,14 @@ static int pack_dataset(pm_engine *e, pm_dataset *d)
     nw = (nw + 1023) / 1024 * 1024 + 1024;          // whole block tiles of the TMA-staged scan + halo
     d->nwords = nw;
     void *p = nullptr;
-    CK(cudaMalloc(&p, (size_t)nw * 4 * 3));
+    const size_t need = (size_t)nw * 4 * 3;
+    if (e->pool_planes && e->pool_planes_cap >= need) {
+        p = e->pool_planes; d->planes_cap = e->pool_planes_cap;
+        e->pool_planes = nullptr; e->pool_planes_cap = 0;
+    } else {
+        CK(cudaMalloc(&p, need));
+        d->planes_cap = need;
+    }
     d->hi = (unsigned *)p; d->lo = d->hi + nw; d->xx = d->lo + nw;
     int rc;
     if ((rc = e->counters.reserve(64))) return rc;
@@ -553,6 +565,8 @@ void pm_engine_destroy(pm_engine *e)
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
+    if (e->pool_text) cudaFree(e->pool_text);
+    if (e->pool_planes) cudaFree(e->pool_planes);
     for (DevBuf *b : {&e->keys, &e->keys2, &e->cands, &e->hits, &e->hits2, &e->sel, &e->tables, &e->counters, &e->cubtmp}) b->release();
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     if (e->h_count) cudaFreeHost(e->h_count);
@@ -603,7 +617,14 @@ int pm_dataset_create(pm_engine *e, const uint8_t *host, int64_t n, pm_dataset *
     pm_dataset *d = new pm_dataset();
     d->e = e; d->n = n;
     void *p = nullptr;
-    cudaError_t rc = cudaMalloc(&p, (size_t)n + 256);
+    cudaError_t rc = cudaSuccess;
+    if (e->pool_text && e->pool_text_cap >= (size_t)n + 256) {
+        p = e->pool_text; d->owned_cap = e->pool_text_cap;
+        e->pool_text = nullptr; e->pool_text_cap = 0;
+    } else {
+        rc = cudaMalloc(&p, (size_t)n + 256);
+        d->owned_cap = (size_t)n + 256;
+    }
     if (rc != cudaSuccess) { delete d; g_err = std::string("cudaMalloc dataset: ") + cudaGetErrorString(rc); return PM_ERR_CUDA; }
     d->owned = p; d->d_text = (const unsigned char *)p;
     if (n > 0) {
@@ -633,9 +654,21 @@ int pm_dataset_wrap_device(pm_engine *e, const uint8_t *dev, int64_t n, pm_datas
 void pm_dataset_destroy(pm_dataset *d)
 {
     if (!d) return;
-    cudaSetDevice(d->e->device);
-    if (d->owned) cudaFree(d->owned);
-    if (d->hi) cudaFree(d->hi);
+    pm_engine *e = d->e;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    if (d->owned) {
+        if (!e->pool_text || e->pool_text_cap < d->owned_cap) {
+            if (e->pool_text) cudaFree(e->pool_text);
+            e->pool_text = d->owned; e->pool_text_cap = d->owned_cap;
+        } else cudaFree(d->owned);
+    }
+    if (d->hi) {
+        if (!e->pool_planes || e->pool_planes_cap < d->planes_cap) {
+            if (e->pool_planes) cudaFree(e->pool_planes);
+            e->pool_planes = d->hi; e->pool_planes_cap = d->planes_cap;
+        } else cudaFree(d->hi);
+    }
     if (d->d_fills) cudaFree(d->d_fills);
     delete d;
 }
