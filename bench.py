@@ -289,7 +289,7 @@ def cpu_baseline(pats, kopt, sample_bytes, procs):
                     oracle_lib.search(pat, data, kopt)
         dt = time.perf_counter() - t0
     v = len(pats) * sample_bytes * procs / dt / 1e9
-    return {"value": round(v, 4), "unit": "pattern*Gbases/s", "cores": procs, "kind": kind, "seconds": round(dt, 2),
+    return {"value": round(v, 7), "unit": "pattern*Gbases/s", "cores": procs, "kind": kind, "seconds": round(dt, 2),
             "sample": "%d process(es) x (one %.1f Mb synthetic chromosome record x %d pattern), nrgrep_coords -i -b 1600000 -k %s" % (procs, sample_bytes / 1e6, len(pats), kopt)}
 
 
@@ -309,12 +309,12 @@ def run_reference(args):
     ms = float(np.mean([b["seconds"] for b in steps])) * 1e3
     total = sum(chrom_lengths(args.bases))
     line = {"impl": "reference", "metric": "pattern.Gbases/s scanned (2-error degenerate motif, both strands)",
-            "value": round(v, 4), "unit": "pattern*Gbases/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "value": round(v, 7), "unit": "pattern*Gbases/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
             "config": {"workload": "configs[4]: single 2-mismatch degenerate motif %s (-k %s), both strands, synthetic %.2f Gb genome; each step a bounded sample" % (MOTIF, kopt, total / 1e9)},
-            "cpu_baseline": dict(steps[-1], value=round(v, 4)),
-            "e2e": {"value": round(v, 4), "unit": "pattern*Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "cpu_baseline": dict(steps[-1], value=round(v, 7)),
+            "e2e": {"value": round(v, 7), "unit": "pattern*Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 

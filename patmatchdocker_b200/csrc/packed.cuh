@@ -396,7 +396,6 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
     __shared__ unsigned queue[NP][BK_QUEUE];            // one queue per piece: a round of candidates shares all parameters
     __shared__ unsigned qcount[NP];
     __shared__ W sT[NP][2][8];                          // match masks by symbol (A,C,T,G,X) for the left / right part of each piece
-    __shared__ int s_fused;
     const int tid = threadIdx.x;
     if (tid < NP * 2 * 5) {
         const int i = tid / 10, side = (tid / 5) & 1, c = tid % 5;
@@ -425,16 +424,6 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
                 sh[2 * BK_ROW + si] = ok ? __ldg(a.xx + q) : 0xffffffffu;
             }
             if (tid < NP) qcount[tid] = 0;
-            if (tid == 0) {
-                int f = v.enabled != 0;
-                if (f && v.ncuts > 0) {
-                    const long long lo = (qb - PK_HALO) * 32, hi = (qb + BK_WORDS + PK_HALO) * 32;
-                    int l = 0, r = v.ncuts;
-                    while (l < r) { const int mid = (l + r) >> 1; if (v.cuts[mid] < lo) l = mid + 1; else r = mid; }
-                    if (l < v.ncuts && v.cuts[l] < hi) f = 0;
-                }
-                s_fused = f;
-            }
         }
         __syncthreads();
         unsigned PA[6], PC[6], PG[6], PT[6], PX[6];
@@ -479,8 +468,9 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
                 for (int w = 0; w < 4; w++) M[i][w] = 0;
             }
         }
-        // tiles next to a forced buffer cut are decided on the raw bytes (s_fused set by thread 0 during staging)
-        const bool fused = s_fused != 0;
+        // The filter ignores record ends and forced buffer cuts: they only take alignments away from the
+        // reference's verification, so a necessary condition computed without them stays necessary.
+        const bool fused = v.enabled != 0;
         // ---- candidates: piece i fires when any piece of trigsets[i] matched at the same start.
         // They are queued per block and per piece in shared memory, then filtered by all threads.
 #pragma unroll
