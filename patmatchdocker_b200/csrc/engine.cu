@@ -801,9 +801,9 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
                         attr_set = true;
                     }
                     const long long nbt = (ntiles + 7) / 8;
-                    const int grid_ex = std::max((int)std::min<long long>(nbt, (long long)e->sms * 4), 1);
-                    if (dp.L > 32) k_scan_packed_exact<true><<<grid_ex, 256, smem, e->stream>>>(a);
-                    else k_scan_packed_exact<false><<<grid_ex, 256, smem, e->stream>>>(a);
+                    const int grid_ex = std::max((int)std::min<long long>(nbt, (long long)e->sms * 5), 1);
+                    if (dp.L > 32) k_scan_packed_exact<true><<<grid_ex, EX_WARPS * 32, smem, e->stream>>>(a);
+                    else k_scan_packed_exact<false><<<grid_ex, EX_WARPS * 32, smem, e->stream>>>(a);
                 } else {
                     PackedArgs<4> a;
                     memset(&a, 0, sizeof a);

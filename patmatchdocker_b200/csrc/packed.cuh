@@ -227,13 +227,27 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
 #define EX_STAGES 3
 #define EX_STAGE_BYTES (3 * EX_ROW * 4)
 
-#define EX_HITBUF 64                     // per-warp hit buffer (keys), flushed with one global atomic
+#define EX_HITBUF 128                   // per-warp hit buffer (keys), flushed with one global atomic
+#define EX_WPL 8                        // words per lane: a warp tile is 256 words (8192 bases)
+#define EX_WARPS 4                      // 128 threads per CTA, block tile = 4 warp tiles = EX_WORDS
 
 template <bool LONG>
-__global__ void __launch_bounds__(256) k_scan_packed_exact(const ExactArgs a)
+__device__ __forceinline__ void exact_apply(unsigned (&M)[EX_WPL], const unsigned (&P)[EX_WPL + 2], int sh)
+{
+    if (!LONG || sh < 32) {
+#pragma unroll
+        for (int w = 0; w < EX_WPL; w++) M[w] &= __funnelshift_r(P[w], P[w + 1], sh);
+    } else {
+#pragma unroll
+        for (int w = 0; w < EX_WPL; w++) M[w] &= __funnelshift_r(P[w + 1], P[w + 2], sh - 32);
+    }
+}
+
+template <bool LONG>
+__global__ void __launch_bounds__(EX_WARPS * 32) k_scan_packed_exact(const ExactArgs a)
 {
     extern __shared__ __align__(128) unsigned char ex_smem[];
-    __shared__ unsigned long long hitbuf_all[8][EX_HITBUF];
+    __shared__ unsigned long long hitbuf_all[EX_WARPS][EX_HITBUF];
     unsigned long long *hitbuf = hitbuf_all[threadIdx.x >> 5];
     unsigned nbuf = 0;                                      // warp-uniform fill of hitbuf
     auto flush = [&]() {
@@ -254,7 +268,7 @@ __global__ void __launch_bounds__(256) k_scan_packed_exact(const ExactArgs a)
     const long long nbt = (a.ntiles + 7) / 8;
     const long long my = blockIdx.x < nbt ? (nbt - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < EX_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+        for (int s = 0; s < EX_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], EX_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -283,54 +297,64 @@ __global__ void __launch_bounds__(256) k_scan_packed_exact(const ExactArgs a)
             }
         }
         mbar_wait(&full[s], ph);
-        const unsigned *sp = stage_base + (size_t)s * (3 * EX_ROW) + wib * 128 + 4 * lane;
-        const uint4 h4 = *reinterpret_cast<const uint4 *>(sp), l4 = *reinterpret_cast<const uint4 *>(sp + EX_ROW),
-                    x4 = *reinterpret_cast<const uint4 *>(sp + 2 * EX_ROW);
-        const uint2 h2 = *reinterpret_cast<const uint2 *>(sp + 4), l2 = *reinterpret_cast<const uint2 *>(sp + EX_ROW + 4),
-                    x2 = *reinterpret_cast<const uint2 *>(sp + 2 * EX_ROW + 4);
+        const unsigned *sp = stage_base + (size_t)s * (3 * EX_ROW) + wib * (32 * EX_WPL) + EX_WPL * lane;
+        unsigned H[EX_WPL + 2], Lw[EX_WPL + 2], X[EX_WPL + 2];
+#pragma unroll
+        for (int v4 = 0; v4 < EX_WPL / 4; v4++) {
+            const uint4 h4 = *reinterpret_cast<const uint4 *>(sp + 4 * v4), l4 = *reinterpret_cast<const uint4 *>(sp + EX_ROW + 4 * v4),
+                        x4 = *reinterpret_cast<const uint4 *>(sp + 2 * EX_ROW + 4 * v4);
+            H[4 * v4] = h4.x; H[4 * v4 + 1] = h4.y; H[4 * v4 + 2] = h4.z; H[4 * v4 + 3] = h4.w;
+            Lw[4 * v4] = l4.x; Lw[4 * v4 + 1] = l4.y; Lw[4 * v4 + 2] = l4.z; Lw[4 * v4 + 3] = l4.w;
+            X[4 * v4] = x4.x; X[4 * v4 + 1] = x4.y; X[4 * v4 + 2] = x4.z; X[4 * v4 + 3] = x4.w;
+        }
+        {
+            const uint2 h2 = *reinterpret_cast<const uint2 *>(sp + EX_WPL), l2 = *reinterpret_cast<const uint2 *>(sp + EX_ROW + EX_WPL),
+                        x2 = *reinterpret_cast<const uint2 *>(sp + 2 * EX_ROW + EX_WPL);
+            H[EX_WPL] = h2.x; H[EX_WPL + 1] = h2.y; Lw[EX_WPL] = l2.x; Lw[EX_WPL + 1] = l2.y; X[EX_WPL] = x2.x; X[EX_WPL + 1] = x2.y;
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);            // this warp's slice is in registers
-        const unsigned H[6] = {h4.x, h4.y, h4.z, h4.w, h2.x, h2.y};
-        const unsigned Lw[6] = {l4.x, l4.y, l4.z, l4.w, l2.x, l2.y};
-        const unsigned X[6] = {x4.x, x4.y, x4.z, x4.w, x2.x, x2.y};
         const long long bt = blockIdx.x + it * gridDim.x;
-        const long long qcur = (a.tile0 * 128) + bt * EX_WORDS + wib * 128 + 4 * lane;
-        unsigned M[4] = {~0u, ~0u, ~0u, ~0u};
-        unsigned P[6];
+        unsigned M[EX_WPL];
+#pragma unroll
+        for (int w = 0; w < EX_WPL; w++) M[w] = ~0u;
+        unsigned P[EX_WPL + 2];
         if (a.npos[0]) {
 #pragma unroll
-            for (int w = 0; w < 6; w++) P[w] = ~(H[w] | Lw[w] | X[w]);
-            for (int e = 0; e < a.npos[0]; e++) packed_apply<LONG>(M, P, a.shift[0][e]);
+            for (int w = 0; w < EX_WPL + 2; w++) P[w] = ~(H[w] | Lw[w] | X[w]);
+            for (int e = 0; e < a.npos[0]; e++) exact_apply<LONG>(M, P, a.shift[0][e]);
         }
         if (a.npos[1]) {
 #pragma unroll
-            for (int w = 0; w < 6; w++) P[w] = Lw[w] & ~H[w];
-            for (int e = 0; e < a.npos[1]; e++) packed_apply<LONG>(M, P, a.shift[1][e]);
+            for (int w = 0; w < EX_WPL + 2; w++) P[w] = Lw[w] & ~H[w];
+            for (int e = 0; e < a.npos[1]; e++) exact_apply<LONG>(M, P, a.shift[1][e]);
         }
         if (a.npos[2]) {
 #pragma unroll
-            for (int w = 0; w < 6; w++) P[w] = H[w] & Lw[w];
-            for (int e = 0; e < a.npos[2]; e++) packed_apply<LONG>(M, P, a.shift[2][e]);
+            for (int w = 0; w < EX_WPL + 2; w++) P[w] = H[w] & Lw[w];
+            for (int e = 0; e < a.npos[2]; e++) exact_apply<LONG>(M, P, a.shift[2][e]);
         }
         if (a.npos[3]) {
 #pragma unroll
-            for (int w = 0; w < 6; w++) P[w] = H[w] & ~Lw[w];
-            for (int e = 0; e < a.npos[3]; e++) packed_apply<LONG>(M, P, a.shift[3][e]);
+            for (int w = 0; w < EX_WPL + 2; w++) P[w] = H[w] & ~Lw[w];
+            for (int e = 0; e < a.npos[3]; e++) exact_apply<LONG>(M, P, a.shift[3][e]);
         }
         if (a.npos[4]) {
-            for (int e = 0; e < a.npos[4]; e++) packed_apply<LONG>(M, X, a.shift[4][e]);
+            for (int e = 0; e < a.npos[4]; e++) exact_apply<LONG>(M, X, a.shift[4][e]);
         }
         for (int e = 0; e < a.npos[5]; e++) {
             const unsigned c = a.cls[e];
             const unsigned sA = (c & 1) ? ~0u : 0u, sC = (c & 2) ? ~0u : 0u, sG = (c & 4) ? ~0u : 0u, sT = (c & 8) ? ~0u : 0u,
                            sX = (c & 16) ? ~0u : 0u;
 #pragma unroll
-            for (int w = 0; w < 6; w++)
+            for (int w = 0; w < EX_WPL + 2; w++)
                 P[w] = (~(H[w] | Lw[w] | X[w]) & sA) | (Lw[w] & ~H[w] & sC) | (H[w] & Lw[w] & sG) | (H[w] & ~Lw[w] & sT) | (X[w] & sX);
-            packed_apply<LONG>(M, P, a.shift[5][e]);
+            exact_apply<LONG>(M, P, a.shift[5][e]);
         }
         // ---- hits of this warp tile: buffered in shared memory, no per-hit global atomics ----
-        const unsigned mine = __popc(M[0]) + __popc(M[1]) + __popc(M[2]) + __popc(M[3]);
+        unsigned mine = 0;
+#pragma unroll
+        for (int w = 0; w < EX_WPL; w++) mine += __popc(M[w]);
         if (!__any_sync(0xffffffffu, mine != 0)) continue;
         unsigned incl = mine;
 #pragma unroll
@@ -339,11 +363,11 @@ __global__ void __launch_bounds__(256) k_scan_packed_exact(const ExactArgs a)
             if (lane >= o) incl += v;
         }
         const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-        const long long wbase = ((a.tile0 * 128) + bt * EX_WORDS + wib * 128) * 32;   // text position of the warp tile
+        const long long wbase = ((a.tile0 * 128) + bt * EX_WORDS + wib * (32 * EX_WPL)) * 32;   // text position of the warp tile
         // only the first / last tiles of the scanned range need the per-hit range test
-        const bool inside = wbase >= a.a0 && wbase + 4096 <= (a.a1 < a.n - a.L + 1 ? a.a1 : a.n - a.L + 1);
+        const bool inside = wbase >= a.a0 && wbase + 32 * 32 * EX_WPL <= (a.a1 < a.n - a.L + 1 ? a.a1 : a.n - a.L + 1);
         const unsigned long long bad = ((unsigned long long)(a.n + 1) << 4) | 15ULL;
-        const unsigned lrel = (unsigned)(4 * lane) * 32;
+        const unsigned lrel = (unsigned)(EX_WPL * lane) * 32;
         if (total > EX_HITBUF) {
             // dense tile: straight to global memory
             flush();
@@ -351,7 +375,7 @@ __global__ void __launch_bounds__(256) k_scan_packed_exact(const ExactArgs a)
             if (lane == 0) basei = atomicAdd(a.count, (unsigned long long)total);
             basei = __shfl_sync(0xffffffffu, basei, 0) + (incl - mine);
 #pragma unroll
-            for (int w = 0; w < 4; w++) {
+            for (int w = 0; w < EX_WPL; w++) {
                 unsigned c = M[w];
                 while (c) {
                     const int b = __ffs(c) - 1;
@@ -368,7 +392,7 @@ __global__ void __launch_bounds__(256) k_scan_packed_exact(const ExactArgs a)
         if (nbuf + total > EX_HITBUF) flush();
         unsigned slot = nbuf + (incl - mine);
 #pragma unroll
-        for (int w = 0; w < 4; w++) {
+        for (int w = 0; w < EX_WPL; w++) {
             unsigned c = M[w];
             while (c) {
                 const int b = __ffs(c) - 1;
