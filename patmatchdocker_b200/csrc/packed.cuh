@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
                     }
                     minL = best;
                 }
-                if (nR > 0) {
+                if (nR > 0 && minL <= v.k) {                       // the left side alone can already rule the candidate out
                     W Pv = (W)~(W)0, Mv = 0;
                     int score = rl, best = rl;
                     unsigned hw = 0, lw = 0, xw = 0;

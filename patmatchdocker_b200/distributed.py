@@ -84,7 +84,8 @@ class DeviceShardedSearch:
             if max(counts) <= self.cap:
                 break
             self._alloc(max(counts) + 1024)                    # some rank overflowed: everybody grows and rescans
-        dist.gather(self.mine, self.bufs, dst=0, group=self.group)
+        mx = max(max(counts), 1)                           # only the used rows travel
+        dist.gather(self.mine[:mx], [b[:mx] for b in self.bufs] if self.rank == 0 else None, dst=0, group=self.group)
         if self.rank != 0:
             return None
         off = 0
