@@ -122,6 +122,63 @@ def test_small_hit_buffer_is_regrown(engine):
     ds.close()
 
 
+def test_scan_kernel_selection_and_equivalence(engine):
+    # auto mode: packed bit-sliced scan for DNA-like datasets, byte Shift-And for proteomes; both kernels
+    # give the same hit list on a genome with lower case, N runs, IUPAC letters and a non-ACGT-accepting class
+    rng = random.Random(12)
+    g = bytearray(genome(21, 6, 3_000_000))
+    for _ in range(200):
+        p = rng.randrange(100, len(g) - 3000)
+        if b"\n" in g[p - 5:p + 2100] or b">" in g[p - 5:p + 2100]:
+            continue
+        kind = rng.randint(0, 2)
+        ln = rng.randint(1, 2000)
+        if kind == 0:
+            g[p:p + ln] = b"N" * ln
+        elif kind == 1:
+            g[p:p + ln] = bytes(g[p:p + ln]).lower()
+        else:
+            g[p:p + 6] = b"RYKMSW"
+    g = bytes(g)
+    ds = engine.load_dataset(g)
+    for pat, kopt in (("(GAT[AG]AG)", "0ids"), ("(GA.AAG[^C])", "0ids"), ("(NNGATAAG)", "0ids"), ("(GATAAGCC[AT]TT)", "1ids"),
+                      ("(TGA[GC]TCA...[AG][CT]GATAAG)", "2ids"), ("(GATAAG[^A]N)", "1s")):
+        engine.set_scan_mode("auto")
+        a = engine.search(ds, pat, kopt)
+        packed = engine.stats()["packed"]
+        engine.set_scan_mode("bytes")
+        b = engine.search(ds, pat, kopt)
+        engine.set_scan_mode("auto")
+        assert np.array_equal(a, b), (pat, kopt)
+        if pm.plan(pat, kopt)["type"] in ("SIMPLE", "SPLIT"):
+            assert packed == 1
+        assert [(int(x), int(y)) for x, y in a] == O.search(pat, g, kopt), (pat, kopt)
+    ds.close()
+    prot = genome(22, 500, 200_000, alphabet=PEP.encode(), name="YORF")
+    ds = engine.load_dataset(prot)
+    engine.search(ds, "(CAAC[ILVM]QQH)", "1s")
+    assert engine.stats()["packed"] == 0
+    ds.close()
+
+
+def test_hit_list_stays_on_device_after_overflow(engine):
+    import ctypes
+    from patmatchdocker_b200 import _native
+    text = (">s\n" + "GATAAGT" * 3000 + "\n").encode()
+    ds = engine.load_dataset(text)
+    L = _native.load()
+    n = ctypes.c_int64()
+    small = np.empty(10, dtype=_native.HIT_DTYPE)
+    rc = L.pm_search(engine._h, ds._h, b"(GATAAG)", b"0ids", ctypes.c_void_p(small.ctypes.data), 10, ctypes.byref(n))
+    assert rc == -5 and n.value == 3000
+    launches = engine.stats()["launches"]
+    big = np.empty(3000, dtype=_native.HIT_DTYPE)
+    assert L.pm_last_hits(engine._h, ctypes.c_void_p(big.ctypes.data), 3000, ctypes.byref(n)) == 0
+    assert engine.stats()["launches"] == launches              # fetched, not searched again
+    assert big["beg"][0] == 3 and big["end"][-1] == 3 + 7 * 2999 + 6
+    ds.close()
+
+
 def test_sharded_candidates_then_resolve_equals_search(engine, scan_mode):
     rng = random.Random(77)
     for it in range(20):
