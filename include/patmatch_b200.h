@@ -125,6 +125,10 @@ int pm_resolve_device(pm_engine *e, pm_dataset *d, const char *pattern, const ch
                       const pm_candidate *dev_cands, int64_t ncands,
                       pm_hit *hits, int64_t cap, int64_t *nhits);
 
+/* page-locked host buffers for large hit arrays (optional; any host pointer works for `hits`) */
+void *pm_host_alloc(int64_t bytes);
+void pm_host_free(void *p);
+
 int pm_get_stats(pm_engine *e, pm_stats *out);
 
 #ifdef __cplusplus

@@ -82,6 +82,10 @@ def load():
     L.pm_resolve.argtypes = [vp, vp, cp, cp, vp, i64, vp, i64, ctypes.POINTER(i64)]
     L.pm_candidates_device.argtypes = [vp, vp, cp, cp, i64, i64, vp, i64, ctypes.POINTER(i64)]
     L.pm_resolve_device.argtypes = [vp, vp, cp, cp, vp, i64, vp, i64, ctypes.POINTER(i64)]
+    L.pm_host_alloc.argtypes = [i64]
+    L.pm_host_alloc.restype = vp
+    L.pm_host_free.argtypes = [vp]
+    L.pm_host_free.restype = None
     L.pm_get_stats.argtypes = [vp, ctypes.POINTER(PmStats)]
     _lib = L
     return L
@@ -94,6 +98,31 @@ def _check(rc):
 
 def _b(s):
     return s if isinstance(s, bytes) else s.encode("latin-1")
+
+
+class _Pinned:
+    """numpy view of page-locked host memory from pm_host_alloc (freed with the last reference)"""
+
+    def __init__(self, count, dtype):
+        self.nbytes = max(int(count), 1) * dtype.itemsize
+        self.ptr = load().pm_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise NativeError(-1, "pm_host_alloc(%d) failed" % self.nbytes)
+        buf = (ctypes.c_char * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(count))
+        self.array_owner = buf
+
+    def __del__(self):
+        try:
+            load().pm_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(count, dtype):
+    """-> (array, keepalive): array lives in page-locked memory as long as keepalive does"""
+    p = _Pinned(count, dtype)
+    return p.array, p
 
 
 def plan(pattern, kopt):
@@ -192,18 +221,28 @@ class Engine:
         return n.value
 
     def search_batch(self, dataset, patterns, kopt="0ids", cap=1 << 20):
+        """-> (hits, offsets): hits[offsets[i]:offsets[i+1]] is the hit list of patterns[i].  Large results
+        are returned in page-locked host memory (fast device-to-host copy)."""
         L = load()
         arr = (ctypes.c_char_p * len(patterns))(*[_b(p) for p in patterns])
         offsets = (ctypes.c_int64 * (len(patterns) + 1))()
-        while True:
-            hits = np.empty(cap, dtype=HIT_DTYPE)
-            rc = L.pm_search_batch(self._h, dataset._h, len(patterns), arr, _b(kopt), ctypes.c_void_p(hits.ctypes.data), cap, offsets)
-            if rc == PM_ERR_OVERFLOW:
-                cap *= 4
-                continue
-            _check(rc)
-            off = np.array(list(offsets), dtype=np.int64)
-            return hits[: off[-1]], off
+        n = ctypes.c_int64()
+        hits = np.empty(cap, dtype=HIT_DTYPE)
+        rc = L.pm_search_batch(self._h, dataset._h, len(patterns), arr, _b(kopt), ctypes.c_void_p(hits.ctypes.data), cap, offsets)
+        if rc == PM_ERR_OVERFLOW:
+            total = int(offsets[len(patterns)])
+            if total > 0 and self.stats()["hits"] == total:      # fused batch: the list is still on the device
+                hits, keep = pinned_empty(total, HIT_DTYPE)
+                self._keep = keep
+                rc = L.pm_last_hits(self._h, ctypes.c_void_p(hits.ctypes.data), total, ctypes.byref(n))
+            else:                                                 # per-pattern fallback: run again with room
+                while rc == PM_ERR_OVERFLOW:
+                    cap *= 4
+                    hits = np.empty(cap, dtype=HIT_DTYPE)
+                    rc = L.pm_search_batch(self._h, dataset._h, len(patterns), arr, _b(kopt), ctypes.c_void_p(hits.ctypes.data), cap, offsets)
+        _check(rc)
+        off = np.array(list(offsets), dtype=np.int64)
+        return hits[: off[-1]], off
 
     def candidates(self, dataset, pattern, kopt, pos_beg, pos_end, cap=1 << 16):
         L = load()

@@ -675,6 +675,21 @@ void pm_dataset_destroy(pm_dataset *d)
 
 int64_t pm_dataset_size(const pm_dataset *d) { return d ? d->n : 0; }
 
+// page-locked host memory for large result arrays (device-to-host copies into pageable memory run at a
+// fraction of the PCIe rate)
+void *pm_host_alloc(int64_t bytes)
+{
+    void *p = nullptr;
+    if (bytes <= 0) return nullptr;
+    if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) { g_err = "cudaMallocHost failed"; (void)cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void pm_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
 int pm_get_stats(pm_engine *e, pm_stats *out)
 {
     if (!e || !out) { g_err = "bad argument"; return PM_ERR_ARG; }
