@@ -109,7 +109,7 @@ class _Pinned:
         if not self.ptr:
             raise NativeError(-1, "pm_host_alloc(%d) failed" % self.nbytes)
         buf = (ctypes.c_char * self.nbytes).from_address(self.ptr)
-        self.array = np.frombuffer(buf, dtype=dtype, count=int(count))
+        self.array = np.frombuffer(buf, dtype=dtype, count=max(int(count), 1))
         self.array_owner = buf
 
     def __del__(self):
@@ -232,8 +232,11 @@ class Engine:
         if rc == PM_ERR_OVERFLOW:
             total = int(offsets[len(patterns)])
             if total > 0 and self.stats()["hits"] == total:      # fused batch: the list is still on the device
-                hits, keep = pinned_empty(total, HIT_DTYPE)
-                self._keep = keep
+                keep = getattr(self, "_keep", None)                # page-locked result buffer, reused across calls
+                if keep is None or keep.array.size < total:
+                    _, keep = pinned_empty(total + total // 8, HIT_DTYPE)
+                    self._keep = keep
+                hits = keep.array
                 rc = L.pm_last_hits(self._h, ctypes.c_void_p(hits.ctypes.data), total, ctypes.byref(n))
             else:                                                 # per-pattern fallback: run again with room
                 while rc == PM_ERR_OVERFLOW:
