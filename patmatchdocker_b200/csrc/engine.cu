@@ -817,8 +817,8 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
                     }
                     const long long nbt = (ntiles + 7) / 8;
                     const int grid_ex = std::max((int)std::min<long long>(nbt, (long long)e->sms * 5), 1);
-                    if (dp.L > 32) k_scan_packed_exact<true><<<grid_ex, EX_WARPS * 32, smem, e->stream>>>(a);
-                    else k_scan_packed_exact<false><<<grid_ex, EX_WARPS * 32, smem, e->stream>>>(a);
+                    if (dp.L > 32) k_scan_packed_exact<true><<<grid_ex, (EX_WARPS + 1) * 32, smem, e->stream>>>(a);
+                    else k_scan_packed_exact<false><<<grid_ex, (EX_WARPS + 1) * 32, smem, e->stream>>>(a);
                 } else {
                     PackedArgs<4> a;
                     memset(&a, 0, sizeof a);

@@ -244,10 +244,10 @@ __device__ __forceinline__ void exact_apply(unsigned (&M)[EX_WPL], const unsigne
 }
 
 template <bool LONG>
-__global__ void __launch_bounds__(EX_WARPS * 32) k_scan_packed_exact(const ExactArgs a)
+__global__ void __launch_bounds__((EX_WARPS + 1) * 32) k_scan_packed_exact(const ExactArgs a)
 {
     extern __shared__ __align__(128) unsigned char ex_smem[];
-    __shared__ unsigned long long hitbuf_all[EX_WARPS][EX_HITBUF];
+    __shared__ unsigned long long hitbuf_all[EX_WARPS + 1][EX_HITBUF];
     unsigned long long *hitbuf = hitbuf_all[threadIdx.x >> 5];
     unsigned nbuf = 0;                                      // warp-uniform fill of hitbuf
     auto flush = [&]() {
@@ -282,20 +282,18 @@ __global__ void __launch_bounds__(EX_WARPS * 32) k_scan_packed_exact(const Exact
         tma_load_1d(dst + EX_ROW, a.lo + q, EX_ROW * 4, &full[s]);
         tma_load_1d(dst + 2 * EX_ROW, a.xx + q, EX_ROW * 4, &full[s]);
     };
-    if (threadIdx.x == 0)
-        for (long long it = 0; it < my && it < EX_STAGES - 1; it++) issue(it);
-
+    if (wib == EX_WARPS) {
+        // producer warp: one lane keeps the ring full, independent of the consumers' progress
+        if (lane == 0)
+            for (long long it = 0; it < my; it++) {
+                if (it >= EX_STAGES) mbar_wait(&empty[it % EX_STAGES], (unsigned)(((it / EX_STAGES) - 1) & 1));
+                issue(it);
+            }
+        return;
+    }
     for (long long it = 0; it < my; it++) {
         const int s = (int)(it % EX_STAGES);
         const unsigned ph = (unsigned)((it / EX_STAGES) & 1);
-        // refill the stage that the previous iteration released
-        if (threadIdx.x == 0) {
-            const long long nx = it + EX_STAGES - 1;
-            if (nx < my) {
-                if (nx >= EX_STAGES) mbar_wait(&empty[nx % EX_STAGES], (unsigned)(((nx / EX_STAGES) - 1) & 1));
-                issue(nx);
-            }
-        }
         mbar_wait(&full[s], ph);
         const unsigned *sp = stage_base + (size_t)s * (3 * EX_ROW) + wib * (32 * EX_WPL) + EX_WPL * lane;
         unsigned H[EX_WPL + 2], Lw[EX_WPL + 2], X[EX_WPL + 2];
