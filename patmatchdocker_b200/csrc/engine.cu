@@ -421,6 +421,7 @@ struct pm_engine {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     DevBuf keys, keys2, cands, hits, hits2, sel, tables, counters, cubtmp;
     unsigned long long *h_count = nullptr;          // pinned
+    void *h_stage = nullptr; size_t h_stage_cap = 0; // pinned staging for small result copies
     int scan_mode = 0;                              // 0 auto, 1 byte Shift-And, 2 packed bit-sliced
     long long bufsize = 1600000;                    // patmatch.py:37 MAX_BUFFER_SIZE (-b, in bytes)
     int fused_filter = 1;                           // packed scan drops candidates whose verification surely fails
@@ -570,6 +571,7 @@ void pm_engine_destroy(pm_engine *e)
     for (DevBuf *b : {&e->keys, &e->keys2, &e->cands, &e->hits, &e->hits2, &e->sel, &e->tables, &e->counters, &e->cubtmp}) b->release();
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     if (e->h_count) cudaFreeHost(e->h_count);
+    if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->own) cudaStreamDestroy(e->own);
     delete e;
 }
@@ -953,6 +955,29 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
     return PM_OK;
 }
 
+// device -> caller's host buffer.  Copies into pageable memory run far below the PCIe rate and block the
+// host; results up to 64 MiB go through a page-locked staging buffer instead.
+static int copy_to_host(pm_engine *e, void *dst, const void *src, size_t bytes)
+{
+    if (bytes == 0) return PM_OK;
+    if (bytes > ((size_t)64 << 20)) {
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        return PM_OK;
+    }
+    if (e->h_stage_cap < bytes) {
+        if (e->h_stage) cudaFreeHost(e->h_stage);
+        e->h_stage = nullptr; e->h_stage_cap = 0;
+        size_t want = std::max(bytes * 2, (size_t)1 << 20);
+        CK(cudaMallocHost(&e->h_stage, want));
+        e->h_stage_cap = want;
+    }
+    CK(cudaMemcpyAsync(e->h_stage, src, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    memcpy(dst, e->h_stage, bytes);
+    return PM_OK;
+}
+
 // chain + select over ncand candidates in d_cands; hits copied to the host
 static int resolve_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, const Cand *d_cands, long long ncand,
                               const unsigned long long *dTL, const unsigned long long *dTR,
@@ -988,11 +1013,11 @@ static int resolve_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, co
     *nhits = nh;
     e->stats.hits = nh;
     bool overflow = false;
+    CK(cudaEventRecord(e->ev[5], e->stream));
     if (hits && nh > 0) {
         if (nh > cap) overflow = true;                   // the list stays on the device for pm_last_hits
-        else CK(cudaMemcpyAsync(hits, e->hits2.p, (size_t)nh * sizeof(pm_hit), cudaMemcpyDeviceToHost, e->stream));
+        else if ((rc = copy_to_host(e, hits, e->hits2.p, (size_t)nh * sizeof(pm_hit)))) return rc;
     }
-    CK(cudaEventRecord(e->ev[5], e->stream));
     CK(cudaStreamSynchronize(e->stream));
     if (overflow) { g_err = "hit buffer too small"; return PM_ERR_OVERFLOW; }
     return PM_OK;

@@ -67,29 +67,37 @@ class DeviceShardedSearch:
     def _alloc(self, cap):
         torch = self.torch
         self.cap = cap
-        self.mine = torch.empty((cap, 4), dtype=torch.int64, device=self.device)
-        self.bufs = [torch.empty((cap, 4), dtype=torch.int64, device=self.device) for _ in range(self.world)] if self.rank == 0 else None
+        self.rows = getattr(self, "rows", cap)                # first exchange: full buffers, then adapted
+        self.mine = torch.zeros((cap, 4), dtype=torch.int64, device=self.device)          # row 0 = header (count)
+        self.allbuf = torch.empty((cap * self.world, 4), dtype=torch.int64, device=self.device)
         self.merged = torch.empty((cap * self.world, 4), dtype=torch.int64, device=self.device) if self.rank == 0 else None
 
     def search(self, dataset, pattern, kopt):
+        """One collective per search: every rank all-gathers `rows` candidate records plus a header row
+        holding its true count, so all ranks learn all counts and agree on the size of the next exchange
+        (and on a retry when a rank had more candidates than rows)."""
         import torch.distributed as dist
         torch = self.torch
         beg, end = shard_ranges(len(dataset), self.world)[self.rank]
+        n = self.engine.candidates_device(dataset, pattern, kopt, beg, end, self.mine[1:].data_ptr(), self.cap - 1)
         while True:
-            n = self.engine.candidates_device(dataset, pattern, kopt, beg, end, self.mine.data_ptr(), self.cap)
-            count = torch.tensor([abs(n)], dtype=torch.int64, device=self.device)
-            counts = [torch.zeros_like(count) for _ in range(self.world)]
-            dist.all_gather(counts, count, group=self.group)
-            counts = [int(c) for c in counts]
-            if max(counts) <= self.cap:
+            self.mine[0, 0] = abs(n)
+            rows = min(self.rows, self.cap)
+            dist.all_gather_into_tensor(self.allbuf[: self.world * rows].view(self.world, rows, 4), self.mine[:rows], group=self.group)
+            counts = self.allbuf[: self.world * rows].view(self.world, rows, 4)[:, 0, 0].tolist()
+            need = max(counts) + 1
+            self.rows = max(256, int(need * 1.25) + 16)      # agreed by construction: everyone saw the same counts
+            if need <= rows:
                 break
-            self._alloc(max(counts) + 1024)                    # some rank overflowed: everybody grows and rescans
-        mx = max(max(counts), 1)                           # only the used rows travel
-        dist.gather(self.mine[:mx], [b[:mx] for b in self.bufs] if self.rank == 0 else None, dst=0, group=self.group)
+            if need > self.cap:                                # some rank overflowed its buffer: grow everywhere, rescan
+                self._alloc(need + 1024)
+                n = self.engine.candidates_device(dataset, pattern, kopt, beg, end, self.mine[1:].data_ptr(), self.cap - 1)
         if self.rank != 0:
             return None
+        view = self.allbuf[: self.world * rows].view(self.world, rows, 4)
         off = 0
         for r in range(self.world):
-            self.merged[off:off + counts[r]] = self.bufs[r][: counts[r]]
-            off += counts[r]
+            c = int(counts[r])
+            self.merged[off:off + c] = view[r, 1:1 + c]
+            off += c
         return self.engine.resolve_device(dataset, pattern, kopt, self.merged.data_ptr(), off)
