@@ -472,20 +472,25 @@ static int pack_dataset(pm_engine *e, pm_dataset *d)
     if ((rc = e->counters.reserve(64))) return rc;
     unsigned long long *d_exc = (unsigned long long *)((char *)e->counters.p + 32);
     CK(cudaMemsetAsync(d_exc, 0, 24, e->stream));
-    const long long groups = nw / 32;
-    const int grid = (int)std::min<long long>((groups + 7) / 8, (long long)e->sms * 16);
-    k_pack<<<std::max(grid, 1), 256, 0, e->stream>>>(d->d_text, n, nw, d->hi, d->lo, d->xx, d_exc);
+    // newline positions are captured by the pack kernel itself (a .seq file has two per sequence);
+    // a file with more lines than the buffer holds falls back to a second pass
+    const long long nl_cap = 1 << 20;
+    if ((rc = e->keys2.reserve((size_t)nl_cap * 8))) return rc;
+    unsigned long long *d_nl = (unsigned long long *)e->keys2.p;
+    const int grid = (int)std::min<long long>((nw + 255) / 256, (long long)e->sms * 16);
+    k_pack<<<std::max(grid, 1), 256, 0, e->stream>>>(d->d_text, n, nw, d->hi, d->lo, d->xx, d_exc, d_nl, nl_cap);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(e->h_count + 4, d_exc, 8, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    CK(cudaMemcpyAsync(e->h_count + 5, d_exc + 1, 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(e->h_count + 4, d_exc, 16, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     d->nexc = (long long)e->h_count[4];
     d->dna_like = n > 0 && d->nexc * 8 <= n;
-    // newline positions for the buffer-fill table
     const long long nnl = (long long)e->h_count[5];
     d->newlines.resize((size_t)nnl);
-    if (nnl > 0) {
+    if (nnl > 0 && nnl <= nl_cap) {
+        CK(cudaMemcpyAsync(d->newlines.data(), d_nl, (size_t)nnl * 8, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        std::sort(d->newlines.begin(), d->newlines.end());
+    } else if (nnl > nl_cap) {
         void *dn = nullptr;
         CK(cudaMalloc(&dn, (size_t)nnl * 8));
         const int g2 = (int)std::min<long long>((n / 16 + 255) / 256 + 1, (long long)e->sms * 16);

@@ -31,39 +31,83 @@ struct PackedArgs {
     long long cap;
 };
 
-__global__ void __launch_bounds__(256) k_pack(const unsigned char *__restrict__ text, long long n, long long nwords,
-                                              unsigned *__restrict__ hi, unsigned *__restrict__ lo, unsigned *__restrict__ xx,
-                                              unsigned long long *__restrict__ nexc)   // [0] non-ACGT bytes, [1] newlines
+// SWAR helpers on 4 packed bytes
+__device__ __forceinline__ unsigned swar_eq(unsigned w, unsigned pat)          // 0x80 in every byte of w equal to the byte of pat
 {
-    const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    unsigned long long exc = 0, nls = 0;
-    for (long long g = warp; g * 32 < nwords; g += nwarps) {
-        unsigned mh = 0, ml = 0, mx = 0;
-        const long long base = g * 1024;
-#pragma unroll 4
-        for (int i = 0; i < 32; i++) {
-            const long long idx = base + 32 * i + lane;
-            const unsigned c = idx < n ? text[idx] : 0xffu;
-            const unsigned f = c | 0x20u;
-            const bool acgt = (f == 'a') | (f == 'c') | (f == 'g') | (f == 't');
-            const unsigned wh = __ballot_sync(0xffffffffu, acgt && (c & 4u));
-            const unsigned wl = __ballot_sync(0xffffffffu, acgt && (c & 2u));
-            const unsigned wx = __ballot_sync(0xffffffffu, !acgt);
-            if (lane == i) { mh = wh; ml = wl; mx = wx; }
-            if (idx < n && !acgt) exc++;
-            if (idx < n && c == '\n') nls++;
-        }
-        const long long q = g * 32 + lane;
-        if (q < nwords) { hi[q] = mh; lo[q] = ml; xx[q] = mx; }
-    }
-    for (int o = 16; o; o >>= 1) { exc += __shfl_xor_sync(0xffffffffu, exc, o); nls += __shfl_xor_sync(0xffffffffu, nls, o); }
-    if (lane == 0 && exc) atomicAdd(nexc, exc);
-    if (lane == 0 && nls) atomicAdd(nexc + 1, nls);
+    const unsigned z = w ^ pat;
+    const unsigned t = (z & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+    return ~(t | z | 0x7f7f7f7fu);
+}
+__device__ __forceinline__ unsigned swar_gather(unsigned m)                    // bit 7 of each byte -> bits 0..3
+{
+    return ((m >> 7) * 0x00204081u >> 21) & 0xfu;                              // bytes 0..3 land on bits 0..3
 }
 
-// positions of the record delimiter, for the host-side buffer-fill table (unordered; sorted on the host)
+// One thread packs 32 consecutive text bytes into one word of each plane and records the positions of
+// '\n' (record delimiter) it meets.  nl_out may overflow its capacity: the count keeps running and the
+// host then falls back to k_newlines.
+__global__ void __launch_bounds__(256) k_pack(const unsigned char *__restrict__ text, long long n, long long nwords,
+                                              unsigned *__restrict__ hi, unsigned *__restrict__ lo, unsigned *__restrict__ xx,
+                                              unsigned long long *__restrict__ nexc,    // [0] non-ACGT bytes, [1] newlines
+                                              unsigned long long *__restrict__ nl_out, long long nl_cap)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const bool aligned = ((size_t)text & 15) == 0;
+    unsigned long long exc = 0;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nwords; q += stride) {
+        const long long base = q * 32;
+        unsigned w[8];
+        if (aligned && base + 32 <= n) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(text + base));
+            const uint4 b = __ldg(reinterpret_cast<const uint4 *>(text + base + 16));
+            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                unsigned v = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const long long idx = base + 4 * k + b;
+                    v |= (unsigned)(idx < n ? text[idx] : 0xffu) << (8 * b);
+                }
+                w[k] = v;
+            }
+        }
+        unsigned mh = 0, ml = 0, mx = 0, mn = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const unsigned f = w[k] | 0x20202020u;
+            const unsigned acgt = swar_eq(f, 0x61616161u) | swar_eq(f, 0x63636363u) | swar_eq(f, 0x67676767u) | swar_eq(f, 0x74747474u);
+            const unsigned h = (w[k] << 5) & acgt;          // ASCII bit 2 -> bit 7
+            const unsigned l = (w[k] << 6) & acgt;          // ASCII bit 1 -> bit 7
+            mh |= swar_gather(h) << (4 * k);
+            ml |= swar_gather(l) << (4 * k);
+            mx |= swar_gather(~acgt & 0x80808080u) << (4 * k);
+            mn |= swar_gather(swar_eq(w[k], 0x0a0a0a0au)) << (4 * k);
+        }
+        if (base + 32 > n) {                                 // bytes past the end are X, never newlines
+            const int valid = n > base ? (int)(n - base) : 0;
+            const unsigned keep = valid >= 32 ? ~0u : ((1u << valid) - 1u);
+            mn &= keep;
+            exc += __popc(mx & keep);
+        } else exc += __popc(mx);
+        hi[q] = mh; lo[q] = ml; xx[q] = mx;
+        if (mn) {
+            const int cnt = __popc(mn);
+            unsigned long long slot = atomicAdd(nexc + 1, (unsigned long long)cnt);
+            while (mn) {
+                const int b = __ffs(mn) - 1;
+                mn &= mn - 1;
+                if ((long long)slot < nl_cap) nl_out[slot] = (unsigned long long)(base + b);
+                slot++;
+            }
+        }
+    }
+    for (int o = 16; o; o >>= 1) exc += __shfl_xor_sync(0xffffffffu, exc, o);
+    if ((threadIdx.x & 31) == 0 && exc) atomicAdd(nexc, exc);
+}
+
+// positions of the record delimiter (fallback when k_pack's newline buffer overflowed; unordered)
 __global__ void __launch_bounds__(256) k_newlines(const unsigned char *__restrict__ text, long long n,
                                                   unsigned long long *__restrict__ out, unsigned long long *__restrict__ count)
 {
