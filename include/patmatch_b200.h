@@ -60,6 +60,7 @@ typedef struct {
     int64_t scan_bases;          /* text positions the scan kernel covered */
     int launches;                /* kernels launched by the last search */
     int packed;                  /* 1: 2-bit packed bit-sliced scan, 0: byte Shift-And / dense */
+    int qgram_chunks;            /* pattern chunks of the bit-sliced q-gram pre-filter (0 = not used) */
 } pm_stats;
 
 const char *pm_last_error(void);
@@ -76,8 +77,9 @@ int pm_engine_set_stream(pm_engine *e, void *cuda_stream);
 int pm_engine_synchronize(pm_engine *e);
 /* scan kernel selection: 0 = auto (packed for DNA-like datasets), 1 = byte Shift-And, 2 = packed */
 int pm_engine_set_scan_mode(pm_engine *e, int mode);
-/* packed scan only: verify candidates inside the scan kernel on the packed planes and drop the ones
- * that surely fail (default on); off = every exact piece hit goes through k_verify */
+/* packed scan only: filter candidates inside the scan kernel on the packed planes and drop the ones
+ * that surely fail.  1 (default) = q-gram pre-filter + Myers filter, 2 = Myers filter only,
+ * 0 = off: every exact piece hit goes through k_verify */
 int pm_engine_set_fused_filter(pm_engine *e, int on);
 /* the reference's -b buffer size in BYTES (patmatch.py:37,733 pass 1600000, the default here):
  * nrgrep_coords scans the file one buffer fill at a time and no hit crosses a fill. 0 = one fill. */

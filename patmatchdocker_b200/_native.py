@@ -35,7 +35,7 @@ class PmStats(ctypes.Structure):
                 ("chain_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
                 ("candidates", ctypes.c_int64), ("verified", ctypes.c_int64), ("hits", ctypes.c_int64),
                 ("scan_bytes", ctypes.c_int64), ("scan_bases", ctypes.c_int64), ("launches", ctypes.c_int),
-                ("packed", ctypes.c_int)]
+                ("packed", ctypes.c_int), ("qgram_chunks", ctypes.c_int)]
 
 
 HIT_DTYPE = np.dtype([("beg", "<i8"), ("end", "<i8")])
@@ -182,7 +182,8 @@ class Engine:
         _check(load().pm_engine_set_scan_mode(self._h, {"auto": 0, "bytes": 1, "packed": 2}[mode]))
 
     def set_fused_filter(self, on):
-        _check(load().pm_engine_set_fused_filter(self._h, int(bool(on))))
+        """True/1 = q-gram pre-filter + Myers filter (default), 2 = Myers filter only, False/0 = off"""
+        _check(load().pm_engine_set_fused_filter(self._h, int(on)))
 
     def set_buffer_size(self, nbytes):
         """the reference's -b (bytes); patmatch.py uses 1600000, the default"""

@@ -425,6 +425,8 @@ struct pm_engine {
     int scan_mode = 0;                              // 0 auto, 1 byte Shift-And, 2 packed bit-sliced
     long long bufsize = 1600000;                    // patmatch.py:37 MAX_BUFFER_SIZE (-b, in bytes)
     int fused_filter = 1;                           // packed scan drops candidates whose verification surely fails
+    int qgram_filter = 1;                           // bit-sliced q-gram pre-filter in front of the Myers filter
+    int split_kernel = 1;                           // register-resident SPLIT scan (k_scan_split) when it applies
     // one spare text buffer and one spare plane buffer, so that re-creating a dataset of the same size
     // (a request that uploads its file every time) does not pay cudaMalloc/cudaFree of gigabytes
     void *pool_text = nullptr; size_t pool_text_cap = 0;
@@ -599,6 +601,8 @@ int pm_engine_set_fused_filter(pm_engine *e, int on)
 {
     if (!e) { g_err = "bad argument"; return PM_ERR_ARG; }
     e->fused_filter = on ? 1 : 0;
+    e->qgram_filter = on == 1 ? 1 : 0;
+    e->split_kernel = on == 3 ? 0 : 1;
     return PM_OK;
 }
 
@@ -864,10 +868,101 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
                         }
                     }
                     const int rows = std::min(std::max(dp.k, 1), 3) + 1;
-                    const int grid_bk = std::max((int)std::min<long long>((ntiles + 7) / 8, (long long)e->sms * 6), 1);
-#define PM_LAUNCH(W, R) k_scan_packed<4, W, R><<<grid_bk, 256, 0, e->stream>>>(a, pv)
+                    // ---- q-gram pre-filter: pick the disjoint chunks (see packed.cuh) ----
+                    QFilter qf;
+                    memset(&qf, 0, sizeof qf);
+                    bool plain_trig = true;
+                    for (int i = 0; i < dp.npieces; i++) if (a.trigsets[i] != (1u << i)) plain_trig = false;
+                    long long t0q = tile0, ntq = ntiles;
+                    // register-resident kernel in pattern-start coordinates (packed.cuh: k_scan_split)
+                    const bool bcoords = pv.enabled && e->split_kernel && plain_trig && dp.k >= 1 && dp.k <= 3 && dp.m + 2 * dp.k <= 64;
+                    if (bcoords && e->qgram_filter) {
+                        const int win = (dp.ins || dp.del) ? 2 * dp.k + 1 : 1;
+                        std::vector<unsigned> pcls((size_t)dp.m);
+                        std::vector<double> pprob((size_t)dp.m);
+                        for (int j = 0; j < dp.m; j++) {
+                            pcls[j] = packed_class(c.P.pos[j]);
+                            pprob[j] = pcls[j] == 31u ? 1.0 : std::max(__builtin_popcount(pcls[j] & 15u), 0) / 4.0 + 0.001;
+                        }
+                        double cand_rate = 0;                         // piece hits per base
+                        for (int i = 0; i < dp.npieces; i++) {
+                            double pr = 1;
+                            for (int j = 0; j < dp.L; j++) pr *= std::min(pprob[dp.V[i] + j], 1.0);
+                            cand_rate += pr;
+                        }
+                        const double myers_cost = 700.0;              // thread operations per queued candidate, divergence included
+                        double best_cost = cand_rate * myers_cost * 0.7;   // worth it only with a clear margin
+                        for (int q = 2; q <= QF_MAXLEN; q++)
+                            for (int a_off = 0; a_off < q; a_off++) {
+                                QFilter cur;
+                                memset(&cur, 0, sizeof cur);
+                                cur.win = win;
+                                std::vector<double> pg;
+                                double ops = 0;
+                                for (int j0 = a_off - q; j0 < dp.m && cur.nch < QF_MAXCH; j0 += q) {
+                                    const int jb = std::max(j0, 0), je = std::min(j0 + q, dp.m);
+                                    if (je <= jb) continue;
+                                    QChunk ch;
+                                    memset(&ch, 0, sizeof ch);
+                                    double pr = 1, chops = 0;
+                                    int first = -1;
+                                    for (int j = jb; j < je; j++) {
+                                        if (pcls[j] == 31u) continue;
+                                        if (first < 0) first = j;
+                                        ch.t[ch.npos] = (unsigned char)(j - first);
+                                        ch.pos[ch.npos].cls = (unsigned char)pcls[j];
+                                        ch.pos[ch.npos].sel = (unsigned char)plane_of(pcls[j]);
+                                        ch.npos++;
+                                        pr *= pprob[j];
+                                        chops += plane_of(pcls[j]) == 5 ? 66 : 12;
+                                    }
+                                    if (first < 0) continue;
+                                    pr = std::min(pr * win, 1.0);
+                                    if (pr > 0.6) continue;                   // hardly ever missing: not worth its operations
+                                    ops += chops;
+                                    ch.off = (unsigned char)(first + (win > 1 ? 0 : dp.k));
+                                    cur.ch[cur.nch++] = ch;
+                                    pg.push_back(pr);
+                                    int steps = 0;
+                                    for (int cw = 1; cw < win; cw += std::min(cw, win - cw)) steps++;
+                                    ops += steps * 12 + 8 + 8 * rows;
+                                }
+                                if (cur.nch <= dp.k) continue;            // k missing chunks are always allowed
+                                // P(at most k chunks missing), chunks taken as independent
+                                std::vector<double> dist((size_t)cur.nch + 1, 0.0);
+                                dist[0] = 1;
+                                for (int g = 0; g < cur.nch; g++)
+                                    for (int r = g + 1; r >= 0; r--)
+                                        dist[r] = dist[r] * pg[g] + (r > 0 ? dist[r - 1] * (1 - pg[g]) : 0.0);
+                                double pass = 0;
+                                for (int r = 0; r <= dp.k && r <= cur.nch; r++) pass += dist[r];
+                                const double cost = ops / 128.0 + cand_rate * pass * myers_cost;
+                                if (cost < best_cost) { best_cost = cost; qf = cur; }
+                            }
+                    }
+                    if (bcoords) {
+                        // pattern starts b = anchor - k - V[i] >= 0 must be covered for every anchor in [a0, wend)
+                        const long long b0 = std::max<long long>(a0 - dp.k - dp.V[dp.npieces - 1], 0);
+                        t0q = (b0 / 32) / 128;
+                        ntq = ((wend - 1) / 32) / 128 + 1 - t0q;
+                        a.tile0 = t0q; a.ntiles = ntq;
+                    }
+                    const int grid_bk = std::max((int)std::min<long long>((ntq + 7) / 8, (long long)e->sms * 6), 1);
+                    const int grid_sp = std::max((int)std::min<long long>((ntq + 7) / 8, (long long)e->sms * 4), 1);
+                    const size_t smem_sp = EX_STAGES * EX_STAGE_BYTES + 2 * EX_STAGES * 8;
+                    static bool sp_attr_set = false;
+                    if (!sp_attr_set) {                    // static queues + dynamic ring exceed the 48 KB default
+#define PM_ATTR(W, R) CK(cudaFuncSetAttribute(k_scan_split<4, W, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sp))
+                        PM_ATTR(unsigned, 2); PM_ATTR(unsigned, 3); PM_ATTR(unsigned, 4);
+                        PM_ATTR(unsigned long long, 2); PM_ATTR(unsigned long long, 3); PM_ATTR(unsigned long long, 4);
+#undef PM_ATTR
+                        sp_attr_set = true;
+                    }
+#define PM_LAUNCH(W, R) do { if (bcoords) k_scan_split<4, W, R><<<grid_sp, (EX_WARPS + 1) * 32, smem_sp, e->stream>>>(a, pv, qf); \
+                             else k_scan_packed<4, W, R, false><<<grid_bk, 256, 0, e->stream>>>(a, pv, qf); } while (0)
                     if (narrow) { if (rows == 2) PM_LAUNCH(unsigned, 2); else if (rows == 3) PM_LAUNCH(unsigned, 3); else PM_LAUNCH(unsigned, 4); }
                     else { if (rows == 2) PM_LAUNCH(unsigned long long, 2); else if (rows == 3) PM_LAUNCH(unsigned long long, 3); else PM_LAUNCH(unsigned long long, 4); }
+                    e->stats.qgram_chunks = qf.nch;
 #undef PM_LAUNCH
                 }
                 e->stats.launches++;

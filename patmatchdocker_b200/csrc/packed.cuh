@@ -451,12 +451,46 @@ __global__ void __launch_bounds__((EX_WARPS + 1) * 32) k_scan_packed_exact(const
     flush();
 }
 
+// ---------------------------------------------------------------------------------------
+// q-gram pre-filter (bit-sliced, 32 pattern starts per instruction).  Take disjoint chunks
+// g_1..g_T of the pattern.  An alignment of the whole pattern with at most k errors leaves at
+// least T-k chunks untouched, and an untouched chunk sits within +-k positions of where the
+// error-free alignment puts it (0 when only substitutions are allowed).  So
+//     #{ g : chunk g occurs in its window } >= T - k
+// is necessary for checkMatch1 @414190 to accept a candidate, whatever piece triggered it.
+// Everything is evaluated in "pattern start" coordinates b = anchor - V[i] - k, so that every
+// offset is non-negative and fits the 6 plane words a thread holds (needs m + 2k <= 64):
+//     chunk at pattern index j  ->  text bits b + j + [0, 2k]   (b + j + k without indels)
+//     piece i                   ->  text bits b + k + V[i] + [0, L)
+// Low-selectivity pieces (e.g. ANNNRY: one window in 16) make this worthwhile: the dense
+// filter costs a few operations per base and removes >90 % of the Myers evaluations.
+#define QF_MAXCH 12
+#define QF_MAXLEN 8
+struct QChunk {
+    unsigned char off;                  // first bit of the window, relative to b
+    unsigned char npos;                 // constrained positions of the chunk
+    unsigned char t[QF_MAXLEN];         // their offsets inside the chunk
+    PackedPos pos[QF_MAXLEN];
+};
+struct QFilter {
+    int nch;                            // 0 = filter off
+    int win;                            // window width: 2k+1 with indels, 1 without
+    QChunk ch[QF_MAXCH];
+};
+
+__device__ __forceinline__ void qf_apply6(unsigned (&G)[6], const unsigned (&P)[6], int t)
+{
+#pragma unroll
+    for (int w = 0; w < 5; w++) G[w] &= __funnelshift_r(P[w], P[w + 1], t);
+    G[5] &= P[5] >> t;
+}
+
 #define BK_WORDS 1024                   // block tile: 8 warp tiles of 128 words (32768 bases) per plane
 #define BK_ROW (BK_WORDS + 2 * PK_HALO)
 #define BK_QUEUE 2048                   // per-block, per-piece candidate queue (overflow goes to k_verify unfiltered)
 
-template <int NP, typename W, int ROWS>
-__global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, const PackedVerify<NP> v)
+template <int NP, typename W, int ROWS, bool QF>
+__global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, const PackedVerify<NP> v, const QFilter qf)
 {
     __shared__ unsigned sh[3 * BK_ROW];                 // hi | lo | x rows of the block tile, with halos
     __shared__ unsigned queue[NP][BK_QUEUE];            // one queue per piece: a round of candidates shares all parameters
@@ -468,6 +502,16 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
         sT[i][side][c] = (W)(c < 4 ? (side ? v.TR[i][c] : v.TL[i][c]) : (side ? v.TRX[i] : v.TLX[i]));
     }
     const long long nbt = (a.ntiles + 7) / 8;
+    if (QF && blockIdx.x == 0 && a.tile0 == 0) {
+        // anchors closer than k + V[i] to the start of the text have no pattern start b >= 0:
+        // they go to k_verify unfiltered (it re-checks the trigger on the raw bytes)
+        for (int i = 0; i < a.npieces; i++)
+            for (long long p = tid; p < v.k + v.V[i]; p += 256) {
+                if (p < a.a0 || p >= a.a1 || p + a.L > a.n) continue;
+                const unsigned long long idx = atomicAdd(a.count, 1ULL);
+                if ((long long)idx < a.cap) a.keys[idx] = ((unsigned long long)p << 4) | (unsigned)i;
+            }
+    }
     for (long long bt = blockIdx.x; bt < nbt; bt += gridDim.x) {
         const long long qb = a.tile0 * 128 + bt * BK_WORDS;             // first word of the block tile
         const long long q0 = qb + 4 * tid;                              // first of this thread's 4 words
@@ -503,31 +547,73 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
             PG[w] = h & l;
             PT[w] = h & ~l;
         }
-        // ---- pieces ----
+        // class plane of one pattern position, handed to f as a 6-word array
+        auto with_plane = [&](const PackedPos pp, auto f) {
+            switch (pp.sel) {
+            case 0: f(PA); break;
+            case 1: f(PC); break;
+            case 2: f(PG); break;
+            case 3: f(PT); break;
+            case 4: f(PX); break;
+            default: {
+                const unsigned sA = (pp.cls & 1) ? ~0u : 0u, sC = (pp.cls & 2) ? ~0u : 0u, sG = (pp.cls & 4) ? ~0u : 0u,
+                               sT = (pp.cls & 8) ? ~0u : 0u, sX = (pp.cls & 16) ? ~0u : 0u;
+                unsigned E[6];
+#pragma unroll
+                for (int w = 0; w < 6; w++)
+                    E[w] = (PA[w] & sA) | (PC[w] & sC) | (PG[w] & sG) | (PT[w] & sT) | (PX[w] & sX);
+                f(E);
+            }
+            }
+        };
+        // ---- q-gram pre-filter: pass[w] bit b <=> at most k chunks are missing for pattern start b ----
+        unsigned pass[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        if (QF) {
+            unsigned miss[ROWS][4];                      // miss[r] : more than r chunks missing
+#pragma unroll
+            for (int r = 0; r < ROWS; r++)
+#pragma unroll
+                for (int w = 0; w < 4; w++) miss[r][w] = 0;
+            for (int g = 0; g < qf.nch; g++) {
+                const QChunk &ch = qf.ch[g];
+                unsigned G[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+                for (int c = 0; c < ch.npos; c++) {
+                    const int t = ch.t[c];
+                    with_plane(ch.pos[c], [&](const unsigned (&P)[6]) { qf_apply6(G, P, t); });
+                }
+                // dilate: G[x] |= G[x+1] | ... | G[x+win-1]   (doubling)
+                int cw = 1;
+                while (cw < qf.win) {
+                    const int s = min(cw, qf.win - cw);
+#pragma unroll
+                    for (int w = 0; w < 5; w++) G[w] |= __funnelshift_r(G[w], G[w + 1], s);
+                    G[5] |= G[5] >> s;
+                    cw += s;
+                }
+                unsigned x[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+                packed_apply<true>(x, G, ch.off);
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    const unsigned ms = ~x[w];
+#pragma unroll
+                    for (int r = ROWS - 1; r > 0; r--) miss[r][w] |= miss[r - 1][w] & ms;
+                    miss[0][w] |= ms;
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < 4; w++) pass[w] = ~miss[ROWS - 1][w];
+        }
+        // ---- pieces (QF: in pattern-start coordinates, piece i shifted by k + V[i]) ----
         unsigned M[NP][4];
 #pragma unroll
         for (int i = 0; i < NP; i++) {
 #pragma unroll
-            for (int w = 0; w < 4; w++) M[i][w] = 0xffffffffu;
+            for (int w = 0; w < 4; w++) M[i][w] = pass[w];
             if (i < a.npieces) {
+                const int base = QF ? v.k + v.V[i] : 0;
                 for (int j = 0; j < a.L; j++) {
-                    const PackedPos pp = a.pos[i][j];
-                    switch (pp.sel) {
-                    case 0: packed_apply(M[i], PA, j); break;
-                    case 1: packed_apply(M[i], PC, j); break;
-                    case 2: packed_apply(M[i], PG, j); break;
-                    case 3: packed_apply(M[i], PT, j); break;
-                    case 4: packed_apply(M[i], PX, j); break;
-                    default: {
-                        const unsigned sA = (pp.cls & 1) ? ~0u : 0u, sC = (pp.cls & 2) ? ~0u : 0u, sG = (pp.cls & 4) ? ~0u : 0u,
-                                       sT = (pp.cls & 8) ? ~0u : 0u, sX = (pp.cls & 16) ? ~0u : 0u;
-                        unsigned E[6];
-#pragma unroll
-                        for (int w = 0; w < 6; w++)
-                            E[w] = (PA[w] & sA) | (PC[w] & sC) | (PG[w] & sG) | (PT[w] & sT) | (PX[w] & sX);
-                        packed_apply(M[i], E, j);
-                    }
-                    }
+                    const int sh_ = base + j;
+                    with_plane(a.pos[i][j], [&](const unsigned (&P)[6]) { packed_apply<true>(M[i], P, sh_); });
                 }
             } else {
 #pragma unroll
@@ -555,7 +641,7 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
                 while (c) {
                     const int b = __ffs(c) - 1;
                     c &= c - 1;
-                    const unsigned rel = (unsigned)((4 * tid + w) * 32 + b);       // window start inside the block tile
+                    const unsigned rel = (unsigned)((4 * tid + w) * 32 + b) + (QF ? (unsigned)(v.k + v.V[i]) : 0u);   // window start inside the block tile
                     const long long p = qb * 32 + rel;
                     if (p < a.a0 || p >= a.a1 || p + a.L > a.n) continue;
                     const unsigned slot = fused ? atomicAdd(&qcount[i], 1u) : BK_QUEUE;
@@ -653,6 +739,346 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// SPLIT scan, register-resident (m + 2k <= 64).  Same TMA ring and warp tiles as the exact
+// scan: a lane holds 8+2 words of the three planes, evaluates the q-gram pre-filter and the
+// k+1 pieces on them in pattern-start coordinates, and queues the surviving anchors per warp
+// and per piece.  Whenever a queue holds 32 anchors the warp runs one lock-step round of the
+// Myers filter on them (all lanes busy, one piece per round so every lane has the same part
+// lengths and tables), reading the few plane words it needs from global memory (L2 hits: the
+// tile has just been streamed).  There is no block-wide synchronisation inside the tile loop.
+#define SP_QUEUE 128                     // per-warp anchor queue (ring): key + 64 symbols of each plane
+
+template <int LUT>
+__device__ __forceinline__ unsigned lop3_const(unsigned a, unsigned b, unsigned c)
+{
+    unsigned r;
+    asm volatile("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT));   // volatile: keeps the 32 cases from being speculated
+    return r;
+}
+// truth table over (hi, lo, x) of a class given as bits A,C,G,T,X ; A=000 C=010 G=110 T=100 X=xx1
+template <int CLS>
+struct SpLut {
+    static const int value = ((CLS & 1) ? 0x01 : 0) | ((CLS & 2) ? 0x04 : 0) | ((CLS & 4) ? 0x40 : 0) | ((CLS & 8) ? 0x10 : 0) | ((CLS & 16) ? 0xAA : 0);
+};
+template <int CLS>
+__device__ __forceinline__ void sp_plane(unsigned (&P)[EX_WPL + 2], const unsigned (&H)[EX_WPL + 2], const unsigned (&L)[EX_WPL + 2],
+                                         const unsigned (&X)[EX_WPL + 2])
+{
+#pragma unroll
+    for (int w = 0; w < EX_WPL + 2; w++) P[w] = lop3_const<SpLut<CLS>::value>(H[w], L[w], X[w]);
+}
+__device__ __forceinline__ void sp_plane_dyn(int cls, unsigned (&P)[EX_WPL + 2], const unsigned (&H)[EX_WPL + 2],
+                                             const unsigned (&L)[EX_WPL + 2], const unsigned (&X)[EX_WPL + 2])
+{
+    switch (cls & 31) {
+#define SP_CASE(c) case c: sp_plane<c>(P, H, L, X); break;
+        SP_CASE(0) SP_CASE(1) SP_CASE(2) SP_CASE(3) SP_CASE(4) SP_CASE(5) SP_CASE(6) SP_CASE(7)
+        SP_CASE(8) SP_CASE(9) SP_CASE(10) SP_CASE(11) SP_CASE(12) SP_CASE(13) SP_CASE(14) SP_CASE(15)
+        SP_CASE(16) SP_CASE(17) SP_CASE(18) SP_CASE(19) SP_CASE(20) SP_CASE(21) SP_CASE(22) SP_CASE(23)
+        SP_CASE(24) SP_CASE(25) SP_CASE(26) SP_CASE(27) SP_CASE(28) SP_CASE(29) SP_CASE(30) SP_CASE(31)
+#undef SP_CASE
+    }
+}
+
+// One lock-step round of the Myers filter on up to 32 queued anchors (one per lane).  A queue entry
+// carries the key (anchor << 4 | piece) and the 64 symbols starting at the anchor's pattern start b,
+// so the round touches no global memory but the keys it emits.  Both sides run interleaved in one
+// loop (two independent dependency chains): the left part P[0..V) against the symbols read leftwards
+// from the anchor, the right part P[V..m) against the symbols read rightwards; each yields the minimum
+// edit distance over all prefixes read, and  min_left + min_right <= k  is necessary for checkMatch1.
+struct SpParams {                        // per piece, in shared memory
+    int base, lb, rl;                    // base = k + V[i] = index of the anchor inside the entry's window
+};
+
+template <typename W>
+__device__ __noinline__ void sp_round(const unsigned long long *__restrict__ qkey, const unsigned long long *__restrict__ qh,
+                                      const unsigned long long *__restrict__ ql, const unsigned long long *__restrict__ qx,
+                                      unsigned head, unsigned cnt, const W *__restrict__ tabs, const SpParams *__restrict__ par, int k,
+                                      unsigned long long *__restrict__ keys, unsigned long long *__restrict__ count, long long cap)
+{
+    const int lane = threadIdx.x & 31;
+    bool keep = false;
+    unsigned long long key = 0;
+    if ((unsigned)lane < cnt) {
+        const unsigned e = (head + lane) & (SP_QUEUE - 1);
+        key = qkey[e];
+        const int i = (int)(key & 15);
+        const SpParams pp = par[i];
+        const unsigned long long h = qh[e], l = ql[e], x = qx[e];
+        const int nL = pp.lb > 0 ? pp.base : 0, nR = pp.rl + k;
+        // left stream: bit t = window bit base-1-t ; right stream: bit t = window bit base+t
+        const int shl = 64 - pp.base;                         // 1 <= base <= 63
+        unsigned long long hL = __brevll(h) >> shl, lL = __brevll(l) >> shl, xL = __brevll(x) >> shl;
+        unsigned long long hR = h >> pp.base, lR = l >> pp.base, xR = x >> pp.base;
+        unsigned h0 = (unsigned)hL, l0 = (unsigned)lL, x0 = (unsigned)xL, h1 = (unsigned)hR, l1 = (unsigned)lR, x1 = (unsigned)xR;
+        const W *tl = tabs + i * 16, *tr = tl + 8;
+        const W topL = pp.lb > 0 ? (W)((W)1 << (pp.lb - 1)) : (W)0, topR = (W)((W)1 << (pp.rl - 1));
+        W PvL = (W)~(W)0, MvL = 0, PvR = (W)~(W)0, MvR = 0;
+        int scL = pp.lb, bestL = pp.lb, scR = pp.rl, bestR = pp.rl;
+        const int nit = max(nL, nR);
+#pragma unroll 1
+        for (int t = 0; t < nit; t++) {
+            if (t == 32) {
+                h0 = (unsigned)(hL >> 32); l0 = (unsigned)(lL >> 32); x0 = (unsigned)(xL >> 32);
+                h1 = (unsigned)(hR >> 32); l1 = (unsigned)(lR >> 32); x1 = (unsigned)(xR >> 32);
+            }
+            const W EqL = tl[((x0 & 1u) << 2) | ((h0 & 1u) << 1) | (l0 & 1u)];
+            const W EqR = tr[((x1 & 1u) << 2) | ((h1 & 1u) << 1) | (l1 & 1u)];
+            h0 >>= 1; l0 >>= 1; x0 >>= 1; h1 >>= 1; l1 >>= 1; x1 >>= 1;
+            {
+                const W Xv = EqL | MvL;
+                const W Xh = (W)((((EqL & PvL) + PvL) ^ PvL) | EqL);
+                W Ph = (W)(MvL | ~(Xh | PvL));
+                W Mh = (W)(PvL & Xh);
+                scL += (Ph & topL) ? 1 : 0;
+                scL -= (Mh & topL) ? 1 : 0;
+                Ph = (W)((Ph << 1) | 1);
+                Mh = (W)(Mh << 1);
+                PvL = (W)(Mh | ~(Xv | Ph));
+                MvL = (W)(Ph & Xv);
+                if (t < nL) bestL = min(bestL, scL);
+            }
+            {
+                const W Xv = EqR | MvR;
+                const W Xh = (W)((((EqR & PvR) + PvR) ^ PvR) | EqR);
+                W Ph = (W)(MvR | ~(Xh | PvR));
+                W Mh = (W)(PvR & Xh);
+                scR += (Ph & topR) ? 1 : 0;
+                scR -= (Mh & topR) ? 1 : 0;
+                Ph = (W)((Ph << 1) | 1);
+                Mh = (W)(Mh << 1);
+                PvR = (W)(Mh | ~(Xv | Ph));
+                MvR = (W)(Ph & Xv);
+                if (t < nR) bestR = min(bestR, scR);
+            }
+        }
+        keep = bestL + bestR <= k;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (bal) {
+        unsigned long long basei = 0;
+        if (lane == 0) basei = atomicAdd(count, (unsigned long long)__popc(bal));
+        basei = __shfl_sync(0xffffffffu, basei, 0) + __popc(bal & ((1u << lane) - 1u));
+        if (keep && (long long)basei < cap) keys[basei] = key;
+    }
+    __syncwarp();
+}
+
+template <int NP, typename W, int ROWS>
+__global__ void __launch_bounds__((EX_WARPS + 1) * 32, 4) k_scan_split(const PackedArgs<NP> a, const PackedVerify<NP> v, const QFilter qf)
+{
+    extern __shared__ __align__(128) unsigned char ex_smem[];
+    __shared__ unsigned long long q_key[EX_WARPS][SP_QUEUE], q_h[EX_WARPS][SP_QUEUE], q_l[EX_WARPS][SP_QUEUE], q_x[EX_WARPS][SP_QUEUE];
+    __shared__ W sT[NP * 16];                           // match masks by symbol (A,C,T,G,X): [piece][left | right][8]
+    __shared__ SpParams spar[NP];
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    if (tid < NP * 2 * 5) {
+        const int i = tid / 10, side = (tid / 5) & 1, c = tid % 5;
+        sT[i * 16 + side * 8 + c] = (W)(c < 4 ? (side ? v.TR[i][c] : v.TL[i][c]) : (side ? v.TRX[i] : v.TLX[i]));
+    }
+    if (tid < NP) { spar[tid].base = v.k + v.V[tid]; spar[tid].lb = v.V[tid]; spar[tid].rl = v.m - v.V[tid]; }
+    unsigned *stage_base = reinterpret_cast<unsigned *>(ex_smem);
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(ex_smem + EX_STAGES * EX_STAGE_BYTES);
+    unsigned long long *empty = full + EX_STAGES;
+    const long long nbt = (a.ntiles + 7) / 8;
+    const long long my = blockIdx.x < nbt ? (nbt - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (tid == 0) {
+        for (int s = 0; s < EX_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], EX_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (wib == EX_WARPS) {
+        // producer warp: one lane keeps the ring full, independent of the consumers' progress
+        if (lane == 0)
+            for (long long it = 0; it < my; it++) {
+                const int s = (int)(it % EX_STAGES);
+                if (it >= EX_STAGES) mbar_wait(&empty[s], (unsigned)(((it / EX_STAGES) - 1) & 1));
+                const long long q = (a.tile0 * 128) + (blockIdx.x + it * gridDim.x) * EX_WORDS;
+                unsigned *dst = stage_base + (size_t)s * (3 * EX_ROW);
+                mbar_expect_tx(&full[s], EX_STAGE_BYTES);
+                tma_load_1d(dst, a.hi + q, EX_ROW * 4, &full[s]);
+                tma_load_1d(dst + EX_ROW, a.lo + q, EX_ROW * 4, &full[s]);
+                tma_load_1d(dst + 2 * EX_ROW, a.xx + q, EX_ROW * 4, &full[s]);
+            }
+        else if (lane == 1 && blockIdx.x == 0 && a.tile0 == 0) {
+            // anchors closer than k + V[i] to the start of the text have no pattern start b >= 0:
+            // they go to k_verify unfiltered (it re-checks the trigger on the raw bytes)
+            for (int i = 0; i < a.npieces; i++)
+                for (long long p = 0; p < v.k + v.V[i]; p++) {
+                    if (p < a.a0 || p >= a.a1 || p + a.L > a.n) continue;
+                    const unsigned long long idx = atomicAdd(a.count, 1ULL);
+                    if ((long long)idx < a.cap) a.keys[idx] = ((unsigned long long)p << 4) | (unsigned)i;
+                }
+        }
+        return;
+    }
+    unsigned long long *qk = q_key[wib], *qh = q_h[wib], *ql = q_l[wib], *qx = q_x[wib];
+    unsigned qhead = 0, qcnt = 0;                       // warp-uniform ring state
+    for (long long it = 0; it < my; it++) {
+        const int s = (int)(it % EX_STAGES);
+        const unsigned ph = (unsigned)((it / EX_STAGES) & 1);
+        mbar_wait(&full[s], ph);
+        const unsigned *sp = stage_base + (size_t)s * (3 * EX_ROW) + wib * (32 * EX_WPL) + EX_WPL * lane;
+        unsigned H[EX_WPL + 2], Lw[EX_WPL + 2], X[EX_WPL + 2];
+#pragma unroll
+        for (int v4 = 0; v4 < EX_WPL / 4; v4++) {
+            const uint4 h4 = *reinterpret_cast<const uint4 *>(sp + 4 * v4), l4 = *reinterpret_cast<const uint4 *>(sp + EX_ROW + 4 * v4),
+                        x4 = *reinterpret_cast<const uint4 *>(sp + 2 * EX_ROW + 4 * v4);
+            H[4 * v4] = h4.x; H[4 * v4 + 1] = h4.y; H[4 * v4 + 2] = h4.z; H[4 * v4 + 3] = h4.w;
+            Lw[4 * v4] = l4.x; Lw[4 * v4 + 1] = l4.y; Lw[4 * v4 + 2] = l4.z; Lw[4 * v4 + 3] = l4.w;
+            X[4 * v4] = x4.x; X[4 * v4 + 1] = x4.y; X[4 * v4 + 2] = x4.z; X[4 * v4 + 3] = x4.w;
+        }
+        {
+            const uint2 h2 = *reinterpret_cast<const uint2 *>(sp + EX_WPL), l2 = *reinterpret_cast<const uint2 *>(sp + EX_ROW + EX_WPL),
+                        x2 = *reinterpret_cast<const uint2 *>(sp + 2 * EX_ROW + EX_WPL);
+            H[EX_WPL] = h2.x; H[EX_WPL + 1] = h2.y; Lw[EX_WPL] = l2.x; Lw[EX_WPL + 1] = l2.y; X[EX_WPL] = x2.x; X[EX_WPL + 1] = x2.y;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);            // this warp's slice is in registers
+        const long long bt = blockIdx.x + it * gridDim.x;
+        unsigned P[EX_WPL + 2];
+        // ---- q-gram pre-filter: pass[w] bit b <=> at most k chunks are missing for pattern start b ----
+        unsigned pass[EX_WPL];
+#pragma unroll
+        for (int w = 0; w < EX_WPL; w++) pass[w] = 0xffffffffu;
+        if (qf.nch > 0) {
+            unsigned miss[ROWS][EX_WPL];                  // miss[r] : more than r chunks missing
+#pragma unroll
+            for (int r = 0; r < ROWS; r++)
+#pragma unroll
+                for (int w = 0; w < EX_WPL; w++) miss[r][w] = 0;
+            for (int g = 0; g < qf.nch; g++) {
+                unsigned G[EX_WPL + 2];
+#pragma unroll
+                for (int w = 0; w < EX_WPL + 2; w++) G[w] = 0xffffffffu;
+                const int npos = qf.ch[g].npos;
+                for (int c = 0; c < npos; c++) {
+                    const int t = qf.ch[g].t[c];
+                    sp_plane_dyn(qf.ch[g].pos[c].cls, P, H, Lw, X);
+#pragma unroll
+                    for (int w = 0; w < EX_WPL + 1; w++) G[w] &= __funnelshift_r(P[w], P[w + 1], t);
+                    G[EX_WPL + 1] &= P[EX_WPL + 1] >> t;
+                }
+                // dilate: G[x] |= G[x+1] | ... | G[x+win-1]   (doubling)
+                int cw = 1;
+                while (cw < qf.win) {
+                    const int sft = min(cw, qf.win - cw);
+#pragma unroll
+                    for (int w = 0; w < EX_WPL + 1; w++) G[w] |= __funnelshift_r(G[w], G[w + 1], sft);
+                    G[EX_WPL + 1] |= G[EX_WPL + 1] >> sft;
+                    cw += sft;
+                }
+                unsigned x[EX_WPL];
+#pragma unroll
+                for (int w = 0; w < EX_WPL; w++) x[w] = 0xffffffffu;
+                exact_apply<true>(x, G, qf.ch[g].off);
+#pragma unroll
+                for (int w = 0; w < EX_WPL; w++) {
+                    const unsigned ms = ~x[w];
+#pragma unroll
+                    for (int r = ROWS - 1; r > 0; r--) miss[r][w] |= miss[r - 1][w] & ms;
+                    miss[0][w] |= ms;
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < EX_WPL; w++) pass[w] = ~miss[ROWS - 1][w];
+        }
+        const long long wbase = ((a.tile0 * 128) + bt * EX_WORDS + wib * (32 * EX_WPL)) * 32;   // first pattern start of the warp tile
+        const unsigned lrel = (unsigned)(EX_WPL * lane) * 32;
+        // ---- pieces, in pattern-start coordinates: piece i sits k + V[i] bits further ----
+#pragma unroll 1
+        for (int i = 0; i < a.npieces; i++) {
+            unsigned M[EX_WPL];
+#pragma unroll
+            for (int w = 0; w < EX_WPL; w++) M[w] = pass[w];
+            const int base = v.k + v.V[i];
+            for (int j = 0; j < a.L; j++) {
+                const int cls = a.pos[i][j].cls;
+                if (cls == 31) continue;                   // accepts every byte
+                sp_plane_dyn(cls, P, H, Lw, X);
+                exact_apply<true>(M, P, base + j);
+            }
+            const long long p0 = wbase + base + lrel;      // anchor of bit 0 of this lane's first word
+            if (!(wbase + base >= a.a0 && wbase + base + 32 * 32 * EX_WPL <= a.a1 && wbase + base + 32 * 32 * EX_WPL + a.L <= a.n)) {
+                // first / last tiles of the scanned range: drop the anchors outside [a0, a1) or too close to the end
+#pragma unroll
+                for (int w = 0; w < EX_WPL; w++) {
+                    unsigned c = M[w];
+                    while (c) {
+                        const int b = __ffs(c) - 1;
+                        c &= c - 1;
+                        const long long p = p0 + w * 32 + b;
+                        if (!(p >= a.a0 && p < a.a1 && p + a.L <= a.n)) M[w] &= ~(1u << b);
+                    }
+                }
+            }
+            unsigned mine = 0;
+#pragma unroll
+            for (int w = 0; w < EX_WPL; w++) mine += __popc(M[w]);
+            if (!__any_sync(0xffffffffu, mine != 0)) continue;
+            unsigned incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+            if (qcnt + total <= SP_QUEUE) {
+                // sparse: every lane appends its anchors at its own offset, then full rounds are drained
+                unsigned slot = qhead + qcnt + (incl - mine);
+#pragma unroll
+                for (int w = 0; w < EX_WPL; w++) {
+                    unsigned c = M[w];
+                    while (c) {
+                        const int b = __ffs(c) - 1;
+                        c &= c - 1;
+                        const unsigned e = slot++ & (SP_QUEUE - 1);
+                        qk[e] = ((unsigned long long)(p0 + w * 32 + b) << 4) | (unsigned)i;
+                        qh[e] = ((unsigned long long)__funnelshift_r(H[w + 1], H[w + 2], b) << 32) | __funnelshift_r(H[w], H[w + 1], b);
+                        ql[e] = ((unsigned long long)__funnelshift_r(Lw[w + 1], Lw[w + 2], b) << 32) | __funnelshift_r(Lw[w], Lw[w + 1], b);
+                        qx[e] = ((unsigned long long)__funnelshift_r(X[w + 1], X[w + 2], b) << 32) | __funnelshift_r(X[w], X[w + 1], b);
+                    }
+                }
+                qcnt += total;
+                __syncwarp();
+                while (qcnt >= 32) {
+                    sp_round<W>(qk, qh, ql, qx, qhead, 32, sT, spar, v.k, a.keys, a.count, a.cap);
+                    qhead = (qhead + 32) & (SP_QUEUE - 1);
+                    qcnt -= 32;
+                }
+            } else {
+                // dense: one anchor per lane and step, a round as soon as 32 are queued
+#pragma unroll
+                for (int w = 0; w < EX_WPL; w++) {
+                    unsigned c = M[w];
+                    while (__any_sync(0xffffffffu, c != 0)) {
+                        const bool have = c != 0;
+                        const unsigned bal = __ballot_sync(0xffffffffu, have);
+                        if (have) {
+                            const int b = __ffs(c) - 1;
+                            c &= c - 1;
+                            const unsigned e = (qhead + qcnt + __popc(bal & ((1u << lane) - 1u))) & (SP_QUEUE - 1);
+                            qk[e] = ((unsigned long long)(p0 + w * 32 + b) << 4) | (unsigned)i;
+                            qh[e] = ((unsigned long long)__funnelshift_r(H[w + 1], H[w + 2], b) << 32) | __funnelshift_r(H[w], H[w + 1], b);
+                            ql[e] = ((unsigned long long)__funnelshift_r(Lw[w + 1], Lw[w + 2], b) << 32) | __funnelshift_r(Lw[w], Lw[w + 1], b);
+                            qx[e] = ((unsigned long long)__funnelshift_r(X[w + 1], X[w + 2], b) << 32) | __funnelshift_r(X[w], X[w + 1], b);
+                        }
+                        qcnt += __popc(bal);
+                        __syncwarp();
+                        if (qcnt >= 32) {
+                            sp_round<W>(qk, qh, ql, qx, qhead, 32, sT, spar, v.k, a.keys, a.count, a.cap);
+                            qhead = (qhead + 32) & (SP_QUEUE - 1);
+                            qcnt -= 32;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (qcnt) sp_round<W>(qk, qh, ql, qx, qhead, qcnt, sT, spar, v.k, a.keys, a.count, a.cap);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -161,6 +161,45 @@ def test_scan_kernel_selection_and_equivalence(engine):
     ds.close()
 
 
+def test_qgram_prefilter_keeps_every_hit(engine):
+    # low-selectivity pieces (many wildcards / wide classes) switch the bit-sliced q-gram pre-filter on; it
+    # may only drop candidates whose verification fails: hit lists equal the oracle's and the unfiltered scan's
+    rng = random.Random(77)
+    engine.set_scan_mode("packed")
+    used = 0
+    try:
+        for it in range(160):
+            k = rng.randint(1, 3)
+            m = rng.randint(max(2 * k + 2, 6), 40)
+            pat, members = random_pattern(rng, DNA, m, cls_pct=0.3, dot_pct=0.3)
+            kopt = "%d%s" % (k, rng.choice(["ids", "ids", "s", "id", "is", "ds", "i", "d"]))
+            try:
+                plan = pm.plan(pat, kopt)
+            except pm.NativeError:
+                continue
+            if plan["type"] != "SPLIT":
+                continue
+            text = random_text(rng, members, DNA, k, nrec=rng.randint(1, 3), lo=200, hi=30000 if it % 8 == 0 else 3000, plant=0.1)
+            if it % 3 == 0:                                   # a (possibly truncated) occurrence at the very start of the file
+                s0 = "".join(rng.choice(c) for c in members)
+                text = s0[rng.randint(0, k):] + text[text.index("\n") + 1:]
+            raw = text.encode("latin-1")
+            ds = engine.load_dataset(raw)
+            engine.set_fused_filter(1)
+            a = engine.search(ds, pat, kopt)
+            st = engine.stats()
+            used += 1 if st["qgram_chunks"] > 0 else 0
+            engine.set_fused_filter(0)
+            b = engine.search(ds, pat, kopt)
+            ds.close()
+            assert np.array_equal(a, b), (pat, kopt)
+            assert [(int(x), int(y)) for x, y in a] == O.search(pat, raw, kopt), (pat, kopt)
+        assert used >= 20, used
+    finally:
+        engine.set_fused_filter(1)
+        engine.set_scan_mode("auto")
+
+
 def test_hit_list_stays_on_device_after_overflow(engine):
     import ctypes
     from patmatchdocker_b200 import _native
