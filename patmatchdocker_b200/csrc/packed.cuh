@@ -749,7 +749,7 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
 // Myers filter on them (all lanes busy, one piece per round so every lane has the same part
 // lengths and tables), reading the few plane words it needs from global memory (L2 hits: the
 // tile has just been streamed).  There is no block-wide synchronisation inside the tile loop.
-#define SP_QUEUE 128                     // per-warp anchor queue (ring): key + 64 symbols of each plane
+#define SP_QUEUE 128                     // per-warp anchor queue (ring of keys)
 
 template <int LUT>
 __device__ __forceinline__ unsigned lop3_const(unsigned a, unsigned b, unsigned c)
@@ -783,95 +783,134 @@ __device__ __forceinline__ void sp_plane_dyn(int cls, unsigned (&P)[EX_WPL + 2],
     }
 }
 
-// One lock-step round of the Myers filter on up to 32 queued anchors (one per lane).  A queue entry
-// carries the key (anchor << 4 | piece) and the 64 symbols starting at the anchor's pattern start b,
-// so the round touches no global memory but the keys it emits.  Both sides run interleaved in one
-// loop (two independent dependency chains): the left part P[0..V) against the symbols read leftwards
-// from the anchor, the right part P[V..m) against the symbols read rightwards; each yields the minimum
-// edit distance over all prefixes read, and  min_left + min_right <= k  is necessary for checkMatch1.
+// One lock-step round of the Myers filter on up to 64 queued anchors, two per lane.  A queue entry is
+// the key (anchor << 4 | piece); the 64 symbols starting at the anchor's pattern start b are fetched
+// from the planes in global memory (L2 hits: the tile has just been streamed), all loads issued before
+// the loop.  Per anchor both sides run interleaved (the left part P[0..V) against the symbols read
+// leftwards from the anchor, the right part P[V..m) against the symbols read rightwards), so a lane
+// carries four independent dependency chains.  Each side yields the minimum edit distance over all
+// prefixes read, and  min_left + min_right <= k  is necessary for checkMatch1 @414190 to succeed.
 struct SpParams {                        // per piece, in shared memory
-    int base, lb, rl;                    // base = k + V[i] = index of the anchor inside the entry's window
+    int base, lb, rl;                    // base = k + V[i] = index of the anchor inside the fetched window
 };
 
+__device__ __forceinline__ unsigned long long sp_window(const unsigned *__restrict__ plane, long long bit)
+{
+    const long long wi = bit >> 5;
+    const int bi = (int)(bit & 31);
+    const unsigned w0 = __ldg(plane + wi), w1 = __ldg(plane + wi + 1), w2 = __ldg(plane + wi + 2);
+    return ((unsigned long long)__funnelshift_r(w1, w2, bi) << 32) | __funnelshift_r(w0, w1, bi);
+}
+
 template <typename W>
-__device__ __noinline__ void sp_round(const unsigned long long *__restrict__ qkey, const unsigned long long *__restrict__ qh,
-                                      const unsigned long long *__restrict__ ql, const unsigned long long *__restrict__ qx,
-                                      unsigned head, unsigned cnt, const W *__restrict__ tabs, const SpParams *__restrict__ par, int k,
+__device__ __noinline__ void sp_round(const unsigned long long *__restrict__ qkey, unsigned head, unsigned cnt,
+                                      const unsigned *__restrict__ hi, const unsigned *__restrict__ lo, const unsigned *__restrict__ xx,
+                                      const W *__restrict__ tabs, const SpParams *__restrict__ par, int k,
                                       unsigned long long *__restrict__ keys, unsigned long long *__restrict__ count, long long cap)
 {
     const int lane = threadIdx.x & 31;
-    bool keep = false;
-    unsigned long long key = 0;
-    if ((unsigned)lane < cnt) {
-        const unsigned e = (head + lane) & (SP_QUEUE - 1);
-        key = qkey[e];
-        const int i = (int)(key & 15);
+    unsigned long long key[2];
+    bool act[2], keep[2];
+    unsigned sL[2][3], sR[2][3];                         // next 32 symbols of the (hi, lo, x) streams, left / right
+    long long b_[2];                                     // pattern start (symbols beyond 32 are fetched again)
+    int base_[2];
+    const W *tl[2];
+    W topL[2], topR[2], PvL[2], MvL[2], PvR[2], MvR[2];
+    int nL[2], nR[2], scL[2], scR[2], bestL[2], bestR[2];
+    int nit = 0;
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        act[c] = (unsigned)(lane + 32 * c) < cnt;
+        key[c] = qkey[(head + lane + 32 * c) & (SP_QUEUE - 1)];
+        const int i = act[c] ? (int)(key[c] & 15) : 0;
         const SpParams pp = par[i];
-        const unsigned long long h = qh[e], l = ql[e], x = qx[e];
-        const int nL = pp.lb > 0 ? pp.base : 0, nR = pp.rl + k;
-        // left stream: bit t = window bit base-1-t ; right stream: bit t = window bit base+t
-        const int shl = 64 - pp.base;                         // 1 <= base <= 63
-        unsigned long long hL = __brevll(h) >> shl, lL = __brevll(l) >> shl, xL = __brevll(x) >> shl;
-        unsigned long long hR = h >> pp.base, lR = l >> pp.base, xR = x >> pp.base;
-        unsigned h0 = (unsigned)hL, l0 = (unsigned)lL, x0 = (unsigned)xL, h1 = (unsigned)hR, l1 = (unsigned)lR, x1 = (unsigned)xR;
-        const W *tl = tabs + i * 16, *tr = tl + 8;
-        const W topL = pp.lb > 0 ? (W)((W)1 << (pp.lb - 1)) : (W)0, topR = (W)((W)1 << (pp.rl - 1));
-        W PvL = (W)~(W)0, MvL = 0, PvR = (W)~(W)0, MvR = 0;
-        int scL = pp.lb, bestL = pp.lb, scR = pp.rl, bestR = pp.rl;
-        const int nit = max(nL, nR);
+        const long long b = act[c] ? (long long)(key[c] >> 4) - pp.base : 0;
+        const unsigned long long h = sp_window(hi, b), l = sp_window(lo, b), x = sp_window(xx, b);
+        // left stream: bit t = window bit base-1-t ; right stream: bit t = window bit base+t   (1 <= base <= 63)
+        const int shl = 64 - pp.base;
+        const unsigned long long hL = __brevll(h) >> shl, lL = __brevll(l) >> shl, xL = __brevll(x) >> shl;
+        const unsigned long long hR = h >> pp.base, lR = l >> pp.base, xR = x >> pp.base;
+        sL[c][0] = (unsigned)hL; sL[c][1] = (unsigned)lL; sL[c][2] = (unsigned)xL;
+        sR[c][0] = (unsigned)hR; sR[c][1] = (unsigned)lR; sR[c][2] = (unsigned)xR;
+        b_[c] = b;
+        base_[c] = pp.base;
+        tl[c] = tabs + i * 16;
+        nL[c] = pp.lb > 0 ? pp.base : 0;
+        nR[c] = pp.rl + k;
+        topL[c] = pp.lb > 0 ? (W)((W)1 << (pp.lb - 1)) : (W)0;
+        topR[c] = (W)((W)1 << (pp.rl - 1));
+        PvL[c] = (W)~(W)0; MvL[c] = 0; PvR[c] = (W)~(W)0; MvR[c] = 0;
+        scL[c] = bestL[c] = pp.lb;
+        scR[c] = bestR[c] = pp.rl;
+        if (act[c]) nit = max(nit, max(nL[c], nR[c]));
+    }
 #pragma unroll 1
-        for (int t = 0; t < nit; t++) {
-            if (t == 32) {
-                h0 = (unsigned)(hL >> 32); l0 = (unsigned)(lL >> 32); x0 = (unsigned)(xL >> 32);
-                h1 = (unsigned)(hR >> 32); l1 = (unsigned)(lR >> 32); x1 = (unsigned)(xR >> 32);
-            }
-            const W EqL = tl[((x0 & 1u) << 2) | ((h0 & 1u) << 1) | (l0 & 1u)];
-            const W EqR = tr[((x1 & 1u) << 2) | ((h1 & 1u) << 1) | (l1 & 1u)];
-            h0 >>= 1; l0 >>= 1; x0 >>= 1; h1 >>= 1; l1 >>= 1; x1 >>= 1;
+    for (int t = 0; t < nit; t++) {
+        if (t == 32) {
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const unsigned long long wq = sp_window(q == 0 ? hi : q == 1 ? lo : xx, b_[c]);
+                    sL[c][q] = (unsigned)((__brevll(wq) >> (64 - base_[c])) >> 32);
+                    sR[c][q] = (unsigned)((wq >> base_[c]) >> 32);
+                }
+        }
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const W EqL = tl[c][((sL[c][2] & 1u) << 2) | ((sL[c][0] & 1u) << 1) | (sL[c][1] & 1u)];
+            const W EqR = tl[c][8 + (((sR[c][2] & 1u) << 2) | ((sR[c][0] & 1u) << 1) | (sR[c][1] & 1u))];
+#pragma unroll
+            for (int q = 0; q < 3; q++) { sL[c][q] >>= 1; sR[c][q] >>= 1; }
             {
-                const W Xv = EqL | MvL;
-                const W Xh = (W)((((EqL & PvL) + PvL) ^ PvL) | EqL);
-                W Ph = (W)(MvL | ~(Xh | PvL));
-                W Mh = (W)(PvL & Xh);
-                scL += (Ph & topL) ? 1 : 0;
-                scL -= (Mh & topL) ? 1 : 0;
+                const W Xv = EqL | MvL[c];
+                const W Xh = (W)((((EqL & PvL[c]) + PvL[c]) ^ PvL[c]) | EqL);
+                W Ph = (W)(MvL[c] | ~(Xh | PvL[c]));
+                W Mh = (W)(PvL[c] & Xh);
+                scL[c] += (Ph & topL[c]) ? 1 : 0;
+                scL[c] -= (Mh & topL[c]) ? 1 : 0;
                 Ph = (W)((Ph << 1) | 1);
                 Mh = (W)(Mh << 1);
-                PvL = (W)(Mh | ~(Xv | Ph));
-                MvL = (W)(Ph & Xv);
-                if (t < nL) bestL = min(bestL, scL);
+                PvL[c] = (W)(Mh | ~(Xv | Ph));
+                MvL[c] = (W)(Ph & Xv);
+                if (t < nL[c]) bestL[c] = min(bestL[c], scL[c]);
             }
             {
-                const W Xv = EqR | MvR;
-                const W Xh = (W)((((EqR & PvR) + PvR) ^ PvR) | EqR);
-                W Ph = (W)(MvR | ~(Xh | PvR));
-                W Mh = (W)(PvR & Xh);
-                scR += (Ph & topR) ? 1 : 0;
-                scR -= (Mh & topR) ? 1 : 0;
+                const W Xv = EqR | MvR[c];
+                const W Xh = (W)((((EqR & PvR[c]) + PvR[c]) ^ PvR[c]) | EqR);
+                W Ph = (W)(MvR[c] | ~(Xh | PvR[c]));
+                W Mh = (W)(PvR[c] & Xh);
+                scR[c] += (Ph & topR[c]) ? 1 : 0;
+                scR[c] -= (Mh & topR[c]) ? 1 : 0;
                 Ph = (W)((Ph << 1) | 1);
                 Mh = (W)(Mh << 1);
-                PvR = (W)(Mh | ~(Xv | Ph));
-                MvR = (W)(Ph & Xv);
-                if (t < nR) bestR = min(bestR, scR);
+                PvR[c] = (W)(Mh | ~(Xv | Ph));
+                MvR[c] = (W)(Ph & Xv);
+                if (t < nR[c]) bestR[c] = min(bestR[c], scR[c]);
             }
         }
-        keep = bestL + bestR <= k;
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    if (bal) {
+#pragma unroll
+    for (int c = 0; c < 2; c++) keep[c] = act[c] && bestL[c] + bestR[c] <= k;
+    const unsigned bal0 = __ballot_sync(0xffffffffu, keep[0]), bal1 = __ballot_sync(0xffffffffu, keep[1]);
+    if (bal0 | bal1) {
         unsigned long long basei = 0;
-        if (lane == 0) basei = atomicAdd(count, (unsigned long long)__popc(bal));
-        basei = __shfl_sync(0xffffffffu, basei, 0) + __popc(bal & ((1u << lane) - 1u));
-        if (keep && (long long)basei < cap) keys[basei] = key;
+        if (lane == 0) basei = atomicAdd(count, (unsigned long long)(__popc(bal0) + __popc(bal1)));
+        basei = __shfl_sync(0xffffffffu, basei, 0);
+        const unsigned below = (1u << lane) - 1u;
+        const unsigned long long i0 = basei + __popc(bal0 & below), i1 = basei + __popc(bal0) + __popc(bal1 & below);
+        if (keep[0] && (long long)i0 < cap) keys[i0] = key[0];
+        if (keep[1] && (long long)i1 < cap) keys[i1] = key[1];
     }
     __syncwarp();
 }
 
 template <int NP, typename W, int ROWS>
-__global__ void __launch_bounds__((EX_WARPS + 1) * 32, 4) k_scan_split(const PackedArgs<NP> a, const PackedVerify<NP> v, const QFilter qf)
+__global__ void __launch_bounds__(EX_WARPS * 32, 4) k_scan_split(const PackedArgs<NP> a, const PackedVerify<NP> v, const QFilter qf)
 {
     extern __shared__ __align__(128) unsigned char ex_smem[];
-    __shared__ unsigned long long q_key[EX_WARPS][SP_QUEUE], q_h[EX_WARPS][SP_QUEUE], q_l[EX_WARPS][SP_QUEUE], q_x[EX_WARPS][SP_QUEUE];
+    __shared__ unsigned long long q_key[EX_WARPS][SP_QUEUE];
+    __shared__ unsigned s_anchor[EX_WARPS][EX_WPL * 32];   // anchor bits of the piece being extracted, [word][lane]
     __shared__ W sT[NP * 16];                           // match masks by symbol (A,C,T,G,X): [piece][left | right][8]
     __shared__ SpParams spar[NP];
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
@@ -890,36 +929,38 @@ __global__ void __launch_bounds__((EX_WARPS + 1) * 32, 4) k_scan_split(const Pac
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (wib == EX_WARPS) {
-        // producer warp: one lane keeps the ring full, independent of the consumers' progress
-        if (lane == 0)
-            for (long long it = 0; it < my; it++) {
-                const int s = (int)(it % EX_STAGES);
-                if (it >= EX_STAGES) mbar_wait(&empty[s], (unsigned)(((it / EX_STAGES) - 1) & 1));
-                const long long q = (a.tile0 * 128) + (blockIdx.x + it * gridDim.x) * EX_WORDS;
-                unsigned *dst = stage_base + (size_t)s * (3 * EX_ROW);
-                mbar_expect_tx(&full[s], EX_STAGE_BYTES);
-                tma_load_1d(dst, a.hi + q, EX_ROW * 4, &full[s]);
-                tma_load_1d(dst + EX_ROW, a.lo + q, EX_ROW * 4, &full[s]);
-                tma_load_1d(dst + 2 * EX_ROW, a.xx + q, EX_ROW * 4, &full[s]);
+    // No producer warp here (it would pin a fifth of the register file): thread 0 refills the ring, always
+    // EX_STAGES-1 tiles ahead, waiting only for the stage every warp has already copied to registers.
+    auto issue = [&](long long it) {
+        const int s = (int)(it % EX_STAGES);
+        if (it >= EX_STAGES) mbar_wait(&empty[s], (unsigned)(((it / EX_STAGES) - 1) & 1));
+        const long long q = (a.tile0 * 128) + (blockIdx.x + it * gridDim.x) * EX_WORDS;
+        unsigned *dst = stage_base + (size_t)s * (3 * EX_ROW);
+        mbar_expect_tx(&full[s], EX_STAGE_BYTES);
+        tma_load_1d(dst, a.hi + q, EX_ROW * 4, &full[s]);
+        tma_load_1d(dst + EX_ROW, a.lo + q, EX_ROW * 4, &full[s]);
+        tma_load_1d(dst + 2 * EX_ROW, a.xx + q, EX_ROW * 4, &full[s]);
+    };
+    if (tid == 0)
+        for (long long it = 0; it < EX_STAGES - 1 && it < my; it++) issue(it);
+    if (tid == 32 && blockIdx.x == 0 && a.tile0 == 0) {
+        // anchors closer than k + V[i] to the start of the text have no pattern start b >= 0:
+        // they go to k_verify unfiltered (it re-checks the trigger on the raw bytes)
+        for (int i = 0; i < a.npieces; i++)
+            for (long long p = 0; p < v.k + v.V[i]; p++) {
+                if (p < a.a0 || p >= a.a1 || p + a.L > a.n) continue;
+                const unsigned long long idx = atomicAdd(a.count, 1ULL);
+                if ((long long)idx < a.cap) a.keys[idx] = ((unsigned long long)p << 4) | (unsigned)i;
             }
-        else if (lane == 1 && blockIdx.x == 0 && a.tile0 == 0) {
-            // anchors closer than k + V[i] to the start of the text have no pattern start b >= 0:
-            // they go to k_verify unfiltered (it re-checks the trigger on the raw bytes)
-            for (int i = 0; i < a.npieces; i++)
-                for (long long p = 0; p < v.k + v.V[i]; p++) {
-                    if (p < a.a0 || p >= a.a1 || p + a.L > a.n) continue;
-                    const unsigned long long idx = atomicAdd(a.count, 1ULL);
-                    if ((long long)idx < a.cap) a.keys[idx] = ((unsigned long long)p << 4) | (unsigned)i;
-                }
-        }
-        return;
     }
-    unsigned long long *qk = q_key[wib], *qh = q_h[wib], *ql = q_l[wib], *qx = q_x[wib];
+    unsigned long long *qk = q_key[wib];
+    unsigned *sM = s_anchor[wib];
     unsigned qhead = 0, qcnt = 0;                       // warp-uniform ring state
     for (long long it = 0; it < my; it++) {
         const int s = (int)(it % EX_STAGES);
         const unsigned ph = (unsigned)((it / EX_STAGES) & 1);
+        if (tid == 0 && it + EX_STAGES - 1 < my) issue(it + EX_STAGES - 1);
+        __syncwarp();
         mbar_wait(&full[s], ph);
         const unsigned *sp = stage_base + (size_t)s * (3 * EX_ROW) + wib * (32 * EX_WPL) + EX_WPL * lane;
         unsigned H[EX_WPL + 2], Lw[EX_WPL + 2], X[EX_WPL + 2];
@@ -988,6 +1029,8 @@ __global__ void __launch_bounds__((EX_WARPS + 1) * 32, 4) k_scan_split(const Pac
         }
         const long long wbase = ((a.tile0 * 128) + bt * EX_WORDS + wib * (32 * EX_WPL)) * 32;   // first pattern start of the warp tile
         const unsigned lrel = (unsigned)(EX_WPL * lane) * 32;
+        // every anchor of this warp tile lies in [a0, a1) and far enough from the end of the text (true for all but the first / last tiles)
+        const bool inside = wbase + v.k >= a.a0 && wbase + v.m + v.k + 32 * 32 * EX_WPL <= a.a1 && wbase + v.m + v.k + 32 * 32 * EX_WPL + a.L <= a.n;
         // ---- pieces, in pattern-start coordinates: piece i sits k + V[i] bits further ----
 #pragma unroll 1
         for (int i = 0; i < a.npieces; i++) {
@@ -1002,23 +1045,30 @@ __global__ void __launch_bounds__((EX_WARPS + 1) * 32, 4) k_scan_split(const Pac
                 exact_apply<true>(M, P, base + j);
             }
             const long long p0 = wbase + base + lrel;      // anchor of bit 0 of this lane's first word
-            if (!(wbase + base >= a.a0 && wbase + base + 32 * 32 * EX_WPL <= a.a1 && wbase + base + 32 * 32 * EX_WPL + a.L <= a.n)) {
-                // first / last tiles of the scanned range: drop the anchors outside [a0, a1) or too close to the end
-#pragma unroll
-                for (int w = 0; w < EX_WPL; w++) {
-                    unsigned c = M[w];
-                    while (c) {
-                        const int b = __ffs(c) - 1;
-                        c &= c - 1;
-                        const long long p = p0 + w * 32 + b;
-                        if (!(p >= a.a0 && p < a.a1 && p + a.L <= a.n)) M[w] &= ~(1u << b);
-                    }
-                }
-            }
             unsigned mine = 0;
 #pragma unroll
             for (int w = 0; w < EX_WPL; w++) mine += __popc(M[w]);
             if (!__any_sync(0xffffffffu, mine != 0)) continue;
+            // the anchors leave the registers here: extraction walks them in shared memory, [word][lane]
+#pragma unroll
+            for (int w = 0; w < EX_WPL; w++) sM[w * 32 + lane] = M[w];
+            if (!inside) {
+                // first / last tiles of the scanned range: drop the anchors outside [a0, a1) or too close to the end
+                mine = 0;
+#pragma unroll 1
+                for (int w = 0; w < EX_WPL; w++) {
+                    unsigned c = sM[w * 32 + lane], keepm = c;
+                    while (c) {
+                        const int b = __ffs(c) - 1;
+                        c &= c - 1;
+                        const long long p = p0 + w * 32 + b;
+                        if (!(p >= a.a0 && p < a.a1 && p + a.L <= a.n)) keepm &= ~(1u << b);
+                    }
+                    sM[w * 32 + lane] = keepm;
+                    mine += __popc(keepm);
+                }
+                if (!__any_sync(0xffffffffu, mine != 0)) continue;
+            }
             unsigned incl = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -1029,56 +1079,50 @@ __global__ void __launch_bounds__((EX_WARPS + 1) * 32, 4) k_scan_split(const Pac
             if (qcnt + total <= SP_QUEUE) {
                 // sparse: every lane appends its anchors at its own offset, then full rounds are drained
                 unsigned slot = qhead + qcnt + (incl - mine);
-#pragma unroll
-                for (int w = 0; w < EX_WPL; w++) {
-                    unsigned c = M[w];
-                    while (c) {
-                        const int b = __ffs(c) - 1;
-                        c &= c - 1;
-                        const unsigned e = slot++ & (SP_QUEUE - 1);
-                        qk[e] = ((unsigned long long)(p0 + w * 32 + b) << 4) | (unsigned)i;
-                        qh[e] = ((unsigned long long)__funnelshift_r(H[w + 1], H[w + 2], b) << 32) | __funnelshift_r(H[w], H[w + 1], b);
-                        ql[e] = ((unsigned long long)__funnelshift_r(Lw[w + 1], Lw[w + 2], b) << 32) | __funnelshift_r(Lw[w], Lw[w + 1], b);
-                        qx[e] = ((unsigned long long)__funnelshift_r(X[w + 1], X[w + 2], b) << 32) | __funnelshift_r(X[w], X[w + 1], b);
+                if (mine) {
+#pragma unroll 1
+                    for (int w = 0; w < EX_WPL; w++) {
+                        unsigned c = sM[w * 32 + lane];
+                        while (c) {
+                            const int b = __ffs(c) - 1;
+                            c &= c - 1;
+                            qk[slot++ & (SP_QUEUE - 1)] = ((unsigned long long)(p0 + w * 32 + b) << 4) | (unsigned)i;
+                        }
                     }
                 }
                 qcnt += total;
                 __syncwarp();
-                while (qcnt >= 32) {
-                    sp_round<W>(qk, qh, ql, qx, qhead, 32, sT, spar, v.k, a.keys, a.count, a.cap);
-                    qhead = (qhead + 32) & (SP_QUEUE - 1);
-                    qcnt -= 32;
+                while (qcnt >= 64) {
+                    sp_round<W>(qk, qhead, 64, a.hi, a.lo, a.xx, sT, spar, v.k, a.keys, a.count, a.cap);
+                    qhead = (qhead + 64) & (SP_QUEUE - 1);
+                    qcnt -= 64;
                 }
             } else {
-                // dense: one anchor per lane and step, a round as soon as 32 are queued
-#pragma unroll
+                // dense: one anchor per lane and step, a round as soon as 64 are queued
+#pragma unroll 1
                 for (int w = 0; w < EX_WPL; w++) {
-                    unsigned c = M[w];
+                    unsigned c = sM[w * 32 + lane];
                     while (__any_sync(0xffffffffu, c != 0)) {
                         const bool have = c != 0;
                         const unsigned bal = __ballot_sync(0xffffffffu, have);
                         if (have) {
                             const int b = __ffs(c) - 1;
                             c &= c - 1;
-                            const unsigned e = (qhead + qcnt + __popc(bal & ((1u << lane) - 1u))) & (SP_QUEUE - 1);
-                            qk[e] = ((unsigned long long)(p0 + w * 32 + b) << 4) | (unsigned)i;
-                            qh[e] = ((unsigned long long)__funnelshift_r(H[w + 1], H[w + 2], b) << 32) | __funnelshift_r(H[w], H[w + 1], b);
-                            ql[e] = ((unsigned long long)__funnelshift_r(Lw[w + 1], Lw[w + 2], b) << 32) | __funnelshift_r(Lw[w], Lw[w + 1], b);
-                            qx[e] = ((unsigned long long)__funnelshift_r(X[w + 1], X[w + 2], b) << 32) | __funnelshift_r(X[w], X[w + 1], b);
+                            qk[(qhead + qcnt + __popc(bal & ((1u << lane) - 1u))) & (SP_QUEUE - 1)] = ((unsigned long long)(p0 + w * 32 + b) << 4) | (unsigned)i;
                         }
                         qcnt += __popc(bal);
                         __syncwarp();
-                        if (qcnt >= 32) {
-                            sp_round<W>(qk, qh, ql, qx, qhead, 32, sT, spar, v.k, a.keys, a.count, a.cap);
-                            qhead = (qhead + 32) & (SP_QUEUE - 1);
-                            qcnt -= 32;
+                        if (qcnt >= 64) {
+                            sp_round<W>(qk, qhead, 64, a.hi, a.lo, a.xx, sT, spar, v.k, a.keys, a.count, a.cap);
+                            qhead = (qhead + 64) & (SP_QUEUE - 1);
+                            qcnt -= 64;
                         }
                     }
                 }
             }
         }
     }
-    if (qcnt) sp_round<W>(qk, qh, ql, qx, qhead, qcnt, sT, spar, v.k, a.keys, a.count, a.cap);
+    if (qcnt) sp_round<W>(qk, qhead, qcnt, a.hi, a.lo, a.xx, sT, spar, v.k, a.keys, a.count, a.cap);
 }
 
 // ---------------------------------------------------------------------------------------
