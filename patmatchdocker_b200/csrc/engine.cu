@@ -948,8 +948,8 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
                         a.tile0 = t0q; a.ntiles = ntq;
                     }
                     const int grid_bk = std::max((int)std::min<long long>((ntq + 7) / 8, (long long)e->sms * 6), 1);
-                    const int grid_sp = std::max((int)std::min<long long>((ntq + 7) / 8, (long long)e->sms * 4), 1);
-                    const size_t smem_sp = EX_STAGES * EX_STAGE_BYTES + 2 * EX_STAGES * 8;
+                    const int grid_sp = std::max((int)std::min<long long>((ntq + 7) / 8, (long long)e->sms * SP_CTAS), 1);
+                    const size_t smem_sp = SP_STAGES * EX_STAGE_BYTES + 2 * SP_STAGES * 8;
                     static bool sp_attr_set = false;
                     if (!sp_attr_set) {                    // static queues + dynamic ring exceed the 48 KB default
 #define PM_ATTR(W, R) CK(cudaFuncSetAttribute(k_scan_split<4, W, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sp))

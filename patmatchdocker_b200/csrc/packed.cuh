@@ -749,6 +749,8 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
 // Myers filter on them (all lanes busy, one piece per round so every lane has the same part
 // lengths and tables), reading the few plane words it needs from global memory (L2 hits: the
 // tile has just been streamed).  There is no block-wide synchronisation inside the tile loop.
+#define SP_STAGES 3
+#define SP_CTAS 4                        // CTAs per SM the register budget is cut for (5 x 96 registers measured slower)
 #define SP_QUEUE 128                     // per-warp anchor queue (ring of keys)
 
 template <int LUT>
@@ -906,7 +908,7 @@ __device__ __noinline__ void sp_round(const unsigned long long *__restrict__ qke
 }
 
 template <int NP, typename W, int ROWS>
-__global__ void __launch_bounds__(EX_WARPS * 32, 4) k_scan_split(const PackedArgs<NP> a, const PackedVerify<NP> v, const QFilter qf)
+__global__ void __launch_bounds__(EX_WARPS * 32, SP_CTAS) k_scan_split(const PackedArgs<NP> a, const PackedVerify<NP> v, const QFilter qf)
 {
     extern __shared__ __align__(128) unsigned char ex_smem[];
     __shared__ unsigned long long q_key[EX_WARPS][SP_QUEUE];
@@ -920,20 +922,20 @@ __global__ void __launch_bounds__(EX_WARPS * 32, 4) k_scan_split(const PackedArg
     }
     if (tid < NP) { spar[tid].base = v.k + v.V[tid]; spar[tid].lb = v.V[tid]; spar[tid].rl = v.m - v.V[tid]; }
     unsigned *stage_base = reinterpret_cast<unsigned *>(ex_smem);
-    unsigned long long *full = reinterpret_cast<unsigned long long *>(ex_smem + EX_STAGES * EX_STAGE_BYTES);
-    unsigned long long *empty = full + EX_STAGES;
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(ex_smem + SP_STAGES * EX_STAGE_BYTES);
+    unsigned long long *empty = full + SP_STAGES;
     const long long nbt = (a.ntiles + 7) / 8;
     const long long my = blockIdx.x < nbt ? (nbt - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     if (tid == 0) {
-        for (int s = 0; s < EX_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], EX_WARPS); }
+        for (int s = 0; s < SP_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], EX_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     // No producer warp here (it would pin a fifth of the register file): thread 0 refills the ring, always
-    // EX_STAGES-1 tiles ahead, waiting only for the stage every warp has already copied to registers.
+    // SP_STAGES-1 tiles ahead, waiting only for the stage every warp has already copied to registers.
     auto issue = [&](long long it) {
-        const int s = (int)(it % EX_STAGES);
-        if (it >= EX_STAGES) mbar_wait(&empty[s], (unsigned)(((it / EX_STAGES) - 1) & 1));
+        const int s = (int)(it % SP_STAGES);
+        if (it >= SP_STAGES) mbar_wait(&empty[s], (unsigned)(((it / SP_STAGES) - 1) & 1));
         const long long q = (a.tile0 * 128) + (blockIdx.x + it * gridDim.x) * EX_WORDS;
         unsigned *dst = stage_base + (size_t)s * (3 * EX_ROW);
         mbar_expect_tx(&full[s], EX_STAGE_BYTES);
@@ -942,7 +944,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32, 4) k_scan_split(const PackedArg
         tma_load_1d(dst + 2 * EX_ROW, a.xx + q, EX_ROW * 4, &full[s]);
     };
     if (tid == 0)
-        for (long long it = 0; it < EX_STAGES - 1 && it < my; it++) issue(it);
+        for (long long it = 0; it < SP_STAGES - 1 && it < my; it++) issue(it);
     if (tid == 32 && blockIdx.x == 0 && a.tile0 == 0) {
         // anchors closer than k + V[i] to the start of the text have no pattern start b >= 0:
         // they go to k_verify unfiltered (it re-checks the trigger on the raw bytes)
@@ -957,9 +959,9 @@ __global__ void __launch_bounds__(EX_WARPS * 32, 4) k_scan_split(const PackedArg
     unsigned *sM = s_anchor[wib];
     unsigned qhead = 0, qcnt = 0;                       // warp-uniform ring state
     for (long long it = 0; it < my; it++) {
-        const int s = (int)(it % EX_STAGES);
-        const unsigned ph = (unsigned)((it / EX_STAGES) & 1);
-        if (tid == 0 && it + EX_STAGES - 1 < my) issue(it + EX_STAGES - 1);
+        const int s = (int)(it % SP_STAGES);
+        const unsigned ph = (unsigned)((it / SP_STAGES) & 1);
+        if (tid == 0 && it + SP_STAGES - 1 < my) issue(it + SP_STAGES - 1);
         __syncwarp();
         mbar_wait(&full[s], ph);
         const unsigned *sp = stage_base + (size_t)s * (3 * EX_ROW) + wib * (32 * EX_WPL) + EX_WPL * lane;
