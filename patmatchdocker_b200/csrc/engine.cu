@@ -23,6 +23,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <cmath>
 #include "../../include/patmatch_b200.h"
 #include "plan.hpp"
 
@@ -885,60 +886,104 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
                             pprob[j] = pcls[j] == 31u ? 1.0 : std::max(__builtin_popcount(pcls[j] & 15u), 0) / 4.0 + 0.001;
                         }
                         double cand_rate = 0;                         // piece hits per base
+                        double piece_rate[PM_MAX_PIECES] = {0};
                         for (int i = 0; i < dp.npieces; i++) {
                             double pr = 1;
                             for (int j = 0; j < dp.L; j++) pr *= std::min(pprob[dp.V[i] + j], 1.0);
+                            piece_rate[i] = pr;
                             cand_rate += pr;
                         }
-                        const double myers_cost = 700.0;              // thread operations per queued candidate, divergence included
-                        double best_cost = cand_rate * myers_cost * 0.7;   // worth it only with a clear margin
-                        for (int q = 2; q <= QF_MAXLEN; q++)
-                            for (int a_off = 0; a_off < q; a_off++) {
-                                QFilter cur;
-                                memset(&cur, 0, sizeof cur);
-                                cur.win = win;
-                                std::vector<double> pg;
-                                double ops = 0;
-                                for (int j0 = a_off - q; j0 < dp.m && cur.nch < QF_MAXCH; j0 += q) {
-                                    const int jb = std::max(j0, 0), je = std::min(j0 + q, dp.m);
-                                    if (je <= jb) continue;
-                                    QChunk ch;
-                                    memset(&ch, 0, sizeof ch);
-                                    double pr = 1, chops = 0;
-                                    int first = -1;
-                                    for (int j = jb; j < je; j++) {
-                                        if (pcls[j] == 31u) continue;
-                                        if (first < 0) first = j;
-                                        ch.t[ch.npos] = (unsigned char)(j - first);
-                                        ch.pos[ch.npos].cls = (unsigned char)pcls[j];
-                                        ch.pos[ch.npos].sel = (unsigned char)plane_of(pcls[j]);
-                                        ch.npos++;
-                                        pr *= pprob[j];
-                                        chops += plane_of(pcls[j]) == 5 ? 66 : 12;
-                                    }
-                                    if (first < 0) continue;
-                                    pr = std::min(pr * win, 1.0);
-                                    if (pr > 0.6) continue;                   // hardly ever missing: not worth its operations
-                                    ops += chops;
-                                    ch.off = (unsigned char)(first + (win > 1 ? 0 : dp.k));
-                                    cur.ch[cur.nch++] = ch;
-                                    pg.push_back(pr);
-                                    int steps = 0;
-                                    for (int cw = 1; cw < win; cw += std::min(cw, win - cw)) steps++;
-                                    ops += steps * 12 + 8 + 8 * rows;
+                        // cost model in thread operations per base: a pattern position costs ~42 warp instructions per
+                        // 8192-base warp tile; a surviving anchor ~80 (latency-bound Myers round + extraction), the value
+                        // that ranked the candidate chunk sets best in a sweep over 11 motifs (tools/qf_bench.py)
+                        const double anchor_cost = 2500.0;
+                        double best_cost = cand_rate * anchor_cost * 0.7;     // worth it only with a clear margin
+                        int steps = 0;
+                        for (int cw = 1; cw < win; cw += std::min(cw, win - cw)) steps++;
+                        auto evaluate = [&](const std::vector<std::pair<int, int>> &segs) {
+                            QFilter cur;
+                            memset(&cur, 0, sizeof cur);
+                            cur.win = win;
+                            double ops = 0;
+                            std::vector<std::pair<int, int>> span;            // constrained positions of each kept chunk: [first, last]
+                            for (const auto &sg : segs) {
+                                if (cur.nch >= QF_MAXCH) break;
+                                QChunk ch;
+                                memset(&ch, 0, sizeof ch);
+                                double pr = 1;
+                                int first = -1, last = -1;
+                                for (int j = sg.first; j < sg.second; j++) {
+                                    if (pcls[j] == 31u) continue;
+                                    if (first < 0) first = j;
+                                    if (ch.npos >= QF_MAXLEN || j - first >= 32) break;
+                                    ch.t[ch.npos] = (unsigned char)(j - first);
+                                    ch.pos[ch.npos].cls = (unsigned char)pcls[j];
+                                    ch.pos[ch.npos].sel = (unsigned char)plane_of(pcls[j]);
+                                    ch.npos++;
+                                    pr *= pprob[j];
+                                    last = j;
                                 }
-                                if (cur.nch <= dp.k) continue;            // k missing chunks are always allowed
-                                // P(at most k chunks missing), chunks taken as independent
+                                if (first < 0) continue;
+                                pr = std::min(pr * win, 1.0);
+                                if (pr > 0.6) continue;                       // hardly ever missing: not worth its operations
+                                ops += 21.0 * ch.npos + 8.0 * steps + 8 + 5 * rows;
+                                ch.off = (unsigned char)(first + (win > 1 ? 0 : dp.k));
+                                cur.ch[cur.nch++] = ch;
+                                span.push_back({first, last});
+                            }
+                            if (cur.nch <= dp.k) return;                      // k missing chunks are always allowed
+                            // Expected anchors that survive.  An anchor of piece i matched that piece exactly, so the chunk
+                            // positions inside the piece are present for free; the others are taken as independent.
+                            double survivors = 0;
+                            for (int i = 0; i < dp.npieces; i++) {
                                 std::vector<double> dist((size_t)cur.nch + 1, 0.0);
                                 dist[0] = 1;
-                                for (int g = 0; g < cur.nch; g++)
+                                for (int g = 0; g < cur.nch; g++) {
+                                    double pout = 1, pall = 1;
+                                    for (int j = span[g].first; j <= span[g].second; j++) {
+                                        if (pcls[j] == 31u) continue;
+                                        pall *= pprob[j];
+                                        if (j < dp.V[i] || j >= dp.V[i] + dp.L) pout *= pprob[j];
+                                    }
+                                    const double pgi = std::min(pout + (win - 1) * pall, 1.0);
                                     for (int r = g + 1; r >= 0; r--)
-                                        dist[r] = dist[r] * pg[g] + (r > 0 ? dist[r - 1] * (1 - pg[g]) : 0.0);
+                                        dist[r] = dist[r] * pgi + (r > 0 ? dist[r - 1] * (1 - pgi) : 0.0);
+                                }
                                 double pass = 0;
                                 for (int r = 0; r <= dp.k && r <= cur.nch; r++) pass += dist[r];
-                                const double cost = ops / 128.0 + cand_rate * pass * myers_cost;
-                                if (cost < best_cost) { best_cost = cost; qf = cur; }
+                                survivors += piece_rate[i] * pass;
                             }
+                            const double cost = ops / 128.0 + survivors * anchor_cost;
+                            if (cost < best_cost) { best_cost = cost; qf = cur; }
+                        };
+                        // (1) uniform tilings of every length and phase
+                        for (int q = 2; q <= QF_MAXLEN; q++)
+                            for (int a_off = 0; a_off < q; a_off++) {
+                                std::vector<std::pair<int, int>> segs;
+                                for (int j0 = a_off - q; j0 < dp.m; j0 += q) {
+                                    const int jb = std::max(j0, 0), je = std::min(j0 + q, dp.m);
+                                    if (je > jb) segs.push_back({jb, je});
+                                }
+                                evaluate(segs);
+                            }
+                        // (2) T segments of (nearly) equal information: wildcards carry none, so chunks stretch over them
+                        {
+                            std::vector<double> cum((size_t)dp.m + 1, 0.0);
+                            for (int j = 0; j < dp.m; j++) cum[j + 1] = cum[j] + (pcls[j] == 31u ? 0.0 : -std::log2(std::min(pprob[j], 1.0)));
+                            for (int T = dp.k + 1; T <= std::min(2 * dp.k + 3, QF_MAXCH); T++) {
+                                std::vector<std::pair<int, int>> segs;
+                                int jb = 0;
+                                for (int r = 1; r <= T && jb < dp.m; r++) {
+                                    const double target = cum[dp.m] * r / T;
+                                    int je = jb + 1;
+                                    while (je < dp.m && std::fabs(cum[je + 1] - target) <= std::fabs(cum[je] - target)) je++;
+                                    if (r == T) je = dp.m;
+                                    segs.push_back({jb, je});
+                                    jb = je;
+                                }
+                                evaluate(segs);
+                            }
+                        }
                     }
                     if (bcoords) {
                         // pattern starts b = anchor - k - V[i] >= 0 must be covered for every anchor in [a0, wend)

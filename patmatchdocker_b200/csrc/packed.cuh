@@ -465,7 +465,7 @@ __global__ void __launch_bounds__((EX_WARPS + 1) * 32) k_scan_packed_exact(const
 // Low-selectivity pieces (e.g. ANNNRY: one window in 16) make this worthwhile: the dense
 // filter costs a few operations per base and removes >90 % of the Myers evaluations.
 #define QF_MAXCH 12
-#define QF_MAXLEN 8
+#define QF_MAXLEN 12
 struct QChunk {
     unsigned char off;                  // first bit of the window, relative to b
     unsigned char npos;                 // constrained positions of the chunk
