@@ -47,6 +47,7 @@ const char *pm_version(void) { return "patmatch_b200 0.1 (sm_100a)"; }
 struct DevPlan {
     int type, m, k, L, npieces;
     int ins, del, subs;
+    int start_line, end_line;     // leading '^' / trailing '$' (recCheckLeftContext @402170 / recCheckRightContext @4021e0)
     int V[PM_MAX_PIECES];
     unsigned long long trig[PM_MAX_PIECES];
     unsigned long long init, fin;
@@ -64,10 +65,19 @@ struct H16 { long long a, b; };                     // == pm_hit
 // delimiter '\n' also stops the walk (recGetRecord @402030).
 // Returns 1 with *ext = bytes consumed by the chosen match, *err = its error row and
 // *steps = bytes examined (for the dependency test of the chain stage).
+// ctx: the pattern is anchored on this side ('^' for dir < 0, '$' for dir > 0): a final state only counts
+// when the match boundary sits at the record / scan-range limit (recCheckLeftContext @402170,
+// recCheckRightContext @4021e0).
 __device__ __forceinline__ int nfa_side(const unsigned char *__restrict__ text, const unsigned long long *__restrict__ T,
-                                        int dir, int plen, int kmax, int ins, int del, int subs,
+                                        int dir, int plen, int kmax, int ins, int del, int subs, int ctx,
                                         long long pos, long long lim, long long *ext, int *err, long long *steps)
 {
+    auto edge_ok = [&](long long step) -> bool {
+        if (!ctx) return true;
+        if (dir < 0) { const long long e = pos - step; return e <= lim || text[e - 1] == '\n'; }
+        const long long e = pos + step;
+        return e >= lim || text[e] == '\n';
+    };
     const unsigned long long fin = 1ULL << (plen - 1);
     const unsigned long long live = (fin << 1) - 1ULL;      // plen == 64 -> all ones
     unsigned long long R[PM_MAXK + 1];
@@ -77,7 +87,7 @@ __device__ __forceinline__ int nfa_side(const unsigned char *__restrict__ text, 
     *steps = 0;
     for (int e = 0; e <= kb; e++) {
         R[e] = del ? (e >= 64 ? ~0ULL : ((1ULL << e) - 1ULL)) : 0ULL;
-        if (R[e] & fin) { best_err = e; kb = e - 1; best_ext = 0; }
+        if ((R[e] & fin) && edge_ok(0)) { best_err = e; kb = e - 1; best_ext = 0; }
     }
     unsigned long long first = 1;
     long long step = 0;
@@ -92,7 +102,7 @@ __device__ __forceinline__ int nfa_side(const unsigned char *__restrict__ text, 
         unsigned long long oldp = R[0];
         R[0] = ((R[0] << 1) | first) & Tc;
         unsigned long long newp = R[0];
-        if (R[0] & fin) { *ext = step; *err = 0; return 1; }
+        if ((R[0] & fin) && edge_ok(step)) { *ext = step; *err = 0; return 1; }
         for (int e = 1; e <= kb; e++) {
             unsigned long long x = 0;
             if (del) x = newp << 1;
@@ -102,7 +112,7 @@ __device__ __forceinline__ int nfa_side(const unsigned char *__restrict__ text, 
             oldp = R[e];
             R[e] = nr;
             newp = nr;
-            if (nr & fin) {
+            if ((nr & fin) && edge_ok(step)) {
                 int ec = e, ed;
                 for (;;) {
                     ed = ec - 1;
@@ -151,12 +161,36 @@ __device__ int check_match(const DevPlan &pl, const unsigned char *__restrict__ 
     long long bext = 0, fext = 0, steps = 0;
     int berr = 0, ferr = 0;
     if (lb > 0) {
-        int ok = nfa_side(text, TL + (size_t)i * 256, -1, lb, pl.k, pl.ins, pl.del, pl.subs, pos, tbeg, &bext, &berr, &steps);
-        *reach = pos - steps;
+        int ok = nfa_side(text, TL + (size_t)i * 256, -1, lb, pl.k, pl.ins, pl.del, pl.subs, pl.start_line, pos, tbeg, &bext, &berr, &steps);
+        *reach = pos - steps - (pl.start_line ? 1 : 0);    // '^' also reads the byte left of the boundary
         if (!ok) return 0;
+    } else if (pl.start_line) {
+        // 4141ef-414236: only inserted text bytes may separate an empty left part from the record start
+        long long ptr = pos;
+        int e = 0;
+        for (;;) {
+            if (ptr <= tbeg || text[ptr - 1] == '\n') break;
+            if (!pl.ins) { *reach = ptr - 1; return 0; }
+            ptr--; e++;
+            if (e > pl.k) { *reach = ptr - 1; return 0; }
+        }
+        *reach = ptr - 1;
+        bext = pos - ptr; berr = e;
     }
     if (rl > 0) {
-        if (!nfa_side(text, TR + (size_t)i * 256, +1, rl, pl.k - berr, pl.ins, pl.del, pl.subs, pos, n, &fext, &ferr, &steps)) return 0;
+        if (!nfa_side(text, TR + (size_t)i * 256, +1, rl, pl.k - berr, pl.ins, pl.del, pl.subs, pl.end_line, pos, n, &fext, &ferr, &steps)) return 0;
+    } else if (pl.end_line) {
+        // 414eae-414f19: the same on the right of an empty right part
+        const int kf = pl.k - berr;
+        long long q = pos;
+        int e = 0;
+        for (;;) {
+            if (q >= n || text[q] == '\n') break;
+            if (!pl.ins) return 0;
+            q++; e++;
+            if (e > kf) return 0;
+        }
+        fext = q - pos;
     }
     *beg = pos - bext;
     *end = pos + fext;
@@ -335,7 +369,7 @@ __global__ void __launch_bounds__(128) k_verify(const DevPlan pl, const unsigned
     if (pos + wlen > E || (recheck && !raw_trigger(pl, B, text, n, pos, i))) {
         c.beg = -1; c.end = -1; c.reach = pos;
     } else if (pl.type == PM_PLAN_SIMPLE) {
-        c.beg = pos; c.end = pos + pl.m; c.reach = pos;
+        c.beg = pos; c.end = pos + pl.m; c.reach = pos - (pl.start_line ? 1 : 0);   // the chain stage applies '^' / '$'
     } else {
         long long b = -1, e = -1, r = pos;
         if (!check_match(pl, text, E, TL, TR, i, pos, S, &b, &e, &r)) { b = -1; e = -1; }
@@ -379,13 +413,19 @@ __global__ void __launch_bounds__(128) k_chain(const DevPlan pl, const unsigned 
         if (t > j0 && independent(t)) break;
         sel[t] = 0;
         const Cand c = cands[t];
-        if (c.beg < 0) continue;
+        // a failed verification is final unless '^' is in play: then a scan start inside the examined bytes can
+        // turn it into a match (the left context is satisfied AT the scan start), so it is redone clipped below
+        if (c.beg < 0 && !(pl.start_line && pl.type != PM_PLAN_SIMPLE && dep_lo(pl, c) < pos)) continue;
         const long long anchor = c.key >> 4;
         const long long p = pl.type == PM_PLAN_FWD ? anchor - 1 : anchor;
         if (p < pos) continue;
         const long long n_fill = fills.E[cur];
         long long b = c.beg, e = c.end;
-        if (pl.type != PM_PLAN_SIMPLE && dep_lo(pl, c) < pos) {
+        if (pl.type == PM_PLAN_SIMPLE) {
+            // simple checkMatch @416790: '^' / '$' look at the byte next to the match unless it touches the scan range
+            if (pl.start_line && anchor > pos && text[anchor - 1] != '\n') continue;
+            if (pl.end_line && e < n_fill && text[e] != '\n') continue;
+        } else if (dep_lo(pl, c) < pos) {
             // the unclipped verification looked left of the new scan start: redo it clipped
             long long r;
             if (!check_match(pl, text, n_fill, TL, TR, (int)(c.key & 15), anchor, pos, &b, &e, &r)) continue;
@@ -726,7 +766,6 @@ static int compile(const char *pattern, const char *kopt, Compiled &c, bool need
     if (rc) { g_err = err; return rc; }
     rc = pm::parse_pattern(pattern, /*icase: patmatch.py always passes -i*/ true, c.P, err);
     if (rc) { g_err = err; return rc; }
-    if (c.P.start_line || c.P.end_line) { g_err = "line anchors (^ $) are not supported on the GPU path yet"; return PM_ERR_UNSUPPORTED; }
     rc = pm::make_plan(c.P, c.o, c.plan, err);
     if (rc) { g_err = err; return rc; }
     if (!need_tables) return PM_OK;
@@ -735,6 +774,7 @@ static int compile(const char *pattern, const char *kopt, Compiled &c, bool need
     memset(&d, 0, sizeof d);
     d.type = c.plan.type; d.m = c.plan.m; d.k = c.plan.k; d.L = c.plan.L; d.npieces = c.plan.npieces;
     d.ins = c.plan.ins; d.del = c.plan.del; d.subs = c.plan.subs;
+    d.start_line = c.P.start_line ? 1 : 0; d.end_line = c.P.end_line ? 1 : 0;
     for (int i = 0; i < PM_MAX_PIECES; i++) { d.V[i] = c.plan.V[i]; d.trig[i] = c.plan.trig[i]; }
     if (c.plan.type == pm::SIMPLE || c.plan.type == pm::SPLIT) {
         pm::build_filter(c.P, c.plan, c.ft);
@@ -1049,6 +1089,7 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
             if (hi > lo) {
                 DenseArgs a;
                 a.pl = dp; a.text = d->d_text; a.n = n; a.a0 = lo; a.a1 = hi; a.TL = dTL; a.TR = dTR;
+                a.pl.start_line = 0;          // '^' is not monotone in the scan start: k_verify / k_chain decide it
                 a.keys = (unsigned long long *)e->keys.p; a.count = d_count; a.cap = cap; a.fills = fills;
                 const long long want = (hi - lo + 255) / 256;
                 const int grid = (int)std::min<long long>(want, (long long)e->sms * 16);

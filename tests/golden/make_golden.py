@@ -130,6 +130,38 @@ def search_fixture():
         text = "\n".join(l if rng.random() < 0.7 else l[: rng.choice([0, 1, 7, 40])] for l in lines)
         cases.append((pat, kopt, text, rng.choice([16, 33, 64, 100, 128, 257, 1000])))
     cases.append(("(A.C)", "0ids", ">s\nGGA\nCGG\nA\nC\n", 6))
+    # line anchors: patmatch_to_nrgrep.pl turns '<' / '>' into a leading '^' / trailing '$' (recCheckLeftContext
+    # @402170, recCheckRightContext @4021e0).  Short records, so that the anchors do fire.  Own generator: the
+    # cases above stay byte-identical.
+    arng = random.Random(4242)
+    for _ in range(120):
+        alpha = arng.choice([DNA, PEP])
+        k = arng.choice([0, 0, 1, 1, 2])
+        m = arng.randint(max(2, 2 * k + 1), 10)
+        pat, kopt, _ = random_case(arng, alpha, m, k, arng.choice(["ids", "s", "id", "is"]) if k else "ids")
+        members = []
+        for tok in re.findall(r"\[\^?[A-Z]+\]|\.|[A-Z]", pat[1:-1]):
+            if tok == ".":
+                members.append(list(alpha))
+            elif tok.startswith("[^"):
+                members.append([c for c in alpha if c not in tok[2:-1]])
+            elif tok.startswith("["):
+                members.append(list(tok[1:-1]))
+            else:
+                members.append([tok])
+        mode = arng.randint(1, 3)
+        pat = ("^" if mode & 1 else "") + pat + ("$" if mode & 2 else "")
+        lines = []
+        for r in range(arng.randint(2, 8)):
+            lines.append(">s%d" % r)
+            s = "".join(arng.choice(c) for c in members)
+            body = "".join(arng.choice(alpha) for _ in range(arng.randint(0, 12)))
+            t = [s + body, body + s, s, s + s + body + s, body + s + body][arng.randint(0, 4)]
+            if k and arng.random() < 0.5 and len(t) > 2:
+                q = arng.randrange(len(t))
+                t = t[:q] + arng.choice(alpha) + t[q + 1:]
+            lines.append(t)
+        cases.append((pat, kopt, "\n".join(lines) + "\n", arng.choice([1600000, 1600000, 1600000, 40, 64])))
     out = []
     with tempfile.TemporaryDirectory() as td:
         path = os.path.join(td, "t.seq")

@@ -200,6 +200,45 @@ def test_qgram_prefilter_keeps_every_hit(engine):
         engine.set_scan_mode("auto")
 
 
+def test_line_anchors_against_oracle(engine, scan_mode):
+    # '<' / '>' of the PatMatch syntax = leading '^' / trailing '$': the match must start / end at a record boundary,
+    # or exactly at the scan start (the end of the previous hit), which makes '^' depend on the chain of hits
+    rng = random.Random(31)
+    n_hits = 0
+    for it in range(220):
+        alpha = rng.choice([DNA, PEP])
+        k = rng.choice([0, 0, 1, 1, 2, 3])
+        m = rng.randint(max(2, 2 * k + 1), 14 if it % 5 else 40)
+        pat, members = random_pattern(rng, alpha, m, cls_pct=0.2, dot_pct=0.1)
+        mode = rng.randint(1, 3)
+        pat = ("^" if mode & 1 else "") + pat + ("$" if mode & 2 else "")
+        kopt = "%d%s" % (k, rng.choice(["ids", "s", "id", "is", "ds", "i"]) if k else "ids")
+        lines = []
+        for r in range(rng.randint(2, 9)):
+            lines.append(">s%d" % r)
+            s0 = "".join(rng.choice(c) for c in members)
+            body = "".join(rng.choice(alpha) for _ in range(rng.randint(0, 12)))
+            t = [s0 + body, body + s0, s0, s0 + s0 + body + s0, body + s0 + body, s0 * 4][rng.randint(0, 5)]
+            if k and rng.random() < 0.5 and len(t) > 2:
+                q = rng.randrange(len(t))
+                t = t[:q] + rng.choice(alpha) + t[q + 1:]
+            if k and rng.random() < 0.3 and len(t) > 3:
+                q = rng.randrange(len(t))
+                t = t[:q] + t[q + 1:]
+            lines.append(t)
+        text = ("\n".join(lines) + ("\n" if rng.random() < 0.8 else "")).encode()
+        for bufsize in (1600000, rng.choice([32, 50, 100])):
+            engine.set_buffer_size(bufsize)
+            try:
+                got = gpu_hits(engine, text, pat, kopt)
+            finally:
+                engine.set_buffer_size(1600000)
+            want = O.search(pat, text, kopt, bufsize=bufsize)
+            assert got == want, (pat, kopt, bufsize, text)
+            n_hits += len(want)
+    assert n_hits > 500
+
+
 def test_hit_list_stays_on_device_after_overflow(engine):
     import ctypes
     from patmatchdocker_b200 import _native
