@@ -26,7 +26,7 @@ extern "C" {
 #define PM_OK               0
 #define PM_ERR_CUDA        -1   /* CUDA runtime failure (message has the cudaError) */
 #define PM_ERR_SYNTAX      -2   /* malformed nrgrep pattern / -k option */
-), anchors, or m > 64 */|), anchors, or m > 64 */
+#define PM_ERR_UNSUPPORTED -3   /* pattern needs nrgrep's EXTENDED/REGULAR engines (?,*,+,|) or has more than 64 positions */
 #define PM_ERR_ARG         -4
 #define PM_ERR_OVERFLOW    -5   /* caller's hit buffer too small; *nhits holds the required size */
 
