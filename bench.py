@@ -47,13 +47,27 @@ def peaks():
 
 
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML every 5 ms from a thread
+    (nvidia-smi -lms as the fallback: its first sample alone can take longer than a short run)."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
-        self.index, self.samples, self.proc = index, [], None
+        self.index, self.samples, self.proc, self.stop_flag, self.thread, self.max_mhz = index, [], None, False, None, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -62,11 +76,28 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append([str(mhz), str(self.max_mhz)] + ["Active" if mask & bit else "Not Active" for bit, _ in self.REASONS])
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.samples.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=1.0)
         if self.proc:
             self.proc.terminate()
         sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
@@ -207,7 +238,7 @@ def run_ours(args):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tp) and stats_acc["packed"]:
-        tr = json.load(open(tp)).get("k_scan_packed")
+        tr = json.load(open(tp)).get("k_scan_split")
         if tr:                                             # DRAM bytes of one launch from the committed ncu capture,
             per_base = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["scan_bases"]   # scaled to this launch's bases
             traffic = int(per_base * total_bases / world)
@@ -226,7 +257,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "hits_per_step": int(nhits),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": traffic, "kernel": "k_scan_packed<4,u32,3> (2-bit planes, fused edit-distance filter; integer-pipe bound, see profiles/r01_scan_packed_approx.txt)" if stats_acc["packed"] else "k_scan_bytes",
+                     "traffic": traffic, "kernel": "k_scan_split<4,u32,3> (2-bit planes via TMA ring, bit-sliced q-gram pre-filter + Myers filter; integer-pipe bound, see profiles/r01_scan_split_approx.txt)" if stats_acc["packed"] else "k_scan_bytes",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(scan_bytes / max(nsearch, 1)),
                      "kernel_ms": round(scan_ms / max(nsearch, 1), 4),
