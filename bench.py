@@ -193,7 +193,8 @@ def run_ours(args):
     def step_e2e():
         # the call a user makes: file bytes in HOST memory -> dataset (H2D copy, 2-bit packing and record
         # index on the device) -> the two searches of the request -> hit lists back in host memory
-        d = eng.load_dataset(host_np)
+        # (N > 1: every rank uploads 1/N of the file over its own PCIe link, NCCL all-gathers the slices over NVLink)
+        d = eng.load_dataset(host_np) if world == 1 else sharded.load_dataset(host)
         hits = [run_search(d, p) for p in pats]
         d.close()
         return sum(len(h) for h in hits if h is not None), sum(h.nbytes for h in hits if h is not None)

@@ -54,6 +54,27 @@ def search_sharded(engine, dataset, pattern, kopt, rank, world, device=None, gro
     return engine.resolve(dataset, pattern, kopt, merged)
 
 
+def assemble_from_host(host, rank, world, device, full=None, group=None):
+    """Bring a file that sits in (pinned) host memory into the memory of every rank with ONE trip over PCIe:
+    rank r copies only its 1/world slice host->device, then the slices are all-gathered in place over
+    NVLink/NVSwitch (NCCL).  `host` is a 1-D uint8 torch tensor, identical on all ranks.  Returns a device
+    tensor whose first len(host) bytes are the file (the tail is padding)."""
+    import torch
+    import torch.distributed as dist
+    n = int(host.numel())
+    per = ((n + world - 1) // world + 255) // 256 * 256
+    if full is None or full.numel() != per * world or full.device != torch.device(device):
+        full = torch.empty(per * world, dtype=torch.uint8, device=device)
+    lo = min(rank * per, n)
+    hi = min(n, lo + per)
+    mine = full[rank * per:(rank + 1) * per]
+    if hi > lo:
+        mine[: hi - lo].copy_(host[lo:hi], non_blocking=True)
+    if world > 1:
+        dist.all_gather_into_tensor(full, mine, group=group)
+    return full
+
+
 class DeviceShardedSearch:
     """search_sharded with the candidates kept in device memory end to end (nccl backend):
     pm_candidates_device -> dist.gather of device tensors -> pm_resolve_device on rank 0."""
@@ -71,6 +92,12 @@ class DeviceShardedSearch:
         self.mine = torch.zeros((cap, 4), dtype=torch.int64, device=self.device)          # row 0 = header (count)
         self.allbuf = torch.empty((cap * self.world, 4), dtype=torch.int64, device=self.device)
         self.merged = torch.empty((cap * self.world, 4), dtype=torch.int64, device=self.device) if self.rank == 0 else None
+
+    def load_dataset(self, host):
+        """Dataset from file bytes in host memory (1-D uint8 torch tensor, pinned for full speed): every rank
+        uploads 1/world of it and NCCL all-gathers the rest; each rank then packs its own copy."""
+        self.full = assemble_from_host(host, self.rank, self.world, self.device, getattr(self, "full", None), self.group)
+        return self.engine.wrap_device(self.full.data_ptr(), int(host.numel()))
 
     def search(self, dataset, pattern, kopt):
         """One collective per search: every rank all-gathers `rows` candidate records plus a header row

@@ -43,6 +43,12 @@ def _worker(rank, world, port, q):
     merged = D.gather_candidates(mine if rank == 0 else mine[:0], rank, world)
     if rank == 0:
         q.put(len(merged) == len(mine))
+    # dataset assembly: each rank uploads its slice, the all-gather completes every rank's copy
+    import torch
+    for nbytes in (1, 255, 1000, 70001):
+        host = torch.from_numpy(np.random.default_rng(nbytes).integers(0, 256, nbytes, dtype=np.uint8))
+        full = D.assemble_from_host(host, rank, world, "cpu")
+        q.put(bool(torch.equal(full[:nbytes], host)) and full.numel() % (256 * world) == 0)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -57,7 +63,7 @@ def test_gather_over_gloo_world_size_2():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=120) for _ in range(3)]
+    results = [q.get(timeout=120) for _ in range(3 + 2 * 4)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
