@@ -855,6 +855,7 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
                     a.tile0 = tile0; a.ntiles = ntiles; a.L = dp.L;
                     for (int j = 0; j < dp.L; j++) {
                         const unsigned cls = packed_class(c.P.pos[j]);
+                        if (cls == 31u) continue;                 // accepts every byte: no constraint (the window bound is checked per hit)
                         const int s = plane_of(cls);
                         if (s == 5) a.cls[a.npos[5]] = (unsigned char)cls;
                         a.shift[s][a.npos[s]++] = (unsigned char)j;

@@ -258,6 +258,22 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_addr(unsigned bar_addr)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_addr(unsigned bar_addr, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar_addr), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -287,8 +303,61 @@ __device__ __forceinline__ void exact_apply(unsigned (&M)[EX_WPL], const unsigne
     }
 }
 
+// class planes: one LOP3 per word with the truth table of the class over (hi, lo, x)
+template <int LUT>
+__device__ __forceinline__ unsigned lop3_const(unsigned a, unsigned b, unsigned c)
+{
+    unsigned r;
+    asm volatile("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT));   // volatile: keeps the 32 cases from being speculated
+    return r;
+}
+// truth table over (hi, lo, x) of a class given as bits A,C,G,T,X ; A=000 C=010 G=110 T=100 X=xx1
+template <int CLS>
+struct SpLut {
+    static const int value = ((CLS & 1) ? 0x01 : 0) | ((CLS & 2) ? 0x04 : 0) | ((CLS & 4) ? 0x40 : 0) | ((CLS & 8) ? 0x10 : 0) | ((CLS & 16) ? 0xAA : 0);
+};
+template <int CLS>
+__device__ __forceinline__ void sp_plane(unsigned (&P)[EX_WPL + 2], const unsigned (&H)[EX_WPL + 2], const unsigned (&L)[EX_WPL + 2],
+                                         const unsigned (&X)[EX_WPL + 2])
+{
+#pragma unroll
+    for (int w = 0; w < EX_WPL + 2; w++) P[w] = lop3_const<SpLut<CLS>::value>(H[w], L[w], X[w]);
+}
+__device__ __forceinline__ void sp_plane_dyn(int cls, unsigned (&P)[EX_WPL + 2], const unsigned (&H)[EX_WPL + 2],
+                                             const unsigned (&L)[EX_WPL + 2], const unsigned (&X)[EX_WPL + 2])
+{
+    switch (cls & 31) {
+#define SP_CASE(c) case c: sp_plane<c>(P, H, L, X); break;
+        SP_CASE(0) SP_CASE(1) SP_CASE(2) SP_CASE(3) SP_CASE(4) SP_CASE(5) SP_CASE(6) SP_CASE(7)
+        SP_CASE(8) SP_CASE(9) SP_CASE(10) SP_CASE(11) SP_CASE(12) SP_CASE(13) SP_CASE(14) SP_CASE(15)
+        SP_CASE(16) SP_CASE(17) SP_CASE(18) SP_CASE(19) SP_CASE(20) SP_CASE(21) SP_CASE(22) SP_CASE(23)
+        SP_CASE(24) SP_CASE(25) SP_CASE(26) SP_CASE(27) SP_CASE(28) SP_CASE(29) SP_CASE(30) SP_CASE(31)
+#undef SP_CASE
+    }
+}
+
+// two positions reading the same plane: one 3-input logic op per word instead of two ANDs
 template <bool LONG>
-__global__ void __launch_bounds__((EX_WARPS + 1) * 32) k_scan_packed_exact(const ExactArgs a)
+__device__ __forceinline__ void exact_apply2(unsigned (&M)[EX_WPL], const unsigned (&P)[EX_WPL + 2], int s1, int s2)
+{
+    if (!LONG || (s1 < 32 && s2 < 32)) {
+#pragma unroll
+        for (int w = 0; w < EX_WPL; w++) M[w] = M[w] & __funnelshift_r(P[w], P[w + 1], s1) & __funnelshift_r(P[w], P[w + 1], s2);
+    } else {
+        exact_apply<LONG>(M, P, s1);
+        exact_apply<LONG>(M, P, s2);
+    }
+}
+template <bool LONG>
+__device__ __forceinline__ void exact_apply_group(unsigned (&M)[EX_WPL], const unsigned (&P)[EX_WPL + 2], const unsigned char *sh, int n)
+{
+    int e = 0;
+    for (; e + 1 < n; e += 2) exact_apply2<LONG>(M, P, sh[e], sh[e + 1]);
+    if (e < n) exact_apply<LONG>(M, P, sh[e]);
+}
+
+template <bool LONG>
+__global__ void __launch_bounds__((EX_WARPS + 1) * 32, 5) k_scan_packed_exact(const ExactArgs a)
 {
     extern __shared__ __align__(128) unsigned char ex_smem[];
     __shared__ unsigned long long hitbuf_all[EX_WARPS + 1][EX_HITBUF];
@@ -316,8 +385,7 @@ __global__ void __launch_bounds__((EX_WARPS + 1) * 32) k_scan_packed_exact(const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](long long it) {                       // thread 0 only
-        const int s = (int)(it % EX_STAGES);
+    auto issue = [&](long long it, int s) {                // producer lane only
         const long long bt = blockIdx.x + it * gridDim.x;
         const long long q = (a.tile0 * 128) + bt * EX_WORDS;
         unsigned *dst = stage_base + (size_t)s * (3 * EX_ROW);
@@ -328,17 +396,23 @@ __global__ void __launch_bounds__((EX_WARPS + 1) * 32) k_scan_packed_exact(const
     };
     if (wib == EX_WARPS) {
         // producer warp: one lane keeps the ring full, independent of the consumers' progress
-        if (lane == 0)
+        if (lane == 0) {
+            int s = 0;
+            unsigned ph = 1;                              // parity of the round before the one being filled
             for (long long it = 0; it < my; it++) {
-                if (it >= EX_STAGES) mbar_wait(&empty[it % EX_STAGES], (unsigned)(((it / EX_STAGES) - 1) & 1));
-                issue(it);
+                if (it >= EX_STAGES) mbar_wait(&empty[s], ph);
+                issue(it, s);
+                if (++s == EX_STAGES) { s = 0; ph ^= 1u; }
             }
+        }
         return;
     }
-    for (long long it = 0; it < my; it++) {
-        const int s = (int)(it % EX_STAGES);
-        const unsigned ph = (unsigned)((it / EX_STAGES) & 1);
-        mbar_wait(&full[s], ph);
+    // ring position kept incrementally: no 64-bit division by EX_STAGES per tile
+    int s = 0;
+    unsigned ph = 0;
+    const unsigned full_base = smem_u32(full), empty_base = smem_u32(empty);
+    for (long long it = 0; it < my; it++, s = (s + 1 == EX_STAGES ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
+        mbar_wait_addr(full_base + 8u * s, ph);
         const unsigned *sp = stage_base + (size_t)s * (3 * EX_ROW) + wib * (32 * EX_WPL) + EX_WPL * lane;
         unsigned H[EX_WPL + 2], Lw[EX_WPL + 2], X[EX_WPL + 2];
 #pragma unroll
@@ -355,7 +429,7 @@ __global__ void __launch_bounds__((EX_WARPS + 1) * 32) k_scan_packed_exact(const
             H[EX_WPL] = h2.x; H[EX_WPL + 1] = h2.y; Lw[EX_WPL] = l2.x; Lw[EX_WPL + 1] = l2.y; X[EX_WPL] = x2.x; X[EX_WPL + 1] = x2.y;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);            // this warp's slice is in registers
+        if (lane == 0) mbar_arrive_addr(empty_base + 8u * s);   // this warp's slice is in registers
         const long long bt = blockIdx.x + it * gridDim.x;
         unsigned M[EX_WPL];
 #pragma unroll
@@ -364,47 +438,50 @@ __global__ void __launch_bounds__((EX_WARPS + 1) * 32) k_scan_packed_exact(const
         if (a.npos[0]) {
 #pragma unroll
             for (int w = 0; w < EX_WPL + 2; w++) P[w] = ~(H[w] | Lw[w] | X[w]);
-            for (int e = 0; e < a.npos[0]; e++) exact_apply<LONG>(M, P, a.shift[0][e]);
+            exact_apply_group<LONG>(M, P, a.shift[0], a.npos[0]);
         }
         if (a.npos[1]) {
 #pragma unroll
             for (int w = 0; w < EX_WPL + 2; w++) P[w] = Lw[w] & ~H[w];
-            for (int e = 0; e < a.npos[1]; e++) exact_apply<LONG>(M, P, a.shift[1][e]);
+            exact_apply_group<LONG>(M, P, a.shift[1], a.npos[1]);
         }
         if (a.npos[2]) {
 #pragma unroll
             for (int w = 0; w < EX_WPL + 2; w++) P[w] = H[w] & Lw[w];
-            for (int e = 0; e < a.npos[2]; e++) exact_apply<LONG>(M, P, a.shift[2][e]);
+            exact_apply_group<LONG>(M, P, a.shift[2], a.npos[2]);
         }
         if (a.npos[3]) {
 #pragma unroll
             for (int w = 0; w < EX_WPL + 2; w++) P[w] = H[w] & ~Lw[w];
-            for (int e = 0; e < a.npos[3]; e++) exact_apply<LONG>(M, P, a.shift[3][e]);
+            exact_apply_group<LONG>(M, P, a.shift[3], a.npos[3]);
         }
         if (a.npos[4]) {
-            for (int e = 0; e < a.npos[4]; e++) exact_apply<LONG>(M, X, a.shift[4][e]);
+            exact_apply_group<LONG>(M, X, a.shift[4], a.npos[4]);
         }
         for (int e = 0; e < a.npos[5]; e++) {
-            const unsigned c = a.cls[e];
-            const unsigned sA = (c & 1) ? ~0u : 0u, sC = (c & 2) ? ~0u : 0u, sG = (c & 4) ? ~0u : 0u, sT = (c & 8) ? ~0u : 0u,
-                           sX = (c & 16) ? ~0u : 0u;
-#pragma unroll
-            for (int w = 0; w < EX_WPL + 2; w++)
-                P[w] = (~(H[w] | Lw[w] | X[w]) & sA) | (Lw[w] & ~H[w] & sC) | (H[w] & Lw[w] & sG) | (H[w] & ~Lw[w] & sT) | (X[w] & sX);
+            sp_plane_dyn(a.cls[e], P, H, Lw, X);
             exact_apply<LONG>(M, P, a.shift[5][e]);
         }
         // ---- hits of this warp tile: buffered in shared memory, no per-hit global atomics ----
         unsigned mine = 0;
 #pragma unroll
         for (int w = 0; w < EX_WPL; w++) mine += __popc(M[w]);
-        if (!__any_sync(0xffffffffu, mine != 0)) continue;
-        unsigned incl = mine;
+        const unsigned have = __ballot_sync(0xffffffffu, mine != 0);
+        if (!have) continue;
+        // offsets: one ballot when no lane holds more than one hit (the usual case), a shuffle scan otherwise
+        unsigned incl, total;
+        if (!__any_sync(0xffffffffu, mine > 1)) {
+            incl = __popc(have & (0xffffffffu >> (31 - lane)));
+            total = __popc(have);
+        } else {
+            incl = mine;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            total = __shfl_sync(0xffffffffu, incl, 31);
         }
-        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
         const long long wbase = ((a.tile0 * 128) + bt * EX_WORDS + wib * (32 * EX_WPL)) * 32;   // text position of the warp tile
         // only the first / last tiles of the scanned range need the per-hit range test
         const bool inside = wbase >= a.a0 && wbase + 32 * 32 * EX_WPL <= (a.a1 < a.n - a.L + 1 ? a.a1 : a.n - a.L + 1);
@@ -752,38 +829,6 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
 #define SP_STAGES 3
 #define SP_CTAS 4                        // CTAs per SM the register budget is cut for (5 x 96 registers measured slower)
 #define SP_QUEUE 128                     // per-warp anchor queue (ring of keys)
-
-template <int LUT>
-__device__ __forceinline__ unsigned lop3_const(unsigned a, unsigned b, unsigned c)
-{
-    unsigned r;
-    asm volatile("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT));   // volatile: keeps the 32 cases from being speculated
-    return r;
-}
-// truth table over (hi, lo, x) of a class given as bits A,C,G,T,X ; A=000 C=010 G=110 T=100 X=xx1
-template <int CLS>
-struct SpLut {
-    static const int value = ((CLS & 1) ? 0x01 : 0) | ((CLS & 2) ? 0x04 : 0) | ((CLS & 4) ? 0x40 : 0) | ((CLS & 8) ? 0x10 : 0) | ((CLS & 16) ? 0xAA : 0);
-};
-template <int CLS>
-__device__ __forceinline__ void sp_plane(unsigned (&P)[EX_WPL + 2], const unsigned (&H)[EX_WPL + 2], const unsigned (&L)[EX_WPL + 2],
-                                         const unsigned (&X)[EX_WPL + 2])
-{
-#pragma unroll
-    for (int w = 0; w < EX_WPL + 2; w++) P[w] = lop3_const<SpLut<CLS>::value>(H[w], L[w], X[w]);
-}
-__device__ __forceinline__ void sp_plane_dyn(int cls, unsigned (&P)[EX_WPL + 2], const unsigned (&H)[EX_WPL + 2],
-                                             const unsigned (&L)[EX_WPL + 2], const unsigned (&X)[EX_WPL + 2])
-{
-    switch (cls & 31) {
-#define SP_CASE(c) case c: sp_plane<c>(P, H, L, X); break;
-        SP_CASE(0) SP_CASE(1) SP_CASE(2) SP_CASE(3) SP_CASE(4) SP_CASE(5) SP_CASE(6) SP_CASE(7)
-        SP_CASE(8) SP_CASE(9) SP_CASE(10) SP_CASE(11) SP_CASE(12) SP_CASE(13) SP_CASE(14) SP_CASE(15)
-        SP_CASE(16) SP_CASE(17) SP_CASE(18) SP_CASE(19) SP_CASE(20) SP_CASE(21) SP_CASE(22) SP_CASE(23)
-        SP_CASE(24) SP_CASE(25) SP_CASE(26) SP_CASE(27) SP_CASE(28) SP_CASE(29) SP_CASE(30) SP_CASE(31)
-#undef SP_CASE
-    }
-}
 
 // One lock-step round of the Myers filter on up to 64 queued anchors, two per lane.  A queue entry is
 // the key (anchor << 4 | piece); the 64 symbols starting at the anchor's pattern start b are fetched
