@@ -175,7 +175,7 @@ def run_ours(args):
     def run_search(d, p):
         if world == 1:
             return eng.search(d, p, kopt)
-        return sharded.search(d, p, kopt)                  # hits on rank 0, None elsewhere
+        return sharded.search_fills(d, p, kopt)            # fill-sharded: hits on rank 0, None elsewhere
 
     def step_resident():
         hits = []
@@ -252,7 +252,7 @@ def run_ours(args):
         "config": {"workload": "configs[4]: single 2-mismatch degenerate motif %s (-k %s), both strands, synthetic %.2f Gb 24-chromosome genome, chromosome-sharded" % (MOTIF, kopt, total_bases / 1e9),
                    "bases": total_bases, "patterns_per_step": 2, "plan": pm.plan(pats[0], kopt)["type"],
                    "l2_policy": "inputs (>= %.1f GB per rank) larger than the 126 MB L2" % (nbytes / 1e9),
-                   "parallelism": "file positions split over %d rank(s); NCCL gather of verified candidates, chain stage on rank 0" % world},
+                   "parallelism": "buffer fills (1.6 MB, independent by the reference's own restart rule) split over %d rank(s) by position; one NCCL all-gather of the per-rank hit lists" % world},
         "e2e": {"value": round(e2e, 3), "unit": "pattern*Gbases/s", "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": round(ms_e2e, 3)},
         "gpu_launches": int(launches),

@@ -127,6 +127,14 @@ int pm_resolve_device(pm_engine *e, pm_dataset *d, const char *pattern, const ch
                       const pm_candidate *dev_cands, int64_t ncands,
                       pm_hit *hits, int64_t cap, int64_t *nhits);
 
+/* Fill-sharded search (the multi-GPU path bench.py uses): nrgrep_coords restarts its scan at every buffer fill
+ * (recSearchFile @402298) and no hit crosses a fill, so fills are independent.  Searches the fills that START in
+ * [pos_beg, pos_end) completely and leaves their hits, in output order, in DEVICE memory; ranks covering the
+ * file with contiguous ranges get the whole hit list by concatenation. */
+int pm_search_fills_device(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt,
+                           int64_t pos_beg, int64_t pos_end, pm_hit *dev_hits, int64_t cap, int64_t *nhits,
+                           int64_t *dev_count /* optional: the count is also stored here, in device memory */);
+
 /* page-locked host buffers for large hit arrays (optional; any host pointer works for `hits`) */
 void *pm_host_alloc(int64_t bytes);
 void pm_host_free(void *p);

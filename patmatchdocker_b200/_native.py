@@ -69,6 +69,7 @@ def load():
     L.pm_engine_set_scan_mode.argtypes = [vp, ctypes.c_int]
     L.pm_engine_set_buffer_size.argtypes = [vp, i64]
     L.pm_engine_set_fused_filter.argtypes = [vp, ctypes.c_int]
+    L.pm_search_fills_device.argtypes = [vp, vp, ctypes.c_char_p, ctypes.c_char_p, i64, i64, vp, i64, ctypes.POINTER(i64), vp]
     L.pm_dataset_create.argtypes = [vp, vp, i64, ctypes.POINTER(vp)]
     L.pm_dataset_wrap_device.argtypes = [vp, vp, i64, ctypes.POINTER(vp)]
     L.pm_dataset_destroy.argtypes = [vp]
@@ -176,6 +177,19 @@ class Engine:
 
     def set_stream(self, cuda_stream_handle):
         _check(load().pm_engine_set_stream(self._h, ctypes.c_void_p(cuda_stream_handle or 0)))
+
+    def search_fills_device(self, dataset, pattern, kopt, pos_beg, pos_end, dev_ptr, cap, dev_count_ptr=None):
+        """pm_search_fills_device: hits of the fills starting in [pos_beg, pos_end) into device memory (cap records
+        of 2 x int64). Returns the number of hits, negated when it exceeds cap (nothing was copied then); the count
+        is also stored at dev_count_ptr (device memory) when given."""
+        n = ctypes.c_int64()
+        rc = load().pm_search_fills_device(self._h, dataset._h, _b(pattern), _b(kopt), int(pos_beg), int(pos_end),
+                                           ctypes.c_void_p(dev_ptr), int(cap), ctypes.byref(n),
+                                           ctypes.c_void_p(dev_count_ptr) if dev_count_ptr else None)
+        if rc == PM_ERR_OVERFLOW:
+            return -int(n.value)
+        _check(rc)
+        return int(n.value)
 
     def set_scan_mode(self, mode):
         """'auto' | 'bytes' | 'packed' -- which scan kernel SIMPLE/SPLIT plans use."""

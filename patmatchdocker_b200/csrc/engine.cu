@@ -489,6 +489,7 @@ struct pm_dataset {
     // buffer fills of the reference for the engine's buffer size
     std::vector<long long> newlines;   // sorted positions of '\n'
     long long fills_bufsize = -1;
+    std::vector<long long> fill_starts; // host copy of S[] (pm_search_fills_device snaps its range to fills)
     long long *d_fills = nullptr;      // S[0..nfills) then E[0..nfills), then the forced cuts
     int nfills = 0;
     int ncuts = 0;                     // fill boundaries that do not fall on a '\n'
@@ -583,6 +584,7 @@ static int ensure_fills(pm_engine *e, pm_dataset *d, Fills *out)
         CK(cudaStreamSynchronize(e->stream));
         d->nfills = (int)S.size();
         d->ncuts = (int)cuts.size();
+        d->fill_starts = S;
         d->fills_bufsize = e->bufsize;
     }
     out->S = d->d_fills; out->E = d->d_fills + d->nfills; out->n = d->nfills;
@@ -1168,7 +1170,7 @@ static int copy_to_host(pm_engine *e, void *dst, const void *src, size_t bytes)
 // chain + select over ncand candidates in d_cands; hits copied to the host
 static int resolve_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, const Cand *d_cands, long long ncand,
                               const unsigned long long *dTL, const unsigned long long *dTR,
-                              pm_hit *hits, int64_t cap, int64_t *nhits)
+                              pm_hit *hits, int64_t cap, int64_t *nhits, bool hits_on_device = false)
 {
     int rc;
     long long nh = 0;
@@ -1203,6 +1205,7 @@ static int resolve_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, co
     CK(cudaEventRecord(e->ev[5], e->stream));
     if (hits && nh > 0) {
         if (nh > cap) overflow = true;                   // the list stays on the device for pm_last_hits
+        else if (hits_on_device) CK(cudaMemcpyAsync(hits, e->hits2.p, (size_t)nh * sizeof(pm_hit), cudaMemcpyDeviceToDevice, e->stream));
         else if ((rc = copy_to_host(e, hits, e->hits2.p, (size_t)nh * sizeof(pm_hit)))) return rc;
     }
     CK(cudaStreamSynchronize(e->stream));
@@ -1236,6 +1239,52 @@ int pm_search(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt
     if ((rc = produce_candidates(e, d, c, 0, d->n + 1, dB, dTL, dTR, &ncand))) return rc;
     e->stats.verified = ncand;
     rc = resolve_candidates(e, d, c, (const Cand *)e->cands.p, ncand, dTL, dTR, hits, cap, nhits);
+    finish_stats(e);
+    return rc;
+}
+
+// Fill-sharded search for multi-GPU runs.  recSearchFile @402298 restarts its scan at every buffer fill and no
+// hit crosses a fill, so whole fills are independent units: this call searches the fills that START in
+// [pos_beg, pos_end) completely (scan, verification, chain stage) and leaves their hits, in output order, in
+// device memory.  Ranks that cover [0, n] with contiguous ranges produce the complete hit list by
+// concatenation, with no candidate exchange and no serial stage on one rank.
+int pm_search_fills_device(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt, int64_t pos_beg, int64_t pos_end,
+                           pm_hit *dev_hits, int64_t cap, int64_t *nhits, int64_t *dev_count)
+{
+    if (!e || !d || !pattern || !kopt || !nhits || d->e != e) { g_err = "bad argument"; return PM_ERR_ARG; }
+    CK(cudaSetDevice(e->device));
+    (void)cudaGetLastError();
+    Compiled c;
+    int rc = compile(pattern, kopt, c, true);
+    if (rc) return rc;
+    e->stats = pm_stats{};
+    *nhits = 0;
+    const unsigned long long *dB, *dTL, *dTR;
+    if ((rc = upload_tables(e, c, &dB, &dTL, &dTR))) return rc;
+    Fills fills;
+    if ((rc = ensure_fills(e, d, &fills))) return rc;
+    const std::vector<long long> &S = d->fill_starts;
+    const long long f0 = std::lower_bound(S.begin(), S.end(), (long long)pos_beg) - S.begin();
+    const long long f1 = std::lower_bound(S.begin(), S.end(), (long long)pos_end) - S.begin();
+    long long ncand = 0;
+    if (f0 < f1) {
+        // anchors whose fill (fill_of: the last fill starting at or before the anchor; FWD plans anchor one byte later)
+        // is one of f0 .. f1-1
+        const long long shift = c.dp.type == PM_PLAN_FWD ? 1 : 0;
+        const long long a0 = S[f0] + shift;
+        const long long a1 = f1 < (long long)S.size() ? S[f1] + shift : d->n + 1;
+        if ((rc = produce_candidates(e, d, c, a0, a1, dB, dTL, dTR, &ncand))) return rc;
+    } else {
+        for (int i = 0; i < 4; i++) CK(cudaEventRecord(e->ev[i], e->stream));
+    }
+    e->stats.verified = ncand;
+    rc = resolve_candidates(e, d, c, (const Cand *)e->cands.p, ncand, dTL, dTR, dev_hits, cap, nhits, true);
+    if (dev_count && (rc == PM_OK || rc == PM_ERR_OVERFLOW)) {
+        // the count travels with the hits (e.g. as the header row of an all-gather) without a host round trip
+        e->h_count[3] = (unsigned long long)*nhits;
+        CK(cudaMemcpyAsync(dev_count, e->h_count + 3, 8, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    }
     finish_stats(e);
     return rc;
 }

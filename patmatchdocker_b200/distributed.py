@@ -99,6 +99,58 @@ class DeviceShardedSearch:
         self.full = assemble_from_host(host, self.rank, self.world, self.device, getattr(self, "full", None), self.group)
         return self.engine.wrap_device(self.full.data_ptr(), int(host.numel()))
 
+    def search_fills(self, dataset, pattern, kopt):
+        """Fill-sharded search (pm_search_fills_device): the reference restarts its scan at every buffer fill, so
+        every rank searches the fills that start in its position range completely, chain stage included, and
+        the only exchange is one all-gather of the per-rank hit lists (16 B per hit; a header row, written on the
+        device, carries the count).  Rank 0 returns the hit list of Engine.search as a view of a pinned buffer
+        that stays valid until the next call; the other ranks return None."""
+        import torch.distributed as dist
+        torch = self.torch
+        from ._native import HIT_DTYPE
+        if not hasattr(self, "hcap"):
+            self.hcap = 1 << 16
+            self.hrows = self.hcap
+            self.hmine = None
+        beg, end = shard_ranges(len(dataset), self.world)[self.rank]
+        on_gpu = str(self.device) != "cpu"
+        while True:
+            if self.hmine is None or self.hmine.shape[0] != self.hcap:
+                self.hmine = torch.zeros((self.hcap, 2), dtype=torch.int64, device=self.device)
+                self.hall = torch.empty((self.hcap * self.world, 2), dtype=torch.int64, device=self.device)
+                self.hhost = torch.empty((self.hcap * self.world, 2), dtype=torch.int64, pin_memory=on_gpu) if self.rank == 0 else None
+            n = self.engine.search_fills_device(dataset, pattern, kopt, beg, end, self.hmine[1:].data_ptr(), self.hcap - 1,
+                                                self.hmine.data_ptr())
+            rows = min(self.hrows, self.hcap)
+            flat = self.hall[: self.world * rows]
+            view = flat.view(self.world, rows, 2)
+            if self.world > 1:
+                dist.all_gather_into_tensor(view, self.hmine[:rows], group=self.group)
+            else:
+                view[0] = self.hmine[:rows]
+            if self.rank == 0:                                     # one D2H of everything gathered, one synchronisation
+                hview = self.hhost[: self.world * rows]
+                hview.copy_(flat, non_blocking=True)
+                if on_gpu:
+                    torch.cuda.current_stream().synchronize()
+                counts = hview.view(self.world, rows, 2)[:, 0, 0].tolist()
+            else:
+                counts = view[:, 0, 0].tolist()
+            need = max(counts) + 1
+            self.hrows = max(256, int(need * 1.25) + 16)          # agreed by construction: everyone saw the same counts
+            if need <= rows:
+                break
+            if need > self.hcap:                                   # some rank overflowed: grow everywhere and search again
+                self.hcap = need + 1024
+        if self.rank != 0:
+            return None
+        h = self.hhost[: self.world * rows].numpy().reshape(self.world, rows, 2)
+        if self.world == 1:
+            out = h[0, 1:1 + counts[0]]
+        else:
+            out = np.concatenate([h[r, 1:1 + int(counts[r])] for r in range(self.world)])
+        return np.ascontiguousarray(out).view(HIT_DTYPE).reshape(-1)
+
     def search(self, dataset, pattern, kopt):
         """One collective per search: every rank all-gathers `rows` candidate records plus a header row
         holding its true count, so all ranks learn all counts and agree on the size of the next exchange

@@ -277,6 +277,40 @@ def test_sharded_candidates_then_resolve_equals_search(engine, scan_mode):
         ds.close()
 
 
+def test_fill_sharded_search_equals_search(engine, scan_mode):
+    # pm_search_fills_device: whole fills are independent (the reference restarts at every fill), so the hit lists of
+    # contiguous position ranges, each snapped to the fills that start inside it, concatenate to the full hit list
+    import torch
+    rng = random.Random(5)
+    buf = torch.zeros((1 << 16, 2), dtype=torch.int64, device="cuda")
+    for it in range(40):
+        k = rng.choice([0, 1, 2])
+        m = rng.randint(max(3, 2 * k + 2), 16)
+        pat, members = random_pattern(rng, DNA, m)
+        if it % 7 == 0:
+            pat = "^" + pat
+        kopt = "%d%s" % (k, rng.choice(["ids", "s", "id"]))
+        text = random_text(rng, members, DNA, k, nrec=rng.randint(2, 6), lo=50, hi=2500).encode("latin-1")
+        bufsize = rng.choice([1600000, 64, 200, 1000])
+        engine.set_buffer_size(bufsize)
+        try:
+            ds = engine.load_dataset(text)
+            full = [(int(b), int(e)) for b, e in engine.search(ds, pat, kopt)]
+            world = rng.randint(2, 5)
+            cuts = sorted(rng.randint(0, len(text) + 1) for _ in range(world - 1))
+            edges = [0] + cuts + [len(text) + 1]
+            got = []
+            for r in range(world):
+                n = engine.search_fills_device(ds, pat, kopt, edges[r], edges[r + 1], buf.data_ptr(), buf.shape[0])
+                assert n >= 0
+                got += [(int(b), int(e)) for b, e in buf[:n].cpu().numpy()]
+            ds.close()
+        finally:
+            engine.set_buffer_size(1600000)
+        assert got == full, (pat, kopt, bufsize, edges)
+        assert full == O.search(pat, text, kopt, bufsize=bufsize)
+
+
 def test_batch_equals_single(engine):
     rng = random.Random(3)
     pats = [random_pattern(rng, DNA, rng.randint(5, 12), cls_pct=0.3)[0] for _ in range(40)]
