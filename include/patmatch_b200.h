@@ -98,6 +98,13 @@ int64_t pm_dataset_size(const pm_dataset *d);
 int pm_search(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt,
               pm_hit *hits, int64_t cap, int64_t *nhits);
 
+/* Cold request (what every nrgrep_coords run is: it reads the file again): the file bytes are still in HOST memory.
+ * Uploads them in chunks (chunk_bytes, 0 = 256 MiB; pinned memory gives the overlap) and, while the next chunk
+ * crosses PCIe, packs the chunk that arrived and searches the buffer fills it completes, for every pattern.
+ * Results as pm_search_batch (offsets has npat+1 entries); *out receives the dataset, resident for later searches. */
+int pm_search_stream(pm_engine *e, const uint8_t *host_bytes, int64_t n, int npat, const char *const *patterns,
+                     const char *kopt, int64_t chunk_bytes, pm_hit *hits, int64_t cap, int64_t *offsets, pm_dataset **out);
+
 /* After pm_search returned PM_ERR_OVERFLOW (or was called with hits = NULL): copy the hit list of that
  * search, which is still on the device, without searching again. */
 int pm_last_hits(pm_engine *e, pm_hit *hits, int64_t cap, int64_t *nhits);

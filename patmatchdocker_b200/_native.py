@@ -70,6 +70,8 @@ def load():
     L.pm_engine_set_buffer_size.argtypes = [vp, i64]
     L.pm_engine_set_fused_filter.argtypes = [vp, ctypes.c_int]
     L.pm_search_fills_device.argtypes = [vp, vp, ctypes.c_char_p, ctypes.c_char_p, i64, i64, vp, i64, ctypes.POINTER(i64), vp]
+    L.pm_search_stream.argtypes = [vp, vp, i64, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_char_p, i64, vp, i64,
+                                   ctypes.POINTER(i64), ctypes.POINTER(vp)]
     L.pm_dataset_create.argtypes = [vp, vp, i64, ctypes.POINTER(vp)]
     L.pm_dataset_wrap_device.argtypes = [vp, vp, i64, ctypes.POINTER(vp)]
     L.pm_dataset_destroy.argtypes = [vp]
@@ -177,6 +179,26 @@ class Engine:
 
     def set_stream(self, cuda_stream_handle):
         _check(load().pm_engine_set_stream(self._h, ctypes.c_void_p(cuda_stream_handle or 0)))
+
+    def search_stream(self, data, patterns, kopt="0ids", chunk_bytes=0, cap=1 << 18):
+        """pm_search_stream: `data` (bytes or a uint8 numpy array, pinned for full speed) is uploaded in chunks while
+        the chunks that have arrived are packed and searched.  -> (Dataset resident for later searches,
+        [hit array per pattern])."""
+        L = load()
+        buf = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) else np.ascontiguousarray(data, dtype=np.uint8)
+        arr = (ctypes.c_char_p * len(patterns))(*[_b(p) for p in patterns])
+        offs = (ctypes.c_int64 * (len(patterns) + 1))()
+        h = ctypes.c_void_p()
+        hits = np.empty(cap, dtype=HIT_DTYPE)            # filled by memcpy from host vectors: pageable is fine
+        rc = L.pm_search_stream(self._h, ctypes.c_void_p(buf.ctypes.data), buf.size, len(patterns), arr, _b(kopt), int(chunk_bytes),
+                                ctypes.c_void_p(hits.ctypes.data), cap, offs, ctypes.byref(h))
+        if rc == PM_ERR_OVERFLOW:                      # the dataset is resident: fetch the lists with ordinary searches
+            ds = Dataset(self, h)
+            return ds, [self.search(ds, p, kopt, cap=max(int(offs[len(patterns)]), 1)) for p in patterns]
+        _check(rc)
+        ds = Dataset(self, h)
+        ds._keep = buf
+        return ds, [hits[offs[i]:offs[i + 1]] for i in range(len(patterns))]
 
     def search_fills_device(self, dataset, pattern, kopt, pos_beg, pos_end, dev_ptr, cap, dev_count_ptr=None):
         """pm_search_fills_device: hits of the fills starting in [pos_beg, pos_end) into device memory (cap records

@@ -458,7 +458,7 @@ struct DevBuf {
 struct pm_engine {
     int device = 0;
     int sms = 148;
-    cudaStream_t own = nullptr, stream = nullptr;
+    cudaStream_t own = nullptr, stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     DevBuf keys, keys2, cands, hits, hits2, sel, tables, counters, cubtmp;
     unsigned long long *h_count = nullptr;          // pinned
@@ -491,6 +491,7 @@ struct pm_dataset {
     long long fills_bufsize = -1;
     std::vector<long long> fill_starts; // host copy of S[] (pm_search_fills_device snaps its range to fills)
     long long *d_fills = nullptr;      // S[0..nfills) then E[0..nfills), then the forced cuts
+    size_t fills_cap = 0;              // entries allocated at d_fills
     int nfills = 0;
     int ncuts = 0;                     // fill boundaries that do not fall on a '\n'
 
@@ -553,38 +554,64 @@ static int pack_dataset(pm_engine *e, pm_dataset *d)
 // recSearchFile @402298-4024f0): a fill of `bufsize` bytes that does not reach EOF is scanned up to and
 // including its last '\n' and the next fill starts AT that '\n'; without a usable '\n' the fill is scanned
 // whole ("Record longer than buffer size ... has been split") and the next one starts right after it.
+// `avail` = number of file bytes whose newlines are known; with complete = false only the fills that are already
+// determined (s0 + bufsize <= avail) are produced -- the streaming upload searches them while the rest arrives.
+static void compute_fills(const std::vector<long long> &newlines, long long n, long long bufsize, long long avail, bool complete,
+                          std::vector<long long> &S, std::vector<long long> &E, std::vector<long long> &cuts)
+{
+    const long long bs = bufsize > 0 ? bufsize : n + 1;
+    long long s0 = 0;
+    while (n - s0 > 0) {
+        const long long dsize = std::min(bs, n - s0);
+        if (!complete && s0 + dsize > avail) break;
+        long long en, next;
+        if (dsize < bs) { en = s0 + dsize; next = n; }
+        else {
+            // last newline p with s0 < p <= s0 + dsize - 1
+            auto it = std::upper_bound(newlines.begin(), newlines.end(), s0 + dsize - 1);
+            long long p = -1;
+            if (it != newlines.begin()) p = *(it - 1);
+            if (p > s0) { en = p + 1; next = p; }
+            else { en = s0 + dsize; next = s0 + dsize; if (next < n) cuts.push_back(next); }
+        }
+        S.push_back(s0); E.push_back(en);
+        s0 = next;
+    }
+    if (complete && S.empty()) { S.push_back(0); E.push_back(0); }
+}
+
+static int upload_fills(pm_engine *e, pm_dataset *d, const std::vector<long long> &S, const std::vector<long long> &E,
+                        const std::vector<long long> &cuts)
+{
+    // S | E | cuts, packed; the buffer is only reallocated when it has to grow (cudaFree synchronises the whole
+    // device, which would serialise the streaming upload with its own copies)
+    const size_t need = S.size() * 2 + cuts.size() + 1;
+    if (need > d->fills_cap) {
+        if (d->d_fills) { cudaFree(d->d_fills); d->d_fills = nullptr; d->fills_cap = 0; }
+        const size_t want = std::max(need * 2, (size_t)4096);
+        CK(cudaMalloc((void **)&d->d_fills, want * 8));
+        d->fills_cap = want;
+    }
+    if (!S.empty()) {
+        CK(cudaMemcpyAsync(d->d_fills, S.data(), S.size() * 8, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(d->d_fills + S.size(), E.data(), S.size() * 8, cudaMemcpyHostToDevice, e->stream));
+    }
+    if (!cuts.empty())
+        CK(cudaMemcpyAsync(d->d_fills + 2 * S.size(), cuts.data(), cuts.size() * 8, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    d->nfills = (int)S.size();
+    d->ncuts = (int)cuts.size();
+    d->fill_starts = S;
+    return PM_OK;
+}
+
 static int ensure_fills(pm_engine *e, pm_dataset *d, Fills *out)
 {
     if (d->fills_bufsize != e->bufsize) {
         std::vector<long long> S, E, cuts;
-        const long long n = d->n, bs = e->bufsize > 0 ? e->bufsize : n + 1;
-        long long s0 = 0;
-        while (n - s0 > 0) {
-            const long long dsize = std::min(bs, n - s0);
-            long long en, next;
-            if (dsize < bs) { en = s0 + dsize; next = n; }
-            else {
-                // last newline p with s0 < p <= s0 + dsize - 1
-                auto it = std::upper_bound(d->newlines.begin(), d->newlines.end(), s0 + dsize - 1);
-                long long p = -1;
-                if (it != d->newlines.begin()) p = *(it - 1);
-                if (p > s0) { en = p + 1; next = p; }
-                else { en = s0 + dsize; next = s0 + dsize; if (next < n) cuts.push_back(next); }
-            }
-            S.push_back(s0); E.push_back(en);
-            s0 = next;
-        }
-        if (S.empty()) { S.push_back(0); E.push_back(0); }
-        if (d->d_fills) { cudaFree(d->d_fills); d->d_fills = nullptr; }
-        CK(cudaMalloc((void **)&d->d_fills, (S.size() * 2 + cuts.size() + 1) * 8));
-        CK(cudaMemcpyAsync(d->d_fills, S.data(), S.size() * 8, cudaMemcpyHostToDevice, e->stream));
-        CK(cudaMemcpyAsync(d->d_fills + S.size(), E.data(), S.size() * 8, cudaMemcpyHostToDevice, e->stream));
-        if (!cuts.empty())
-            CK(cudaMemcpyAsync(d->d_fills + 2 * S.size(), cuts.data(), cuts.size() * 8, cudaMemcpyHostToDevice, e->stream));
-        CK(cudaStreamSynchronize(e->stream));
-        d->nfills = (int)S.size();
-        d->ncuts = (int)cuts.size();
-        d->fill_starts = S;
+        compute_fills(d->newlines, d->n, e->bufsize, d->n, true, S, E, cuts);
+        int rc = upload_fills(e, d, S, E, cuts);
+        if (rc) return rc;
         d->fills_bufsize = e->bufsize;
     }
     out->S = d->d_fills; out->E = d->d_fills + d->nfills; out->n = d->nfills;
@@ -623,6 +650,7 @@ void pm_engine_destroy(pm_engine *e)
     if (e->h_count) cudaFreeHost(e->h_count);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->own) cudaStreamDestroy(e->own);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     delete e;
 }
 
@@ -1243,6 +1271,29 @@ int pm_search(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt
     return rc;
 }
 
+// scan + verification + chain stage of the fills f0 .. f1-1 (whole fills are independent units); the fill table of
+// the dataset must hold at least f1 entries
+static int search_fill_range(pm_engine *e, pm_dataset *d, const Compiled &c, const unsigned long long *dB,
+                             const unsigned long long *dTL, const unsigned long long *dTR, long long f0, long long f1,
+                             pm_hit *hits, int64_t cap, int64_t *nhits, bool hits_on_device)
+{
+    const std::vector<long long> &S = d->fill_starts;
+    long long ncand = 0;
+    int rc;
+    if (f0 < f1) {
+        // anchors whose fill (fill_of: the last fill starting at or before the anchor; FWD plans anchor one byte later)
+        // is one of f0 .. f1-1
+        const long long shift = c.dp.type == PM_PLAN_FWD ? 1 : 0;
+        const long long a0 = S[f0] + shift;
+        const long long a1 = f1 < (long long)S.size() ? S[f1] + shift : d->n + 1;
+        if ((rc = produce_candidates(e, d, c, a0, a1, dB, dTL, dTR, &ncand))) return rc;
+    } else {
+        for (int i = 0; i < 4; i++) CK(cudaEventRecord(e->ev[i], e->stream));
+    }
+    e->stats.verified = ncand;
+    return resolve_candidates(e, d, c, (const Cand *)e->cands.p, ncand, dTL, dTR, hits, cap, nhits, hits_on_device);
+}
+
 // Fill-sharded search for multi-GPU runs.  recSearchFile @402298 restarts its scan at every buffer fill and no
 // hit crosses a fill, so whole fills are independent units: this call searches the fills that START in
 // [pos_beg, pos_end) completely (scan, verification, chain stage) and leaves their hits, in output order, in
@@ -1266,19 +1317,7 @@ int pm_search_fills_device(pm_engine *e, pm_dataset *d, const char *pattern, con
     const std::vector<long long> &S = d->fill_starts;
     const long long f0 = std::lower_bound(S.begin(), S.end(), (long long)pos_beg) - S.begin();
     const long long f1 = std::lower_bound(S.begin(), S.end(), (long long)pos_end) - S.begin();
-    long long ncand = 0;
-    if (f0 < f1) {
-        // anchors whose fill (fill_of: the last fill starting at or before the anchor; FWD plans anchor one byte later)
-        // is one of f0 .. f1-1
-        const long long shift = c.dp.type == PM_PLAN_FWD ? 1 : 0;
-        const long long a0 = S[f0] + shift;
-        const long long a1 = f1 < (long long)S.size() ? S[f1] + shift : d->n + 1;
-        if ((rc = produce_candidates(e, d, c, a0, a1, dB, dTL, dTR, &ncand))) return rc;
-    } else {
-        for (int i = 0; i < 4; i++) CK(cudaEventRecord(e->ev[i], e->stream));
-    }
-    e->stats.verified = ncand;
-    rc = resolve_candidates(e, d, c, (const Cand *)e->cands.p, ncand, dTL, dTR, dev_hits, cap, nhits, true);
+    rc = search_fill_range(e, d, c, dB, dTL, dTR, f0, f1, dev_hits, cap, nhits, true);
     if (dev_count && (rc == PM_OK || rc == PM_ERR_OVERFLOW)) {
         // the count travels with the hits (e.g. as the header row of an all-gather) without a host round trip
         e->h_count[3] = (unsigned long long)*nhits;
@@ -1287,6 +1326,162 @@ int pm_search_fills_device(pm_engine *e, pm_dataset *d, const char *pattern, con
     }
     finish_stats(e);
     return rc;
+}
+
+int pm_last_hits(pm_engine *e, pm_hit *hits, int64_t cap, int64_t *nhits);
+
+// Cold request: the file is still in host memory.  Upload it in chunks on a copy stream and, while the next chunk
+// is on the PCIe bus, pack the chunk that has arrived into the 2-bit planes and search the buffer fills that it
+// completes (fills are independent, see pm_search_fills_device).  What remains after the last byte has landed is the
+// last chunk's packing and the search of the last few fills.
+int pm_search_stream(pm_engine *e, const uint8_t *host, int64_t n, int npat, const char *const *patterns, const char *kopt,
+                     int64_t chunk_bytes, pm_hit *hits, int64_t cap, int64_t *offsets, pm_dataset **out)
+{
+    if (!e || !out || n < 0 || (!host && n > 0) || npat < 1 || !patterns || !kopt || !offsets) { g_err = "bad argument"; return PM_ERR_ARG; }
+    CK(cudaSetDevice(e->device));
+    (void)cudaGetLastError();
+    std::vector<Compiled> comp((size_t)npat);
+    for (int p = 0; p < npat; p++) {
+        int rc = compile(patterns[p], kopt, comp[p], true);
+        if (rc) return rc;
+    }
+    const long long gran = 32LL * 1024;                                    // chunk edges on block-tile boundaries of the planes
+    long long chunk = chunk_bytes > 0 ? chunk_bytes : (256LL << 20);
+    chunk = std::max(gran, chunk / gran * gran);
+    const int nchunks = (int)std::max<long long>(1, (n + chunk - 1) / chunk);
+    pm_dataset *d = new pm_dataset();
+    d->e = e; d->n = n;
+    {
+        void *p = nullptr;
+        if (e->pool_text && e->pool_text_cap >= (size_t)n + 256) {
+            p = e->pool_text; d->owned_cap = e->pool_text_cap;
+            e->pool_text = nullptr; e->pool_text_cap = 0;
+        } else {
+            cudaError_t rc = cudaMalloc(&p, (size_t)n + 256);
+            if (rc != cudaSuccess) { delete d; g_err = std::string("cudaMalloc dataset: ") + cudaGetErrorString(rc); return PM_ERR_CUDA; }
+            d->owned_cap = (size_t)n + 256;
+        }
+        d->owned = p; d->d_text = (const unsigned char *)p;
+    }
+    auto fail = [&](int rc) { pm_dataset_destroy(d); return rc; };
+#define CKD(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { g_err = std::string(#x) + " (engine.cu:" + std::to_string(__LINE__) + "): " + cudaGetErrorString(e_); return fail(PM_ERR_CUDA); } } while (0)
+    long long nw = (n + 31) / 32;
+    nw = (nw + 1023) / 1024 * 1024 + 1024;
+    d->nwords = nw;
+    {
+        void *p = nullptr;
+        const size_t need = (size_t)nw * 4 * 3;
+        if (e->pool_planes && e->pool_planes_cap >= need) {
+            p = e->pool_planes; d->planes_cap = e->pool_planes_cap;
+            e->pool_planes = nullptr; e->pool_planes_cap = 0;
+        } else {
+            CKD(cudaMalloc(&p, need));
+            d->planes_cap = need;
+        }
+        d->hi = (unsigned *)p; d->lo = d->hi + nw; d->xx = d->lo + nw;
+    }
+    // all copies are queued at once on their own stream; one event per chunk
+    if (!e->copy_stream) CKD(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    std::vector<cudaEvent_t> arrived((size_t)nchunks, nullptr);
+    auto drop_events = [&]() { for (auto ev : arrived) if (ev) cudaEventDestroy(ev); };
+    CKD(cudaEventRecord(e->ev[0], e->stream));
+    CKD(cudaStreamWaitEvent(e->copy_stream, e->ev[0], 0));                 // the buffers may still be in use by earlier work
+    for (int c = 0; c < nchunks; c++) {
+        const long long off = (long long)c * chunk, len = std::min<long long>(chunk, n - off);
+        if (len > 0) CKD(cudaMemcpyAsync((char *)d->owned + off, host + off, (size_t)len, cudaMemcpyHostToDevice, e->copy_stream));
+        if (c == nchunks - 1) CKD(cudaMemsetAsync((char *)d->owned + n, 0, 256, e->copy_stream));
+        CKD(cudaEventCreateWithFlags(&arrived[c], cudaEventDisableTiming));
+        CKD(cudaEventRecord(arrived[c], e->copy_stream));
+    }
+    int rc = PM_OK;
+    if ((rc = e->counters.reserve(64))) { drop_events(); return fail(rc); }
+    unsigned long long *d_exc = (unsigned long long *)((char *)e->counters.p + 32);
+    const long long nl_cap = 1 << 20;
+    std::vector<std::vector<pm_hit>> found((size_t)npat);
+    std::vector<pm_hit> tmp;
+    pm_stats total{};
+    long long ndone = 0;                                                   // fills already searched
+    d->fills_bufsize = e->bufsize;                                         // the fill table is maintained here, chunk by chunk
+    {
+        const long long bs = e->bufsize > 0 ? e->bufsize : n + 1;
+        const size_t want = (size_t)(n / bs + 2) * 3 + 8192;               // room for S, E and cuts of every fill, plus record ends
+        cudaError_t ce = cudaMalloc((void **)&d->d_fills, want * 8);
+        if (ce != cudaSuccess) { drop_events(); g_err = std::string("cudaMalloc fills: ") + cudaGetErrorString(ce); return fail(PM_ERR_CUDA); }
+        d->fills_cap = want;
+    }
+    for (int c = 0; c < nchunks && rc == PM_OK; c++) {
+        const long long off = (long long)c * chunk, end = std::min<long long>(n, off + chunk);
+        const bool last = c == nchunks - 1;
+        const long long q0 = off / 32, q1 = last ? nw : end / 32;          // plane words of this chunk (the last one also pads)
+        cudaError_t ce = cudaStreamWaitEvent(e->stream, arrived[c], 0);
+        if (ce == cudaSuccess) ce = cudaMemsetAsync(d_exc, 0, 24, e->stream);
+        if (ce != cudaSuccess) { g_err = std::string("stream upload: ") + cudaGetErrorString(ce); rc = PM_ERR_CUDA; break; }
+        if ((rc = e->keys2.reserve((size_t)nl_cap * 8))) break;
+        unsigned long long *d_nl = (unsigned long long *)e->keys2.p;
+        const int grid = (int)std::min<long long>((q1 - q0 + 255) / 256, (long long)e->sms * 16);
+        k_pack<<<std::max(grid, 1), 256, 0, e->stream>>>(d->d_text + off, n - off, q1 - q0, d->hi + q0, d->lo + q0, d->xx + q0, d_exc, d_nl, nl_cap, off);
+        ce = cudaGetLastError();
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->h_count + 4, d_exc, 16, cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        if (ce != cudaSuccess) { g_err = std::string("stream pack: ") + cudaGetErrorString(ce); rc = PM_ERR_CUDA; break; }
+        d->nexc += (long long)e->h_count[4];
+        if (c == 0) d->dna_like = end > 0 && d->nexc * 8 <= end;          // decided on the first chunk, like the whole-file rule
+        const long long nnl = (long long)e->h_count[5];
+        if (nnl > nl_cap) { g_err = "stream upload: more than 2^20 lines in one chunk (use pm_dataset_create)"; rc = PM_ERR_UNSUPPORTED; break; }
+        if (nnl > 0) {
+            const size_t base = d->newlines.size();
+            d->newlines.resize(base + (size_t)nnl);
+            ce = cudaMemcpyAsync(d->newlines.data() + base, d_nl, (size_t)nnl * 8, cudaMemcpyDeviceToHost, e->stream);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+            if (ce != cudaSuccess) { g_err = std::string("stream newlines: ") + cudaGetErrorString(ce); rc = PM_ERR_CUDA; break; }
+            std::sort(d->newlines.begin() + (long)base, d->newlines.end());
+        }
+        // fills that this chunk completes
+        std::vector<long long> S, E, cuts;
+        compute_fills(d->newlines, n, e->bufsize, end, last, S, E, cuts);
+        const long long nfinal = (long long)S.size();
+        if (nfinal <= ndone && !last) continue;
+        if ((rc = upload_fills(e, d, S, E, cuts))) break;
+        for (int p = 0; p < npat && rc == PM_OK; p++) {
+            const unsigned long long *dB, *dTL, *dTR;
+            e->stats = pm_stats{};
+            if ((rc = upload_tables(e, comp[p], &dB, &dTL, &dTR))) break;
+            int64_t nh = 0;
+            tmp.resize(std::max<size_t>(tmp.size(), 1 << 16));
+            rc = search_fill_range(e, d, comp[p], dB, dTL, dTR, ndone, nfinal, tmp.data(), (int64_t)tmp.size(), &nh, false);
+            if (rc == PM_ERR_OVERFLOW) {                                   // the list is still on the device
+                tmp.resize((size_t)nh);
+                rc = pm_last_hits(e, tmp.data(), nh, &nh);
+            }
+            if (rc) break;
+            found[p].insert(found[p].end(), tmp.begin(), tmp.begin() + nh);
+            finish_stats(e);
+            total.scan_ms += e->stats.scan_ms; total.sort_ms += e->stats.sort_ms; total.verify_ms += e->stats.verify_ms;
+            total.chain_ms += e->stats.chain_ms; total.total_ms += e->stats.total_ms;
+            total.candidates += e->stats.candidates; total.verified += e->stats.verified; total.hits += e->stats.hits;
+            total.scan_bytes += e->stats.scan_bytes; total.scan_bases += e->stats.scan_bases; total.launches += e->stats.launches;
+            total.packed = e->stats.packed; total.qgram_chunks = e->stats.qgram_chunks;
+        }
+        ndone = nfinal;
+    }
+    cudaStreamSynchronize(e->copy_stream);
+    drop_events();
+#undef CKD
+    if (rc) return fail(rc);
+    e->stats = total;
+    *out = d;
+    int64_t off = 0;
+    bool overflow = false;
+    for (int p = 0; p < npat; p++) {
+        offsets[p] = off;
+        const int64_t k = (int64_t)found[p].size();
+        if (hits && off + k <= cap) memcpy(hits + off, found[p].data(), (size_t)k * sizeof(pm_hit));
+        else if (hits) overflow = true;
+        off += k;
+    }
+    offsets[npat] = off;
+    if (overflow) { g_err = "hit buffer too small (the dataset is resident: search it again with pm_search)"; return PM_ERR_OVERFLOW; }
+    return PM_OK;
 }
 
 int pm_last_hits(pm_engine *e, pm_hit *hits, int64_t cap, int64_t *nhits)

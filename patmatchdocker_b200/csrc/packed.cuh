@@ -49,7 +49,8 @@ __device__ __forceinline__ unsigned swar_gather(unsigned m)                    /
 __global__ void __launch_bounds__(256) k_pack(const unsigned char *__restrict__ text, long long n, long long nwords,
                                               unsigned *__restrict__ hi, unsigned *__restrict__ lo, unsigned *__restrict__ xx,
                                               unsigned long long *__restrict__ nexc,    // [0] non-ACGT bytes, [1] newlines
-                                              unsigned long long *__restrict__ nl_out, long long nl_cap)
+                                              unsigned long long *__restrict__ nl_out, long long nl_cap,
+                                              long long pos0 = 0)                       // file offset of text[0] (chunked packing)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
     const bool aligned = ((size_t)text & 15) == 0;
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(256) k_pack(const unsigned char *__restrict__ 
             while (mn) {
                 const int b = __ffs(mn) - 1;
                 mn &= mn - 1;
-                if ((long long)slot < nl_cap) nl_out[slot] = (unsigned long long)(base + b);
+                if ((long long)slot < nl_cap) nl_out[slot] = (unsigned long long)(pos0 + base + b);
                 slot++;
             }
         }

@@ -311,6 +311,37 @@ def test_fill_sharded_search_equals_search(engine, scan_mode):
         assert full == O.search(pat, text, kopt, bufsize=bufsize)
 
 
+def test_streaming_upload_search_equals_search(engine, scan_mode):
+    # pm_search_stream: chunks are packed and their completed fills searched while later chunks are still in flight;
+    # hit lists and the dataset left behind must equal the plain path for any chunking and buffer size
+    rng = random.Random(9)
+    for it in range(24):
+        k = rng.choice([0, 1, 2])
+        m = rng.randint(max(3, 2 * k + 2), 14)
+        pat, members = random_pattern(rng, DNA, m)
+        pat2, _ = random_pattern(rng, DNA, m)
+        if it % 5 == 0:
+            pat = "^" + pat
+        kopt = "%d%s" % (k, rng.choice(["ids", "s", "id"]))
+        nrec = rng.randint(1, 5)
+        text = random_text(rng, members, DNA, k, nrec=nrec, lo=20000, hi=120000, plant=0.02).encode("latin-1")
+        bufsize = rng.choice([1600000, 5000, 40000, 1000])
+        engine.set_buffer_size(bufsize)
+        try:
+            ds, lists = engine.search_stream(text, [pat, pat2], kopt, chunk_bytes=rng.choice([32768, 65536, 1 << 20]))
+            for p, got in zip((pat, pat2), lists):
+                want = O.search(p, text, kopt, bufsize=bufsize)
+                assert [(int(b), int(e)) for b, e in got] == want, (p, kopt, bufsize)
+                again = engine.search(ds, p, kopt)                 # the resident dataset is complete
+                assert [(int(b), int(e)) for b, e in again] == want, (p, kopt, bufsize)
+            ds.close()
+        finally:
+            engine.set_buffer_size(1600000)
+    ds, lists = engine.search_stream(b"", ["(ACGT)"], "1ids")
+    assert len(lists[0]) == 0
+    ds.close()
+
+
 def test_batch_equals_single(engine):
     rng = random.Random(3)
     pats = [random_pattern(rng, DNA, rng.randint(5, 12), cls_pct=0.3)[0] for _ in range(40)]
