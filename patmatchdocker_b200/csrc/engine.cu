@@ -1075,7 +1075,7 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
                         sp_attr_set = true;
                     }
 #define PM_LAUNCH(W, R) do { if (bcoords) k_scan_split<4, W, R><<<grid_sp, EX_WARPS * 32, smem_sp, e->stream>>>(a, pv, qf); \
-                             else k_scan_packed<4, W, R, false><<<grid_bk, 256, 0, e->stream>>>(a, pv, qf); } while (0)
+                             else k_scan_packed<4, W, R><<<grid_bk, 256, 0, e->stream>>>(a, pv); } while (0)
                     if (narrow) { if (rows == 2) PM_LAUNCH(unsigned, 2); else if (rows == 3) PM_LAUNCH(unsigned, 3); else PM_LAUNCH(unsigned, 4); }
                     else { if (rows == 2) PM_LAUNCH(unsigned long long, 2); else if (rows == 3) PM_LAUNCH(unsigned long long, 3); else PM_LAUNCH(unsigned long long, 4); }
                     e->stats.qgram_chunks = qf.nch;

@@ -134,17 +134,19 @@ __device__ __forceinline__ void packed_apply(unsigned (&M)[4], const unsigned (&
 
 // ---------------------------------------------------------------------------------------
 // Fused candidate filter.  For SPLIT plans every exact piece hit is a candidate the reference
-// verifies (checkMatch1 @414190); with short pieces that is one candidate per ~40-100 bases
-// and almost all of them fail.  The scan kernel therefore runs the same anchored k-error NFA
-// right away, reading the text from the packed planes staged in shared memory, and drops a
-// candidate only when that verification fails for certain.  Whenever the walk meets a
-// non-ACGT byte (X plane: '\n', N, header text ...) or the tile is near a forced buffer cut,
-// the candidate is kept and decided later on the raw bytes by k_verify.  Dropping is safe for
-// the chain stage as well: a scan start that clips the verification can only remove matches.
+// verifies (checkMatch1 @414190); with short or degenerate pieces that is one candidate per
+// 16-100 bases and almost all of them fail.  The scan kernels therefore apply NECESSARY
+// conditions of that verification on the packed planes and only pass on what survives:
+//   * Myers' bit-vector edit distance of the pattern part left of the anchor against the text
+//     read leftwards, and of the right part against the text read rightwards:
+//     min_left + min_right <= k.  The reference's NFA accepts a subset of the edit-distance
+//     alignments; record ends, fill cuts, line anchors and the scan start only take alignments
+//     away.  An X symbol (any non-ACGT byte) matches every position whose class accepts some
+//     non-ACGT byte, so the condition stays necessary on headers, N runs and IUPAC letters.
+//   * k_scan_split additionally runs the bit-sliced q-gram pre-filter below in front of it.
+// Every survivor is decided on the raw bytes by k_verify; dropping is safe for the chain stage as
+// well ('^' patterns included: a dropped candidate fails for every scan start).
 #define PK_HALO 4                       // words of halo on each side of a 128-word warp tile
-#define PK_ROW (128 + 2 * PK_HALO)
-#define PK_QUEUE 192                    // per-warp, per-piece candidate queue (entries beyond it go to k_verify unfiltered)
-#define PK_PRE 5                        // steps of the lock-step pre-check of round A
 
 template <int NP>
 struct PackedVerify {
@@ -156,67 +158,6 @@ struct PackedVerify {
     const long long *cuts;                       // forced buffer cuts (fill starts not at a '\n'), sorted
     int ncuts;
 };
-
-// one side of checkMatch1 on packed symbols; *bail is set when the outcome needs the raw bytes.
-// W = state word (uint32 when the pattern part fits 32 bits), ROWS = k+1 error rows.
-template <int DIR, typename W, int ROWS>
-__device__ __forceinline__ int nfa_packed(const unsigned *__restrict__ sh, long long base, const unsigned long long (&T64)[4],
-                                          int plen, int kmax, int ins, int del, int subs, long long pos, int *err, bool *bail,
-                                          int maxsteps = 96, bool *undecided = nullptr)
-{
-    const W fin = (W)1 << (plen - 1);
-    const W live = (W)((fin << 1) - 1);
-    const W T[4] = {(W)T64[0], (W)T64[1], (W)T64[2], (W)T64[3]};
-    W R[ROWS];
-    int kb = kmax;
-    int best_err = -1;
-#pragma unroll
-    for (int e = 0; e < ROWS; e++) {
-        R[e] = del ? (W)(((W)1 << e) - 1) : (W)0;
-        if (e <= kb && (R[e] & fin)) { best_err = e; kb = e - 1; }
-    }
-    W first = 1;
-    int rel = (int)(pos - base) + (DIR < 0 ? -1 : 0);          // bit index of the next symbol in the staged row
-    for (int step = 0;; step++, rel += DIR) {
-        if (step >= maxsteps) {                              // capped pre-check: still alive, decide later
-            if (undecided) *undecided = true; else *bail = true;
-            return 0;
-        }
-        const int wi = rel >> 5, bi = rel & 31;
-        if (wi < 0 || wi >= PK_ROW) { *bail = true; return 0; }
-        if ((sh[2 * PK_ROW + wi] >> bi) & 1u) { *bail = true; return 0; }
-        const unsigned code = (((sh[wi] >> bi) & 1u) << 1) | ((sh[PK_ROW + wi] >> bi) & 1u);
-        const W Tc = code == 0 ? T[0] : code == 1 ? T[1] : code == 2 ? T[2] : T[3];
-        W oldp = R[0];
-        R[0] = (W)(((R[0] << 1) | first) & Tc);
-        W newp = R[0];
-        if (R[0] & fin) { *err = 0; return 1; }
-        bool lowered = false;
-#pragma unroll
-        for (int e = 1; e < ROWS; e++) {
-            if (e <= kb && !lowered) {
-                W x = 0;
-                if (del) x = (W)(newp << 1);
-                if (ins) x |= oldp;
-                if (subs) x |= (W)((oldp << 1) | first);
-                const W nr = (W)((((R[e] << 1) | first) & Tc) | x);
-                oldp = R[e];
-                R[e] = nr;
-                newp = nr;
-                if (nr & fin) { best_err = e; kb = e - 1; lowered = true; }   // rows below e lacked the final bit in this step
-            }
-        }
-        if (kb < 0) break;
-        W alive = R[0];
-#pragma unroll
-        for (int e = 1; e < ROWS; e++) if (kb == e) alive = R[e];
-        if (!(alive & live)) break;
-        first = 0;
-    }
-    if (best_err < 0) return 0;
-    *err = best_err;
-    return 1;
-}
 
 // ---------------------------------------------------------------------------------------
 // Exact (k = 0, SIMPLE) scan: one piece, registers only, next tile prefetched while the current
@@ -556,19 +497,12 @@ struct QFilter {
     QChunk ch[QF_MAXCH];
 };
 
-__device__ __forceinline__ void qf_apply6(unsigned (&G)[6], const unsigned (&P)[6], int t)
-{
-#pragma unroll
-    for (int w = 0; w < 5; w++) G[w] &= __funnelshift_r(P[w], P[w + 1], t);
-    G[5] &= P[5] >> t;
-}
-
 #define BK_WORDS 1024                   // block tile: 8 warp tiles of 128 words (32768 bases) per plane
 #define BK_ROW (BK_WORDS + 2 * PK_HALO)
 #define BK_QUEUE 2048                   // per-block, per-piece candidate queue (overflow goes to k_verify unfiltered)
 
-template <int NP, typename W, int ROWS, bool QF>
-__global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, const PackedVerify<NP> v, const QFilter qf)
+template <int NP, typename W, int ROWS>
+__global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, const PackedVerify<NP> v)
 {
     __shared__ unsigned sh[3 * BK_ROW];                 // hi | lo | x rows of the block tile, with halos
     __shared__ unsigned queue[NP][BK_QUEUE];            // one queue per piece: a round of candidates shares all parameters
@@ -580,16 +514,6 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
         sT[i][side][c] = (W)(c < 4 ? (side ? v.TR[i][c] : v.TL[i][c]) : (side ? v.TRX[i] : v.TLX[i]));
     }
     const long long nbt = (a.ntiles + 7) / 8;
-    if (QF && blockIdx.x == 0 && a.tile0 == 0) {
-        // anchors closer than k + V[i] to the start of the text have no pattern start b >= 0:
-        // they go to k_verify unfiltered (it re-checks the trigger on the raw bytes)
-        for (int i = 0; i < a.npieces; i++)
-            for (long long p = tid; p < v.k + v.V[i]; p += 256) {
-                if (p < a.a0 || p >= a.a1 || p + a.L > a.n) continue;
-                const unsigned long long idx = atomicAdd(a.count, 1ULL);
-                if ((long long)idx < a.cap) a.keys[idx] = ((unsigned long long)p << 4) | (unsigned)i;
-            }
-    }
     for (long long bt = blockIdx.x; bt < nbt; bt += gridDim.x) {
         const long long qb = a.tile0 * 128 + bt * BK_WORDS;             // first word of the block tile
         const long long q0 = qb + 4 * tid;                              // first of this thread's 4 words
@@ -644,55 +568,15 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
             }
             }
         };
-        // ---- q-gram pre-filter: pass[w] bit b <=> at most k chunks are missing for pattern start b ----
-        unsigned pass[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-        if (QF) {
-            unsigned miss[ROWS][4];                      // miss[r] : more than r chunks missing
-#pragma unroll
-            for (int r = 0; r < ROWS; r++)
-#pragma unroll
-                for (int w = 0; w < 4; w++) miss[r][w] = 0;
-            for (int g = 0; g < qf.nch; g++) {
-                const QChunk &ch = qf.ch[g];
-                unsigned G[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-                for (int c = 0; c < ch.npos; c++) {
-                    const int t = ch.t[c];
-                    with_plane(ch.pos[c], [&](const unsigned (&P)[6]) { qf_apply6(G, P, t); });
-                }
-                // dilate: G[x] |= G[x+1] | ... | G[x+win-1]   (doubling)
-                int cw = 1;
-                while (cw < qf.win) {
-                    const int s = min(cw, qf.win - cw);
-#pragma unroll
-                    for (int w = 0; w < 5; w++) G[w] |= __funnelshift_r(G[w], G[w + 1], s);
-                    G[5] |= G[5] >> s;
-                    cw += s;
-                }
-                unsigned x[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-                packed_apply<true>(x, G, ch.off);
-#pragma unroll
-                for (int w = 0; w < 4; w++) {
-                    const unsigned ms = ~x[w];
-#pragma unroll
-                    for (int r = ROWS - 1; r > 0; r--) miss[r][w] |= miss[r - 1][w] & ms;
-                    miss[0][w] |= ms;
-                }
-            }
-#pragma unroll
-            for (int w = 0; w < 4; w++) pass[w] = ~miss[ROWS - 1][w];
-        }
-        // ---- pieces (QF: in pattern-start coordinates, piece i shifted by k + V[i]) ----
+        // ---- pieces ----
         unsigned M[NP][4];
 #pragma unroll
         for (int i = 0; i < NP; i++) {
 #pragma unroll
-            for (int w = 0; w < 4; w++) M[i][w] = pass[w];
+            for (int w = 0; w < 4; w++) M[i][w] = 0xffffffffu;
             if (i < a.npieces) {
-                const int base = QF ? v.k + v.V[i] : 0;
-                for (int j = 0; j < a.L; j++) {
-                    const int sh_ = base + j;
-                    with_plane(a.pos[i][j], [&](const unsigned (&P)[6]) { packed_apply<true>(M[i], P, sh_); });
-                }
+                for (int j = 0; j < a.L; j++)
+                    with_plane(a.pos[i][j], [&](const unsigned (&P)[6]) { packed_apply<true>(M[i], P, j); });
             } else {
 #pragma unroll
                 for (int w = 0; w < 4; w++) M[i][w] = 0;
@@ -719,7 +603,7 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
                 while (c) {
                     const int b = __ffs(c) - 1;
                     c &= c - 1;
-                    const unsigned rel = (unsigned)((4 * tid + w) * 32 + b) + (QF ? (unsigned)(v.k + v.V[i]) : 0u);   // window start inside the block tile
+                    const unsigned rel = (unsigned)((4 * tid + w) * 32 + b);       // window start inside the block tile
                     const long long p = qb * 32 + rel;
                     if (p < a.a0 || p >= a.a1 || p + a.L > a.n) continue;
                     const unsigned slot = fused ? atomicAdd(&qcount[i], 1u) : BK_QUEUE;
