@@ -658,3 +658,253 @@ int64_t nro_search(const nro_pattern *P, const nro_plan *pl, const uint8_t *t, i
     if (n <= 0) return 0;
     return search_range(P, pl, t, 0, n, hits, cap, 0);
 }
+
+/* ========================================================================= */
+/* EXTENDED patterns, k = 0 (positions followed by '?', '*' or '+').  PatMatch's */
+/* X{m,n} repeats reach the engine in this form (patmatch_to_nrgrep.pl:184-211). */
+/* Restated: extendedPreproc @413260 (plan), extendedFindBest @411fe0 (which     */
+/* sub-pattern is scanned for, bit-exact doubles), and the language-level        */
+/* meaning of extendedScan @4116f0 + checkMatch @411aa0: anchors are tried in    */
+/* increasing order and the first one whose verification succeeds is reported;   */
+/* the verification takes the SHORTEST extension to the left of the anchor that  */
+/* matches the pattern part before it, then the shortest one to the right.       */
+/* Not covered (NRO_ERR_UNSUPPORTED): groups, alternation, and patterns whose    */
+/* first or last position carries an operator (the parser simplifies those).     */
+
+int nrx_parse(const char *pattern, int icase, nrx_pattern *X)
+{
+    memset(X, 0, sizeof *X);
+    nro_pattern *P = &X->P;
+    int n = (int)strlen(pattern);
+    const char *s = pattern;
+    if (n > 0 && s[0] == '^') { P->start_line = 1; s++; n--; }
+    if (n > 0 && s[n - 1] == '$') { P->end_line = 1; n--; }
+    /* one pair of parentheses around the whole pattern is what patmatch_to_nrgrep.pl writes */
+    if (n >= 2 && s[0] == '(' && s[n - 1] == ')') { s++; n -= 2; }
+    int i = 0, m = 0, nops = 0;
+    while (i < n) {
+        unsigned c = (unsigned char)s[i++];
+        if (c == '(' || c == ')' || c == '|' || c == '\\' || c == '#') return NRO_ERR_UNSUPPORTED;
+        if (c == '?' || c == '*' || c == '+') {
+            if (m == 0 || X->op[m - 1] != NRX_NONE) return NRO_ERR_UNSUPPORTED;
+            X->op[m - 1] = c == '?' ? NRX_OPT : c == '*' ? NRX_STAR : NRX_PLUS;
+            nops++;
+            continue;
+        }
+        if (m >= 64) return NRO_ERR_TOOLONG;
+        if (c == '[') {
+            int rc = parse_class(s, &i, n, P, m, icase);
+            if (rc) return rc;
+        } else if (c == '.') {
+            memset(P->cls[m], 0xff, sizeof P->cls[m]);
+        } else {
+            memset(P->cls[m], 0, sizeof P->cls[m]);
+            cls_add(P, m, c, icase);
+        }
+        m++;
+    }
+    if (m == 0) return NRO_ERR_SYNTAX;
+    P->m = m;
+    if (nops == 0) return NRO_ERR_UNSUPPORTED;                 /* a SIMPLE pattern: not this path */
+    if (X->op[0] != NRX_NONE || X->op[m - 1] != NRX_NONE) return NRO_ERR_UNSUPPORTED;
+    return NRO_OK;
+}
+
+static inline int nrx_optional(const nrx_pattern *X, int j) { return X->op[j] == NRX_OPT || X->op[j] == NRX_STAR; }
+static inline int nrx_repeat(const nrx_pattern *X, int j) { return X->op[j] == NRX_STAR || X->op[j] == NRX_PLUS; }
+
+/* extendedFindBest @411fe0 with K = 0.  T[d][a][l], U[d][a][l]: d = first position, a = last position, l = symbols  */
+/* read; rows are filled lazily per last position (last[a] = highest l done), exactly in the binary's order.        */
+static double ext_find_best(const nrx_pattern *X, int K, int *beg, int *end, int *wlen)
+{
+    const nro_pattern *P = &X->P;
+    const int m = P->m, N1 = m + 1, NN = m * N1;
+    double *prob = malloc(sizeof(double) * (size_t)m), *prob2 = malloc(sizeof(double) * (size_t)m);
+    for (int j = 0; j < m; j++) {
+        double p = 0.0, q = 0.0;
+        for (unsigned c = 0; c < 256; c++)
+            if (cls_has(P, j, c)) { p += (double)letter_ppm[c] / 1000000.0; if (nrx_repeat(X, j)) q += (double)letter_ppm[c] / 1000000.0; }
+        prob[j] = p; prob2[j] = q;
+    }
+    double *T = calloc((size_t)NN * (size_t)N1, sizeof(double)), *U = calloc((size_t)NN * (size_t)N1, sizeof(double));
+    int *last = malloc(sizeof(int) * (size_t)m);
+#define IX(d, a, l) ((size_t)(d) * (size_t)NN + (size_t)(a) * (size_t)N1 + (size_t)(l))
+    for (int a = 0; a < m; a++) {
+        last[a] = 0;
+        for (int d = 0; d <= a; d++) { U[IX(d, a, 0)] = 1.0; T[IX(d, a, 0)] = 1.0; }
+        U[IX(a + 1, a, 0)] = 0.0; T[IX(a + 1, a, 0)] = 0.0;
+    }
+    double best = 0.7;
+    *beg = 0; *end = 0; *wlen = 0;
+    const int K2 = 2 * K;
+    const double dK1 = (double)K + 1.0;
+    for (int i = 0; i < m; i++) {
+        int count = 0;
+        for (int pos = i; pos < m; pos++) {
+            if ((unsigned)(pos - i + 1) > 64u) continue;
+            double sum = dK1, dlk1;
+            int lk;
+            if (nrx_optional(X, pos)) {
+                if (K2 >= count) continue;
+            } else {
+                count++;
+                if (count <= K2) continue;
+            }
+            if (count > 0) {
+                lk = count - K;
+                dlk1 = (double)(lk + 1);
+                if (!(dK1 >= dlk1)) {
+                    const double dlk = (double)lk;
+                    double c0 = dK1 / ((dlk - dK1) + 1.0);
+                    if (!(c0 >= best)) {
+                        int l = 1;
+                        for (;;) {
+                            if (last[pos] < l) {
+                                U[IX(pos + 1, pos, l)] = 0.0; T[IX(pos + 1, pos, l)] = 0.0;
+                                for (int q = pos; q >= 0; q--) {
+                                    double s1 = prob[q] * T[IX(q + 1, pos, l - 1)];
+                                    double s0 = prob2[q] * T[IX(q, pos, l - 1)];
+                                    s1 = s1 + s0;
+                                    double s = nrx_optional(X, q) ? T[IX(q + 1, pos, l)] + s1 : 0.0 + s1;
+                                    double one_minus;
+                                    if (s > 1.0) { T[IX(q, pos, l)] = 1.0; one_minus = 0.0; }
+                                    else { T[IX(q, pos, l)] = s; one_minus = 1.0 - s; }
+                                    U[IX(q, pos, l)] = 1.0 - (1.0 - U[IX(q + 1, pos, l)]) * one_minus;
+                                }
+                                last[pos] = l;
+                            }
+                            sum += U[IX(i, pos, l)];
+                            l++;
+                            if (l > count) break;
+                            if (sum >= dlk1) break;
+                            double c = sum / ((dlk - sum) + 1.0);
+                            if (!(c < best)) break;
+                        }
+                    }
+                }
+            } else {
+                lk = -K;
+                dlk1 = (double)(1 - K);
+            }
+            if (dlk1 > sum) {
+                double c = sum / (((double)lk - sum) + 1.0);
+                if (best > c) { best = c; *beg = i; *end = pos + 1; *wlen = count; }
+            }
+        }
+    }
+#undef IX
+    free(prob); free(prob2); free(T); free(U); free(last);
+    if (*wlen > 0) {
+        while (*beg < *end && nrx_optional(X, *beg)) (*beg)++;
+        while (*beg < *end && nrx_optional(X, *end - 1)) (*end)--;
+        if (*beg == *end) *wlen = 0;
+    }
+    if (*wlen == 0) {
+        *end = m > 64 ? 64 : m;
+        while (nrx_optional(X, *end - 1)) (*end)--;
+        best = 1.0;
+    }
+    return best;
+}
+
+int nrx_plan_make(const nrx_pattern *X, nrx_plan *pl)
+{
+    memset(pl, 0, sizeof *pl);
+    pl->cost = ext_find_best(X, 0, &pl->beg, &pl->end, &pl->wlen);
+    if (pl->wlen > 0) { pl->type = 2; pl->anchor = pl->beg; }       /* 413550: verification split at the sub-pattern's start */
+    else { pl->type = 3; pl->anchor = pl->end; }                    /* 413371: ... at its end (forward scan) */
+    return NRO_OK;
+}
+
+/* One direction of checkMatch @411aa0 with the tables of extendedLoadVerif @412c60, restated literally (single     */
+/* 64-bit word: the oracle takes m <= 64).  Elements are numbered in walk order: u = 0 is the pattern position next to */
+/* the anchor (`from`), u grows away from it (`step` = +1 / -1).  State bit u = element u has consumed a byte or was  */
+/* skipped.  Quirk kept on purpose: the initial state only pre-skips the FIRST element when it is optional; a run of   */
+/* two or more optional elements next to the anchor cannot be skipped as a whole on the first byte, so e.g.            */
+/* (GAT.?.?.?AAGTCC) does not match GATAAGTCC (the binary prints nothing for it).                                      */
+static int64_t ext_side(const nrx_pattern *X, int from, int len, int step, const uint8_t *t, int64_t pos, int64_t lim)
+{
+    const nro_pattern *P = &X->P;
+    uint64_t I = 0, F = 0, A = 0, init = 0;
+    int flag = 0;
+    for (int u = 0; u < len; u++) {                       /* 412ee0-412fdc */
+        const int j = from + u * step;
+        if (!nrx_optional(X, j)) continue;
+        if (u > 0) {
+            if ((F >> (u - 1)) & 1ULL) {
+                F &= ~(1ULL << (u - 1)); F |= 1ULL << u;
+                if (flag) A |= 1ULL << u; else init |= 1ULL << u;
+            } else {
+                I |= 1ULL << (u - 1); F |= 1ULL << u; flag = 1; A |= 1ULL << u;
+            }
+        } else {
+            if (flag) A |= 1ULL << u; else init |= 1ULL << u;
+        }
+    }
+    const uint64_t fin = 1ULL << (len - 1);
+    uint64_t D = init, carry = 1;
+    int64_t n = 0;
+    for (;;) {
+        if (D & fin) {
+            const int64_t edge = step > 0 ? pos + n : pos - n;
+            if (step < 0 ? leftctx(P, t, edge, lim) : rightctx(P, t, edge, lim)) return n;
+        }
+        const int64_t tp = step > 0 ? pos + n : pos - n - 1;
+        if (step > 0 ? tp >= lim : tp < lim) return -1;
+        const unsigned c = t[tp];
+        uint64_t Bc = 0, Sc = 0;
+        for (int u = 0; u < len; u++) {
+            const int j = from + u * step;
+            if (cls_has(P, j, c)) { Bc |= 1ULL << u; if (nrx_repeat(X, j)) Sc |= 1ULL << u; }
+        }
+        D = (((D << 1) | carry) & Bc) | (D & Sc);
+        carry = 0;
+        n++;
+        if (!D) return -1;
+        const uint64_t x = D | F;
+        D = (((~(x - I)) ^ x) & A) | D;
+    }
+}
+
+/* checkMatch @411aa0 at anchor `pos` (type 2: start of the sub-pattern occurrence, type 3: its end) */
+static int ext_check(const nrx_pattern *X, const nrx_plan *pl, const uint8_t *t, int64_t pos, int64_t tbeg, int64_t tend,
+                     int64_t *beg, int64_t *end)
+{
+    const int64_t p = pl->type == 3 ? pos - 1 : pos;
+    int64_t rbeg = tbeg, rend = tend;
+    for (int64_t q = p - 1; q >= tbeg; q--) if (t[q] == '\n') { rbeg = q + 1; break; }
+    for (int64_t q = p; q < tend; q++) if (t[q] == '\n') { rend = q; break; }
+    if (p < rbeg || p >= rend) return 0;
+    const int m = X->P.m, a = pl->anchor;
+    int64_t bext = 0, fext = 0;
+    if (a == 0) { if (!leftctx(&X->P, t, pos, rbeg)) return 0; }
+    else if ((bext = ext_side(X, a - 1, a, -1, t, pos, rbeg)) < 0) return 0;
+    if (a == m) { if (!rightctx(&X->P, t, pos, rend)) return 0; }
+    else if ((fext = ext_side(X, a, m - a, +1, t, pos, rend)) < 0) return 0;
+    *beg = pos - bext;
+    *end = pos + fext;
+    return 1;
+}
+
+int64_t nrx_search(const nrx_pattern *X, const nrx_plan *pl, const uint8_t *text, int64_t n, nro_hit *hits, int64_t cap)
+{
+    int64_t cnt = 0, pos = 0;
+    while (pos < n || (pos == 0 && n == 0)) {
+        int found = 0;
+        int64_t b = 0, e = 0;
+        if (pl->type == 2) {
+            for (int64_t w = pos; w + pl->wlen <= n; w++)
+                if (ext_check(X, pl, text, w, pos, n, &b, &e)) { found = 1; break; }
+        } else {
+            for (int64_t q = pos + 1; q <= n; q++)
+                if (ext_check(X, pl, text, q, pos, n, &b, &e)) { found = 1; break; }
+        }
+        if (!found) break;
+        if (cnt < cap) { hits[cnt].beg = b; hits[cnt].end = e; }
+        cnt++;
+        if (e == n) break;
+        if (e <= pos && b == e) break;
+        pos = e;
+    }
+    return cnt;
+}

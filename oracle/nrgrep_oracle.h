@@ -79,6 +79,14 @@ int nro_check_match(const nro_pattern *P, const nro_plan *plan, int i,
                     const uint8_t *text, int64_t pos, int64_t tbeg, int64_t tend,
                     int64_t *beg, int64_t *end);
 
+/* ---- EXTENDED patterns, k = 0 (see the end of nrgrep_oracle.c and NOTES_extended.md) ---- */
+enum { NRX_NONE = 0, NRX_OPT = 1, NRX_STAR = 2, NRX_PLUS = 3 };
+typedef struct { nro_pattern P; unsigned char op[NRO_MAXM]; } nrx_pattern;
+typedef struct { int type, anchor, wlen, beg, end; double cost; } nrx_plan;
+int nrx_parse(const char *pattern, int icase, nrx_pattern *X);
+int nrx_plan_make(const nrx_pattern *X, nrx_plan *plan);
+int64_t nrx_search(const nrx_pattern *X, const nrx_plan *plan, const uint8_t *text, int64_t n, nro_hit *hits, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif
