@@ -886,25 +886,55 @@ static int ext_check(const nrx_pattern *X, const nrx_plan *pl, const uint8_t *t,
     return 1;
 }
 
-int64_t nrx_search(const nrx_pattern *X, const nrx_plan *pl, const uint8_t *text, int64_t n, nro_hit *hits, int64_t cap)
+/* recSearchFile @402250 over one scan range [lo, hi) (a buffer fill) */
+static int64_t ext_search_range(const nrx_pattern *X, const nrx_plan *pl, const uint8_t *text, int64_t lo, int64_t hi,
+                                nro_hit *hits, int64_t cap, int64_t cnt)
 {
-    int64_t cnt = 0, pos = 0;
-    while (pos < n || (pos == 0 && n == 0)) {
+    int64_t pos = lo;
+    while (pos < hi) {
         int found = 0;
         int64_t b = 0, e = 0;
         if (pl->type == 2) {
-            for (int64_t w = pos; w + pl->wlen <= n; w++)
-                if (ext_check(X, pl, text, w, pos, n, &b, &e)) { found = 1; break; }
+            for (int64_t w = pos; w + pl->wlen <= hi; w++)
+                if (ext_check(X, pl, text, w, pos, hi, &b, &e)) { found = 1; break; }
         } else {
-            for (int64_t q = pos + 1; q <= n; q++)
-                if (ext_check(X, pl, text, q, pos, n, &b, &e)) { found = 1; break; }
+            for (int64_t q = pos + 1; q <= hi; q++)
+                if (ext_check(X, pl, text, q, pos, hi, &b, &e)) { found = 1; break; }
         }
         if (!found) break;
         if (cnt < cap) { hits[cnt].beg = b; hits[cnt].end = e; }
         cnt++;
-        if (e == n) break;
+        if (e == hi) break;
         if (e <= pos && b == e) break;
         pos = e;
     }
     return cnt;
+}
+
+int64_t nrx_search(const nrx_pattern *X, const nrx_plan *pl, const uint8_t *text, int64_t n, nro_hit *hits, int64_t cap)
+{
+    if (n <= 0) return 0;
+    return ext_search_range(X, pl, text, 0, n, hits, cap, 0);
+}
+
+/* with the reference's buffer fills (same rule as nro_search_buffered) */
+int64_t nrx_search_buffered(const nrx_pattern *X, const nrx_plan *pl, const uint8_t *t, int64_t n, int64_t bufsize,
+                            nro_hit *hits, int64_t cap)
+{
+    int64_t count = 0, S = 0;
+    if (bufsize <= 0) bufsize = n + 1;
+    while (n - S > 0) {
+        int64_t lo, hi, next;
+        int64_t dsize = n - S < bufsize ? n - S : bufsize;
+        if (dsize < bufsize) { lo = S; hi = S + dsize; next = n; }
+        else {
+            int64_t p = S + dsize - 1;
+            while (p > S && t[p] != '\n') p--;
+            if (p > S) { lo = S; hi = p + 1; next = p; }
+            else { lo = S; hi = S + dsize; next = S + dsize; }
+        }
+        count = ext_search_range(X, pl, t, lo, hi, hits, cap, count);
+        S = next;
+    }
+    return count;
 }

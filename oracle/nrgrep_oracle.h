@@ -86,6 +86,8 @@ typedef struct { int type, anchor, wlen, beg, end; double cost; } nrx_plan;
 int nrx_parse(const char *pattern, int icase, nrx_pattern *X);
 int nrx_plan_make(const nrx_pattern *X, nrx_plan *plan);
 int64_t nrx_search(const nrx_pattern *X, const nrx_plan *plan, const uint8_t *text, int64_t n, nro_hit *hits, int64_t cap);
+int64_t nrx_search_buffered(const nrx_pattern *X, const nrx_plan *plan, const uint8_t *text, int64_t n, int64_t bufsize,
+                            nro_hit *hits, int64_t cap);
 
 #ifdef __cplusplus
 }

@@ -162,6 +162,53 @@ def search_fixture():
                 t = t[:q] + arng.choice(alpha) + t[q + 1:]
             lines.append(t)
         cases.append((pat, kopt, "\n".join(lines) + "\n", arng.choice([1600000, 1600000, 1600000, 40, 64])))
+    # EXTENDED patterns (k = 0): what PatMatch's X{m,n} / X{m,} repeats become (patmatch_to_nrgrep.pl:184-211).
+    # First and last position mandatory (the shapes the parser does not rewrite).  Own generator again.
+    xrng = random.Random(777)
+    for it in range(140):
+        alpha = xrng.choice([DNA, DNA, PEP])
+        m = xrng.randint(3, 14)
+        pat, members, ops = "(", [], []
+        for j in range(m):
+            r = xrng.random()
+            if r < 0.12:
+                pat += "."
+                members.append(list(alpha))
+            elif r < 0.27:
+                chars = xrng.sample(alpha, 2)
+                pat += "[" + "".join(chars) + "]"
+                members.append(chars)
+            else:
+                c = xrng.choice(alpha)
+                pat += c
+                members.append([c])
+            op = ""
+            if 0 < j < m - 1:
+                q = xrng.random()
+                op = "?" if q < 0.3 else "*" if q < 0.36 else "+" if q < 0.4 else ""
+            pat += op
+            ops.append(op)
+        pat += ")"
+        if not any(ops):
+            continue
+        if it % 9 == 0:
+            pat = "^" + pat
+        lines = []
+        for r in range(xrng.randint(1, 4)):
+            lines.append(">x%d" % r)
+            t = ""
+            target = xrng.randint(40, 400)
+            while len(t) < target:
+                if xrng.random() < 0.35:
+                    for c, op in zip(members, ops):
+                        reps = 1 if op == "" else xrng.randint(0, 1) if op == "?" else xrng.randint(0, 2) if op == "*" else xrng.randint(1, 2)
+                        t += "".join(xrng.choice(c) for _ in range(reps))
+                else:
+                    t += "".join(xrng.choice(alpha) for _ in range(xrng.randint(1, 10)))
+            lines.append(t)
+        cases.append((pat, "0ids", "\n".join(lines) + "\n", xrng.choice([1600000, 1600000, 1600000, 50, 200])))
+    # the reference's quirk: a run of two or more optional positions next to the anchor cannot be skipped as a whole
+    cases.append(("(GAT.?.?.?AAGTCC)", "0ids", ">q\nCCGATAAGTCCAA\nCCGATCAAGTCCAA\nCCGATCCCAAGTCCAA\n", 1600000))
     out = []
     with tempfile.TemporaryDirectory() as td:
         path = os.path.join(td, "t.seq")

@@ -30,6 +30,15 @@ class NroPlan(ctypes.Structure):
                 ("fb_flag", ctypes.c_int), ("fb_beg", ctypes.c_int), ("fb_end", ctypes.c_int)]
 
 
+class NrxPattern(ctypes.Structure):          # EXTENDED patterns (?, *, +), k = 0
+    _fields_ = [("P", NroPattern), ("op", ctypes.c_ubyte * NRO_MAXM)]
+
+
+class NrxPlan(ctypes.Structure):
+    _fields_ = [("type", ctypes.c_int), ("anchor", ctypes.c_int), ("wlen", ctypes.c_int), ("beg", ctypes.c_int),
+                ("end", ctypes.c_int), ("cost", ctypes.c_double)]
+
+
 class NroHit(ctypes.Structure):
     _fields_ = [("beg", ctypes.c_int64), ("end", ctypes.c_int64)]
 
@@ -59,6 +68,13 @@ def lib():
         L.nro_search_buffered.argtypes = [ctypes.POINTER(NroPattern), ctypes.POINTER(NroPlan), ctypes.c_char_p,
                                           ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(NroHit), ctypes.c_int64]
         L.nro_search_buffered.restype = ctypes.c_int64
+        L.nrx_parse.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(NrxPattern)]
+        L.nrx_parse.restype = ctypes.c_int
+        L.nrx_plan_make.argtypes = [ctypes.POINTER(NrxPattern), ctypes.POINTER(NrxPlan)]
+        L.nrx_plan_make.restype = ctypes.c_int
+        L.nrx_search_buffered.argtypes = [ctypes.POINTER(NrxPattern), ctypes.POINTER(NrxPlan), ctypes.c_char_p,
+                                          ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(NroHit), ctypes.c_int64]
+        L.nrx_search_buffered.restype = ctypes.c_int64
         _lib = L
     return _lib
 
@@ -90,13 +106,37 @@ def plan(pattern, kopt="0ids", icase=True):
 BUFSIZE = 1600000          # patmatch.py:37 MAX_BUFFER_SIZE, passed as -b
 
 
+def plan_ext(pattern, icase=True):
+    """EXTENDED pattern (k = 0): -> (NrxPattern, NrxPlan); ValueError when the oracle does not cover it."""
+    L = lib()
+    X = NrxPattern()
+    rc = L.nrx_parse(pattern.encode("latin-1"), int(icase), ctypes.byref(X))
+    if rc:
+        raise ValueError("oracle cannot parse %r as an EXTENDED pattern: %d" % (pattern, rc))
+    pl = NrxPlan()
+    L.nrx_plan_make(ctypes.byref(X), ctypes.byref(pl))
+    return X, pl
+
+
+def is_extended(pattern):
+    return any(ch in pattern for ch in "?*+")
+
+
 def search(pattern, text, kopt="0ids", icase=True, cap=1 << 20, bufsize=BUFSIZE):
     """-> list of (beg, end) byte offsets, the hit list `nrgrep_coords -b bufsize` prints."""
     L = lib()
-    P, pl = plan(pattern, kopt, icase)
     if isinstance(text, str):
         text = text.encode("latin-1")
     hits = (NroHit * cap)()
+    if is_extended(pattern):
+        if parse_kopt(kopt)[0] != 0:
+            raise ValueError("EXTENDED patterns with errors are not covered by the oracle")
+        X, xpl = plan_ext(pattern, icase)
+        n = L.nrx_search_buffered(ctypes.byref(X), ctypes.byref(xpl), text, len(text), bufsize, hits, cap)
+        if n > cap:
+            raise OverflowError("oracle hit buffer too small: %d" % n)
+        return [(hits[i].beg, hits[i].end) for i in range(n)]
+    P, pl = plan(pattern, kopt, icase)
     n = L.nro_search_buffered(ctypes.byref(P), ctypes.byref(pl), text, len(text), bufsize, hits, cap)
     if n > cap:
         raise OverflowError("oracle hit buffer too small: %d" % n)

@@ -36,7 +36,12 @@ def test_reference_golden_vectors(engine, search_golden, scan_mode):
     try:
         for c in search_golden:
             engine.set_buffer_size(c["bufsize"])
-            got = [list(h) for h in gpu_hits(engine, c["text"], c["pattern"], c["kopt"])]
+            try:
+                got = [list(h) for h in gpu_hits(engine, c["text"], c["pattern"], c["kopt"])]
+            except pm.NativeError as e:
+                # the only patterns the engine may refuse: EXTENDED ones outside what it covers ('*' / '+' repeats)
+                assert e.code == -3 and any(ch in c["pattern"] for ch in "*+"), (c["pattern"], str(e))
+                continue
             if got != c["hits"]:
                 bad.append((c["pattern"], c["kopt"], c["bufsize"], got[:4], c["hits"][:4]))
     finally:

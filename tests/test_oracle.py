@@ -14,15 +14,20 @@ def test_oracle_matches_reference_golden(search_golden):
 def test_golden_covers_every_plan_type(search_golden):
     seen = set()
     for c in search_golden:
+        if O.is_extended(c["pattern"]):
+            _, xpl = O.plan_ext(c["pattern"])
+            seen.add("EXT%d" % xpl.type)
+            continue
         _, pl = O.plan(c["pattern"], c["kopt"])
         seen.add(O.TYPE_NAMES[pl.type])
-    assert seen == {"SIMPLE", "SPLIT", "BWD", "FWD"}
+    assert seen == {"SIMPLE", "SPLIT", "BWD", "FWD", "EXT2", "EXT3"}
 
 
 def test_banner(search_golden):
     for c in search_golden:
         k = O.parse_kopt(c["kopt"])[0]
-        assert c["banner"] == ("SIMPLE search" if k == 0 else "ESIMPLE search")
+        want = "EXTENDED search" if O.is_extended(c["pattern"]) else "SIMPLE search" if k == 0 else "ESIMPLE search"
+        assert c["banner"] == want
 
 
 def test_known_answers():
