@@ -6,7 +6,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PM_MAX_PIECES = 16
-PLAN_NAMES = {0: "SIMPLE", 1: "SPLIT", 2: "BWD", 3: "FWD"}
+PLAN_NAMES = {0: "SIMPLE", 1: "SPLIT", 2: "BWD", 3: "FWD", 4: "EXT_BEG", 5: "EXT_END"}
 PM_ERR_OVERFLOW = -5
 
 

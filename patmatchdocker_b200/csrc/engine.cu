@@ -24,6 +24,7 @@
 #include <vector>
 #include <algorithm>
 #include <cmath>
+#include <memory>
 #include "../../include/patmatch_b200.h"
 #include "plan.hpp"
 
@@ -51,7 +52,20 @@ struct DevPlan {
     int V[PM_MAX_PIECES];
     unsigned long long trig[PM_MAX_PIECES];
     unsigned long long init, fin;
+    // EXTENDED plans: keys carry the start of the scanned window of plain positions; the anchor sits ext_off bytes
+    // further and splits the pattern at position ext_anchor.  Closure masks per walk (extendedLoadVerif @412c60).
+    int ext_off, ext_anchor;
+    unsigned long long IL, FL, AL, initL, IR, FR, AR, initR;
 };
+
+__device__ __forceinline__ bool plan_is_ext(const DevPlan &pl) { return pl.type == PM_PLAN_EXT_BEG || pl.type == PM_PLAN_EXT_END; }
+// text position the verification is anchored at, from a candidate key
+__device__ __forceinline__ long long anchor_of(const DevPlan &pl, long long key) { return (key >> 4) + (plan_is_ext(pl) ? pl.ext_off : 0); }
+// the byte that decides which record / fill a candidate belongs to
+__device__ __forceinline__ long long locus_of(const DevPlan &pl, long long anchor)
+{
+    return (pl.type == PM_PLAN_FWD || pl.type == PM_PLAN_EXT_END) ? anchor - 1 : anchor;
+}
 
 struct Cand { long long key, beg, end, reach; };   // == pm_candidate
 struct H16 { long long a, b; };                     // == pm_hit
@@ -194,6 +208,74 @@ __device__ int check_match(const DevPlan &pl, const unsigned char *__restrict__ 
     }
     *beg = pos - bext;
     *end = pos + fext;
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------
+// EXTENDED patterns (positions with '?'), k = 0: one walk of checkMatch @411aa0.  State bit u = element u (counted
+// away from the anchor) has consumed a byte or was skipped; T[c] = elements accepting byte c; I / F / A are the
+// closure masks of the runs of optional elements.  The initial state only pre-skips the FIRST element when it is
+// optional -- a run of two or more optional elements next to the anchor cannot be skipped as a whole on the first
+// byte (the reference's observable behaviour: (GAT.?.?.?AAGTCC) does not match GATAAGTCC).
+// Returns the bytes consumed by the shortest accepted extension, -1 if none; *steps = bytes examined.
+__device__ __forceinline__ long long ext_side(const unsigned char *__restrict__ text, const unsigned long long *__restrict__ T,
+                                              int len, unsigned long long I, unsigned long long F, unsigned long long A,
+                                              unsigned long long init, int dir, int ctx, long long pos, long long lim, long long *steps)
+{
+    const unsigned long long fin = 1ULL << (len - 1);
+    unsigned long long D = init, carry = 1;
+    long long n = 0;
+    *steps = 0;
+    for (;;) {
+        if (D & fin) {
+            bool ok = true;
+            if (ctx) {
+                if (dir < 0) { const long long e = pos - n; ok = e <= lim || text[e - 1] == '\n'; }
+                else { const long long e = pos + n; ok = e >= lim || text[e] == '\n'; }
+            }
+            if (ok) return n;
+        }
+        const long long tp = dir > 0 ? pos + n : pos - n - 1;
+        if (dir > 0 ? tp >= lim : tp < lim) return -1;
+        const unsigned c = text[tp];
+        if (c == '\n') return -1;                                      // record delimiter (recGetRecord @402030)
+        n++;
+        *steps = n;
+        D = ((D << 1) | carry) & T[c];
+        carry = 0;
+        if (!D) return -1;
+        const unsigned long long x = D | F;
+        D = (((~(x - I)) ^ x) & A) | D;
+    }
+}
+
+// checkMatch @411aa0 at `anchor` with scan range [tbeg, n)
+__device__ int check_match_ext(const DevPlan &pl, const unsigned char *__restrict__ text, long long n,
+                               const unsigned long long *__restrict__ TL, const unsigned long long *__restrict__ TR,
+                               long long anchor, long long tbeg, long long *beg, long long *end, long long *reach)
+{
+    const long long p = locus_of(pl, anchor);
+    *reach = anchor;
+    if (p < tbeg || p >= n) return 0;
+    if (text[p] == '\n') return 0;
+    const int a = pl.ext_anchor, m = pl.m;
+    long long bext = 0, fext = 0, steps = 0;
+    if (a == 0) {
+        *reach = anchor - (pl.start_line ? 1 : 0);
+        if (pl.start_line && !(anchor <= tbeg || text[anchor - 1] == '\n')) return 0;
+    } else {
+        bext = ext_side(text, TL, a, pl.IL, pl.FL, pl.AL, pl.initL, -1, pl.start_line, anchor, tbeg, &steps);
+        *reach = anchor - steps - (pl.start_line ? 1 : 0);
+        if (bext < 0) return 0;
+    }
+    if (a == m) {
+        if (pl.end_line && !(anchor >= n || text[anchor] == '\n')) return 0;
+    } else {
+        fext = ext_side(text, TR, m - a, pl.IR, pl.FR, pl.AR, pl.initR, +1, pl.end_line, anchor, n, &steps);
+        if (fext < 0) return 0;
+    }
+    *beg = anchor - bext;
+    *end = anchor + fext;
     return 1;
 }
 
@@ -361,13 +443,19 @@ __global__ void __launch_bounds__(128) k_verify(const DevPlan pl, const unsigned
     const int i = (int)(key & 15);
     Cand c;
     c.key = (long long)key;
-    const long long p = pl.type == PM_PLAN_FWD ? pos - 1 : pos;
+    const long long anchor = anchor_of(pl, (long long)key);
+    const long long p = locus_of(pl, anchor);
     const int f = fill_of(fills, p);
     const long long S = fills.S[f], E = fills.E[f];
     // the scanned window of the candidate must lie inside its fill
-    const long long wlen = pl.type == PM_PLAN_SIMPLE ? pl.m : pl.type == PM_PLAN_SPLIT ? pl.L : pl.type == PM_PLAN_BWD ? pl.L - pl.k : 0;
-    if (pos + wlen > E || (recheck && !raw_trigger(pl, B, text, n, pos, i))) {
-        c.beg = -1; c.end = -1; c.reach = pos;
+    const long long wlen = pl.type == PM_PLAN_SIMPLE ? pl.m : (pl.type == PM_PLAN_SPLIT || plan_is_ext(pl)) ? pl.L
+                         : pl.type == PM_PLAN_BWD ? pl.L - pl.k : 0;
+    if (pos + wlen > E || (plan_is_ext(pl) && pos < S) || (recheck && !raw_trigger(pl, B, text, n, pos, i))) {
+        c.beg = -1; c.end = -1; c.reach = anchor;
+    } else if (plan_is_ext(pl)) {
+        long long b = -1, e = -1, r = anchor;
+        if (!check_match_ext(pl, text, E, TL, TR, anchor, S, &b, &e, &r)) { b = -1; e = -1; }
+        c.beg = b; c.end = e; c.reach = r;
     } else if (pl.type == PM_PLAN_SIMPLE) {
         c.beg = pos; c.end = pos + pl.m; c.reach = pos - (pl.start_line ? 1 : 0);   // the chain stage applies '^' / '$'
     } else {
@@ -384,8 +472,7 @@ __global__ void __launch_bounds__(128) k_verify(const DevPlan pl, const unsigned
 // produce a hit that ends right of everything j depends on.
 __device__ __forceinline__ long long dep_lo(const DevPlan &pl, const Cand &c)
 {
-    long long a = c.key >> 4;
-    if (pl.type == PM_PLAN_FWD) a -= 1;
+    const long long a = locus_of(pl, anchor_of(pl, c.key));
     return c.reach < a ? c.reach : a;
 }
 
@@ -398,12 +485,11 @@ __global__ void __launch_bounds__(128) k_chain(const DevPlan pl, const unsigned 
     if (j0 >= ncand) return;
     const long long span = pl.m + pl.k;
     auto fill_at = [&](long long j) -> int {
-        const long long a = cands[j].key >> 4;
-        return fill_of(fills, pl.type == PM_PLAN_FWD ? a - 1 : a);
+        return fill_of(fills, locus_of(pl, anchor_of(pl, cands[j].key)));
     };
     auto independent = [&](long long j) -> bool {
         if (j == 0) return true;
-        if ((cands[j - 1].key >> 4) + span <= dep_lo(pl, cands[j])) return true;
+        if (anchor_of(pl, cands[j - 1].key) + span <= dep_lo(pl, cands[j])) return true;
         return fill_at(j) != fill_at(j - 1);               // a new fill restarts the scan
     };
     if (!independent(j0)) return;
@@ -416,8 +502,8 @@ __global__ void __launch_bounds__(128) k_chain(const DevPlan pl, const unsigned 
         // a failed verification is final unless '^' is in play: then a scan start inside the examined bytes can
         // turn it into a match (the left context is satisfied AT the scan start), so it is redone clipped below
         if (c.beg < 0 && !(pl.start_line && pl.type != PM_PLAN_SIMPLE && dep_lo(pl, c) < pos)) continue;
-        const long long anchor = c.key >> 4;
-        const long long p = pl.type == PM_PLAN_FWD ? anchor - 1 : anchor;
+        const long long anchor = anchor_of(pl, c.key);
+        const long long p = locus_of(pl, anchor);
         if (p < pos) continue;
         const long long n_fill = fills.E[cur];
         long long b = c.beg, e = c.end;
@@ -428,7 +514,8 @@ __global__ void __launch_bounds__(128) k_chain(const DevPlan pl, const unsigned 
         } else if (dep_lo(pl, c) < pos) {
             // the unclipped verification looked left of the new scan start: redo it clipped
             long long r;
-            if (!check_match(pl, text, n_fill, TL, TR, (int)(c.key & 15), anchor, pos, &b, &e, &r)) continue;
+            if (plan_is_ext(pl)) { if (!check_match_ext(pl, text, n_fill, TL, TR, anchor, pos, &b, &e, &r)) continue; }
+            else if (!check_match(pl, text, n_fill, TL, TR, (int)(c.key & 15), anchor, pos, &b, &e, &r)) continue;
         }
         hits[t].beg = b;
         hits[t].end = e;
@@ -787,6 +874,8 @@ struct Compiled {
     DevPlan dp;
     pm::FilterTables ft;
     pm::VerifyTables vt;
+    // EXTENDED plans: the exact scan runs on the window of plain positions around the anchor, compiled as a SIMPLE pattern
+    std::shared_ptr<Compiled> scan;
 };
 
 static int compile(const char *pattern, const char *kopt, Compiled &c, bool need_tables)
@@ -806,6 +895,27 @@ static int compile(const char *pattern, const char *kopt, Compiled &c, bool need
     d.ins = c.plan.ins; d.del = c.plan.del; d.subs = c.plan.subs;
     d.start_line = c.P.start_line ? 1 : 0; d.end_line = c.P.end_line ? 1 : 0;
     for (int i = 0; i < PM_MAX_PIECES; i++) { d.V[i] = c.plan.V[i]; d.trig[i] = c.plan.trig[i]; }
+    if (c.plan.type == pm::EXT_BEG || c.plan.type == pm::EXT_END) {
+        auto s = std::make_shared<Compiled>();
+        s->o = c.o;
+        for (int j = c.plan.win_lo; j < c.plan.win_hi; j++) { s->P.pos.push_back(c.P.pos[j]); s->P.op.push_back(pm::OP_NONE); }
+        s->plan.type = pm::SIMPLE; s->plan.m = s->plan.L = s->P.m(); s->plan.npieces = 1;
+        DevPlan &sd = s->dp;
+        memset(&sd, 0, sizeof sd);
+        sd.type = PM_PLAN_SIMPLE; sd.m = sd.L = s->P.m(); sd.npieces = 1; sd.ins = sd.del = sd.subs = 1;
+        pm::build_filter(s->P, s->plan, s->ft);
+        sd.init = s->ft.init; sd.fin = s->ft.fin; sd.trig[0] = s->ft.fin;
+        c.ft = s->ft;                                       // k_verify re-checks the window on the raw bytes with it
+        d.init = c.ft.init; d.fin = c.ft.fin; d.trig[0] = c.ft.fin;
+        d.ext_off = c.plan.anchor - c.plan.win_lo; d.ext_anchor = c.plan.anchor;
+        d.IL = c.plan.IL; d.FL = c.plan.FL; d.AL = c.plan.AL; d.initL = c.plan.initL;
+        d.IR = c.plan.IR; d.FR = c.plan.FR; d.AR = c.plan.AR; d.initR = c.plan.initR;
+        pm::Plan vp = c.plan;
+        vp.npieces = 1; vp.V[0] = c.plan.anchor;            // TL: positions anchor-1, anchor-2, ... ; TR: anchor, anchor+1, ...
+        pm::build_verify(c.P, vp, c.vt);
+        c.scan = s;
+        return PM_OK;
+    }
     if (c.plan.type == pm::SIMPLE || c.plan.type == pm::SPLIT) {
         pm::build_filter(c.P, c.plan, c.ft);
         d.init = c.ft.init; d.fin = c.ft.fin;
@@ -849,11 +959,13 @@ static int upload_tables(pm_engine *e, const Compiled &c, const unsigned long lo
 static unsigned packed_class_of(const pm::ByteSet &bs, bool *mixed);
 
 // scan + sort + verify: leaves ncand verified candidates (sorted) in e->cands
-static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, long long a0, long long a1,
+static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c_full, long long a0, long long a1,
                               const unsigned long long *dB, const unsigned long long *dTL, const unsigned long long *dTR,
                               long long *ncand_out)
 {
+    const Compiled &c = c_full.scan ? *c_full.scan : c_full;   // what the scan kernels see (EXTENDED: the plain window)
     const DevPlan &dp = c.dp;
+    const DevPlan &vdp = c_full.dp;                             // what verification sees
     const long long n = d->n;
     int rc;
     Fills fills;
@@ -1162,7 +1274,7 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, lo
     // ---- verify ----
     if (ncand > 0) {
         if ((rc = e->cands.reserve((size_t)ncand * sizeof(Cand)))) return rc;
-        k_verify<<<(unsigned)((ncand + 127) / 128), 128, 0, e->stream>>>(dp, d->d_text, n, dB, dTL, dTR, keys, ncand, (Cand *)e->cands.p,
+        k_verify<<<(unsigned)((ncand + 127) / 128), 128, 0, e->stream>>>(vdp, d->d_text, n, dB, dTL, dTR, keys, ncand, (Cand *)e->cands.p,
                                                                         use_packed ? 1 : 0, fills);
         CK(cudaGetLastError());
         e->stats.launches++;
@@ -1283,8 +1395,10 @@ static int search_fill_range(pm_engine *e, pm_dataset *d, const Compiled &c, con
     if (f0 < f1) {
         // anchors whose fill (fill_of: the last fill starting at or before the anchor; FWD plans anchor one byte later)
         // is one of f0 .. f1-1
-        const long long shift = c.dp.type == PM_PLAN_FWD ? 1 : 0;
-        const long long a0 = S[f0] + shift;
+        // (EXTENDED plans: keys are window starts, the deciding byte lies ext_off further, one less for anchors at an end)
+        const long long shift = c.dp.type == PM_PLAN_FWD ? 1
+                              : (c.dp.type == PM_PLAN_EXT_BEG || c.dp.type == PM_PLAN_EXT_END) ? (c.dp.type == PM_PLAN_EXT_END ? 1 : 0) - c.dp.ext_off : 0;
+        const long long a0 = std::max<long long>(S[f0] + shift, 0);
         const long long a1 = f1 < (long long)S.size() ? S[f1] + shift : d->n + 1;
         if ((rc = produce_candidates(e, d, c, a0, a1, dB, dTL, dTR, &ncand))) return rc;
     } else {
@@ -1528,7 +1642,7 @@ static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char 
     for (int b = 0; b < npat; b++) {
         pm::Pattern P;
         if (pm::parse_pattern(patterns[b], true, P, err)) return 1;
-        if (P.start_line || P.end_line || P.m() > 32 || P.m() < 1) return 1;
+        if (P.start_line || P.end_line || P.extended() || P.m() > 32 || P.m() < 1) return 1;
         MultiPat &m = mp[b];
         memset(&m, 0, sizeof m);
         m.m = (unsigned short)P.m();

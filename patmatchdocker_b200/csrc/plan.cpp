@@ -68,8 +68,18 @@ int parse_pattern(const char *pattern, bool icase, Pattern &P, std::string &err)
         unsigned c = (unsigned char)s[i++];
         if (c == '(') { depth++; continue; }
         if (c == ')') { if (--depth < 0) { err = "unbalanced ')'"; return PM_ERR_SYNTAX; } continue; }
-        if (c == '?' || c == '*' || c == '+' || c == '|' || c == '\\' || c == '#') {
-            err = std::string("operator '") + (char)c + "' selects nrgrep's EXTENDED/REGULAR engine (not this path)";
+        if (c == '?' || c == '*' || c == '+') {
+            // EXTENDED pattern: an operator on a single position (what PatMatch's X{m,n} / X{m,} become);
+            // operators on groups would be nrgrep's REGULAR engine
+            if (P.pos.empty() || P.op.back() != OP_NONE || (i >= 2 && s[i - 2] == ')')) {
+                err = std::string("operator '") + (char)c + "' on a group or doubled: nrgrep's REGULAR engine (not this path)";
+                return PM_ERR_UNSUPPORTED;
+            }
+            P.op.back() = c == '?' ? OP_OPT : c == '*' ? OP_STAR : OP_PLUS;
+            continue;
+        }
+        if (c == '|' || c == '\\' || c == '#') {
+            err = std::string("operator '") + (char)c + "' selects nrgrep's REGULAR engine (not this path)";
             return PM_ERR_UNSUPPORTED;
         }
         ByteSet b;
@@ -92,9 +102,22 @@ int parse_pattern(const char *pattern, bool icase, Pattern &P, std::string &err)
             if (neg) b.invert();
         } else add_byte(b, c, icase);
         P.pos.push_back(b);
+        P.op.push_back(OP_NONE);
     }
     if (depth != 0) { err = "unbalanced '('"; return PM_ERR_SYNTAX; }
     if (P.pos.empty()) { err = "empty pattern"; return PM_ERR_SYNTAX; }
+    if (P.extended()) {
+        // the reference's parser rewrites patterns that begin or end with an operator position (it drops one leading
+        // optional, every trailing one, ...); those shapes are not restated
+        if (P.op.front() != OP_NONE || P.op.back() != OP_NONE) {
+            err = "EXTENDED pattern whose first or last position carries ? * +: not supported yet";
+            return PM_ERR_UNSUPPORTED;
+        }
+        // nested groups would change what the operators bind to
+        int opens = 0;
+        for (char ch : s) opens += ch == '(';
+        if (opens > 1) { err = "EXTENDED pattern with inner groups: not supported yet"; return PM_ERR_UNSUPPORTED; }
+    }
     return PM_OK;
 }
 
@@ -181,11 +204,136 @@ static double find_best_window(const Pattern &P, int k, int &flag, int &beg, int
     return best < 0.8 ? best : 1.0;
 }
 
+// extendedFindBest @411fe0 for K errors (the EXTENDED engine only runs with K = 0 here): cost of scanning for
+// every sub-pattern [i, pos] from tables of the probability that a text window of l bytes matches a factor ending
+// at `a` and starting at `d` (T) and that any such factor start survives (U).  Rows are filled lazily per end
+// position, in the same order and with the same doubles as the reference, because ties between sub-patterns are
+// decided by strict comparisons.  Returns the best cost; wlen = mandatory positions of the chosen sub-pattern
+// (0: no sub-pattern beats 0.7 -- forward scan for the whole pattern).
+static double find_best_extended(const Pattern &P, int K, int &beg, int &end, int &wlen)
+{
+    const int m = P.m(), N1 = m + 1, NN = m * N1;
+    std::vector<double> prob((size_t)m), prob2((size_t)m);
+    for (int j = 0; j < m; j++) {
+        double p = 0.0, q = 0.0;
+        for (unsigned c = 0; c < 256; c++)
+            if (P.pos[j].has(c)) { p += (double)kBytePpm[c] / 1000000.0; if (P.repeats(j)) q += (double)kBytePpm[c] / 1000000.0; }
+        prob[j] = p; prob2[j] = q;
+    }
+    std::vector<double> T((size_t)NN * N1, 0.0), U((size_t)NN * N1, 0.0);
+    std::vector<int> last((size_t)m, 0);
+    auto ix = [&](int d, int a, int l) { return (size_t)d * NN + (size_t)a * N1 + (size_t)l; };
+    for (int a = 0; a < m; a++) {
+        for (int d = 0; d <= a; d++) { U[ix(d, a, 0)] = 1.0; T[ix(d, a, 0)] = 1.0; }
+        U[ix(a + 1, a, 0)] = 0.0; T[ix(a + 1, a, 0)] = 0.0;
+    }
+    double best = 0.7;
+    beg = end = wlen = 0;
+    const int K2 = 2 * K;
+    const double dK1 = (double)K + 1.0;
+    for (int i = 0; i < m; i++) {
+        int count = 0;                                  // mandatory positions in [i, pos]
+        for (int pos = i; pos < m; pos++) {
+            if ((unsigned)(pos - i + 1) > 64u) continue;
+            if (P.optional(pos)) { if (K2 >= count) continue; }
+            else { count++; if (count <= K2) continue; }
+            double sum = dK1, dlk1;
+            int lk;
+            if (count > 0) {
+                lk = count - K;
+                dlk1 = (double)(lk + 1);
+                if (!(dK1 >= dlk1)) {
+                    const double dlk = (double)lk;
+                    const double c0 = dK1 / ((dlk - dK1) + 1.0);
+                    if (!(c0 >= best)) {
+                        for (int l = 1;;) {
+                            if (last[pos] < l) {
+                                U[ix(pos + 1, pos, l)] = 0.0; T[ix(pos + 1, pos, l)] = 0.0;
+                                for (int q = pos; q >= 0; q--) {
+                                    double s1 = prob[q] * T[ix(q + 1, pos, l - 1)];
+                                    const double s0 = prob2[q] * T[ix(q, pos, l - 1)];
+                                    s1 = s1 + s0;
+                                    const double s = P.optional(q) ? T[ix(q + 1, pos, l)] + s1 : 0.0 + s1;
+                                    double one_minus;
+                                    if (s > 1.0) { T[ix(q, pos, l)] = 1.0; one_minus = 0.0; }
+                                    else { T[ix(q, pos, l)] = s; one_minus = 1.0 - s; }
+                                    U[ix(q, pos, l)] = 1.0 - (1.0 - U[ix(q + 1, pos, l)]) * one_minus;
+                                }
+                                last[pos] = l;
+                            }
+                            sum += U[ix(i, pos, l)];
+                            l++;
+                            if (l > count) break;
+                            if (sum >= dlk1) break;
+                            const double c = sum / ((dlk - sum) + 1.0);
+                            if (!(c < best)) break;
+                        }
+                    }
+                }
+            } else { lk = -K; dlk1 = (double)(1 - K); }
+            if (dlk1 > sum) {
+                const double c = sum / (((double)lk - sum) + 1.0);
+                if (best > c) { best = c; beg = i; end = pos + 1; wlen = count; }
+            }
+        }
+    }
+    if (wlen > 0) {
+        while (beg < end && P.optional(beg)) beg++;
+        while (beg < end && P.optional(end - 1)) end--;
+        if (beg == end) wlen = 0;
+    }
+    if (wlen == 0) {
+        end = m > 64 ? 64 : m;
+        while (P.optional(end - 1)) end--;
+        best = 1.0;
+    }
+    return best;
+}
+
+// closure masks of one verification walk (extendedLoadVerif @412c60); element u = pattern position from + u*step
+static void closure_masks(const Pattern &P, int from, int len, int step, uint64_t &I, uint64_t &F, uint64_t &A, uint64_t &init)
+{
+    I = F = A = init = 0;
+    bool flag = false;
+    for (int u = 0; u < len; u++) {
+        if (!P.optional(from + u * step)) continue;
+        if (u > 0) {
+            if ((F >> (u - 1)) & 1ULL) {
+                F &= ~(1ULL << (u - 1)); F |= 1ULL << u;
+                if (flag) A |= 1ULL << u; else init |= 1ULL << u;
+            } else { I |= 1ULL << (u - 1); F |= 1ULL << u; flag = true; A |= 1ULL << u; }
+        } else { if (flag) A |= 1ULL << u; else init |= 1ULL << u; }
+    }
+}
+
+static int make_plan_extended(const Pattern &P, const Options &o, Plan &plan, std::string &err)
+{
+    const int m = P.m();
+    if (o.k != 0) { err = "EXTENDED pattern with errors (nrgrep's eextended engine): not supported yet"; return PM_ERR_UNSUPPORTED; }
+    if (m > 64) { err = "EXTENDED pattern longer than 64 positions"; return PM_ERR_UNSUPPORTED; }
+    for (int j = 0; j < m; j++)
+        if (P.repeats(j)) { err = "EXTENDED pattern with '*' / '+' repeats (unbounded hits): not supported yet"; return PM_ERR_UNSUPPORTED; }
+    plan.fb_cost = find_best_extended(P, 0, plan.ext_beg, plan.ext_end, plan.ext_wlen);
+    if (plan.ext_wlen > 0) { plan.type = EXT_BEG; plan.anchor = plan.ext_beg; }
+    else { plan.type = EXT_END; plan.anchor = plan.ext_end; }
+    // plain positions next to the anchor: present in every match at a fixed offset, so an exact scan finds all anchors
+    int lo = plan.anchor, hi = plan.anchor;
+    while (lo > 0 && P.op[lo - 1] == OP_NONE) lo--;
+    while (hi < m && P.op[hi] == OP_NONE) hi++;
+    plan.win_lo = lo; plan.win_hi = hi;
+    plan.L = hi - lo; plan.npieces = 1; plan.V[0] = plan.anchor;      // V[0]: where the verification splits the pattern
+    if (plan.L < 1) { err = "internal: empty scan window"; return PM_ERR_UNSUPPORTED; }
+    closure_masks(P, plan.anchor - 1, plan.anchor, -1, plan.IL, plan.FL, plan.AL, plan.initL);
+    closure_masks(P, plan.anchor, m - plan.anchor, +1, plan.IR, plan.FR, plan.AR, plan.initR);
+    return PM_OK;
+}
+
 int make_plan(const Pattern &P, const Options &o, Plan &plan, std::string &err)
 {
     plan = Plan();
     const int m = P.m(), k = o.k;
     plan.m = m; plan.k = k; plan.ins = o.ins; plan.del = o.del; plan.subs = o.subs;
+    if (P.extended()) return make_plan_extended(P, o, plan, err);
     if (k == 0) { plan.type = SIMPLE; plan.L = m; plan.npieces = 1; plan.V[0] = 0; return PM_OK; }
     if (k >= m) { err = "k >= pattern length"; return PM_ERR_UNSUPPORTED; }
     const int K1 = k + 1, K2 = k + 2;

@@ -20,15 +20,23 @@ struct ByteSet {                       // 256-bit byte class of one pattern posi
     void fill() { for (auto &x : w) x = ~0ULL; }
 };
 
+enum PosOp : unsigned char { OP_NONE = 0, OP_OPT = 1, OP_STAR = 2, OP_PLUS = 3 };   // position followed by '?', '*', '+'
+
 struct Pattern {
     std::vector<ByteSet> pos;          // one class per pattern position
+    std::vector<unsigned char> op;     // PosOp per position (all OP_NONE for SIMPLE / ESIMPLE patterns)
     bool start_line = false, end_line = false;
     int m() const { return (int)pos.size(); }
+    bool extended() const { for (unsigned char o : op) if (o) return true; return false; }
+    bool optional(int j) const { return op[j] == OP_OPT || op[j] == OP_STAR; }
+    bool repeats(int j) const { return op[j] == OP_STAR || op[j] == OP_PLUS; }
 };
 
 struct Options { int k = 0; bool ins = true, del = true, subs = true; };
 
-enum PlanType { SIMPLE = 0, SPLIT = 1, BWD = 2, FWD = 3 };
+enum PlanType { SIMPLE = 0, SPLIT = 1, BWD = 2, FWD = 3,
+                EXT_BEG = 4,          // EXTENDED pattern, verification anchored at the START of the scanned sub-pattern
+                EXT_END = 5 };        // ... at its END (extendedPreproc @413260: types 2 and 3 of that engine)
 
 struct Plan {
     PlanType type = SIMPLE;
@@ -40,6 +48,12 @@ struct Plan {
     uint64_t trig[16] = {0};           // SPLIT: mask over piece-top bits that make piece i a candidate
     double split_cost = 0, fb_cost = 0;
     int fb_flag = 0, fb_beg = 0, fb_end = 0;
+    // EXTENDED plans (k = 0): what extendedFindBest @411fe0 chose, and the run of plain positions around the
+    // anchor that the exact scan looks for (every match contains it at a fixed offset from the anchor)
+    int ext_beg = 0, ext_end = 0, ext_wlen = 0, anchor = 0;
+    int win_lo = 0, win_hi = 0;
+    // closure masks of the two verification walks (extendedLoadVerif @412c60), elements numbered away from the anchor
+    uint64_t IL = 0, FL = 0, AL = 0, initL = 0, IR = 0, FR = 0, AR = 0, initR = 0;
 };
 
 // error codes follow include/patmatch_b200.h

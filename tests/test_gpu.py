@@ -244,6 +244,66 @@ def test_line_anchors_against_oracle(engine, scan_mode):
     assert n_hits > 500
 
 
+def test_extended_patterns_against_oracle(engine, scan_mode):
+    # nrgrep's EXTENDED engine (k = 0): PatMatch's X{m,n} repeats arrive as runs of optional positions.  Anchors come
+    # from an exact scan of the plain positions around the chosen sub-pattern, verification is the reference's walk
+    # (shortest extension, with its initial-state quirk), the chain stage is the common one.
+    rng = random.Random(404)
+    n_hits = 0
+    types = set()
+    for it in range(200):
+        alpha = rng.choice([DNA, DNA, PEP])
+        m = rng.randint(3, 20 if it % 4 else 40)
+        pat, members, ops = "(", [], []
+        for j in range(m):
+            r = rng.random()
+            if r < 0.12:
+                pat += "."; members.append(list(alpha))
+            elif r < 0.27:
+                ch = rng.sample(alpha, 2); pat += "[" + "".join(ch) + "]"; members.append(ch)
+            else:
+                c = rng.choice(alpha); pat += c; members.append([c])
+            op = "?" if 0 < j < m - 1 and rng.random() < 0.3 else ""
+            pat += op
+            ops.append(op)
+        pat += ")"
+        if not any(ops):
+            continue
+        if it % 6 == 0:
+            pat = "^" + pat
+        if it % 10 == 0:
+            pat = pat + "$"
+        lines = []
+        for r in range(rng.randint(1, 5)):
+            lines.append(">x%d" % r)
+            t = ""
+            target = rng.randint(30, 3000 if it % 5 else 40000)
+            while len(t) < target:
+                if rng.random() < 0.3:
+                    for cls, op in zip(members, ops):
+                        if op == "" or rng.random() < 0.5:
+                            t += rng.choice(cls)
+                else:
+                    t += "".join(rng.choice(alpha) for _ in range(rng.randint(1, 10)))
+            if rng.random() < 0.3:
+                t = "".join(ch.lower() if rng.random() < 0.3 else ch for ch in t)
+            lines.append(t)
+        text = ("\n".join(lines) + "\n").encode()
+        types.add(pm.plan(pat, "0ids")["type"])
+        for bufsize in (1600000, rng.choice([64, 300, 2000])):
+            engine.set_buffer_size(bufsize)
+            try:
+                got = gpu_hits(engine, text, pat, "0ids")
+            finally:
+                engine.set_buffer_size(1600000)
+            want = O.search(pat, text, "0ids", bufsize=bufsize)
+            assert got == want, (pat, bufsize, got[:4], want[:4])
+            n_hits += len(want)
+    assert n_hits > 1000 and types == {"EXT_BEG", "EXT_END"}
+    # the reference's quirk: zero occurrences of a run of two or more optional positions next to the anchor do not match
+    assert gpu_hits(engine, b">q\nCCGATAAGTCCAA\nCCGATCAAGTCCAA\n", "(GAT.?.?.?AAGTCC)", "0ids") == [(19, 29)]
+
+
 def test_hit_list_stays_on_device_after_overflow(engine):
     import ctypes
     from patmatchdocker_b200 import _native

@@ -46,7 +46,7 @@ def test_plan_is_bit_exact_with_oracle():
 
 
 def test_unsupported_patterns_fail_loudly():
-    for pat in ("(GATA?AG)", "(GA(TA)*AG)", "(GAT|AAG)"):
+    for pat in ("(GATA*AG)", "(GATA+AG)", "(GA(TA)*AG)", "(GA(TA)?AG)", "(GAT|AAG)", "(G?ATAAG)", "(GATAAG?)"):
         with pytest.raises(pm.NativeError) as ei:
             pm.plan(pat, "0ids")
         assert ei.value.code == -3
@@ -112,3 +112,37 @@ def test_record_index_matches_reference_layout():
     assert offs == [0, 8, 13, 17, 20, 23]
     assert names == {0: ">a", 8: "a", 13: ">b,", 17: "b,", 20: ">c", 23: "c"}
     assert host.get_name_offset(10, offs) == 8
+
+
+def test_extended_plan_matches_oracle():
+    # EXTENDED patterns (positions with '?'): the product's planner (find_best_extended in csrc/plan.cpp) must choose the
+    # same verification type and anchor as the oracle's restatement of extendedFindBest, which is pinned on the binary
+    import random
+    import oracle_lib as O
+    import patmatchdocker_b200 as pm
+    rng = random.Random(123)
+    seen = set()
+    for _ in range(400):
+        alpha = rng.choice(["ACGT", "ACDEFGHIKLMNPQRSTVWY"])
+        m = rng.randint(3, 24)
+        pat, nops = "(", 0
+        for j in range(m):
+            r = rng.random()
+            pat += "." if r < 0.12 else "[" + "".join(rng.sample(alpha, 2)) + "]" if r < 0.27 else rng.choice(alpha)
+            if 0 < j < m - 1 and rng.random() < 0.3:
+                pat += "?"
+                nops += 1
+        pat += ")"
+        if not nops:
+            continue
+        _, xpl = O.plan_ext(pat)
+        p = pm.plan(pat, "0ids")
+        assert p["type"] == {2: "EXT_BEG", 3: "EXT_END"}[xpl.type], pat
+        assert p["V"][0] == xpl.anchor, pat
+        seen.add(p["type"])
+    assert seen == {"EXT_BEG", "EXT_END"}
+    for bad in ("(AC*GT)", "(AC+GT)", "(A?CGT)", "(ACG?)", "(A(CG)?T)"):
+        with pytest.raises(pm.NativeError):
+            pm.plan(bad, "0ids")
+    with pytest.raises(pm.NativeError):
+        pm.plan("(AC?GT)", "1ids")
