@@ -679,18 +679,22 @@ int nrx_parse(const char *pattern, int icase, nrx_pattern *X)
     const char *s = pattern;
     if (n > 0 && s[0] == '^') { P->start_line = 1; s++; n--; }
     if (n > 0 && s[n - 1] == '$') { P->end_line = 1; n--; }
-    /* one pair of parentheses around the whole pattern is what patmatch_to_nrgrep.pl writes */
-    if (n >= 2 && s[0] == '(' && s[n - 1] == ')') { s++; n -= 2; }
-    int i = 0, m = 0, nops = 0;
+    /* parentheses that no operator applies to only group a concatenation (patmatch_to_nrgrep.pl wraps the whole
+     * pattern in one pair, the reverse complement in two): they are skipped */
+    int i = 0, m = 0, nops = 0, depth = 0, after_close = 0;
     while (i < n) {
         unsigned c = (unsigned char)s[i++];
-        if (c == '(' || c == ')' || c == '|' || c == '\\' || c == '#') return NRO_ERR_UNSUPPORTED;
+        if (c == '(') { depth++; after_close = 0; continue; }
+        if (c == ')') { if (--depth < 0) return NRO_ERR_SYNTAX; after_close = 1; continue; }
+        if (c == '|' || c == '\\' || c == '#') return NRO_ERR_UNSUPPORTED;
         if (c == '?' || c == '*' || c == '+') {
+            if (after_close) return NRO_ERR_UNSUPPORTED;              /* operator on a group: REGULAR engine */
             if (m == 0 || X->op[m - 1] != NRX_NONE) return NRO_ERR_UNSUPPORTED;
             X->op[m - 1] = c == '?' ? NRX_OPT : c == '*' ? NRX_STAR : NRX_PLUS;
             nops++;
             continue;
         }
+        after_close = 0;
         if (m >= 64) return NRO_ERR_TOOLONG;
         if (c == '[') {
             int rc = parse_class(s, &i, n, P, m, icase);
@@ -703,7 +707,7 @@ int nrx_parse(const char *pattern, int icase, nrx_pattern *X)
         }
         m++;
     }
-    if (m == 0) return NRO_ERR_SYNTAX;
+    if (m == 0 || depth != 0) return NRO_ERR_SYNTAX;
     P->m = m;
     if (nops == 0) return NRO_ERR_UNSUPPORTED;                 /* a SIMPLE pattern: not this path */
     if (X->op[0] != NRX_NONE || X->op[m - 1] != NRX_NONE) return NRO_ERR_UNSUPPORTED;

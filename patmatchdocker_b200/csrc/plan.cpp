@@ -113,10 +113,8 @@ int parse_pattern(const char *pattern, bool icase, Pattern &P, std::string &err)
             err = "EXTENDED pattern whose first or last position carries ? * +: not supported yet";
             return PM_ERR_UNSUPPORTED;
         }
-        // nested groups would change what the operators bind to
-        int opens = 0;
-        for (char ch : s) opens += ch == '(';
-        if (opens > 1) { err = "EXTENDED pattern with inner groups: not supported yet"; return PM_ERR_UNSUPPORTED; }
+        // (parentheses that no operator applies to only group a concatenation: patmatch_to_nrgrep.pl wraps the
+        // pattern in one pair and its reverse complement in two)
     }
     return PM_OK;
 }

@@ -320,6 +320,11 @@ def request_fixture():
             dict(pattern="J[^P]OB", seqtype="pep", max_hits=25),
             dict(pattern="AC", seqtype="dna"),
             dict(pattern="GATEAG", seqtype="dna"),
+            # X{m,n} repeats: nrgrep's EXTENDED engine (appended: the requests above keep their fixtures)
+            dict(pattern="TGACN{2,4}CAGA", seqtype="dna", strand="Both strands"),
+            dict(pattern="GAN{0,3}TAAG", seqtype="dna", strand="Watson strand"),
+            dict(pattern="CX{2,4}C[ILVM]", seqtype="pep"),
+            dict(pattern="MX{0,2}K", seqtype="pep", max_hits=50),
         ]
         for r in reqs:
             kw = dict(r)
