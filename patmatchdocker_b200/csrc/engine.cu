@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -54,7 +55,8 @@ struct DevPlan {
     unsigned long long init, fin;
     // EXTENDED plans: keys carry the start of the scanned window of plain positions; the anchor sits ext_off bytes
     // further and splits the pattern at position ext_anchor.  Closure masks per walk (extendedLoadVerif @412c60).
-    int ext_off, ext_anchor;
+    int ext_off, ext_anchor, ext_repeats;
+    int maxleft;                  // bytes left of its anchor a verification can examine at most (bounded plans)
     unsigned long long IL, FL, AL, initL, IR, FR, AR, initR;
 };
 
@@ -218,7 +220,7 @@ __device__ int check_match(const DevPlan &pl, const unsigned char *__restrict__ 
 // optional -- a run of two or more optional elements next to the anchor cannot be skipped as a whole on the first
 // byte (the reference's observable behaviour: (GAT.?.?.?AAGTCC) does not match GATAAGTCC).
 // Returns the bytes consumed by the shortest accepted extension, -1 if none; *steps = bytes examined.
-__device__ __forceinline__ long long ext_side(const unsigned char *__restrict__ text, const unsigned long long *__restrict__ T,
+__device__ __forceinline__ long long ext_side(const unsigned char *__restrict__ text, const unsigned long long *__restrict__ T, int repeats,
                                               int len, unsigned long long I, unsigned long long F, unsigned long long A,
                                               unsigned long long init, int dir, int ctx, long long pos, long long lim, long long *steps)
 {
@@ -241,7 +243,7 @@ __device__ __forceinline__ long long ext_side(const unsigned char *__restrict__ 
         if (c == '\n') return -1;                                      // record delimiter (recGetRecord @402030)
         n++;
         *steps = n;
-        D = ((D << 1) | carry) & T[c];
+        D = (((D << 1) | carry) & T[c]) | (repeats ? D & T[256 + c] : 0ULL);     // advance | stay ('*' / '+')
         carry = 0;
         if (!D) return -1;
         const unsigned long long x = D | F;
@@ -264,14 +266,14 @@ __device__ int check_match_ext(const DevPlan &pl, const unsigned char *__restric
         *reach = anchor - (pl.start_line ? 1 : 0);
         if (pl.start_line && !(anchor <= tbeg || text[anchor - 1] == '\n')) return 0;
     } else {
-        bext = ext_side(text, TL, a, pl.IL, pl.FL, pl.AL, pl.initL, -1, pl.start_line, anchor, tbeg, &steps);
+        bext = ext_side(text, TL, pl.ext_repeats, a, pl.IL, pl.FL, pl.AL, pl.initL, -1, pl.start_line, anchor, tbeg, &steps);
         *reach = anchor - steps - (pl.start_line ? 1 : 0);
         if (bext < 0) return 0;
     }
     if (a == m) {
         if (pl.end_line && !(anchor >= n || text[anchor] == '\n')) return 0;
     } else {
-        fext = ext_side(text, TR, m - a, pl.IR, pl.FR, pl.AR, pl.initR, +1, pl.end_line, anchor, n, &steps);
+        fext = ext_side(text, TR, pl.ext_repeats, m - a, pl.IR, pl.FR, pl.AR, pl.initR, +1, pl.end_line, anchor, n, &steps);
         if (fext < 0) return 0;
     }
     *beg = anchor - bext;
@@ -479,7 +481,9 @@ __device__ __forceinline__ long long dep_lo(const DevPlan &pl, const Cand &c)
 __global__ void __launch_bounds__(128) k_chain(const DevPlan pl, const unsigned char *__restrict__ text, long long n,
                                                const unsigned long long *__restrict__ TL, const unsigned long long *__restrict__ TR,
                                                const Cand *__restrict__ cands, long long ncand,
-                                               pm_hit *__restrict__ hits, unsigned char *__restrict__ sel, const Fills fills)
+                                               pm_hit *__restrict__ hits, unsigned char *__restrict__ sel, const Fills fills,
+                                               const long long *__restrict__ maxend,        // prefix maxima of Cand.end, or null
+                                               const long long *__restrict__ mindep_rev)    // prefix minima of dep_lo over the REVERSED list
 {
     const long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j0 >= ncand) return;
@@ -487,9 +491,15 @@ __global__ void __launch_bounds__(128) k_chain(const DevPlan pl, const unsigned 
     auto fill_at = [&](long long j) -> int {
         return fill_of(fills, locus_of(pl, anchor_of(pl, cands[j].key)));
     };
+    // Candidate j opens a cluster when nothing before it can influence it OR ANY LATER candidate: every hit of an
+    // earlier candidate ends at or before the leftmost byte that j and its successors can examine.  Bounded plans:
+    // a hit ends within `span` of its anchor and a verification looks at most maxleft (+ the '^' context byte, + the
+    // one-byte locus offset of end-anchored plans) to the left.  '*' / '+' patterns: prefix maxima of the hit ends
+    // against suffix minima of the examined ranges.
     auto independent = [&](long long j) -> bool {
         if (j == 0) return true;
-        if (anchor_of(pl, cands[j - 1].key) + span <= dep_lo(pl, cands[j])) return true;
+        if (maxend ? maxend[j - 1] <= mindep_rev[ncand - 1 - j]
+                   : anchor_of(pl, cands[j - 1].key) + span + pl.maxleft + 2 <= anchor_of(pl, cands[j].key)) return true;
         return fill_at(j) != fill_at(j - 1);               // a new fill restarts the scan
     };
     if (!independent(j0)) return;
@@ -523,6 +533,20 @@ __global__ void __launch_bounds__(128) k_chain(const DevPlan pl, const unsigned 
         if (e <= pos && b == e) break;                      // zero-length hit: the reference would not advance either
         pos = e;
     }
+}
+
+struct MaxLL { __host__ __device__ long long operator()(long long a, long long b) const { return a > b ? a : b; } };
+
+struct MinLL { __host__ __device__ long long operator()(long long a, long long b) const { return a < b ? a : b; } };
+
+// hit ends in list order and leftmost examined bytes in reversed order (inputs of the two scans of the chain stage)
+__global__ void k_cand_ends(const DevPlan pl, const Cand *__restrict__ cands, long long n, long long *__restrict__ ends,
+                            long long *__restrict__ deps_rev)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    ends[j] = cands[j].end;
+    deps_rev[n - 1 - j] = dep_lo(pl, cands[j]);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -907,12 +931,11 @@ static int compile(const char *pattern, const char *kopt, Compiled &c, bool need
         sd.init = s->ft.init; sd.fin = s->ft.fin; sd.trig[0] = s->ft.fin;
         c.ft = s->ft;                                       // k_verify re-checks the window on the raw bytes with it
         d.init = c.ft.init; d.fin = c.ft.fin; d.trig[0] = c.ft.fin;
-        d.ext_off = c.plan.anchor - c.plan.win_lo; d.ext_anchor = c.plan.anchor;
+        d.ext_off = c.plan.anchor - c.plan.win_lo; d.ext_anchor = c.plan.anchor; d.ext_repeats = c.plan.ext_repeats;
+        d.maxleft = c.plan.anchor;
         d.IL = c.plan.IL; d.FL = c.plan.FL; d.AL = c.plan.AL; d.initL = c.plan.initL;
         d.IR = c.plan.IR; d.FR = c.plan.FR; d.AR = c.plan.AR; d.initR = c.plan.initR;
-        pm::Plan vp = c.plan;
-        vp.npieces = 1; vp.V[0] = c.plan.anchor;            // TL: positions anchor-1, anchor-2, ... ; TR: anchor, anchor+1, ...
-        pm::build_verify(c.P, vp, c.vt);
+        pm::build_verify(c.P, c.plan, c.vt);               // TL: positions anchor-1, anchor-2, ... ; TR: anchor, anchor+1, ...
         c.scan = s;
         return PM_OK;
     }
@@ -920,6 +943,11 @@ static int compile(const char *pattern, const char *kopt, Compiled &c, bool need
         pm::build_filter(c.P, c.plan, c.ft);
         d.init = c.ft.init; d.fin = c.ft.fin;
         if (c.plan.type == pm::SIMPLE) d.trig[0] = c.ft.fin;
+    }
+    if (c.plan.type != pm::SIMPLE) {
+        int vmax = 0;
+        for (int i = 0; i < c.plan.npieces; i++) vmax = std::max(vmax, c.plan.V[i]);
+        d.maxleft = vmax + c.plan.k;                        // the left walk reads at most V + k bytes
     }
     if (c.plan.type != pm::SIMPLE) pm::build_verify(c.P, c.plan, c.vt);
     return PM_OK;
@@ -1322,8 +1350,24 @@ static int resolve_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, co
         if ((rc = e->sel.reserve((size_t)ncand))) return rc;
         if ((rc = e->counters.reserve(64))) return rc;
         CK(cudaMemsetAsync(e->sel.p, 0, (size_t)ncand, e->stream));
+        const long long *d_maxend = nullptr, *d_mindep = nullptr;
+        if (c.dp.ext_repeats) {
+            // prefix maxima of the hit ends, suffix minima of the examined ranges (keys2 is free at this point)
+            if ((rc = e->keys2.reserve((size_t)ncand * 32))) return rc;
+            long long *ends = (long long *)e->keys2.p, *mx = ends + ncand, *deps = mx + ncand, *mn = deps + ncand;
+            k_cand_ends<<<(unsigned)((ncand + 255) / 256), 256, 0, e->stream>>>(c.dp, d_cands, ncand, ends, deps);
+            size_t tmpb = 0, tmpc = 0;
+            CK(cub::DeviceScan::InclusiveScan(nullptr, tmpb, ends, mx, MaxLL(), (int)ncand, e->stream));
+            CK(cub::DeviceScan::InclusiveScan(nullptr, tmpc, deps, mn, MinLL(), (int)ncand, e->stream));
+            tmpb = std::max(tmpb, tmpc);
+            if ((rc = e->cubtmp.reserve(tmpb))) return rc;
+            CK(cub::DeviceScan::InclusiveScan(e->cubtmp.p, tmpb, ends, mx, MaxLL(), (int)ncand, e->stream));
+            CK(cub::DeviceScan::InclusiveScan(e->cubtmp.p, tmpb, deps, mn, MinLL(), (int)ncand, e->stream));
+            d_maxend = mx; d_mindep = mn;
+            e->stats.launches += 3;
+        }
         k_chain<<<(unsigned)((ncand + 127) / 128), 128, 0, e->stream>>>(c.dp, d->d_text, d->n, dTL, dTR, d_cands, ncand,
-                                                                       (pm_hit *)e->hits.p, (unsigned char *)e->sel.p, fills);
+                                                                       (pm_hit *)e->hits.p, (unsigned char *)e->sel.p, fills, d_maxend, d_mindep);
         CK(cudaGetLastError());
         CK(cudaEventRecord(e->ev[4], e->stream));
         size_t tmp = 0;

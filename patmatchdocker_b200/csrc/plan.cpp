@@ -310,14 +310,24 @@ static int make_plan_extended(const Pattern &P, const Options &o, Plan &plan, st
     if (o.k != 0) { err = "EXTENDED pattern with errors (nrgrep's eextended engine): not supported yet"; return PM_ERR_UNSUPPORTED; }
     if (m > 64) { err = "EXTENDED pattern longer than 64 positions"; return PM_ERR_UNSUPPORTED; }
     for (int j = 0; j < m; j++)
-        if (P.repeats(j)) { err = "EXTENDED pattern with '*' / '+' repeats (unbounded hits): not supported yet"; return PM_ERR_UNSUPPORTED; }
+        if (P.repeats(j)) plan.ext_repeats = 1;
+    if (plan.ext_repeats && P.start_line) {
+        // '^' makes failed verifications depend on the scan start and '*' / '+' make hits arbitrarily long: the chain
+        // stage's independence test covers either, not both
+        err = "EXTENDED pattern with '*' / '+' repeats and a '^' anchor: not supported yet";
+        return PM_ERR_UNSUPPORTED;
+    }
     plan.fb_cost = find_best_extended(P, 0, plan.ext_beg, plan.ext_end, plan.ext_wlen);
     if (plan.ext_wlen > 0) { plan.type = EXT_BEG; plan.anchor = plan.ext_beg; }
     else { plan.type = EXT_END; plan.anchor = plan.ext_end; }
     // plain positions next to the anchor: present in every match at a fixed offset, so an exact scan finds all anchors
+    // (a '+' position next to the run still pins one byte -- its first occurrence on the right of the anchor, its last
+    // on the left -- but nothing beyond it)
     int lo = plan.anchor, hi = plan.anchor;
     while (lo > 0 && P.op[lo - 1] == OP_NONE) lo--;
+    if (lo > 0 && P.op[lo - 1] == OP_PLUS) lo--;
     while (hi < m && P.op[hi] == OP_NONE) hi++;
+    if (hi < m && P.op[hi] == OP_PLUS) hi++;
     plan.win_lo = lo; plan.win_hi = hi;
     plan.L = hi - lo; plan.npieces = 1; plan.V[0] = plan.anchor;      // V[0]: where the verification splits the pattern
     if (plan.L < 1) { err = "internal: empty scan window"; return PM_ERR_UNSUPPORTED; }
@@ -433,6 +443,20 @@ void build_filter(const Pattern &P, const Plan &plan, FilterTables &ft)
 void build_verify(const Pattern &P, const Plan &plan, VerifyTables &vt)
 {
     const int np = plan.npieces, m = P.m();
+    if (plan.type == EXT_BEG || plan.type == EXT_END) {
+        // [0,256): elements accepting the byte (walk order, away from the anchor); [256,512): those that may also stay
+        // on it ('*' / '+')
+        const int a = plan.anchor;
+        vt.TL.assign(512, 0);
+        vt.TR.assign(512, 0);
+        for (unsigned c = 0; c < 256; c++) {
+            for (int u = 0; u < a; u++)
+                if (P.pos[a - 1 - u].has(c)) { vt.TL[c] |= 1ULL << u; if (P.repeats(a - 1 - u)) vt.TL[256 + c] |= 1ULL << u; }
+            for (int u = 0; u < m - a; u++)
+                if (P.pos[a + u].has(c)) { vt.TR[c] |= 1ULL << u; if (P.repeats(a + u)) vt.TR[256 + c] |= 1ULL << u; }
+        }
+        return;
+    }
     vt.TL.assign((size_t)np * 256, 0);
     vt.TR.assign((size_t)np * 256, 0);
     for (int i = 0; i < np; i++) {

@@ -51,6 +51,7 @@ struct Plan {
     // EXTENDED plans (k = 0): what extendedFindBest @411fe0 chose, and the run of plain positions around the
     // anchor that the exact scan looks for (every match contains it at a fixed offset from the anchor)
     int ext_beg = 0, ext_end = 0, ext_wlen = 0, anchor = 0;
+    int ext_repeats = 0;               // some position carries '*' or '+': hits have no length bound
     int win_lo = 0, win_hi = 0;
     // closure masks of the two verification walks (extendedLoadVerif @412c60), elements numbered away from the anchor
     uint64_t IL = 0, FL = 0, AL = 0, initL = 0, IR = 0, FR = 0, AR = 0, initR = 0;

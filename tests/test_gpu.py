@@ -39,8 +39,8 @@ def test_reference_golden_vectors(engine, search_golden, scan_mode):
             try:
                 got = [list(h) for h in gpu_hits(engine, c["text"], c["pattern"], c["kopt"])]
             except pm.NativeError as e:
-                # the only patterns the engine may refuse: EXTENDED ones outside what it covers ('*' / '+' repeats)
-                assert e.code == -3 and any(ch in c["pattern"] for ch in "*+"), (c["pattern"], str(e))
+                # the only patterns the engine may refuse: '*' / '+' repeats together with a '^' anchor
+                assert e.code == -3 and any(ch in c["pattern"] for ch in "*+") and c["pattern"].startswith("^"), (c["pattern"], str(e))
                 continue
             if got != c["hits"]:
                 bad.append((c["pattern"], c["kopt"], c["bufsize"], got[:4], c["hits"][:4]))
@@ -263,13 +263,13 @@ def test_extended_patterns_against_oracle(engine, scan_mode):
                 ch = rng.sample(alpha, 2); pat += "[" + "".join(ch) + "]"; members.append(ch)
             else:
                 c = rng.choice(alpha); pat += c; members.append([c])
-            op = "?" if 0 < j < m - 1 and rng.random() < 0.3 else ""
+            op = rng.choice("????*+") if 0 < j < m - 1 and rng.random() < 0.3 else ""
             pat += op
             ops.append(op)
         pat += ")"
         if not any(ops):
             continue
-        if it % 6 == 0:
+        if it % 6 == 0 and "*" not in ops and "+" not in ops:
             pat = "^" + pat
         if it % 10 == 0:
             pat = pat + "$"
@@ -281,8 +281,8 @@ def test_extended_patterns_against_oracle(engine, scan_mode):
             while len(t) < target:
                 if rng.random() < 0.3:
                     for cls, op in zip(members, ops):
-                        if op == "" or rng.random() < 0.5:
-                            t += rng.choice(cls)
+                        reps = 1 if op == "" else rng.randint(0, 1) if op == "?" else rng.randint(0, 3) if op == "*" else rng.randint(1, 3)
+                        t += "".join(rng.choice(cls) for _ in range(reps))
                 else:
                     t += "".join(rng.choice(alpha) for _ in range(rng.randint(1, 10)))
             if rng.random() < 0.3:
@@ -302,6 +302,36 @@ def test_extended_patterns_against_oracle(engine, scan_mode):
     assert n_hits > 1000 and types == {"EXT_BEG", "EXT_END"}
     # the reference's quirk: zero occurrences of a run of two or more optional positions next to the anchor do not match
     assert gpu_hits(engine, b">q\nCCGATAAGTCCAA\nCCGATCAAGTCCAA\n", "(GAT.?.?.?AAGTCC)", "0ids") == [(19, 29)]
+
+
+def test_chain_stage_on_tandem_repeats(engine, scan_mode):
+    # back-to-back (mutated) occurrences: hits end where the next candidates begin to look, so the chain stage's cluster
+    # boundaries are exercised hard -- a boundary is only sound when no LATER candidate of the cluster can reach left of
+    # an earlier hit's end
+    from synth import planted
+    rng = random.Random(2024)
+    n_hits = 0
+    for it in range(150):
+        alpha = rng.choice([DNA, DNA, PEP])
+        k = rng.choice([1, 1, 2, 3])
+        m = rng.randint(max(4, 2 * k + 2), 16)
+        pat, members = random_pattern(rng, alpha, m, cls_pct=0.1, dot_pct=0.05)
+        kopt = "%d%s" % (k, rng.choice(["ids", "ids", "s", "id", "is"]))
+        lines = []
+        for r in range(rng.randint(1, 3)):
+            lines.append(">t%d" % r)
+            t = ""
+            for _ in range(rng.randint(3, 60)):
+                t += planted(rng, members, alpha, k)
+                if rng.random() < 0.3:
+                    t += "".join(rng.choice(alpha) for _ in range(rng.randint(1, m + k + 2)))
+            lines.append(t)
+        text = ("\n".join(lines) + "\n").encode()
+        got = gpu_hits(engine, text, pat, kopt)
+        want = O.search(pat, text, kopt)
+        assert got == want, (pat, kopt, text)
+        n_hits += len(want)
+    assert n_hits > 2000
 
 
 def test_hit_list_stays_on_device_after_overflow(engine):
