@@ -26,8 +26,9 @@ extern "C" {
 #define PM_OK               0
 #define PM_ERR_CUDA        -1   /* CUDA runtime failure (message has the cudaError) */
 #define PM_ERR_SYNTAX      -2   /* malformed nrgrep pattern / -k option */
-#define PM_ERR_UNSUPPORTED -3   /* pattern needs nrgrep's REGULAR engine (groups with operators, |), '*' / '+' repeats, an
-                                 * EXTENDED pattern with errors or with ? on its first / last position, or has more than 64 positions */
+#define PM_ERR_UNSUPPORTED -3   /* pattern needs nrgrep's REGULAR engine (groups with operators, |), is an EXTENDED pattern
+                                 * (? * +) with errors, with an operator on its first / last position or with * / + and '^',
+                                 * or has more than 64 positions */
 #define PM_ERR_ARG         -4
 #define PM_ERR_OVERFLOW    -5   /* caller's hit buffer too small; *nhits holds the required size */
 
@@ -38,7 +39,7 @@ extern "C" {
 #define PM_PLAN_SPLIT  1        /* k+1 exact pieces + verification */
 #define PM_PLAN_BWD    2        /* backward approximate filter */
 #define PM_PLAN_FWD    3        /* forward approximate filter */
-/* nrgrep's EXTENDED engine, k = 0 (positions followed by '?': PatMatch's X{m,n}); extendedPreproc @413260 */
+/* nrgrep's EXTENDED engine, k = 0 (positions followed by ? * +: PatMatch's X{m,n} / X{m,}); extendedPreproc @413260 */
 #define PM_PLAN_EXT_BEG 4       /* verification anchored at the START of the scanned sub-pattern */
 #define PM_PLAN_EXT_END 5       /* ... at its END (forward scan) */
 
