@@ -81,6 +81,7 @@ int nro_check_match(const nro_pattern *P, const nro_plan *plan, int i,
 
 /* ---- EXTENDED patterns, k = 0 (see the end of nrgrep_oracle.c and NOTES_extended.md) ---- */
 enum { NRX_NONE = 0, NRX_OPT = 1, NRX_STAR = 2, NRX_PLUS = 3 };
+#define NRX_REWRITTEN_SIMPLE 1   /* nrx_parse: the parser's rewrites left a SIMPLE pattern in X->P */
 typedef struct { nro_pattern P; unsigned char op[NRO_MAXM]; } nrx_pattern;
 typedef struct { int type, anchor, wlen, beg, end; double cost; } nrx_plan;
 int nrx_parse(const char *pattern, int icase, nrx_pattern *X);

@@ -19,12 +19,13 @@ static void *zmalloc(size_t n) { return calloc(1, n ? n : 1); }
 
 int main(int argc, char **argv)
 {
-    long cases = 2000; int verbose = 0; const char *alpha = "ACGT";
+    long cases = 2000; int verbose = 0, edges = 0; const char *alpha = "ACGT";
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "-n")) cases = atol(argv[++i]);
         else if (!strcmp(argv[i], "-s")) rs ^= (unsigned long long)atol(argv[++i]) * 0x9E3779B97F4A7C15ULL;
         else if (!strcmp(argv[i], "-a")) alpha = !strcmp(argv[++i], "pep") ? "ACDEFGHIKLMNPQRSTVWY" : "ACGT";
         else if (!strcmp(argv[i], "-v")) verbose++;
+        else if (!strcmp(argv[i], "-e")) edges = 1;            /* operators on the first / last position too */
     }
     ref_override("puts", (void *)my_puts);
     ref_override("malloc", (void *)zmalloc);
@@ -33,7 +34,7 @@ int main(int argc, char **argv)
     const int na = (int)strlen(alpha);
     static unsigned char buf[1 << 16];
     unsigned char *text = buf + 256;
-    long plan_bad = 0, hit_bad = 0, total_hits = 0, t2 = 0, t3 = 0, simple_scan = 0;
+    long plan_bad = 0, hit_bad = 0, total_hits = 0, t2 = 0, t3 = 0, simple_scan = 0, nsimple = 0;
     for (long cs = 0; cs < cases; cs++) {
         int m = 3 + (int)rint_(rint_(3) ? 10 : 22);
         char pat[1024]; int o = 0;
@@ -47,7 +48,7 @@ int main(int argc, char **argv)
             else if (r < 27) { char a = alpha[rint_(na)], b = alpha[rint_(na)]; pat[o++] = '['; pat[o++] = a; pat[o++] = b; pat[o++] = ']'; member[j] = rint_(2) ? a : b; }
             else { char a = alpha[rint_(na)]; pat[o++] = a; member[j] = a; }
             ops[j] = 0;
-            if (j > 0 && j < m - 1) {
+            if ((j > 0 && j < m - 1) || (edges && rint_(2))) {
                 unsigned q = rint_(100);
                 if (q < 25) { pat[o++] = '?'; ops[j] = 1; nops++; }
                 else if (q < 33) { pat[o++] = '*'; ops[j] = 2; nops++; }
@@ -59,8 +60,13 @@ int main(int argc, char **argv)
         char pat2[1024]; strcpy(pat2, pat);
         nrx_pattern X; nrx_plan pl;
         int rc = nrx_parse(pat, 1, &X);
-        if (rc) { fprintf(stderr, "oracle parse failed %d on %s\n", rc, pat); return 1; }
-        nrx_plan_make(&X, &pl);
+        if (rc == NRO_ERR_UNSUPPORTED && edges) { cs--; continue; }       /* nothing left after the rewrites */
+        if (rc != NRO_OK && rc != NRX_REWRITTEN_SIMPLE) { fprintf(stderr, "oracle parse failed %d on %s\n", rc, pat); return 1; }
+        const int simple = rc == NRX_REWRITTEN_SIMPLE;
+        nro_plan spl;
+        memset(&pl, 0, sizeof pl);
+        if (simple) nro_plan_make(&X.P, 0, 1, 1, 1, &spl);
+        else if (nrx_plan_make(&X, &pl) == NRO_ERR_UNSUPPORTED) { cs--; continue; }
 
         REF_OptCaseInsensitive = 1; REF_OptErrors = 0; REF_OptIns = 1; REF_OptDel = 1; REF_OptSubs = 1; REF_OptTransp = 0;
         REF_OptStartLine = 0; REF_OptEndLine = 0;
@@ -69,7 +75,8 @@ int main(int argc, char **argv)
         int rtype = (int)sd[0];
         unsigned char *E = (unsigned char *)sd[1];
         int bad = 0, vt = -1, anchor = -1, rwl = -1; unsigned long scanfn = 0;
-        if (rtype != 2) bad = 1;
+        if (simple) { if (rtype != 1) bad = 1; nsimple++; }
+        else if (rtype != 2) bad = 1;
         else {
             scanfn = *(unsigned long *)E;
             anchor = *(int *)(E + 0x2060); vt = *(int *)(E + 0x2068);
@@ -79,7 +86,7 @@ int main(int argc, char **argv)
             if (scanfn == 0x416600UL) { simple_scan++; if (rwl != pl.end - pl.beg) bad = 1; }
             else if (rwl != pl.wlen) bad = 1;
         }
-        if (pl.type == 2) t2++; else t3++;
+        if (!simple) { if (pl.type == 2) t2++; else t3++; }
         if (bad || verbose > 1)
             fprintf(stderr, "%s plan: %s  ref: class=%d scan=%lx vtype=%d anchor=%d win=%d   oracle: type=%d anchor=%d beg=%d end=%d wlen=%d cost=%.17g\n",
                     bad ? "BAD" : "ok", pat, rtype, scanfn, vt, anchor, rwl, pl.type, pl.anchor, pl.beg, pl.end, pl.wlen, pl.cost);
@@ -100,7 +107,7 @@ int main(int argc, char **argv)
             }
             if (rint_(4) == 0) for (int x = 0; x < n; x++) if (rint_(3) == 0) text[x] = (unsigned char)tolower(text[x]);
             text[n] = '\n'; text[-1] = '\n';
-            nro_hit oh[512]; int64_t on = nrx_search(&X, &pl, text, n, oh, 512);
+            nro_hit oh[512]; int64_t on = simple ? nro_search(&X.P, &spl, text, n, oh, 512) : nrx_search(&X, &pl, text, n, oh, 512);
             nro_hit rh[512]; int64_t rn = 0;
             unsigned char *pos = text, *top = text + n;
             for (;;) {
@@ -128,7 +135,7 @@ int main(int argc, char **argv)
         }
         ((ref_free_t)REF_searchFree)(sd);
     }
-    printf("cases=%ld plan_mismatch=%ld hit_mismatch=%ld  type2=%ld type3=%ld simple_scan=%ld ref_hits=%ld\n",
-           cases, plan_bad, hit_bad, t2, t3, simple_scan, total_hits);
+    printf("cases=%ld plan_mismatch=%ld hit_mismatch=%ld  type2=%ld type3=%ld simple_scan=%ld rewritten_to_simple=%ld ref_hits=%ld\n",
+           cases, plan_bad, hit_bad, t2, t3, simple_scan, nsimple, total_hits);
     return (plan_bad || hit_bad) ? 1 : 0;
 }

@@ -107,14 +107,21 @@ int parse_pattern(const char *pattern, bool icase, Pattern &P, std::string &err)
     if (depth != 0) { err = "unbalanced '('"; return PM_ERR_SYNTAX; }
     if (P.pos.empty()) { err = "empty pattern"; return PM_ERR_SYNTAX; }
     if (P.extended()) {
-        // the reference's parser rewrites patterns that begin or end with an operator position (it drops one leading
-        // optional, every trailing one, ...); those shapes are not restated
-        if (P.op.front() != OP_NONE || P.op.back() != OP_NONE) {
-            err = "EXTENDED pattern whose first or last position carries ? * +: not supported yet";
-            return PM_ERR_UNSUPPORTED;
-        }
-        // (parentheses that no operator applies to only group a concatenation: patmatch_to_nrgrep.pl wraps the
-        // pattern in one pair and its reverse complement in two)
+        P.had_ops = true;
+        // The reference's parser rewrites operator positions at the two ends of the pattern (they cannot change
+        // whether a line matches; the reported coordinates then follow the rewritten pattern).  Rules observed on the
+        // binary and pinned by oracle/ref/difftest_ext -e:
+        //   front: ONE rewrite -- an optional first position ('?', '*') is dropped, a '+' one loses its operator;
+        //   back : every trailing optional position is dropped; if none was, a trailing '+' loses its operator.
+        size_t lo = 0, hi = P.pos.size();
+        if (P.op[0] == OP_OPT || P.op[0] == OP_STAR) lo = 1;
+        else if (P.op[0] == OP_PLUS) P.op[0] = OP_NONE;
+        bool dropped = false;
+        while (hi > lo && (P.op[hi - 1] == OP_OPT || P.op[hi - 1] == OP_STAR)) { hi--; dropped = true; }
+        if (!dropped && hi > lo && hi - 1 != 0 && P.op[hi - 1] == OP_PLUS) P.op[hi - 1] = OP_NONE;
+        if (hi <= lo) { err = "nothing is left of the pattern once its optional ends are dropped"; return PM_ERR_SYNTAX; }
+        P.pos.erase(P.pos.begin() + (long)hi, P.pos.end()); P.op.erase(P.op.begin() + (long)hi, P.op.end());
+        P.pos.erase(P.pos.begin(), P.pos.begin() + (long)lo); P.op.erase(P.op.begin(), P.op.begin() + (long)lo);
     }
     return PM_OK;
 }
@@ -320,6 +327,12 @@ static int make_plan_extended(const Pattern &P, const Options &o, Plan &plan, st
     plan.fb_cost = find_best_extended(P, 0, plan.ext_beg, plan.ext_end, plan.ext_wlen);
     if (plan.ext_wlen > 0) { plan.type = EXT_BEG; plan.anchor = plan.ext_beg; }
     else { plan.type = EXT_END; plan.anchor = plan.ext_end; }
+    if (plan.type == EXT_END && P.optional(0)) {
+        // only possible after the parser's rewrite, e.g. (A?A?C) -> A?C: the binary's forward scan has no initial closure
+        // and misses matches at the first byte of a scan range
+        err = "EXTENDED pattern that begins with an optional position and is scanned forwards: not supported yet";
+        return PM_ERR_UNSUPPORTED;
+    }
     // plain positions next to the anchor: present in every match at a fixed offset, so an exact scan finds all anchors
     // (a '+' position next to the run still pins one byte -- its first occurrence on the right of the anchor, its last
     // on the left -- but nothing beyond it)
@@ -342,6 +355,7 @@ int make_plan(const Pattern &P, const Options &o, Plan &plan, std::string &err)
     const int m = P.m(), k = o.k;
     plan.m = m; plan.k = k; plan.ins = o.ins; plan.del = o.del; plan.subs = o.subs;
     if (P.extended()) return make_plan_extended(P, o, plan, err);
+    if (P.had_ops && k != 0) { err = "pattern with ? * + and errors (nrgrep's eextended engine): not supported yet"; return PM_ERR_UNSUPPORTED; }
     if (k == 0) { plan.type = SIMPLE; plan.L = m; plan.npieces = 1; plan.V[0] = 0; return PM_OK; }
     if (k >= m) { err = "k >= pattern length"; return PM_ERR_UNSUPPORTED; }
     const int K1 = k + 1, K2 = k + 2;

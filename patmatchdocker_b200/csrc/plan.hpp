@@ -26,6 +26,7 @@ struct Pattern {
     std::vector<ByteSet> pos;          // one class per pattern position
     std::vector<unsigned char> op;     // PosOp per position (all OP_NONE for SIMPLE / ESIMPLE patterns)
     bool start_line = false, end_line = false;
+    bool had_ops = false;              // the pattern was written with ? * + (possibly all rewritten away by the parser rules)
     int m() const { return (int)pos.size(); }
     bool extended() const { for (unsigned char o : op) if (o) return true; return false; }
     bool optional(int j) const { return op[j] == OP_OPT || op[j] == OP_STAR; }

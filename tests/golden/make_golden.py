@@ -207,6 +207,27 @@ def search_fixture():
                     t += "".join(xrng.choice(alpha) for _ in range(xrng.randint(1, 10)))
             lines.append(t)
         cases.append((pat, "0ids", "\n".join(lines) + "\n", xrng.choice([1600000, 1600000, 1600000, 50, 200])))
+    # operators on the first / last position: the reference's parser rewrites them (one optional first position dropped
+    # or a leading '+' stripped; every trailing optional position dropped, else a trailing '+' stripped)
+    erng = random.Random(888)
+    for it in range(70):
+        alpha = erng.choice([DNA, DNA, PEP])
+        m = erng.randint(3, 10)
+        toks, ops = [], []
+        for j in range(m):
+            r = erng.random()
+            toks.append("." if r < 0.1 else "[" + "".join(erng.sample(alpha, 2)) + "]" if r < 0.25 else erng.choice(alpha))
+            ops.append(erng.choice(["", "", "?", "?", "*", "+"]) if (j in (0, m - 1) or erng.random() < 0.25) else "")
+        if ops[0] in ("?", "*") and ops[1] in ("?", "*"):
+            ops[1] = ""                        # would still begin with an optional position after the rewrite
+        if not any(ops):
+            ops[-1] = "?"
+        pat = "(" + "".join(a + b for a, b in zip(toks, ops)) + ")"
+        lines = []
+        for r in range(erng.randint(1, 3)):
+            lines.append(">e%d" % r)
+            lines.append("".join(erng.choice(alpha) for _ in range(erng.randint(30, 300))))
+        cases.append((pat, "0ids", "\n".join(lines) + "\n", erng.choice([1600000, 1600000, 100])))
     # the reference's quirk: a run of two or more optional positions next to the anchor cannot be skipped as a whole
     cases.append(("(GAT.?.?.?AAGTCC)", "0ids", ">q\nCCGATAAGTCCAA\nCCGATCAAGTCCAA\nCCGATCCCAAGTCCAA\n", 1600000))
     out = []
@@ -325,6 +346,8 @@ def request_fixture():
             dict(pattern="GAN{0,3}TAAG", seqtype="dna", strand="Watson strand"),
             dict(pattern="CX{2,4}C[ILVM]", seqtype="pep"),
             dict(pattern="MX{0,2}K", seqtype="pep", max_hits=50),
+            dict(pattern="N{0,2}GATAAG", seqtype="dna", strand="Both strands"),       # repeats at the ends: parser rewrites
+            dict(pattern="CAACX{1,}", seqtype="pep"),
         ]
         for r in reqs:
             kw = dict(r)

@@ -111,10 +111,14 @@ def plan_ext(pattern, icase=True):
     L = lib()
     X = NrxPattern()
     rc = L.nrx_parse(pattern.encode("latin-1"), int(icase), ctypes.byref(X))
+    if rc == 1:                                   # NRX_REWRITTEN_SIMPLE: the parser's rewrites left a SIMPLE pattern in X.P
+        return X, None
     if rc:
         raise ValueError("oracle cannot parse %r as an EXTENDED pattern: %d" % (pattern, rc))
     pl = NrxPlan()
-    L.nrx_plan_make(ctypes.byref(X), ctypes.byref(pl))
+    rc = L.nrx_plan_make(ctypes.byref(X), ctypes.byref(pl))
+    if rc:
+        raise ValueError("oracle does not cover the plan of %r: %d" % (pattern, rc))
     return X, pl
 
 
@@ -132,7 +136,12 @@ def search(pattern, text, kopt="0ids", icase=True, cap=1 << 20, bufsize=BUFSIZE)
         if parse_kopt(kopt)[0] != 0:
             raise ValueError("EXTENDED patterns with errors are not covered by the oracle")
         X, xpl = plan_ext(pattern, icase)
-        n = L.nrx_search_buffered(ctypes.byref(X), ctypes.byref(xpl), text, len(text), bufsize, hits, cap)
+        if xpl is None:
+            spl = NroPlan()
+            L.nro_plan_make(ctypes.byref(X.P), 0, 1, 1, 1, ctypes.byref(spl))
+            n = L.nro_search_buffered(ctypes.byref(X.P), ctypes.byref(spl), text, len(text), bufsize, hits, cap)
+        else:
+            n = L.nrx_search_buffered(ctypes.byref(X), ctypes.byref(xpl), text, len(text), bufsize, hits, cap)
         if n > cap:
             raise OverflowError("oracle hit buffer too small: %d" % n)
         return [(hits[i].beg, hits[i].end) for i in range(n)]
