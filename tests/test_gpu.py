@@ -22,6 +22,42 @@ def scan_mode(request, engine):
     engine.set_scan_mode("auto")
 
 
+def extended_pattern(rng, alpha, m):
+    """random EXTENDED pattern (operators on inner positions) and, per position, the accepted letters and the operator"""
+    pat, members, ops = "(", [], []
+    for j in range(m):
+        r = rng.random()
+        if r < 0.12:
+            pat += "."; members.append(list(alpha))
+        elif r < 0.27:
+            ch = rng.sample(alpha, 2); pat += "[" + "".join(ch) + "]"; members.append(ch)
+        else:
+            c = rng.choice(alpha); pat += c; members.append([c])
+        op = rng.choice("????*+") if 0 < j < m - 1 and rng.random() < 0.3 else ""
+        pat += op
+        ops.append(op)
+    if not any(ops):
+        return extended_pattern(rng, alpha, m)
+    return pat + ")", members, ops
+
+
+def extended_text(rng, alpha, members, ops, nrec, lo, hi):
+    lines = []
+    for r in range(nrec):
+        lines.append(">x%d" % r)
+        t = ""
+        target = rng.randint(lo, hi)
+        while len(t) < target:
+            if rng.random() < 0.3:
+                for cls, op in zip(members, ops):
+                    reps = 1 if op == "" else rng.randint(0, 1) if op == "?" else rng.randint(0, 3) if op == "*" else rng.randint(1, 3)
+                    t += "".join(rng.choice(cls) for _ in range(reps))
+            else:
+                t += "".join(rng.choice(alpha) for _ in range(rng.randint(1, 10)))
+        lines.append(t)
+    return ("\n".join(lines) + "\n").encode()
+
+
 def gpu_hits(engine, text, pattern, kopt):
     raw = text.encode("latin-1") if isinstance(text, str) else text
     ds = engine.load_dataset(raw)
@@ -360,6 +396,10 @@ def test_sharded_candidates_then_resolve_equals_search(engine, scan_mode):
         kopt = "%dids" % k
         pat, members = random_pattern(rng, DNA, m)
         text = random_text(rng, members, DNA, k, nrec=4, lo=2000, hi=9000, plant=0.1).encode()
+        if it % 4 == 3:                                    # EXTENDED plans shard by window start like any other
+            pat, members, ops = extended_pattern(rng, DNA, rng.randint(4, 14))
+            kopt = "0ids"
+            text = extended_text(rng, DNA, members, ops, 4, 2000, 9000)
         ds = engine.load_dataset(text)
         whole = engine.search(ds, pat, kopt)
         n = len(text)
@@ -386,6 +426,10 @@ def test_fill_sharded_search_equals_search(engine, scan_mode):
             pat = "^" + pat
         kopt = "%d%s" % (k, rng.choice(["ids", "s", "id"]))
         text = random_text(rng, members, DNA, k, nrec=rng.randint(2, 6), lo=50, hi=2500).encode("latin-1")
+        if it % 3 == 1:                                    # EXTENDED plans: keys are window starts, fills go by the anchor
+            pat, members, ops = extended_pattern(rng, DNA, rng.randint(4, 14))
+            kopt = "0ids"
+            text = extended_text(rng, DNA, members, ops, rng.randint(2, 6), 50, 2500)
         bufsize = rng.choice([1600000, 64, 200, 1000])
         engine.set_buffer_size(bufsize)
         try:
@@ -420,6 +464,11 @@ def test_streaming_upload_search_equals_search(engine, scan_mode):
         kopt = "%d%s" % (k, rng.choice(["ids", "s", "id"]))
         nrec = rng.randint(1, 5)
         text = random_text(rng, members, DNA, k, nrec=nrec, lo=20000, hi=120000, plant=0.02).encode("latin-1")
+        if it % 3 == 1:
+            pat, members, ops = extended_pattern(rng, DNA, rng.randint(5, 14))
+            pat2, _, _ = extended_pattern(rng, DNA, rng.randint(5, 14))
+            kopt = "0ids"
+            text = extended_text(rng, DNA, members, ops, nrec, 20000, 120000)
         bufsize = rng.choice([1600000, 5000, 40000, 1000])
         engine.set_buffer_size(bufsize)
         try:
