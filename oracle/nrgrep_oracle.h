@@ -9,7 +9,10 @@
  * site in the reference's Python that invokes it
  * (www/FlaskApp/FlaskApp/patmatch.py:733-743).
  *
- * Parity pinning: oracle/ref/difftest.c maps the reference binary into the
+ * Covered: the SIMPLE (k = 0) and ESIMPLE (k > 0) engines, line anchors, buffer fills, and the EXTENDED engine
+ * for k = 0 (nrx_*: positions followed by ? * +).
+ *
+ * Parity pinning: oracle/ref/difftest.c (and difftest_ext.c for EXTENDED patterns) maps the reference binary into the
  * test process (oracle/ref/refload.c) and compares this restatement against
  * the reference's own searchPreproc/searchScan on millions of random
  * (pattern, options, text) cases; tests/golden/ holds vectors produced by
