@@ -545,7 +545,9 @@ __global__ void k_cand_ends(const DevPlan pl, const Cand *__restrict__ cands, lo
 {
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    ends[j] = cands[j].end;
+    // with '^' a failed verification can still succeed for a scan start inside the bytes it examined, and where that
+    // hit would end is not known: it keeps every later candidate of the fill in the same cluster
+    ends[j] = (cands[j].beg < 0 && pl.start_line && cands[j].reach < anchor_of(pl, cands[j].key)) ? (1LL << 60) : cands[j].end;
     deps_rev[n - 1 - j] = dep_lo(pl, cands[j]);
 }
 

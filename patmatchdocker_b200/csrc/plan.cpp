@@ -318,12 +318,6 @@ static int make_plan_extended(const Pattern &P, const Options &o, Plan &plan, st
     if (m > 64) { err = "EXTENDED pattern longer than 64 positions"; return PM_ERR_UNSUPPORTED; }
     for (int j = 0; j < m; j++)
         if (P.repeats(j)) plan.ext_repeats = 1;
-    if (plan.ext_repeats && P.start_line) {
-        // '^' makes failed verifications depend on the scan start and '*' / '+' make hits arbitrarily long: the chain
-        // stage's independence test covers either, not both
-        err = "EXTENDED pattern with '*' / '+' repeats and a '^' anchor: not supported yet";
-        return PM_ERR_UNSUPPORTED;
-    }
     plan.fb_cost = find_best_extended(P, 0, plan.ext_beg, plan.ext_end, plan.ext_wlen);
     if (plan.ext_wlen > 0) { plan.type = EXT_BEG; plan.anchor = plan.ext_beg; }
     else { plan.type = EXT_END; plan.anchor = plan.ext_end; }
