@@ -1,5 +1,6 @@
+"""Device and wall time of a fill-sharded search per phase.  torchrun --nproc-per-node N tools/fills_phases.py"""
 import os, sys, time, json
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
 import patmatchdocker_b200 as pm
 from patmatchdocker_b200 import distributed as pmd
