@@ -845,7 +845,6 @@ int nrx_plan_make(const nrx_pattern *X, nrx_plan *pl)
     /* forward scan of a pattern that begins with an optional position (only possible after the parser's rewrite, e.g.
      * (A?A?C) -> A?C): the binary's scan automaton has no initial closure and misses matches at the first byte of a
      * scan range; not restated */
-    if (pl->type == 3 && nrx_optional(X, 0)) return NRO_ERR_UNSUPPORTED;
     return NRO_OK;
 }
 
@@ -919,6 +918,34 @@ static int ext_check(const nrx_pattern *X, const nrx_plan *pl, const uint8_t *t,
     return 1;
 }
 
+/* extendedScan @4116f0, forward mode (wlen <= 0): Shift-And over the sub-pattern [beg, end) with the closure of its
+ * optional runs.  The closure is applied AFTER each byte and the state starts empty (and is emptied by the record
+ * delimiter), so a run of optional positions at the start of the sub-pattern is "always on" except for the very first
+ * byte of a scan range or record: an occurrence that has to skip it on that byte is not seen. */
+typedef struct { uint64_t I, F, A, fin; int beg, len; } ext_fwd;
+
+static void ext_fwd_init(const nrx_pattern *X, const nrx_plan *pl, ext_fwd *f)
+{
+    memset(f, 0, sizeof *f);
+    f->beg = pl->beg; f->len = pl->end - pl->beg;
+    for (int u = 0; u < f->len; u++) {
+        if (!nrx_optional(X, f->beg + u)) continue;
+        if (u > 0 && ((f->F >> (u - 1)) & 1ULL)) { f->F &= ~(1ULL << (u - 1)); f->F |= 1ULL << u; f->A |= 1ULL << u; }
+        else { if (u > 0) f->I |= 1ULL << (u - 1); f->F |= 1ULL << u; f->A |= 1ULL << u; }
+    }
+    f->fin = 1ULL << (f->len - 1);
+}
+
+static inline uint64_t ext_fwd_step(const nrx_pattern *X, const ext_fwd *f, uint64_t D, unsigned c)
+{
+    uint64_t Bc = 0, Sc = 0;
+    for (int u = 0; u < f->len; u++)
+        if (cls_has(&X->P, f->beg + u, c)) { Bc |= 1ULL << u; if (nrx_repeat(X, f->beg + u)) Sc |= 1ULL << u; }
+    D = (((D << 1) | 1ULL) & Bc) | (D & Sc);
+    const uint64_t x = D | f->F;
+    return (((~(x - f->I)) ^ x) & f->A) | D;
+}
+
 /* recSearchFile @402250 over one scan range [lo, hi) (a buffer fill) */
 static int64_t ext_search_range(const nrx_pattern *X, const nrx_plan *pl, const uint8_t *text, int64_t lo, int64_t hi,
                                 nro_hit *hits, int64_t cap, int64_t cnt)
@@ -931,8 +958,15 @@ static int64_t ext_search_range(const nrx_pattern *X, const nrx_plan *pl, const 
             for (int64_t w = pos; w + pl->wlen <= hi; w++)
                 if (ext_check(X, pl, text, w, pos, hi, &b, &e)) { found = 1; break; }
         } else {
-            for (int64_t q = pos + 1; q <= hi; q++)
-                if (ext_check(X, pl, text, q, pos, hi, &b, &e)) { found = 1; break; }
+            ext_fwd f;
+            ext_fwd_init(X, pl, &f);
+            uint64_t D = 0;
+            for (int64_t q = pos + 1; q <= hi; q++) {
+                const unsigned c = text[q - 1];
+                if (c == '\n') { D = 0; continue; }
+                D = ext_fwd_step(X, &f, D, c);
+                if ((D & f.fin) && ext_check(X, pl, text, q, pos, hi, &b, &e)) { found = 1; break; }
+            }
         }
         if (!found) break;
         if (cnt < cap) { hits[cnt].beg = b; hits[cnt].end = e; }

@@ -58,6 +58,8 @@ struct DevPlan {
     int ext_off, ext_anchor, ext_repeats;
     int maxleft;                  // bytes left of its anchor a verification can examine at most (bounded plans)
     unsigned long long IL, FL, AL, initL, IR, FR, AR, initR;
+    int ext_lead_opt;             // end-anchored plan, pattern begins with an optional position: forward-scan quirk
+    unsigned long long IS, FS, AS;
 };
 
 __device__ __forceinline__ bool plan_is_ext(const DevPlan &pl) { return pl.type == PM_PLAN_EXT_BEG || pl.type == PM_PLAN_EXT_END; }
@@ -269,6 +271,27 @@ __device__ int check_match_ext(const DevPlan &pl, const unsigned char *__restric
         bext = ext_side(text, TL, pl.ext_repeats, a, pl.IL, pl.FL, pl.AL, pl.initL, -1, pl.start_line, anchor, tbeg, &steps);
         *reach = anchor - steps - (pl.start_line ? 1 : 0);
         if (bext < 0) return 0;
+        if (pl.ext_lead_opt) {
+            // extendedScan @4116f0 (forward mode) proposes this anchor only if ITS automaton is in a final state here.
+            // It starts empty at the scan start and after every '\n', and the run of optional positions at the start
+            // of the pattern becomes enterable only through the closure that follows each byte.  An occurrence that
+            // starts later than such a byte is always seen; one that starts ON it is seen only if that automaton,
+            // re-run from there, ends final at the anchor.
+            const long long b = anchor - bext;
+            if (b - 1 < *reach) *reach = b - 1;                               // the outcome depends on the byte before b
+            if (b <= tbeg || text[b - 1] == '\n') {
+                unsigned long long D = 0;
+                for (long long q = b; q < anchor; q++) {
+                    const unsigned c = text[q];
+                    const unsigned long long Bc = __brevll(TL[c]) >> (64 - a);      // forward order of P[0, anchor)
+                    const unsigned long long Sc = pl.ext_repeats ? __brevll(TL[256 + c]) >> (64 - a) : 0ULL;
+                    D = (((D << 1) | 1ULL) & Bc) | (D & Sc);
+                    const unsigned long long x = D | pl.FS;
+                    D = (((~(x - pl.IS)) ^ x) & pl.AS) | D;
+                }
+                if (!(D & (1ULL << (a - 1)))) return 0;
+            }
+        }
     }
     if (a == m) {
         if (pl.end_line && !(anchor >= n || text[anchor] == '\n')) return 0;
@@ -914,6 +937,12 @@ static int compile(const char *pattern, const char *kopt, Compiled &c, bool need
     rc = pm::make_plan(c.P, c.o, c.plan, err);
     if (rc) { g_err = err; return rc; }
     if (!need_tables) return PM_OK;
+    if (c.plan.type == pm::SIMPLE && c.P.m() == 1 && c.P.pos[0].has('\n')) {
+        // a buffer fill that ends at a '\n' shares that byte with the next one, and the reference reports a one-byte
+        // hit on it once per fill; candidates here are keyed by position and belong to one fill
+        g_err = "single-position pattern that matches the record delimiter: not supported";
+        return PM_ERR_UNSUPPORTED;
+    }
     if (c.P.m() > 64) { g_err = "patterns longer than 64 positions are not supported on the GPU path yet"; return PM_ERR_UNSUPPORTED; }
     DevPlan &d = c.dp;
     memset(&d, 0, sizeof d);
@@ -937,6 +966,7 @@ static int compile(const char *pattern, const char *kopt, Compiled &c, bool need
         d.maxleft = c.plan.anchor;
         d.IL = c.plan.IL; d.FL = c.plan.FL; d.AL = c.plan.AL; d.initL = c.plan.initL;
         d.IR = c.plan.IR; d.FR = c.plan.FR; d.AR = c.plan.AR; d.initR = c.plan.initR;
+        d.ext_lead_opt = c.plan.ext_lead_opt; d.IS = c.plan.IS; d.FS = c.plan.FS; d.AS = c.plan.AS;
         pm::build_verify(c.P, c.plan, c.vt);               // TL: positions anchor-1, anchor-2, ... ; TR: anchor, anchor+1, ...
         c.scan = s;
         return PM_OK;

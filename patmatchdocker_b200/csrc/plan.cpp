@@ -322,10 +322,17 @@ static int make_plan_extended(const Pattern &P, const Options &o, Plan &plan, st
     if (plan.ext_wlen > 0) { plan.type = EXT_BEG; plan.anchor = plan.ext_beg; }
     else { plan.type = EXT_END; plan.anchor = plan.ext_end; }
     if (plan.type == EXT_END && P.optional(0)) {
-        // only possible after the parser's rewrite, e.g. (A?A?C) -> A?C: the binary's forward scan has no initial closure
-        // and misses matches at the first byte of a scan range
-        err = "EXTENDED pattern that begins with an optional position and is scanned forwards: not supported yet";
-        return PM_ERR_UNSUPPORTED;
+        // Only possible after the parser's rewrite, e.g. (A?A?C) -> A?C.  The binary's forward scan (extendedScan
+        // @4116f0, wlen <= 0) applies the closure of the optional runs after each byte and starts from an empty state,
+        // so an occurrence that has to skip the leading optional run on the very first byte of a scan range or record
+        // is not seen.  The verification re-runs that automaton for candidates whose match starts at such a byte;
+        // closure masks of the scan, forward order over P[0, anchor):
+        plan.ext_lead_opt = 1;
+        for (int u = 0; u < plan.anchor; u++) {
+            if (!P.optional(u)) continue;
+            if (u > 0 && ((plan.FS >> (u - 1)) & 1ULL)) { plan.FS &= ~(1ULL << (u - 1)); plan.FS |= 1ULL << u; plan.AS |= 1ULL << u; }
+            else { if (u > 0) plan.IS |= 1ULL << (u - 1); plan.FS |= 1ULL << u; plan.AS |= 1ULL << u; }
+        }
     }
     // plain positions next to the anchor: present in every match at a fixed offset, so an exact scan finds all anchors
     // (a '+' position next to the run still pins one byte -- its first occurrence on the right of the anchor, its last

@@ -56,6 +56,8 @@ struct Plan {
     int win_lo = 0, win_hi = 0;
     // closure masks of the two verification walks (extendedLoadVerif @412c60), elements numbered away from the anchor
     uint64_t IL = 0, FL = 0, AL = 0, initL = 0, IR = 0, FR = 0, AR = 0, initR = 0;
+    int ext_lead_opt = 0;              // EXT_END plan whose pattern begins with an optional position (scan quirk, see plan.cpp)
+    uint64_t IS = 0, FS = 0, AS = 0;   // closure masks of the forward scan over P[0, anchor)
 };
 
 // error codes follow include/patmatch_b200.h

@@ -41,6 +41,23 @@ def extended_pattern(rng, alpha, m):
     return pat + ")", members, ops
 
 
+def extended_pattern_with_ends(rng, alpha, m):
+    """like extended_pattern, operators on the first / last positions too (the reference's parser rewrites those)"""
+    toks, members, ops = [], [], []
+    for j in range(m):
+        r = rng.random()
+        if r < 0.12:
+            toks.append("."); members.append(list(alpha))
+        elif r < 0.27:
+            ch = rng.sample(alpha, 2); toks.append("[" + "".join(ch) + "]"); members.append(ch)
+        else:
+            c = rng.choice(alpha); toks.append(c); members.append([c])
+        ops.append(rng.choice("????*+") if rng.random() < (0.5 if j in (0, 1, m - 1) else 0.25) else "")
+    if not any(ops):
+        ops[0] = "?"
+    return "(" + "".join(a + b for a, b in zip(toks, ops)) + ")", members, ops
+
+
 def extended_text(rng, alpha, members, ops, nrec, lo, hi):
     lines = []
     for r in range(nrec):
@@ -75,9 +92,7 @@ def test_reference_golden_vectors(engine, search_golden, scan_mode):
             try:
                 got = [list(h) for h in gpu_hits(engine, c["text"], c["pattern"], c["kopt"])]
             except pm.NativeError as e:
-                # the only patterns the engine may refuse: forward-scanned ones that begin with an optional position
-                assert e.code == -3 and "scanned forwards" in str(e), (c["pattern"], str(e))
-                continue
+                raise AssertionError((c["pattern"], str(e)))
             if got != c["hits"]:
                 bad.append((c["pattern"], c["kopt"], c["bufsize"], got[:4], c["hits"][:4]))
     finally:
@@ -336,6 +351,30 @@ def test_extended_patterns_against_oracle(engine, scan_mode):
             assert got == want, (pat, bufsize, got[:4], want[:4])
             n_hits += len(want)
     assert n_hits > 1000 and types == {"EXT_BEG", "EXT_END"}
+    # operators at the pattern ends: parser rewrites, and the forward scan's blind spot at the first byte of a range
+    n_hits = 0
+    for it in range(200):
+        alpha = rng.choice([DNA, DNA, PEP])
+        pat, members, ops = extended_pattern_with_ends(rng, alpha, rng.randint(2, 9))
+        try:
+            O.plan_ext(pat)
+        except ValueError:
+            continue                                       # nothing left after the rewrites
+        text = extended_text(rng, alpha, members, ops, rng.randint(1, 6), 5, 400)
+        for bufsize in (1600000, rng.choice([16, 64, 300])):
+            engine.set_buffer_size(bufsize)
+            try:
+                got = gpu_hits(engine, text, pat, "0ids")
+            except pm.NativeError as e:
+                assert "single-position pattern" in str(e), (pat, str(e))      # e.g. (Y?.) -> '.', refused
+                continue
+            finally:
+                engine.set_buffer_size(1600000)
+            want = O.search(pat, text, "0ids", bufsize=bufsize)
+            assert got == want, (pat, bufsize, text, got[:6], want[:6])
+            n_hits += len(want)
+    assert n_hits > 1000
+    assert gpu_hits(engine, b"AATAAC\n", "(T?[TG]*A)", "0ids") == [(1, 2), (3, 4)]      # A0 and A4 open a scan range
     # the reference's quirk: zero occurrences of a run of two or more optional positions next to the anchor do not match
     assert gpu_hits(engine, b">q\nCCGATAAGTCCAA\nCCGATCAAGTCCAA\n", "(GAT.?.?.?AAGTCC)", "0ids") == [(19, 29)]
 
