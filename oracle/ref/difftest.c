@@ -72,9 +72,10 @@ static void mutate_into(unsigned char *t, int *n, int cap, const nro_pattern *P,
 
 int main(int argc, char **argv)
 {
-    long cases = 20000; int verbose = 0, zero = 0; const char *amode = "mix";
+    long cases = 20000; int verbose = 0, zero = 0, longm = 0; const char *amode = "mix";
     int opt;
-    while ((opt = getopt(argc, argv, "n:s:a:zv")) != -1) {
+    while ((opt = getopt(argc, argv, "n:s:a:zvM:")) != -1) {
+        if (opt == 'M') longm = atoi(optarg);            /* patterns of 65 .. M positions (multi-word masks) */
         if (opt == 'n') cases = atol(optarg);
         else if (opt == 's') rng_state ^= (uint64_t)atol(optarg) * 0x9E3779B97F4A7C15ULL;
         else if (opt == 'a') amode = optarg;
@@ -91,7 +92,7 @@ int main(int argc, char **argv)
     long plan_bad = 0, hit_bad = 0, types[4] = {0, 0, 0, 0}, total_hits = 0;
     for (long cs = 0; cs < cases; cs++) {
         const char *alpha = !strcmp(amode, "dna") ? DNA : !strcmp(amode, "pep") ? PEP : (rint_(2) ? DNA : PEP);
-        int m = 3 + rint_(rint_(4) ? 22 : 60);
+        int m = longm > 64 ? 65 + (int)rint_((unsigned)(longm - 64)) : 3 + rint_(rint_(4) ? 22 : 60);
         int k = rint_(8) == 0 ? 0 : 1 + rint_(3);
         if (k >= m) k = m - 1;
         int ids = 1 + rint_(7);

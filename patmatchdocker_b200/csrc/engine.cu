@@ -482,7 +482,13 @@ __global__ void __launch_bounds__(128) k_verify(const DevPlan pl, const unsigned
         if (!check_match_ext(pl, text, E, TL, TR, anchor, S, &b, &e, &r)) { b = -1; e = -1; }
         c.beg = b; c.end = e; c.reach = r;
     } else if (pl.type == PM_PLAN_SIMPLE) {
-        c.beg = pos; c.end = pos + pl.m; c.reach = pos - (pl.start_line ? 1 : 0);   // the chain stage applies '^' / '$'
+        bool ok = true;
+        for (int jj = 64; jj < pl.m && ok; jj++) {                                  // positions beyond the scanned window
+            const unsigned ch = text[pos + jj];
+            ok = (TL[(size_t)(jj - 64) * 4 + (ch >> 6)] >> (ch & 63)) & 1ULL;
+        }
+        if (ok) { c.beg = pos; c.end = pos + pl.m; c.reach = pos - (pl.start_line ? 1 : 0); }   // the chain stage applies '^' / '$'
+        else { c.beg = -1; c.end = -1; c.reach = pos; }
     } else {
         long long b = -1, e = -1, r = pos;
         if (!check_match(pl, text, E, TL, TR, i, pos, S, &b, &e, &r)) { b = -1; e = -1; }
@@ -943,13 +949,39 @@ static int compile(const char *pattern, const char *kopt, Compiled &c, bool need
         g_err = "single-position pattern that matches the record delimiter: not supported";
         return PM_ERR_UNSUPPORTED;
     }
-    if (c.P.m() > 64) { g_err = "patterns longer than 64 positions are not supported on the GPU path yet"; return PM_ERR_UNSUPPORTED; }
+    const bool long_simple = c.plan.type == pm::SIMPLE && c.P.m() > 64 && c.P.m() <= 255;
+    if (c.P.m() > 64 && !long_simple) {
+        g_err = "patterns longer than 64 positions are only supported for exact searches (k = 0, up to 255 positions)";
+        return PM_ERR_UNSUPPORTED;
+    }
     DevPlan &d = c.dp;
     memset(&d, 0, sizeof d);
     d.type = c.plan.type; d.m = c.plan.m; d.k = c.plan.k; d.L = c.plan.L; d.npieces = c.plan.npieces;
     d.ins = c.plan.ins; d.del = c.plan.del; d.subs = c.plan.subs;
     d.start_line = c.P.start_line ? 1 : 0; d.end_line = c.P.end_line ? 1 : 0;
     for (int i = 0; i < PM_MAX_PIECES; i++) { d.V[i] = c.plan.V[i]; d.trig[i] = c.plan.trig[i]; }
+    if (long_simple) {
+        // exact pattern of 65..255 positions: the scan kernels look for its first 64 positions, k_verify compares the
+        // rest on the raw bytes (the classes of positions 64.. travel in the TL table slot, 4 words per position)
+        auto s = std::make_shared<Compiled>();
+        s->o = c.o;
+        for (int j = 0; j < 64; j++) { s->P.pos.push_back(c.P.pos[j]); s->P.op.push_back(pm::OP_NONE); }
+        s->plan.type = pm::SIMPLE; s->plan.m = s->plan.L = 64; s->plan.npieces = 1;
+        DevPlan &sd = s->dp;
+        memset(&sd, 0, sizeof sd);
+        sd.type = PM_PLAN_SIMPLE; sd.m = sd.L = 64; sd.npieces = 1; sd.ins = sd.del = sd.subs = 1;
+        pm::build_filter(s->P, s->plan, s->ft);
+        sd.init = s->ft.init; sd.fin = s->ft.fin; sd.trig[0] = s->ft.fin;
+        c.ft = s->ft;
+        d.L = 64; d.init = c.ft.init; d.fin = c.ft.fin; d.trig[0] = c.ft.fin;
+        const int tail = c.P.m() - 64;
+        c.vt.TL.assign((size_t)tail * 4, 0);
+        c.vt.TR.assign((size_t)tail * 4, 0);
+        for (int j = 0; j < tail; j++)
+            for (int w = 0; w < 4; w++) c.vt.TL[(size_t)j * 4 + w] = c.P.pos[64 + j].w[w];
+        c.scan = s;
+        return PM_OK;
+    }
     if (c.plan.type == pm::EXT_BEG || c.plan.type == pm::EXT_END) {
         auto s = std::make_shared<Compiled>();
         s->o = c.o;

@@ -236,6 +236,27 @@ def search_fixture():
                       ("(C*C?[AG]?T)", "TTCTAT\nT\nGT\nCCCGT\n")):
         cases.append((pat, "0ids", text, 1600000))
         cases.append((pat, "0ids", text, 8))
+    # exact patterns of more than 64 positions (multi-word masks in the reference)
+    lrng = random.Random(6500)
+    for it in range(14):
+        alpha = lrng.choice([DNA, DNA, PEP])
+        m = lrng.randint(65, 200)
+        pat, kopt, _ = random_case(lrng, alpha, m, 0, "ids")
+        members = []
+        for tok in re.findall(r"\[\^?[A-Z]+\]|\.|[A-Z]", pat[1:-1]):
+            members.append(list(alpha) if tok == "." else [c for c in alpha if c not in tok[2:-1]] if tok.startswith("[^")
+                           else list(tok[1:-1]) if tok.startswith("[") else [tok])
+        lines = []
+        for r in range(lrng.randint(1, 3)):
+            lines.append(">L%d" % r)
+            t = ""
+            for _ in range(lrng.randint(1, 8)):
+                s = [lrng.choice(c) for c in members]
+                if lrng.random() < 0.4:
+                    s[lrng.randrange(len(s))] = lrng.choice(alpha)
+                t += "".join(s) + "".join(lrng.choice(alpha) for _ in range(lrng.randint(0, 25)))
+            lines.append(t)
+        cases.append((pat, "0ids", "\n".join(lines) + "\n", lrng.choice([1600000, 1600000, 500])))
     out = []
     with tempfile.TemporaryDirectory() as td:
         path = os.path.join(td, "t.seq")

@@ -409,6 +409,41 @@ def test_chain_stage_on_tandem_repeats(engine, scan_mode):
     assert n_hits > 2000
 
 
+def test_exact_patterns_longer_than_64_positions(engine, scan_mode):
+    # oligo-sized exact patterns: the scan looks for the first 64 positions, k_verify compares the rest
+    rng = random.Random(65)
+    n_hits = 0
+    for it in range(40):
+        alpha = rng.choice([DNA, DNA, PEP])
+        m = rng.randint(65, 255 if it % 3 else 80)
+        pat, members = random_pattern(rng, alpha, m, cls_pct=0.1, dot_pct=0.05)
+        if it % 5 == 0:
+            pat = "^" + pat
+        lines = []
+        for r in range(rng.randint(1, 4)):
+            lines.append(">o%d" % r)
+            t = ""
+            for _ in range(rng.randint(1, 12)):
+                s0 = [rng.choice(c) for c in members]
+                if rng.random() < 0.4:                         # spoil it somewhere (often beyond the first 64 positions)
+                    s0[rng.randrange(len(s0))] = rng.choice(alpha)
+                t += "".join(s0) + "".join(rng.choice(alpha) for _ in range(rng.randint(0, 30)))
+            lines.append(t)
+        text = ("\n".join(lines) + "\n").encode()
+        for bufsize in (1600000, rng.choice([300, 1000])):
+            engine.set_buffer_size(bufsize)
+            try:
+                got = gpu_hits(engine, text, pat, "0ids")
+            finally:
+                engine.set_buffer_size(1600000)
+            want = O.search(pat, text, "0ids", bufsize=bufsize)
+            assert got == want, (pat, bufsize)
+            n_hits += len(want)
+    assert n_hits > 100
+    with pytest.raises(pm.NativeError):                        # approximate search of a long pattern: not yet
+        gpu_hits(engine, b">s\nACGT\n", "(" + "ACGT" * 20 + ")", "1ids")
+
+
 def test_hit_list_stays_on_device_after_overflow(engine):
     import ctypes
     from patmatchdocker_b200 import _native
