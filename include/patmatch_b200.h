@@ -27,8 +27,8 @@ extern "C" {
 #define PM_ERR_CUDA        -1   /* CUDA runtime failure (message has the cudaError) */
 #define PM_ERR_SYNTAX      -2   /* malformed nrgrep pattern / -k option */
 #define PM_ERR_UNSUPPORTED -3   /* pattern needs nrgrep's REGULAR engine (groups with operators, |), is an EXTENDED pattern
-                                 * (? * +) with errors, is a single position that accepts '\n', or has more than 64 positions
-                                 * and k > 0 (exact patterns: up to 255 positions) */
+                                 * (? * +) with errors, is a single position that accepts '\n', or has more than 255 positions
+                                 * (64 for EXTENDED patterns) */
 #define PM_ERR_ARG         -4
 #define PM_ERR_OVERFLOW    -5   /* caller's hit buffer too small; *nhits holds the required size */
 

@@ -166,6 +166,112 @@ __device__ __forceinline__ int fill_of(const Fills &f, long long x)      // last
     return lo;
 }
 
+// ---------------------------------------------------------------------------------------
+// Patterns of 65..255 positions: the same anchored k-error NFA with PM_MW-word state vectors (the reference keeps
+// multi-word masks too, createMask @41b430).  Tables: T[byte][PM_MW].  Only verification needs this: the scan
+// kernels look at pieces / sub-patterns of at most 64 positions.
+#define PM_MW 4
+struct MWord { unsigned long long w[PM_MW]; };
+
+__device__ __forceinline__ MWord mw_shl1(const MWord &a, unsigned long long in)
+{
+    MWord r;
+    unsigned long long carry = in;
+#pragma unroll
+    for (int w = 0; w < PM_MW; w++) { r.w[w] = (a.w[w] << 1) | carry; carry = a.w[w] >> 63; }
+    return r;
+}
+
+__device__ int nfa_side_mw(const unsigned char *__restrict__ text, const unsigned long long *__restrict__ T,
+                           int dir, int plen, int kmax, int ins, int del, int subs, int ctx,
+                           long long pos, long long lim, long long *ext, int *err, long long *steps)
+{
+    auto edge_ok = [&](long long step) -> bool {
+        if (!ctx) return true;
+        if (dir < 0) { const long long e = pos - step; return e <= lim || text[e - 1] == '\n'; }
+        const long long e = pos + step;
+        return e >= lim || text[e] == '\n';
+    };
+    const int fw = (plen - 1) >> 6;
+    const unsigned long long fin = 1ULL << ((plen - 1) & 63);
+    auto has_fin = [&](const MWord &a) -> bool { return (a.w[fw] & fin) != 0; };
+    auto alive = [&](const MWord &a) -> bool {
+        for (int w = 0; w < fw; w++) if (a.w[w]) return true;
+        return (a.w[fw] & ((fin << 1) - 1ULL)) != 0;
+    };
+    MWord R[PM_MAXK + 1];
+    int kb = kmax;
+    long long best_ext = -1;
+    int best_err = kmax;
+    *steps = 0;
+    for (int e = 0; e <= kb; e++) {
+#pragma unroll
+        for (int w = 0; w < PM_MW; w++) R[e].w[w] = 0;
+        if (del) R[e].w[0] = (1ULL << e) - 1ULL;                       // e <= 15
+        if (has_fin(R[e]) && edge_ok(0)) { best_err = e; kb = e - 1; best_ext = 0; }
+    }
+    unsigned long long first = 1;
+    long long step = 0;
+    for (;;) {
+        const long long tp = dir < 0 ? pos - step - 1 : pos + step;
+        if (dir < 0 ? (tp < lim) : (tp >= lim)) break;
+        const unsigned c = text[tp];
+        if (c == '\n') break;
+        step++;
+        *steps = step;
+        const unsigned long long *Tc = T + (size_t)c * PM_MW;
+        MWord oldp = R[0];
+        MWord sh = mw_shl1(R[0], first);
+#pragma unroll
+        for (int w = 0; w < PM_MW; w++) R[0].w[w] = sh.w[w] & Tc[w];
+        MWord newp = R[0];
+        if (has_fin(R[0]) && edge_ok(step)) { *ext = step; *err = 0; return 1; }
+        bool lowered = false;
+        for (int e = 1; e <= kb; e++) {
+            MWord x;
+#pragma unroll
+            for (int w = 0; w < PM_MW; w++) x.w[w] = 0;
+            if (del) x = mw_shl1(newp, 0);
+            if (ins) {
+#pragma unroll
+                for (int w = 0; w < PM_MW; w++) x.w[w] |= oldp.w[w];
+            }
+            if (subs) {
+                const MWord s = mw_shl1(oldp, first);
+#pragma unroll
+                for (int w = 0; w < PM_MW; w++) x.w[w] |= s.w[w];
+            }
+            const MWord y = mw_shl1(R[e], first);
+            MWord nr;
+#pragma unroll
+            for (int w = 0; w < PM_MW; w++) nr.w[w] = (y.w[w] & Tc[w]) | x.w[w];
+            oldp = R[e];
+            R[e] = nr;
+            newp = nr;
+            if (has_fin(nr) && edge_ok(step)) {
+                int ec = e, ed;
+                for (;;) {
+                    ed = ec - 1;
+                    if (ed < 0) break;
+                    if (!has_fin(R[ed])) break;
+                    ec = ed;
+                }
+                if (ed < 0) { *ext = step; *err = 0; return 1; }
+                kb = ed; best_err = ec; best_ext = step;
+                lowered = true;
+                break;
+            }
+        }
+        (void)lowered;
+        if (!alive(R[kb])) break;
+        first = 0;
+    }
+    if (best_ext < 0) return 0;
+    *ext = best_ext;
+    *err = best_err;
+    return 1;
+}
+
 // esimple checkMatch @4151d0 for candidate (piece i, anchor pos) with scan range [tbeg, n).
 __device__ int check_match(const DevPlan &pl, const unsigned char *__restrict__ text, long long n,
                            const unsigned long long *__restrict__ TL, const unsigned long long *__restrict__ TR,
@@ -179,7 +285,8 @@ __device__ int check_match(const DevPlan &pl, const unsigned char *__restrict__ 
     long long bext = 0, fext = 0, steps = 0;
     int berr = 0, ferr = 0;
     if (lb > 0) {
-        int ok = nfa_side(text, TL + (size_t)i * 256, -1, lb, pl.k, pl.ins, pl.del, pl.subs, pl.start_line, pos, tbeg, &bext, &berr, &steps);
+        int ok = pl.m > 64 ? nfa_side_mw(text, TL + (size_t)i * 256 * PM_MW, -1, lb, pl.k, pl.ins, pl.del, pl.subs, pl.start_line, pos, tbeg, &bext, &berr, &steps)
+                           : nfa_side(text, TL + (size_t)i * 256, -1, lb, pl.k, pl.ins, pl.del, pl.subs, pl.start_line, pos, tbeg, &bext, &berr, &steps);
         *reach = pos - steps - (pl.start_line ? 1 : 0);    // '^' also reads the byte left of the boundary
         if (!ok) return 0;
     } else if (pl.start_line) {
@@ -196,7 +303,8 @@ __device__ int check_match(const DevPlan &pl, const unsigned char *__restrict__ 
         bext = pos - ptr; berr = e;
     }
     if (rl > 0) {
-        if (!nfa_side(text, TR + (size_t)i * 256, +1, rl, pl.k - berr, pl.ins, pl.del, pl.subs, pl.end_line, pos, n, &fext, &ferr, &steps)) return 0;
+        if (!(pl.m > 64 ? nfa_side_mw(text, TR + (size_t)i * 256 * PM_MW, +1, rl, pl.k - berr, pl.ins, pl.del, pl.subs, pl.end_line, pos, n, &fext, &ferr, &steps)
+                        : nfa_side(text, TR + (size_t)i * 256, +1, rl, pl.k - berr, pl.ins, pl.del, pl.subs, pl.end_line, pos, n, &fext, &ferr, &steps))) return 0;
     } else if (pl.end_line) {
         // 414eae-414f19: the same on the right of an empty right part
         const int kf = pl.k - berr;
@@ -950,8 +1058,8 @@ static int compile(const char *pattern, const char *kopt, Compiled &c, bool need
         return PM_ERR_UNSUPPORTED;
     }
     const bool long_simple = c.plan.type == pm::SIMPLE && c.P.m() > 64 && c.P.m() <= 255;
-    if (c.P.m() > 64 && !long_simple) {
-        g_err = "patterns longer than 64 positions are only supported for exact searches (k = 0, up to 255 positions)";
+    if (c.P.m() > 255 || (c.P.m() > 64 && c.P.extended())) {
+        g_err = "patterns longer than 255 positions (64 with ? * +) are not supported";
         return PM_ERR_UNSUPPORTED;
     }
     DevPlan &d = c.dp;
@@ -1126,7 +1234,7 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c_ful
                     a.keys = (unsigned long long *)e->keys.p; a.count = d_count; a.cap = cap;
                     PackedVerify<4> pv;
                     memset(&pv, 0, sizeof pv);
-                    pv.enabled = (dp.k <= 3 && e->fused_filter) ? 1 : 0;
+                    pv.enabled = (dp.k <= 3 && e->fused_filter && dp.m <= 64) ? 1 : 0;   // the Myers filter keeps 64-bit parts
                     pv.m = dp.m; pv.k = dp.k; pv.ins = dp.ins; pv.del = dp.del; pv.subs = dp.subs;
                     pv.cuts = d->d_fills + 2 * (size_t)d->nfills; pv.ncuts = d->ncuts;
                     bool narrow = true;                                   // every pattern part fits a 32-bit state word

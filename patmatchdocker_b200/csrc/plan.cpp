@@ -472,6 +472,21 @@ void build_verify(const Pattern &P, const Plan &plan, VerifyTables &vt)
         }
         return;
     }
+    if (m > 64) {
+        // 65..255 positions: four words per byte, [piece][byte][word]
+        const int NW = 4;
+        vt.TL.assign((size_t)np * 256 * NW, 0);
+        vt.TR.assign((size_t)np * 256 * NW, 0);
+        for (int i = 0; i < np; i++) {
+            const int lb = plan.V[i], rl = m - lb;
+            for (unsigned c = 0; c < 256; c++) {
+                uint64_t *l = &vt.TL[((size_t)i * 256 + c) * NW], *r = &vt.TR[((size_t)i * 256 + c) * NW];
+                for (int j = 0; j < lb; j++) if (P.pos[lb - 1 - j].has(c)) l[j >> 6] |= 1ULL << (j & 63);
+                for (int j = 0; j < rl; j++) if (P.pos[lb + j].has(c)) r[j >> 6] |= 1ULL << (j & 63);
+            }
+        }
+        return;
+    }
     vt.TL.assign((size_t)np * 256, 0);
     vt.TR.assign((size_t)np * 256, 0);
     for (int i = 0; i < np; i++) {

@@ -257,6 +257,11 @@ def search_fixture():
                 t += "".join(s) + "".join(lrng.choice(alpha) for _ in range(lrng.randint(0, 25)))
             lines.append(t)
         cases.append((pat, "0ids", "\n".join(lines) + "\n", lrng.choice([1600000, 1600000, 500])))
+    # ... and approximate ones (the verification NFA runs on multi-word masks)
+    for it in range(12):
+        alpha = lrng.choice([DNA, DNA, PEP])
+        m, k = lrng.randint(65, 160), lrng.choice([1, 1, 2])
+        cases.append(random_case(lrng, alpha, m, k, lrng.choice(["ids", "s", "id"])) + (lrng.choice([1600000, 1600000, 800]),))
     out = []
     with tempfile.TemporaryDirectory() as td:
         path = os.path.join(td, "t.seq")

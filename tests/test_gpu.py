@@ -440,8 +440,39 @@ def test_exact_patterns_longer_than_64_positions(engine, scan_mode):
             assert got == want, (pat, bufsize)
             n_hits += len(want)
     assert n_hits > 100
-    with pytest.raises(pm.NativeError):                        # approximate search of a long pattern: not yet
-        gpu_hits(engine, b">s\nACGT\n", "(" + "ACGT" * 20 + ")", "1ids")
+
+
+def test_approximate_patterns_longer_than_64_positions(engine, scan_mode):
+    # multi-word verification (nfa_side_mw): SPLIT pieces / BWD sub-patterns still fit 64 positions, the anchored NFA
+    # walks parts of up to 255
+    from synth import planted
+    rng = random.Random(650)
+    n_hits, types = 0, set()
+    for it in range(40):
+        alpha = rng.choice([DNA, DNA, PEP])
+        k = rng.choice([1, 1, 2, 3])
+        m = rng.randint(65, 200 if it % 3 else 70)
+        pat, members = random_pattern(rng, alpha, m, cls_pct=0.1, dot_pct=0.05)
+        kopt = "%d%s" % (k, rng.choice(["ids", "ids", "s", "id"]))
+        types.add(pm.plan(pat, kopt)["type"])
+        lines = []
+        for r in range(rng.randint(1, 3)):
+            lines.append(">a%d" % r)
+            t = ""
+            for _ in range(rng.randint(1, 8)):
+                t += planted(rng, members, alpha, k) + "".join(rng.choice(alpha) for _ in range(rng.randint(0, 40)))
+            lines.append(t)
+        text = ("\n".join(lines) + "\n").encode()
+        for bufsize in (1600000, rng.choice([700, 3000])):
+            engine.set_buffer_size(bufsize)
+            try:
+                got = gpu_hits(engine, text, pat, kopt)
+            finally:
+                engine.set_buffer_size(1600000)
+            want = O.search(pat, text, kopt, bufsize=bufsize)
+            assert got == want, (pat, kopt, bufsize)
+            n_hits += len(want)
+    assert n_hits > 60 and {"SPLIT", "BWD"} <= types
 
 
 def test_hit_list_stays_on_device_after_overflow(engine):
