@@ -14,6 +14,11 @@
  * All functions return 0 on success, a negative PM_ERR_* code otherwise;
  * pm_last_error() gives the message for the calling thread.  There is no CPU
  * fallback: without a CUDA device pm_engine_create fails.
+ *
+ * Threads: a pm_engine owns mutable scratch (candidate buffers, pinned staging, statistics).  Every entry point
+ * that takes an engine holds the engine's mutex for its duration, so concurrent callers are serialised per engine;
+ * pm_last_hits / pm_get_stats refer to the last call of ANY thread, so callers that need them must hold their own
+ * lock around the pair or use one engine per thread.
  */
 #ifndef PATMATCH_B200_H
 #define PATMATCH_B200_H
@@ -66,6 +71,7 @@ typedef struct {
     int launches;                /* kernels launched by the last search */
     int packed;                  /* 1: 2-bit packed bit-sliced scan, 0: byte Shift-And / dense */
     int qgram_chunks;            /* pattern chunks of the bit-sliced q-gram pre-filter (0 = not used) */
+    int syncs;                   /* host synchronisations of the last pm_search_request */
 } pm_stats;
 
 const char *pm_last_error(void);
@@ -77,7 +83,8 @@ int pm_plan(const char *pattern, const char *kopt, pm_plan_info *info);
 
 int pm_engine_create(int device, pm_engine **out);
 void pm_engine_destroy(pm_engine *e);
-/* launch on this cudaStream_t instead of the engine's own stream (0 = back to own) */
+/* launch on this cudaStream_t instead of the engine's own (non-blocking) stream; 0 = back to own.  To share the
+ * legacy default stream (handle 0, e.g. torch's default stream) pass cudaStreamLegacy, (void *)1. */
 int pm_engine_set_stream(pm_engine *e, void *cuda_stream);
 int pm_engine_synchronize(pm_engine *e);
 /* scan kernel selection: 0 = auto (packed for DNA-like datasets), 1 = byte Shift-And, 2 = packed */
@@ -118,6 +125,27 @@ int pm_last_hits(pm_engine *e, pm_hit *hits, int64_t cap, int64_t *nhits);
  * delimit pattern i.  offsets has npat+1 entries. */
 int pm_search_batch(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns,
                     const char *kopt, pm_hit *hits, int64_t cap, int64_t *offsets);
+
+/* One PatMatch request in ONE pass (replaces BOTH nrgrep_coords runs of patmatch.py:733-735 and :739-743: the pattern
+ * and its reverse complement; any number of patterns with the same -k works).  All patterns are evaluated on each
+ * staged tile of the dataset, their candidates share one sort / verification / chain / select pipeline, and the host
+ * synchronises once.  Results as pm_search_batch: hits[offsets[i] .. offsets[i+1]) belong to patterns[i], each list
+ * bit-identical to pm_search of that pattern.  A page-locked `hits` buffer (pm_host_alloc) is filled directly by
+ * the device-to-host copy.  On PM_ERR_OVERFLOW offsets[] are valid and the list is still on the device (pm_last_hits). */
+int pm_search_request(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
+                      pm_hit *hits, int64_t cap, int64_t *offsets);
+
+/* The same request restricted to the buffer fills that START in [pos_beg, pos_end) (see pm_search_fills_device), fully
+ * asynchronous on the engine's stream: NO host synchronisation.  dev_out (device memory, out_rows rows of 2 x int64)
+ * receives a header followed by the hits in output order:
+ *   row 0: hits, candidates          row 1: placeholders, 0          then ceil(npat / 2) rows of per-pattern hit counts;
+ *   hits start at row PM_REQUEST_HEADER_ROWS(npat).
+ * sort_cap = candidate capacity of this call (0: engine default).  The caller inspects the header after its own
+ * synchronisation (e.g. after the all-gather + D2H of a multi-GPU merge): candidates > sort_cap or
+ * hits > out_rows - header rows means the call has to be repeated with more room. */
+#define PM_REQUEST_HEADER_ROWS(npat) ((4 + (npat) + 1) / 2)
+int pm_request_fills_device(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
+                            int64_t pos_beg, int64_t pos_end, int64_t sort_cap, void *dev_out, int64_t out_rows);
 
 /* Sharded search for multi-GPU runs: only candidates whose anchor position lies in
  * [pos_beg, pos_end) are produced; they are verified but NOT chained.  The caller

@@ -1,6 +1,7 @@
 """ctypes binding of lib/libpatmatch_b200.so (C ABI: include/patmatch_b200.h)."""
 import ctypes
 import os
+import threading
 
 import numpy as np
 
@@ -35,7 +36,7 @@ class PmStats(ctypes.Structure):
                 ("chain_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
                 ("candidates", ctypes.c_int64), ("verified", ctypes.c_int64), ("hits", ctypes.c_int64),
                 ("scan_bytes", ctypes.c_int64), ("scan_bases", ctypes.c_int64), ("launches", ctypes.c_int),
-                ("packed", ctypes.c_int), ("qgram_chunks", ctypes.c_int)]
+                ("packed", ctypes.c_int), ("qgram_chunks", ctypes.c_int), ("syncs", ctypes.c_int)]
 
 
 HIT_DTYPE = np.dtype([("beg", "<i8"), ("end", "<i8")])
@@ -81,6 +82,8 @@ def load():
     L.pm_search.argtypes = [vp, vp, cp, cp, vp, i64, ctypes.POINTER(i64)]
     L.pm_last_hits.argtypes = [vp, vp, i64, ctypes.POINTER(i64)]
     L.pm_search_batch.argtypes = [vp, vp, ctypes.c_int, ctypes.POINTER(cp), cp, vp, i64, ctypes.POINTER(i64)]
+    L.pm_search_request.argtypes = [vp, vp, ctypes.c_int, ctypes.POINTER(cp), cp, vp, i64, ctypes.POINTER(i64)]
+    L.pm_request_fills_device.argtypes = [vp, vp, ctypes.c_int, ctypes.POINTER(cp), cp, i64, i64, i64, vp, i64]
     L.pm_candidates.argtypes = [vp, vp, cp, cp, i64, i64, vp, i64, ctypes.POINTER(i64)]
     L.pm_resolve.argtypes = [vp, vp, cp, cp, vp, i64, vp, i64, ctypes.POINTER(i64)]
     L.pm_candidates_device.argtypes = [vp, vp, cp, cp, i64, i64, vp, i64, ctypes.POINTER(i64)]
@@ -158,13 +161,58 @@ class Dataset:
             pass
 
 
+def request_header_rows(npat):
+    """rows (2 x int64) of the header in front of the hit list of pm_request_fills_device"""
+    return (4 + npat + 1) // 2
+
+
+def _locked(fn):
+    def wrapper(self, *a, **kw):
+        with self._lock:
+            return fn(self, *a, **kw)
+    wrapper.__name__, wrapper.__doc__ = fn.__name__, fn.__doc__
+    return wrapper
+
+
 class Engine:
-    """One engine per GPU (one process per GPU in multi-GPU runs)."""
+    """One engine per GPU (one process per GPU in multi-GPU runs).
+
+    An engine owns mutable scratch (candidate buffers, pinned staging, statistics), so calls are serialised: the C
+    entry points take the engine's mutex, and the methods here that combine several calls (a search followed by
+    pm_last_hits after an overflow, ...) hold `self._lock` across the combination.  Safe to share between the request
+    threads of a WSGI process; use one engine per thread for concurrency."""
 
     def __init__(self, device=0):
         self._h = ctypes.c_void_p()
+        self._lock = threading.RLock()
         _check(load().pm_engine_create(int(device), ctypes.byref(self._h)))
         self.device = device
+
+    @_locked
+    def search_request(self, dataset, patterns, kopt="0ids", out=None, cap=1 << 16):
+        """pm_search_request: all patterns of one PatMatch request (the motif and its reverse complement) in ONE pass
+        over the dataset and one pipeline.  -> list of hit arrays, one per pattern, each equal to search() of it.
+        `out`: optional page-locked result array (pinned_empty(...)[0], HIT_DTYPE) that the device-to-host copy fills
+        directly; the returned arrays are then views of it, valid until the caller reuses it."""
+        L = load()
+        arr = (ctypes.c_char_p * len(patterns))(*[_b(p) for p in patterns])
+        offs = (ctypes.c_int64 * (len(patterns) + 1))()
+        hits = out if out is not None else np.empty(cap, dtype=HIT_DTYPE)
+        rc = L.pm_search_request(self._h, dataset._h, len(patterns), arr, _b(kopt), ctypes.c_void_p(hits.ctypes.data), len(hits), offs)
+        if rc == PM_ERR_OVERFLOW:                      # the list is still on the device
+            n = ctypes.c_int64()
+            hits = np.empty(int(offs[len(patterns)]), dtype=HIT_DTYPE)
+            rc = L.pm_last_hits(self._h, ctypes.c_void_p(hits.ctypes.data), len(hits), ctypes.byref(n))
+        _check(rc)
+        return [hits[offs[i]:offs[i + 1]] for i in range(len(patterns))]
+
+    def request_fills_device(self, dataset, patterns, kopt, pos_beg, pos_end, sort_cap, dev_ptr, out_rows):
+        """pm_request_fills_device: asynchronous; header + hits of the fills starting in [pos_beg, pos_end) are written
+        to device memory at dev_ptr (out_rows rows of 2 x int64).  Nothing is returned: read the header after your own
+        synchronisation (row 0 = hits, candidates; per-pattern counts from row 2)."""
+        arr = (ctypes.c_char_p * len(patterns))(*[_b(p) for p in patterns])
+        _check(load().pm_request_fills_device(self._h, dataset._h, len(patterns), arr, _b(kopt), int(pos_beg), int(pos_end),
+                                              int(sort_cap), ctypes.c_void_p(dev_ptr), int(out_rows)))
 
     def close(self):
         if self._h:
@@ -178,8 +226,18 @@ class Engine:
             pass
 
     def set_stream(self, cuda_stream_handle):
+        """launch on this cudaStream_t (0 / None = back to the engine's own non-blocking stream)"""
         _check(load().pm_engine_set_stream(self._h, ctypes.c_void_p(cuda_stream_handle or 0)))
 
+    def use_torch_stream(self, stream=None):
+        """Share torch's stream (default: the current one), so that engine work and torch work (NCCL collectives,
+        copy_) are ordered.  torch's default stream has handle 0 = the legacy default stream, which the C ABI
+        spells cudaStreamLegacy (1) because 0 means "the engine's own stream" there."""
+        import torch
+        s = stream if stream is not None else torch.cuda.current_stream(torch.device("cuda", self.device))
+        self.set_stream(s.cuda_stream or 1)
+
+    @_locked
     def search_stream(self, data, patterns, kopt="0ids", chunk_bytes=0, cap=1 << 18):
         """pm_search_stream: `data` (bytes or a uint8 numpy array, pinned for full speed) is uploaded in chunks while
         the chunks that have arrived are packed and searched.  -> (Dataset resident for later searches,
@@ -240,6 +298,7 @@ class Engine:
         _check(load().pm_dataset_wrap_device(self._h, ctypes.c_void_p(device_ptr), nbytes, ctypes.byref(h)))
         return Dataset(self, h)
 
+    @_locked
     def search(self, dataset, pattern, kopt="0ids", cap=1 << 16):
         """-> numpy structured array (beg, end): the '[beg, end]' pairs nrgrep_coords prints, in order."""
         L = load()
@@ -252,14 +311,16 @@ class Engine:
         _check(rc)
         return hits[: n.value]
 
+    @_locked
     def count(self, dataset, pattern, kopt="0ids"):
         n = ctypes.c_int64()
         _check(load().pm_search(self._h, dataset._h, _b(pattern), _b(kopt), None, 0, ctypes.byref(n)))
         return n.value
 
+    @_locked
     def search_batch(self, dataset, patterns, kopt="0ids", cap=1 << 20):
         """-> (hits, offsets): hits[offsets[i]:offsets[i+1]] is the hit list of patterns[i].  Large results
-        are returned in page-locked host memory (fast device-to-host copy)."""
+        cross PCIe into a page-locked staging buffer owned by the engine; the caller always receives its own copy."""
         L = load()
         arr = (ctypes.c_char_p * len(patterns))(*[_b(p) for p in patterns])
         offsets = (ctypes.c_int64 * (len(patterns) + 1))()
@@ -282,8 +343,11 @@ class Engine:
                     rc = L.pm_search_batch(self._h, dataset._h, len(patterns), arr, _b(kopt), ctypes.c_void_p(hits.ctypes.data), cap, offsets)
         _check(rc)
         off = np.array(list(offsets), dtype=np.int64)
+        if hits is getattr(getattr(self, "_keep", None), "array", None):
+            return hits[: off[-1]].copy(), off          # the pinned staging buffer is reused by the next call: hand out a copy
         return hits[: off[-1]], off
 
+    @_locked
     def candidates(self, dataset, pattern, kopt, pos_beg, pos_end, cap=1 << 16):
         L = load()
         n = ctypes.c_int64()
@@ -306,6 +370,7 @@ class Engine:
         _check(rc)
         return int(n.value)
 
+    @_locked
     def resolve_device(self, dataset, pattern, kopt, dev_ptr, ncands, cap=1 << 16):
         L = load()
         n = ctypes.c_int64()

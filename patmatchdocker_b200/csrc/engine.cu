@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cmath>
 #include <memory>
+#include <mutex>
 #include "../../include/patmatch_b200.h"
 #include "plan.hpp"
 
@@ -62,9 +63,15 @@ struct DevPlan {
     unsigned long long IS, FS, AS;
 };
 
+// candidate key = pattern id << PM_PID_SHIFT | text position << 4 | piece  (pattern id 0 for single-pattern searches)
+#define PM_POS_BITS 36
+#define PM_PID_SHIFT 40
+__host__ __device__ __forceinline__ long long key_pos(unsigned long long key) { return (long long)((key >> 4) & ((1ULL << PM_POS_BITS) - 1ULL)); }
+__host__ __device__ __forceinline__ int key_pid(unsigned long long key) { return (int)(key >> PM_PID_SHIFT); }
+
 __device__ __forceinline__ bool plan_is_ext(const DevPlan &pl) { return pl.type == PM_PLAN_EXT_BEG || pl.type == PM_PLAN_EXT_END; }
 // text position the verification is anchored at, from a candidate key
-__device__ __forceinline__ long long anchor_of(const DevPlan &pl, long long key) { return (key >> 4) + (plan_is_ext(pl) ? pl.ext_off : 0); }
+__device__ __forceinline__ long long anchor_of(const DevPlan &pl, long long key) { return key_pos((unsigned long long)key) + (plan_is_ext(pl) ? pl.ext_off : 0); }
 // the byte that decides which record / fill a candidate belongs to
 __device__ __forceinline__ long long locus_of(const DevPlan &pl, long long anchor)
 {
@@ -438,6 +445,7 @@ struct ScanArgs {
     unsigned long long *keys;
     unsigned long long *count;   // [0] = candidates produced
     long long cap;
+    unsigned long long keytag;   // pid << PM_PID_SHIFT (multi-pattern requests)
 };
 
 template <typename T>
@@ -448,7 +456,7 @@ __device__ __forceinline__ void scan_emit(const ScanArgs<T> &a, T hit, long long
     for (int i = 0; i < a.npieces; i++) {
         if (hit & a.trig[i]) {
             unsigned long long idx = atomicAdd(a.count, 1ULL);
-            if ((long long)idx < a.cap) a.keys[idx] = ((unsigned long long)w << 4) | (unsigned)i;
+            if ((long long)idx < a.cap) a.keys[idx] = a.keytag | ((unsigned long long)w << 4) | (unsigned)i;
         }
     }
 }
@@ -530,6 +538,7 @@ struct DenseArgs {
     unsigned long long *keys, *count;
     long long cap;
     Fills fills;
+    unsigned long long keytag;
 };
 
 __global__ void __launch_bounds__(256) k_scan_dense(const DenseArgs a)
@@ -543,7 +552,7 @@ __global__ void __launch_bounds__(256) k_scan_dense(const DenseArgs a)
         if (a.pl.type == PM_PLAN_BWD && pos + (a.pl.L - a.pl.k) > E) continue;
         if (check_match(a.pl, a.text, E, a.TL, a.TR, 0, pos, S, &b, &e, &r)) {
             unsigned long long idx = atomicAdd(a.count, 1ULL);
-            if ((long long)idx < a.cap) a.keys[idx] = (unsigned long long)pos << 4;
+            if ((long long)idx < a.cap) a.keys[idx] = a.keytag | ((unsigned long long)pos << 4);
         }
     }
 }
@@ -710,14 +719,23 @@ struct pm_engine {
     int sms = 148;
     cudaStream_t own = nullptr, stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    DevBuf keys, keys2, cands, hits, hits2, sel, tables, counters, cubtmp;
+    DevBuf keys, keys2, cands, hits, hits2, sel, tables, counters, cubtmp, scanbuf;
+    // A pm_engine owns mutable scratch (the buffers above, pinned staging, stats): every entry point that takes an
+    // engine holds this lock, so concurrent callers (e.g. mod_wsgi request threads) are serialised per engine.
+    std::recursive_mutex mu;
+    std::vector<unsigned char> h_blob;              // host staging of the per-request tables
+    long long req_cap_hint = 1 << 16;               // candidate capacity of the next request (adapted from the last one)
+    long long req_hits_hint = 4096;                 // hits copied speculatively with the header
+    const pm_hit *last_hits = nullptr;              // device hit list of the last search (pm_last_hits)
+    bool stats_pending = false;                     // device timings not yet read back (done lazily by pm_get_stats)
     unsigned long long *h_count = nullptr;          // pinned
     void *h_stage = nullptr; size_t h_stage_cap = 0; // pinned staging for small result copies
     int scan_mode = 0;                              // 0 auto, 1 byte Shift-And, 2 packed bit-sliced
     long long bufsize = 1600000;                    // patmatch.py:37 MAX_BUFFER_SIZE (-b, in bytes)
     int fused_filter = 1;                           // packed scan drops candidates whose verification surely fails
     int qgram_filter = 1;                           // bit-sliced q-gram pre-filter in front of the Myers filter
-    int split_kernel = 1;                           // register-resident SPLIT scan (k_scan_split) when it applies
+    int split_kernel = 1;                           // 1: k_scan_apx (chunk-built pieces + Landau-Vishkin check), 2: k_scan_split (first generation), 0: block-tile kernel
+    bool attr_exact = false, attr_split = false, attr_apx = false;   // cudaFuncSetAttribute is per device: kept per engine
     // one spare text buffer and one spare plane buffer, so that re-creating a dataset of the same size
     // (a request that uploads its file every time) does not pay cudaMalloc/cudaFree of gigabytes
     void *pool_text = nullptr; size_t pool_text_cap = 0;
@@ -740,6 +758,8 @@ struct pm_dataset {
     std::vector<long long> newlines;   // sorted positions of '\n'
     long long fills_bufsize = -1;
     std::vector<long long> fill_starts; // host copy of S[] (pm_search_fills_device snaps its range to fills)
+    std::vector<long long> fill_ends;   // host copy of E[]
+    bool fills_complete = true;         // false while pm_search_stream is still extending the table
     long long *d_fills = nullptr;      // S[0..nfills) then E[0..nfills), then the forced cuts
     size_t fills_cap = 0;              // entries allocated at d_fills
     int nfills = 0;
@@ -852,6 +872,7 @@ static int upload_fills(pm_engine *e, pm_dataset *d, const std::vector<long long
     d->nfills = (int)S.size();
     d->ncuts = (int)cuts.size();
     d->fill_starts = S;
+    d->fill_ends = E;
     return PM_OK;
 }
 
@@ -895,7 +916,7 @@ void pm_engine_destroy(pm_engine *e)
     cudaStreamSynchronize(e->stream);
     if (e->pool_text) cudaFree(e->pool_text);
     if (e->pool_planes) cudaFree(e->pool_planes);
-    for (DevBuf *b : {&e->keys, &e->keys2, &e->cands, &e->hits, &e->hits2, &e->sel, &e->tables, &e->counters, &e->cubtmp}) b->release();
+    for (DevBuf *b : {&e->keys, &e->keys2, &e->cands, &e->hits, &e->hits2, &e->sel, &e->tables, &e->counters, &e->cubtmp, &e->scanbuf}) b->release();
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     if (e->h_count) cudaFreeHost(e->h_count);
     if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -907,6 +928,7 @@ void pm_engine_destroy(pm_engine *e)
 int pm_engine_set_stream(pm_engine *e, void *s)
 {
     if (!e) { g_err = "engine is NULL"; return PM_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     e->stream = s ? (cudaStream_t)s : e->own;
     return PM_OK;
 }
@@ -914,6 +936,7 @@ int pm_engine_set_stream(pm_engine *e, void *s)
 int pm_engine_set_scan_mode(pm_engine *e, int mode)
 {
     if (!e || mode < 0 || mode > 2) { g_err = "bad argument"; return PM_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     e->scan_mode = mode;
     return PM_OK;
 }
@@ -921,15 +944,17 @@ int pm_engine_set_scan_mode(pm_engine *e, int mode)
 int pm_engine_set_fused_filter(pm_engine *e, int on)
 {
     if (!e) { g_err = "bad argument"; return PM_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     e->fused_filter = on ? 1 : 0;
-    e->qgram_filter = on == 1 ? 1 : 0;
-    e->split_kernel = on == 3 ? 0 : 1;
+    e->qgram_filter = (on == 1 || on == 4) ? 1 : 0;
+    e->split_kernel = on == 3 ? 0 : (on == 4 || on == 5) ? 2 : 1;   // 4 / 5: first-generation k_scan_split with / without the q-gram count
     return PM_OK;
 }
 
 int pm_engine_set_buffer_size(pm_engine *e, int64_t bytes)
 {
     if (!e || bytes < 0) { g_err = "bad argument"; return PM_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     e->bufsize = bytes;
     return PM_OK;
 }
@@ -937,6 +962,7 @@ int pm_engine_set_buffer_size(pm_engine *e, int64_t bytes)
 int pm_engine_synchronize(pm_engine *e)
 {
     if (!e) { g_err = "engine is NULL"; return PM_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     CK(cudaSetDevice(e->device));
     CK(cudaStreamSynchronize(e->stream));
     return PM_OK;
@@ -945,7 +971,9 @@ int pm_engine_synchronize(pm_engine *e)
 int pm_dataset_create(pm_engine *e, const uint8_t *host, int64_t n, pm_dataset **out)
 {
     if (!e || !out || n < 0 || (!host && n > 0)) { g_err = "bad argument"; return PM_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     CK(cudaSetDevice(e->device));
+    if (n >= (1LL << PM_POS_BITS) - 4096) { g_err = "dataset too large (candidate keys hold 36-bit positions)"; return PM_ERR_UNSUPPORTED; }
     pm_dataset *d = new pm_dataset();
     d->e = e; d->n = n;
     void *p = nullptr;
@@ -974,6 +1002,8 @@ int pm_dataset_create(pm_engine *e, const uint8_t *host, int64_t n, pm_dataset *
 int pm_dataset_wrap_device(pm_engine *e, const uint8_t *dev, int64_t n, pm_dataset **out)
 {
     if (!e || !out || n < 0 || (!dev && n > 0)) { g_err = "bad argument"; return PM_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
+    if (n >= (1LL << PM_POS_BITS) - 4096) { g_err = "dataset too large (candidate keys hold 36-bit positions)"; return PM_ERR_UNSUPPORTED; }
     pm_dataset *d = new pm_dataset();
     d->e = e; d->n = n; d->d_text = dev; d->owned = nullptr;
     CK(cudaSetDevice(e->device));
@@ -987,6 +1017,7 @@ void pm_dataset_destroy(pm_dataset *d)
 {
     if (!d) return;
     pm_engine *e = d->e;
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     if (d->owned) {
@@ -1022,9 +1053,17 @@ void pm_host_free(void *p)
     if (p) cudaFreeHost(p);
 }
 
+static void finish_stats(pm_engine *e);
+
 int pm_get_stats(pm_engine *e, pm_stats *out)
 {
     if (!e || !out) { g_err = "bad argument"; return PM_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
+    if (e->stats_pending) {                              // asynchronous request: the events are read here
+        CK(cudaSetDevice(e->device));
+        CK(cudaStreamSynchronize(e->stream));
+        finish_stats(e);
+    }
     *out = e->stats;
     return PM_OK;
 }
@@ -1157,69 +1196,376 @@ static int upload_tables(pm_engine *e, const Compiled &c, const unsigned long lo
 }
 
 static unsigned packed_class_of(const pm::ByteSet &bs, bool *mixed);
+static inline int plane_of_class(unsigned cls) { return cls == 1 ? 0 : cls == 2 ? 1 : cls == 4 ? 2 : cls == 8 ? 3 : cls == 16 ? 4 : 5; }
 
-// scan + sort + verify: leaves ncand verified candidates (sorted) in e->cands
-static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c_full, long long a0, long long a1,
-                              const unsigned long long *dB, const unsigned long long *dTL, const unsigned long long *dTR,
-                              long long *ncand_out)
+// where the scan kernels append their candidate keys
+struct ScanTarget { unsigned long long *keys, *count; long long cap; };
+
+// does the scan of this compiled pattern run on the 2-bit planes?
+static bool scan_uses_packed(const pm_engine *e, const pm_dataset *d, const Compiled &c_full)
+{
+    const Compiled &c = c_full.scan ? *c_full.scan : c_full;
+    const bool packable = (c.dp.type == PM_PLAN_SIMPLE || c.dp.type == PM_PLAN_SPLIT) && c.dp.npieces <= 4 && d->hi != nullptr;
+    return packable && (e->scan_mode == 2 || (e->scan_mode == 0 && d->dna_like));
+}
+
+// ---- exact scan (k_scan_packed_exact): up to EX_MAXPAT patterns per pass over the planes ----
+static void fill_exact_pat(const Compiled &c, long long a0, long long a1, long long n, unsigned long long tag, ExactPat &pt)
+{
+    memset(&pt, 0, sizeof pt);
+    const DevPlan &dp = c.dp;
+    pt.a0 = a0; pt.a1 = std::min(a1, n - dp.L + 1); pt.keytag = tag; pt.L = dp.L;
+    for (int j = 0; j < dp.L; j++) {
+        const unsigned cls = packed_class_of(c.P.pos[j], nullptr);
+        if (cls == 31u) continue;                 // accepts every byte: no constraint (the window bound is checked per hit)
+        const int s = plane_of_class(cls);
+        if (s == 5) pt.cls[pt.npos[5]] = (unsigned char)cls;
+        pt.shift[s][pt.npos[s]++] = (unsigned char)j;
+    }
+}
+
+static int launch_exact(pm_engine *e, pm_dataset *d, const ExactPat *pats, int npat, unsigned long long bad, const ScanTarget &t)
+{
+    ExactArgs a;
+    memset(&a, 0, sizeof a);
+    long long lo = -1, hi = -1;
+    bool longp = false;
+    for (int p = 0; p < npat; p++) {
+        if (pats[p].a1 <= pats[p].a0) continue;
+        a.pat[a.npat++] = pats[p];
+        lo = lo < 0 ? pats[p].a0 : std::min(lo, pats[p].a0);
+        hi = std::max(hi, pats[p].a1);
+        longp = longp || pats[p].L > 32;
+    }
+    if (a.npat == 0) return PM_OK;
+    a.hi = d->hi; a.lo = d->lo; a.xx = d->xx; a.nwords = d->nwords; a.n = d->n;
+    a.tile0 = (lo / 32) / 128;
+    a.ntiles = ((hi - 1) / 32) / 128 + 1 - a.tile0;
+    a.bad = bad;
+    a.keys = t.keys; a.count = t.count; a.cap = t.cap;
+    const size_t smem = EX_STAGES * EX_STAGE_BYTES + 2 * EX_STAGES * 8;
+    if (!e->attr_exact) {
+        CK(cudaFuncSetAttribute(k_scan_packed_exact<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_scan_packed_exact<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        e->attr_exact = true;
+    }
+    const long long nbt = (a.ntiles + 7) / 8;
+    const int grid_ex = std::max((int)std::min<long long>(nbt, (long long)e->sms * 5), 1);
+    if (longp) k_scan_packed_exact<true><<<grid_ex, (EX_WARPS + 1) * 32, smem, e->stream>>>(a);
+    else k_scan_packed_exact<false><<<grid_ex, (EX_WARPS + 1) * 32, smem, e->stream>>>(a);
+    CK(cudaGetLastError());
+    e->stats.launches++;
+    e->stats.scan_bytes += a.ntiles * 128 * 4 * 3;
+    e->stats.scan_bases += (hi - lo) * a.npat;
+    e->stats.packed = 1;
+    return PM_OK;
+}
+
+// ---- approximate scan, second generation (k_scan_apx) ----
+static bool plain_triggers(const DevPlan &dp)
+{
+    for (int i = 0; i < dp.npieces; i++)
+        if (dp.trig[i] != (1ULL << (i * dp.L + dp.L - 1))) return false;
+    return true;
+}
+
+static bool apx_eligible(const pm_engine *e, const pm_dataset *d, const Compiled &c)
+{
+    const DevPlan &dp = c.dp;
+    return !c.scan && dp.type == PM_PLAN_SPLIT && scan_uses_packed(e, d, c) && e->fused_filter && e->split_kernel == 1 &&
+           dp.k >= 1 && dp.k <= 3 && dp.m + 2 * dp.k <= 64 && plain_triggers(dp);
+}
+
+// Chunk selection for k_scan_apx.  Candidate chunk sets: (A) every piece cut into 1..3 sub-chunks of about equal
+// information (then piece planes are ANDs of chunk planes and every pattern position is evaluated once), (B) uniform
+// tilings and equal-information segmentations that ignore the piece borders (pieces evaluated position by position),
+// (C) no q-gram count at all.  Cost in warp instructions per 8192-base warp tile: dense work + expected pattern starts
+// that reach the per-anchor check.
+static void build_apx_pat(const pm_engine *e, const Compiled &c, long long a0, long long a1, unsigned long long tag, ApxPat &out)
+{
+    const DevPlan &dp = c.dp;
+    const int m = dp.m, k = dp.k, L = dp.L, np = dp.npieces;
+    const int win = (dp.ins || dp.del) ? 2 * k + 1 : 1;
+    const int rows = k + 1;
+    memset(&out, 0, sizeof out);
+    out.a0 = a0; out.a1 = a1; out.keytag = tag;
+    out.m = m; out.k = k; out.L = L; out.npieces = np; out.indel = (dp.ins || dp.del) ? 1 : 0;
+    for (int i = 0; i < np; i++) out.V[i] = dp.V[i];
+    out.win = win;
+    std::vector<unsigned> pcls((size_t)m);
+    std::vector<double> pprob((size_t)m), info((size_t)m);
+    static const unsigned code_bit[4] = {1u, 2u, 8u, 4u};              // code = hi<<1|lo : A, C, T, G
+    for (int j = 0; j < m; j++) {
+        pcls[j] = packed_class_of(c.P.pos[j], nullptr);
+        pprob[j] = pcls[j] == 31u ? 1.0 : std::min(__builtin_popcount(pcls[j] & 15u) / 4.0 + 0.001, 1.0);
+        info[j] = pcls[j] == 31u ? 0.0 : -std::log2(pprob[j]);
+        for (int q = 0; q < 4; q++) if (pcls[j] & code_bit[q]) out.posmask[q] |= 1ULL << j;
+        if (pcls[j] & 16u) out.posmask[4] |= 1ULL << j;
+    }
+    double piece_rate[PM_MAX_PIECES] = {0};
+    for (int i = 0; i < np; i++) {
+        double pr = 1;
+        for (int j = 0; j < L; j++) pr *= pprob[dp.V[i] + j];
+        piece_rate[i] = pr;
+    }
+    int steps = 0;
+    for (int cw = 1; cw < win; cw += std::min(cw, win - cw)) steps++;
+    // per pattern start that reaches the sparse stage: extraction + 1/32 of a Landau-Vishkin round
+    const double anchor_ops = (m + 2 * k <= 32 ? 1.0 : 1.6) * (4.0 + 1.2 * (2 * k + 1) * (k + 1)) + 3.0;
+    struct Seg { int b, e, piece; };
+    ApxPat best = out;
+    double best_cost = -1;
+    auto evaluate = [&](const std::vector<Seg> &segs, bool derive) {
+        ApxPat cur = out;
+        double ops = 0;
+        std::vector<std::pair<int, int>> span;                         // constrained positions of each COUNTED chunk: [first, last]
+        std::vector<int> covered((size_t)m, 0);
+        for (const Seg &sg : segs) {
+            if (cur.nch >= AX_MAXCH) { if (derive) return; break; }
+            ApxChunk ch;
+            memset(&ch, 0, sizeof ch);
+            ch.piece = 0xff;
+            double pr = 1;
+            int first = -1, last = -1;
+            bool cut = false;
+            for (int j = sg.b; j < sg.e; j++) {
+                if (pcls[j] == 31u) continue;
+                if (first < 0) first = j;
+                if (ch.npos >= AX_MAXLEN || j - first >= 32) { cut = true; break; }
+                ch.t[ch.npos] = (unsigned char)(j - first);
+                ch.cls[ch.npos] = (unsigned char)pcls[j];
+                ch.npos++;
+                pr *= pprob[j];
+                last = j;
+            }
+            if (first < 0) continue;
+            if (cut && derive) return;                                 // a derived piece needs all its positions in chunks
+            pr = std::min(pr * win, 1.0);
+            ch.counted = pr <= 0.6 ? 1 : 0;                            // hardly ever missing: not worth counting
+            if (!ch.counted && !derive) continue;
+            ch.off = (unsigned char)(first + (win > 1 ? 0 : k));
+            ch.poff = (unsigned char)(first + k);
+            if (derive) ch.piece = (unsigned char)sg.piece;
+            ops += 45.0 * ch.npos + (derive ? 18.0 : 0.0);
+            if (ch.counted) { ops += 20.0 * steps + 26.0 + 16.0 * rows; span.push_back({first, last}); }
+            for (int t = 0; t < ch.npos; t++) covered[first + ch.t[t]] = 1;
+            cur.ch[cur.nch++] = ch;
+        }
+        int ncounted = (int)span.size();
+        if (ncounted <= k) {                                           // k missing chunks are always allowed: no count
+            if (!derive) { cur.nch = 0; ops = 0; }
+            else for (int g = 0; g < cur.nch; g++) {
+                if (cur.ch[g].counted) ops -= 20.0 * steps + 26.0 + 16.0 * rows;
+                cur.ch[g].counted = 0;
+            }
+            ncounted = 0;
+            span.clear();
+        }
+        cur.ncounted = ncounted;
+        // pieces: derived from their chunks, or position by position
+        int dp_n = 0;
+        for (int i = 0; i < np; i++) {
+            int ncons = 0, ncov = 0;
+            for (int j = dp.V[i]; j < dp.V[i] + L; j++) if (pcls[j] != 31u) { ncons++; ncov += covered[j]; }
+            if (ncons == 0) { cur.dwild[i] = 1; continue; }
+            bool derived = derive && ncov == ncons;
+            if (derived) {
+                int gf = -1, gl = -1;
+                for (int g = 0; g < cur.nch; g++) if (cur.ch[g].piece == i) { if (gf < 0) gf = g; gl = g; }
+                if (gf < 0) derived = false;
+                else { cur.ch[gf].first = 1; cur.ch[gl].last = 1; }
+            }
+            if (!derived) {
+                for (int g = 0; g < cur.nch; g++) if (cur.ch[g].piece == i) { cur.ch[g].piece = 0xff; ops -= 18.0; }
+                for (int j = dp.V[i]; j < dp.V[i] + L; j++) {
+                    if (pcls[j] == 31u) continue;
+                    if (dp_n >= AX_MAXDENSE) return;
+                    cur.dshift[dp_n] = (unsigned char)(k + j);
+                    cur.dcls[dp_n] = (unsigned char)pcls[j];
+                    dp_n++;
+                    cur.dn[i]++;
+                    ops += 43.0;
+                }
+                ops += 12.0;
+            }
+        }
+        // uncounted chunks that build no piece are useless
+        {
+            int w = 0;
+            for (int g = 0; g < cur.nch; g++) {
+                if (!cur.ch[g].counted && cur.ch[g].piece == 0xff) { ops -= 45.0 * cur.ch[g].npos; continue; }
+                cur.ch[w++] = cur.ch[g];
+            }
+            cur.nch = w;
+        }
+        // Expected pattern starts that survive.  An anchor of piece i matched that piece exactly, so the chunk
+        // positions inside the piece are present for free; the others are taken as independent.
+        double survivors = 0;
+        for (int i = 0; i < np; i++) {
+            double pass = 1;
+            if (ncounted > 0) {
+                std::vector<double> dist((size_t)ncounted + 1, 0.0);
+                dist[0] = 1;
+                for (int g = 0; g < ncounted; g++) {
+                    double pout = 1, pall = 1;
+                    for (int j = span[g].first; j <= span[g].second; j++) {
+                        if (pcls[j] == 31u) continue;
+                        pall *= pprob[j];
+                        if (j < dp.V[i] || j >= dp.V[i] + L) pout *= pprob[j];
+                    }
+                    const double pgi = std::min(pout + (win - 1) * pall, 1.0);
+                    for (int r = g + 1; r >= 0; r--)
+                        dist[r] = dist[r] * pgi + (r > 0 ? dist[r - 1] * (1 - pgi) : 0.0);
+                }
+                pass = 0;
+                for (int r = 0; r <= k && r <= ncounted; r++) pass += dist[r];
+            }
+            survivors += piece_rate[i] * pass;
+        }
+        const double cost = ops + std::min(survivors, 1.0) * 8192.0 * anchor_ops;
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = cur; }
+    };
+    // (C) no count, pieces position by position
+    evaluate({}, false);
+    if (e->qgram_filter) {
+        // (A) pieces cut into 1..3 sub-chunks of about equal information
+        {
+            std::vector<int> parts((size_t)np, 1);
+            for (;;) {
+                std::vector<Seg> segs;
+                for (int i = 0; i < np; i++) {
+                    const int pb = dp.V[i], pe = dp.V[i] + L;
+                    double tot = 0;
+                    for (int j = pb; j < pe; j++) tot += info[j];
+                    int jb = pb;
+                    double acc = 0;
+                    for (int r = 1; r <= parts[i] && jb < pe; r++) {
+                        const double target = tot * r / parts[i];
+                        int je = jb;
+                        double a2 = acc;
+                        while (je < pe && (je == jb || std::fabs(a2 + info[je] - target) <= std::fabs(a2 - target))) { a2 += info[je]; je++; }
+                        if (r == parts[i]) { je = pe; }
+                        segs.push_back({jb, je, i});
+                        acc = 0;
+                        for (int j = pb; j < je; j++) acc += info[j];
+                        jb = je;
+                    }
+                }
+                evaluate(segs, true);
+                int q = 0;
+                while (q < np && ++parts[q] > 3) parts[q++] = 1;
+                if (q == np) break;
+            }
+        }
+        // (B1) uniform tilings of every length and phase
+        for (int q = 2; q <= AX_MAXLEN; q++)
+            for (int a_off = 0; a_off < q; a_off++) {
+                std::vector<Seg> segs;
+                for (int j0 = a_off - q; j0 < m; j0 += q) {
+                    const int jb = std::max(j0, 0), je = std::min(j0 + q, m);
+                    if (je > jb) segs.push_back({jb, je, -1});
+                }
+                evaluate(segs, false);
+            }
+        // (B2) T segments of (nearly) equal information: wildcards carry none, so chunks stretch over them
+        {
+            std::vector<double> cum((size_t)m + 1, 0.0);
+            for (int j = 0; j < m; j++) cum[j + 1] = cum[j] + info[j];
+            for (int T = k + 1; T <= std::min(2 * k + 3, AX_MAXCH); T++) {
+                std::vector<Seg> segs;
+                int jb = 0;
+                for (int r = 1; r <= T && jb < m; r++) {
+                    const double target = cum[m] * r / T;
+                    int je = jb + 1;
+                    while (je < m && std::fabs(cum[je + 1] - target) <= std::fabs(cum[je] - target)) je++;
+                    if (r == T) je = m;
+                    segs.push_back({jb, je, -1});
+                    jb = je;
+                }
+                evaluate(segs, false);
+            }
+        }
+    }
+    out = best;
+}
+
+static int launch_apx(pm_engine *e, pm_dataset *d, const ApxPat *pats, int npat, const ScanTarget &t)
+{
+    ApxArgs a;
+    memset(&a, 0, sizeof a);
+    long long lo = -1, hi = -1;
+    bool narrow = true;
+    int k = 0;
+    for (int p = 0; p < npat; p++) {
+        if (pats[p].a1 <= pats[p].a0) continue;
+        a.pat[a.npat++] = pats[p];
+        // pattern starts b = anchor - k - V[i] >= 0 must be covered for every anchor in [a0, a1)
+        const long long b0 = std::max<long long>(pats[p].a0 - pats[p].k - pats[p].V[pats[p].npieces - 1], 0);
+        lo = lo < 0 ? b0 : std::min(lo, b0);
+        hi = std::max(hi, pats[p].a1);
+        if (pats[p].m + 2 * pats[p].k > 32) narrow = false;
+        k = pats[p].k;
+    }
+    if (a.npat == 0) return PM_OK;
+    a.hi = d->hi; a.lo = d->lo; a.xx = d->xx; a.nwords = d->nwords; a.n = d->n;
+    a.tile0 = (lo / 32) / 128;
+    a.ntiles = ((hi - 1) / 32) / 128 + 1 - a.tile0;
+    a.keys = t.keys; a.count = t.count; a.cap = t.cap;
+    const size_t smem = SP_STAGES * EX_STAGE_BYTES + 2 * SP_STAGES * 8;
+    if (!e->attr_apx) {
+#define PM_ATTR(R, W) CK(cudaFuncSetAttribute(k_scan_apx<R, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+        PM_ATTR(2, unsigned); PM_ATTR(3, unsigned); PM_ATTR(4, unsigned);
+        PM_ATTR(2, unsigned long long); PM_ATTR(3, unsigned long long); PM_ATTR(4, unsigned long long);
+#undef PM_ATTR
+        e->attr_apx = true;
+    }
+    const long long nbt = (a.ntiles + 7) / 8;
+    const int grid = std::max((int)std::min<long long>(nbt, (long long)e->sms * SP_CTAS), 1);
+#define PM_LAUNCH(R, W) k_scan_apx<R, W><<<grid, EX_WARPS * 32, smem, e->stream>>>(a)
+    if (narrow) { if (k == 1) PM_LAUNCH(2, unsigned); else if (k == 2) PM_LAUNCH(3, unsigned); else PM_LAUNCH(4, unsigned); }
+    else { if (k == 1) PM_LAUNCH(2, unsigned long long); else if (k == 2) PM_LAUNCH(3, unsigned long long); else PM_LAUNCH(4, unsigned long long); }
+#undef PM_LAUNCH
+    CK(cudaGetLastError());
+    e->stats.launches++;
+    e->stats.scan_bytes += a.ntiles * 128 * 4 * 3;
+    e->stats.scan_bases += (hi - lo) * a.npat;
+    e->stats.packed = 1;
+    e->stats.qgram_chunks = a.pat[0].ncounted;
+    return PM_OK;
+}
+
+// One scan launch for one compiled pattern over the anchors [a0, a1): candidate keys (tagged) are appended to t.
+static int launch_scan(pm_engine *e, pm_dataset *d, const Compiled &c_full, long long a0, long long a1, const Fills &fills,
+                       const unsigned long long *dB, const unsigned long long *dTL, const unsigned long long *dTR,
+                       const ScanTarget &t, unsigned long long tag, unsigned long long bad)
 {
     const Compiled &c = c_full.scan ? *c_full.scan : c_full;   // what the scan kernels see (EXTENDED: the plain window)
     const DevPlan &dp = c.dp;
-    const DevPlan &vdp = c_full.dp;                             // what verification sees
     const long long n = d->n;
-    int rc;
-    Fills fills;
-    if ((rc = ensure_fills(e, d, &fills))) return rc;
-    const bool packable = (dp.type == PM_PLAN_SIMPLE || dp.type == PM_PLAN_SPLIT) && dp.npieces <= 4 && d->hi != nullptr;
-    const bool use_packed = packable && (e->scan_mode == 2 || (e->scan_mode == 0 && d->dna_like));
-    if ((rc = e->counters.reserve(64))) return rc;
-    unsigned long long *d_count = (unsigned long long *)e->counters.p;
-    long long cap = std::max<long long>((long long)(e->keys.cap / 8), 1 << 16);
-    long long ncand = 0;
-    for (int attempt = 0; attempt < 3; attempt++) {
-        if ((rc = e->keys.reserve((size_t)cap * 8))) return rc;
-        CK(cudaMemsetAsync(d_count, 0, 16, e->stream));
-        CK(cudaEventRecord(e->ev[0], e->stream));
+    const bool use_packed = scan_uses_packed(e, d, c_full);
+    {
         if (use_packed) {
             const long long wend = std::min(a1, n - dp.L + 1);
             if (wend > a0) {
                 const long long tile0 = (a0 / 32) / 128;
                 const long long ntiles = ((wend - 1) / 32) / 128 + 1 - tile0;
-                const long long warps_needed = ntiles;
-                const int grid = std::max((int)std::min<long long>((warps_needed + 7) / 8, (long long)e->sms * 8), 1);
-                // class of one pattern position over the packed alphabet: bits A,C,G,T and X (= any non-ACGT byte)
                 auto packed_class = [&](const pm::ByteSet &bs) -> unsigned { return packed_class_of(bs, nullptr); };
-                auto plane_of = [](unsigned cls) -> int { return cls == 1 ? 0 : cls == 2 ? 1 : cls == 4 ? 2 : cls == 8 ? 3 : cls == 16 ? 4 : 5; };
+                auto plane_of = [](unsigned cls) -> int { return plane_of_class(cls); };
                 if (dp.type == PM_PLAN_SIMPLE) {
-                    ExactArgs a;
-                    memset(&a, 0, sizeof a);
-                    a.hi = d->hi; a.lo = d->lo; a.xx = d->xx; a.nwords = d->nwords; a.n = n; a.a0 = a0; a.a1 = wend;
-                    a.tile0 = tile0; a.ntiles = ntiles; a.L = dp.L;
-                    for (int j = 0; j < dp.L; j++) {
-                        const unsigned cls = packed_class(c.P.pos[j]);
-                        if (cls == 31u) continue;                 // accepts every byte: no constraint (the window bound is checked per hit)
-                        const int s = plane_of(cls);
-                        if (s == 5) a.cls[a.npos[5]] = (unsigned char)cls;
-                        a.shift[s][a.npos[s]++] = (unsigned char)j;
-                    }
-                    a.keys = (unsigned long long *)e->keys.p; a.count = d_count; a.cap = cap;
-                    const size_t smem = EX_STAGES * EX_STAGE_BYTES + 2 * EX_STAGES * 8;
-                    static bool attr_set = false;
-                    if (!attr_set) {
-                        CK(cudaFuncSetAttribute(k_scan_packed_exact<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                        CK(cudaFuncSetAttribute(k_scan_packed_exact<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                        attr_set = true;
-                    }
-                    const long long nbt = (ntiles + 7) / 8;
-                    const int grid_ex = std::max((int)std::min<long long>(nbt, (long long)e->sms * 5), 1);
-                    if (dp.L > 32) k_scan_packed_exact<true><<<grid_ex, (EX_WARPS + 1) * 32, smem, e->stream>>>(a);
-                    else k_scan_packed_exact<false><<<grid_ex, (EX_WARPS + 1) * 32, smem, e->stream>>>(a);
+                    ExactPat pt;
+                    fill_exact_pat(c, a0, a1, n, tag, pt);
+                    return launch_exact(e, d, &pt, 1, bad, t);
+                } else if (apx_eligible(e, d, c)) {
+                    ApxPat ap;
+                    build_apx_pat(e, c, a0, wend, tag, ap);
+                    return launch_apx(e, d, &ap, 1, t);
                 } else {
                     PackedArgs<4> a;
                     memset(&a, 0, sizeof a);
                     a.hi = d->hi; a.lo = d->lo; a.xx = d->xx; a.nwords = d->nwords; a.n = n; a.a0 = a0; a.a1 = wend;
                     a.tile0 = tile0; a.ntiles = ntiles;
                     a.L = dp.L; a.npieces = dp.npieces;
+                    a.keytag = tag;
                     for (int i = 0; i < dp.npieces; i++) {
                         for (int j = 0; j < dp.npieces; j++)
                             if (dp.trig[i] & (1ULL << (j * dp.L + dp.L - 1))) a.trigsets[i] |= 1u << j;
@@ -1231,7 +1577,7 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c_ful
                             a.pos[i][j] = pp;
                         }
                     }
-                    a.keys = (unsigned long long *)e->keys.p; a.count = d_count; a.cap = cap;
+                    a.keys = t.keys; a.count = t.count; a.cap = t.cap;
                     PackedVerify<4> pv;
                     memset(&pv, 0, sizeof pv);
                     pv.enabled = (dp.k <= 3 && e->fused_filter && dp.m <= 64) ? 1 : 0;   // the Myers filter keeps 64-bit parts
@@ -1259,7 +1605,7 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c_ful
                     for (int i = 0; i < dp.npieces; i++) if (a.trigsets[i] != (1u << i)) plain_trig = false;
                     long long t0q = tile0, ntq = ntiles;
                     // register-resident kernel in pattern-start coordinates (packed.cuh: k_scan_split)
-                    const bool bcoords = pv.enabled && e->split_kernel && plain_trig && dp.k >= 1 && dp.k <= 3 && dp.m + 2 * dp.k <= 64;
+                    const bool bcoords = pv.enabled && e->split_kernel == 2 && plain_trig && dp.k >= 1 && dp.k <= 3 && dp.m + 2 * dp.k <= 64;
                     if (bcoords && e->qgram_filter) {
                         const int win = (dp.ins || dp.del) ? 2 * dp.k + 1 : 1;
                         std::vector<unsigned> pcls((size_t)dp.m);
@@ -1378,13 +1724,12 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c_ful
                     const int grid_bk = std::max((int)std::min<long long>((ntq + 7) / 8, (long long)e->sms * 6), 1);
                     const int grid_sp = std::max((int)std::min<long long>((ntq + 7) / 8, (long long)e->sms * SP_CTAS), 1);
                     const size_t smem_sp = SP_STAGES * EX_STAGE_BYTES + 2 * SP_STAGES * 8;
-                    static bool sp_attr_set = false;
-                    if (!sp_attr_set) {                    // static queues + dynamic ring exceed the 48 KB default
+                    if (!e->attr_split) {                    // static queues + dynamic ring exceed the 48 KB default
 #define PM_ATTR(W, R) CK(cudaFuncSetAttribute(k_scan_split<4, W, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sp))
                         PM_ATTR(unsigned, 2); PM_ATTR(unsigned, 3); PM_ATTR(unsigned, 4);
                         PM_ATTR(unsigned long long, 2); PM_ATTR(unsigned long long, 3); PM_ATTR(unsigned long long, 4);
 #undef PM_ATTR
-                        sp_attr_set = true;
+                        e->attr_split = true;
                     }
 #define PM_LAUNCH(W, R) do { if (bcoords) k_scan_split<4, W, R><<<grid_sp, EX_WARPS * 32, smem_sp, e->stream>>>(a, pv, qf); \
                              else k_scan_packed<4, W, R><<<grid_bk, 256, 0, e->stream>>>(a, pv); } while (0)
@@ -1394,8 +1739,8 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c_ful
 #undef PM_LAUNCH
                 }
                 e->stats.launches++;
-                e->stats.scan_bytes = ntiles * 128 * 4 * 3;
-                e->stats.scan_bases = wend - a0;
+                e->stats.scan_bytes += ntiles * 128 * 4 * 3;
+                e->stats.scan_bases += wend - a0;
                 e->stats.packed = 1;
             }
         } else if (dp.type == PM_PLAN_SIMPLE || dp.type == PM_PLAN_SPLIT) {
@@ -1410,19 +1755,19 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c_ful
                     a.text = d->d_text; a.n = n; a.p0 = p0; a.p1 = p1; a.tile0 = tile0; a.ntiles = ntiles; a.B = dB;
                     a.init = (unsigned)dp.init; a.fin = (unsigned)dp.fin;
                     for (int i = 0; i < PM_MAX_PIECES; i++) a.trig[i] = (unsigned)dp.trig[i];
-                    a.L = dp.L; a.npieces = dp.npieces; a.keys = (unsigned long long *)e->keys.p; a.count = d_count; a.cap = cap;
+                    a.L = dp.L; a.npieces = dp.npieces; a.keys = t.keys; a.count = t.count; a.cap = t.cap; a.keytag = tag;
                     k_scan_bytes<unsigned><<<grid, SCAN_THREADS, 0, e->stream>>>(a);
                 } else {
                     ScanArgs<unsigned long long> a;
                     a.text = d->d_text; a.n = n; a.p0 = p0; a.p1 = p1; a.tile0 = tile0; a.ntiles = ntiles; a.B = dB;
                     a.init = dp.init; a.fin = dp.fin;
                     for (int i = 0; i < PM_MAX_PIECES; i++) a.trig[i] = dp.trig[i];
-                    a.L = dp.L; a.npieces = dp.npieces; a.keys = (unsigned long long *)e->keys.p; a.count = d_count; a.cap = cap;
+                    a.L = dp.L; a.npieces = dp.npieces; a.keys = t.keys; a.count = t.count; a.cap = t.cap; a.keytag = tag;
                     k_scan_bytes<unsigned long long><<<grid, SCAN_THREADS, 0, e->stream>>>(a);
                 }
                 e->stats.launches++;
-                e->stats.scan_bytes = p1 - p0;
-                e->stats.scan_bases = p1 - p0;
+                e->stats.scan_bytes += p1 - p0;
+                e->stats.scan_bases += p1 - p0;
             }
         } else {
             // BWD: anchors w with w + (L - k) <= n ; FWD: anchors pos in [1, n]
@@ -1433,15 +1778,43 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c_ful
                 DenseArgs a;
                 a.pl = dp; a.text = d->d_text; a.n = n; a.a0 = lo; a.a1 = hi; a.TL = dTL; a.TR = dTR;
                 a.pl.start_line = 0;          // '^' is not monotone in the scan start: k_verify / k_chain decide it
-                a.keys = (unsigned long long *)e->keys.p; a.count = d_count; a.cap = cap; a.fills = fills;
+                a.keys = t.keys; a.count = t.count; a.cap = t.cap; a.fills = fills; a.keytag = tag;
                 const long long want = (hi - lo + 255) / 256;
                 const int grid = (int)std::min<long long>(want, (long long)e->sms * 16);
                 k_scan_dense<<<grid, 256, 0, e->stream>>>(a);
                 e->stats.launches++;
-                e->stats.scan_bytes = hi - lo;
-                e->stats.scan_bases = hi - lo;
+                e->stats.scan_bytes += hi - lo;
+                e->stats.scan_bases += hi - lo;
             }
         }
+
+    }
+    CK(cudaGetLastError());
+    return PM_OK;
+}
+
+// scan + sort + verify: leaves ncand verified candidates (sorted) in e->cands
+static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c_full, long long a0, long long a1,
+                              const unsigned long long *dB, const unsigned long long *dTL, const unsigned long long *dTR,
+                              long long *ncand_out)
+{
+    const DevPlan &vdp = c_full.dp;                             // what verification sees
+    const long long n = d->n;
+    int rc;
+    Fills fills;
+    if ((rc = ensure_fills(e, d, &fills))) return rc;
+    const bool use_packed = scan_uses_packed(e, d, c_full);
+    if ((rc = e->counters.reserve(64))) return rc;
+    unsigned long long *d_count = (unsigned long long *)e->counters.p;
+    long long cap = std::max<long long>((long long)(e->keys.cap / 8), 1 << 16);
+    long long ncand = 0;
+    for (int attempt = 0; attempt < 3; attempt++) {
+        if ((rc = e->keys.reserve((size_t)cap * 8))) return rc;
+        CK(cudaMemsetAsync(d_count, 0, 16, e->stream));
+        CK(cudaEventRecord(e->ev[0], e->stream));
+        e->stats.scan_bytes = 0; e->stats.scan_bases = 0;
+        const ScanTarget tgt{(unsigned long long *)e->keys.p, d_count, cap};
+        if ((rc = launch_scan(e, d, c_full, a0, a1, fills, dB, dTL, dTR, tgt, 0ULL, ((unsigned long long)(n + 1) << 4) | 15ULL))) return rc;
         CK(cudaGetLastError());
         CK(cudaEventRecord(e->ev[1], e->stream));
         CK(cudaMemcpyAsync(e->h_count, d_count, 16, cudaMemcpyDeviceToHost, e->stream));
@@ -1450,6 +1823,8 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c_ful
         if (ncand <= cap) break;
         cap = ncand + 1024;                                    // grow and rescan
     }
+    if (ncand > cap) { g_err = "candidate buffer keeps overflowing"; return PM_ERR_CUDA; }
+    if (ncand >= (1LL << 31) - 1) { g_err = "more than 2^31 candidates: not supported"; return PM_ERR_UNSUPPORTED; }
     const long long nplaceholders = (long long)e->h_count[1];  // out-of-range slots written by k_scan_packed_exact
     e->stats.candidates = ncand - nplaceholders;
     // ---- sort ----
@@ -1557,6 +1932,7 @@ static int resolve_candidates(pm_engine *e, pm_dataset *d, const Compiled &c, co
     }
     *nhits = nh;
     e->stats.hits = nh;
+    e->last_hits = (const pm_hit *)e->hits2.p;
     bool overflow = false;
     CK(cudaEventRecord(e->ev[5], e->stream));
     if (hits && nh > 0) {
@@ -1577,11 +1953,13 @@ static void finish_stats(pm_engine *e)
     cudaEventElapsedTime(&e->stats.chain_ms, e->ev[3], e->ev[5]);
     cudaEventElapsedTime(&e->stats.total_ms, e->ev[0], e->ev[5]);
     (void)cudaGetLastError();                            // an unrecorded event must not poison later calls
+    e->stats_pending = false;
 }
 
 int pm_search(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt, pm_hit *hits, int64_t cap, int64_t *nhits)
 {
     if (!e || !d || !pattern || !kopt || !nhits || d->e != e) { g_err = "bad argument"; return PM_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     CK(cudaSetDevice(e->device));
     (void)cudaGetLastError();
     Compiled c;
@@ -1633,6 +2011,7 @@ int pm_search_fills_device(pm_engine *e, pm_dataset *d, const char *pattern, con
                            pm_hit *dev_hits, int64_t cap, int64_t *nhits, int64_t *dev_count)
 {
     if (!e || !d || !pattern || !kopt || !nhits || d->e != e) { g_err = "bad argument"; return PM_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     CK(cudaSetDevice(e->device));
     (void)cudaGetLastError();
     Compiled c;
@@ -1660,6 +2039,8 @@ int pm_search_fills_device(pm_engine *e, pm_dataset *d, const char *pattern, con
 
 int pm_last_hits(pm_engine *e, pm_hit *hits, int64_t cap, int64_t *nhits);
 
+#include "request.cuh"
+
 // Cold request: the file is still in host memory.  Upload it in chunks on a copy stream and, while the next chunk
 // is on the PCIe bus, pack the chunk that has arrived into the 2-bit planes and search the buffer fills that it
 // completes (fills are independent, see pm_search_fills_device).  What remains after the last byte has landed is the
@@ -1668,13 +2049,15 @@ int pm_search_stream(pm_engine *e, const uint8_t *host, int64_t n, int npat, con
                      int64_t chunk_bytes, pm_hit *hits, int64_t cap, int64_t *offsets, pm_dataset **out)
 {
     if (!e || !out || n < 0 || (!host && n > 0) || npat < 1 || !patterns || !kopt || !offsets) { g_err = "bad argument"; return PM_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     CK(cudaSetDevice(e->device));
     (void)cudaGetLastError();
-    std::vector<Compiled> comp((size_t)npat);
-    for (int p = 0; p < npat; p++) {
-        int rc = compile(patterns[p], kopt, comp[p], true);
+    Request rq;
+    {
+        int rc = compile_request(npat, patterns, kopt, rq);
         if (rc) return rc;
     }
+    std::vector<int64_t> offs((size_t)npat + 1, 0);
     const long long gran = 32LL * 1024;                                    // chunk edges on block-tile boundaries of the planes
     long long chunk = chunk_bytes > 0 ? chunk_bytes : (256LL << 20);
     chunk = std::max(gran, chunk / gran * gran);
@@ -1772,25 +2155,25 @@ int pm_search_stream(pm_engine *e, const uint8_t *host, int64_t n, int npat, con
         const long long nfinal = (long long)S.size();
         if (nfinal <= ndone && !last) continue;
         if ((rc = upload_fills(e, d, S, E, cuts))) break;
-        for (int p = 0; p < npat && rc == PM_OK; p++) {
-            const unsigned long long *dB, *dTL, *dTR;
-            e->stats = pm_stats{};
-            if ((rc = upload_tables(e, comp[p], &dB, &dTL, &dTR))) break;
-            int64_t nh = 0;
+        d->fills_complete = last;
+        {
+            // the fills this chunk completed, every pattern of the request in one pass (request.cuh)
+            for (int p = 0; p < npat; p++) fill_anchor_range(d, rq.comp[p], ndone, nfinal, &rq.a0[p], &rq.a1[p]);
             tmp.resize(std::max<size_t>(tmp.size(), 1 << 16));
-            rc = search_fill_range(e, d, comp[p], dB, dTL, dTR, ndone, nfinal, tmp.data(), (int64_t)tmp.size(), &nh, false);
+            rc = run_request_host(e, d, rq, tmp.data(), (int64_t)tmp.size(), offs.data());
             if (rc == PM_ERR_OVERFLOW) {                                   // the list is still on the device
+                int64_t nh = offs[(size_t)npat];
                 tmp.resize((size_t)nh);
                 rc = pm_last_hits(e, tmp.data(), nh, &nh);
             }
             if (rc) break;
-            found[p].insert(found[p].end(), tmp.begin(), tmp.begin() + nh);
+            for (int p = 0; p < npat; p++) found[p].insert(found[p].end(), tmp.begin() + offs[(size_t)p], tmp.begin() + offs[(size_t)p + 1]);
             finish_stats(e);
             total.scan_ms += e->stats.scan_ms; total.sort_ms += e->stats.sort_ms; total.verify_ms += e->stats.verify_ms;
             total.chain_ms += e->stats.chain_ms; total.total_ms += e->stats.total_ms;
             total.candidates += e->stats.candidates; total.verified += e->stats.verified; total.hits += e->stats.hits;
             total.scan_bytes += e->stats.scan_bytes; total.scan_bases += e->stats.scan_bases; total.launches += e->stats.launches;
-            total.packed = e->stats.packed; total.qgram_chunks = e->stats.qgram_chunks;
+            total.packed = e->stats.packed; total.qgram_chunks = e->stats.qgram_chunks; total.syncs += e->stats.syncs;
         }
         ndone = nfinal;
     }
@@ -1798,6 +2181,7 @@ int pm_search_stream(pm_engine *e, const uint8_t *host, int64_t n, int npat, con
     drop_events();
 #undef CKD
     if (rc) return fail(rc);
+    d->fills_complete = true;
     e->stats = total;
     *out = d;
     int64_t off = 0;
@@ -1817,12 +2201,13 @@ int pm_search_stream(pm_engine *e, const uint8_t *host, int64_t n, int npat, con
 int pm_last_hits(pm_engine *e, pm_hit *hits, int64_t cap, int64_t *nhits)
 {
     if (!e || !nhits) { g_err = "bad argument"; return PM_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     CK(cudaSetDevice(e->device));
     const long long nh = e->stats.hits;
     *nhits = nh;
     if (hits && nh > 0) {
         if (nh > cap) { g_err = "hit buffer too small"; return PM_ERR_OVERFLOW; }
-        CK(cudaMemcpyAsync(hits, e->hits2.p, (size_t)nh * sizeof(pm_hit), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(hits, e->last_hits ? (const void *)e->last_hits : e->hits2.p, (size_t)nh * sizeof(pm_hit), cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
     }
     return PM_OK;
@@ -1958,6 +2343,7 @@ static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char 
     offsets[0] = 0;
     for (int b = 0; b < npat; b++) offsets[b + 1] = offsets[b] + (int64_t)perpat[b];
     e->stats.hits = nh;
+    e->last_hits = (const pm_hit *)e->hits2.p;
     bool overflow = false;
     if (hits && nh > 0) {
         if (nh > cap) overflow = true;
@@ -1970,30 +2356,47 @@ static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char 
     return PM_OK;
 }
 
+int pm_search_request(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
+                      pm_hit *hits, int64_t cap, int64_t *offsets);
+
 int pm_search_batch(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
                     pm_hit *hits, int64_t cap, int64_t *offsets)
 {
     if (!e || !d || npat < 0 || !patterns || !offsets || !kopt) { g_err = "bad argument"; return PM_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     {
         const int frc = search_batch_fused(e, d, npat, patterns, kopt, hits, cap, offsets);
         if (frc != 1) return frc;
     }
+    // general batches (errors allowed, any plan type): groups of patterns through the request pipeline
+    const int group = 32;
     int64_t total = 0;
     offsets[0] = 0;
     pm_stats acc{};
-    for (int i = 0; i < npat; i++) {
-        int64_t nh = 0;
-        int rc = pm_search(e, d, patterns[i], kopt, hits ? hits + total : nullptr, hits ? cap - total : 0, &nh);
+    bool overflow = false;
+    std::vector<int64_t> off((size_t)group + 1);
+    for (int i0 = 0; i0 < npat; i0 += group) {
+        const int g = std::min(group, npat - i0);
+        const bool room = hits && total <= cap && !overflow;
+        int rc = pm_search_request(e, d, g, patterns + i0, kopt, room ? hits + total : nullptr, room ? cap - total : 0, off.data());
+        if (rc == PM_ERR_OVERFLOW) { overflow = true; rc = PM_OK; }
         if (rc) return rc;
-        total += nh;
-        offsets[i + 1] = total;
-        acc.scan_ms += e->stats.scan_ms; acc.sort_ms += e->stats.sort_ms; acc.verify_ms += e->stats.verify_ms;
-        acc.chain_ms += e->stats.chain_ms; acc.total_ms += e->stats.total_ms;
-        acc.candidates += e->stats.candidates; acc.verified += e->stats.verified; acc.hits += e->stats.hits;
-        acc.scan_bytes += e->stats.scan_bytes; acc.scan_bases += e->stats.scan_bases; acc.launches += e->stats.launches;
-        acc.packed = e->stats.packed;
+        for (int q = 0; q < g; q++) offsets[i0 + q + 1] = total + off[(size_t)q + 1];
+        total += off[(size_t)g];
+        pm_stats st{};
+        pm_get_stats(e, &st);
+        acc.scan_ms += st.scan_ms; acc.sort_ms += st.sort_ms; acc.verify_ms += st.verify_ms;
+        acc.chain_ms += st.chain_ms; acc.total_ms += st.total_ms;
+        acc.candidates += st.candidates; acc.verified += st.verified; acc.hits += st.hits;
+        acc.scan_bytes += st.scan_bytes; acc.scan_bases += st.scan_bases; acc.launches += st.launches; acc.syncs += st.syncs;
+        acc.packed = st.packed;
     }
     e->stats = acc;
+    if (overflow || (hits && total > cap)) {
+        if (npat > group) e->stats.hits = -1;            // the device holds only the last group's list: pm_last_hits does not apply
+        g_err = "hit buffer too small";
+        return PM_ERR_OVERFLOW;
+    }
     return PM_OK;
 }
 
@@ -2016,6 +2419,7 @@ static int candidates_impl(pm_engine *e, pm_dataset *d, const char *pattern, con
                            pm_candidate *cands, int64_t cap, int64_t *ncands, cudaMemcpyKind kind)
 {
     if (!e || !d || !pattern || !kopt || !ncands || d->e != e) { g_err = "bad argument"; return PM_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     CK(cudaSetDevice(e->device));
     Compiled c;
     int rc = compile(pattern, kopt, c, true);
@@ -2056,6 +2460,7 @@ static int resolve_impl(pm_engine *e, pm_dataset *d, const char *pattern, const 
                         pm_hit *hits, int64_t cap, int64_t *nhits, cudaMemcpyKind kind)
 {
     if (!e || !d || !pattern || !kopt || !nhits || ncands < 0 || (ncands && !cands) || d->e != e) { g_err = "bad argument"; return PM_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     CK(cudaSetDevice(e->device));
     Compiled c;
     int rc = compile(pattern, kopt, c, true);
@@ -2078,3 +2483,4 @@ static int resolve_impl(pm_engine *e, pm_dataset *d, const char *pattern, const 
     e->stats.launches = launches;                        // resolve_candidates added its launches to the kept count
     return rc;
 }
+

@@ -29,6 +29,7 @@ struct PackedArgs {
     PackedPos pos[NP][64];
     unsigned long long *keys, *count;
     long long cap;
+    unsigned long long keytag;   // pattern id of a multi-pattern request, already shifted (pid << PM_PID_SHIFT)
 };
 
 // SWAR helpers on 4 packed bytes
@@ -163,13 +164,21 @@ struct PackedVerify {
 // Exact (k = 0, SIMPLE) scan: one piece, registers only, next tile prefetched while the current
 // one is evaluated.  Positions are grouped by the plane they read so that no per-position
 // dispatch is needed.
-struct ExactArgs {
-    const unsigned *hi, *lo, *xx;
-    long long nwords, n, a0, a1, tile0, ntiles;
+#define EX_MAXPAT 2                     // patterns evaluated per staged tile: a motif and its reverse complement (one PatMatch request)
+struct ExactPat {
+    long long a0, a1;                     // window starts a0 <= w < a1 (already cut to n - L + 1)
+    unsigned long long keytag;            // pid << PM_PID_SHIFT
     int L;
     unsigned char npos[6];                // positions reading plane A,C,G,T,X and general classes
     unsigned char shift[6][64];
     unsigned char cls[64];                // general classes: bits A,C,G,T,X (parallel to shift[5])
+};
+struct ExactArgs {
+    const unsigned *hi, *lo, *xx;
+    long long nwords, n, tile0, ntiles;
+    int npat;
+    unsigned long long bad;               // placeholder key of out-of-range hits: sorts after every real key
+    ExactPat pat[EX_MAXPAT];
     unsigned long long *keys, *count;
     long long cap;
 };
@@ -373,68 +382,90 @@ __global__ void __launch_bounds__((EX_WARPS + 1) * 32, 5) k_scan_packed_exact(co
         __syncwarp();
         if (lane == 0) mbar_arrive_addr(empty_base + 8u * s);   // this warp's slice is in registers
         const long long bt = blockIdx.x + it * gridDim.x;
-        unsigned M[EX_WPL];
-#pragma unroll
-        for (int w = 0; w < EX_WPL; w++) M[w] = ~0u;
-        unsigned P[EX_WPL + 2];
-        if (a.npos[0]) {
-#pragma unroll
-            for (int w = 0; w < EX_WPL + 2; w++) P[w] = ~(H[w] | Lw[w] | X[w]);
-            exact_apply_group<LONG>(M, P, a.shift[0], a.npos[0]);
-        }
-        if (a.npos[1]) {
-#pragma unroll
-            for (int w = 0; w < EX_WPL + 2; w++) P[w] = Lw[w] & ~H[w];
-            exact_apply_group<LONG>(M, P, a.shift[1], a.npos[1]);
-        }
-        if (a.npos[2]) {
-#pragma unroll
-            for (int w = 0; w < EX_WPL + 2; w++) P[w] = H[w] & Lw[w];
-            exact_apply_group<LONG>(M, P, a.shift[2], a.npos[2]);
-        }
-        if (a.npos[3]) {
-#pragma unroll
-            for (int w = 0; w < EX_WPL + 2; w++) P[w] = H[w] & ~Lw[w];
-            exact_apply_group<LONG>(M, P, a.shift[3], a.npos[3]);
-        }
-        if (a.npos[4]) {
-            exact_apply_group<LONG>(M, X, a.shift[4], a.npos[4]);
-        }
-        for (int e = 0; e < a.npos[5]; e++) {
-            sp_plane_dyn(a.cls[e], P, H, Lw, X);
-            exact_apply<LONG>(M, P, a.shift[5][e]);
-        }
-        // ---- hits of this warp tile: buffered in shared memory, no per-hit global atomics ----
-        unsigned mine = 0;
-#pragma unroll
-        for (int w = 0; w < EX_WPL; w++) mine += __popc(M[w]);
-        const unsigned have = __ballot_sync(0xffffffffu, mine != 0);
-        if (!have) continue;
-        // offsets: one ballot when no lane holds more than one hit (the usual case), a shuffle scan otherwise
-        unsigned incl, total;
-        if (!__any_sync(0xffffffffu, mine > 1)) {
-            incl = __popc(have & (0xffffffffu >> (31 - lane)));
-            total = __popc(have);
-        } else {
-            incl = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            total = __shfl_sync(0xffffffffu, incl, 31);
-        }
         const long long wbase = ((a.tile0 * 128) + bt * EX_WORDS + wib * (32 * EX_WPL)) * 32;   // text position of the warp tile
-        // only the first / last tiles of the scanned range need the per-hit range test
-        const bool inside = wbase >= a.a0 && wbase + 32 * 32 * EX_WPL <= (a.a1 < a.n - a.L + 1 ? a.a1 : a.n - a.L + 1);
-        const unsigned long long bad = ((unsigned long long)(a.n + 1) << 4) | 15ULL;
         const unsigned lrel = (unsigned)(EX_WPL * lane) * 32;
-        if (total > EX_HITBUF) {
-            // dense tile: straight to global memory
-            flush();
-            unsigned long long basei = 0;
-            if (lane == 0) basei = atomicAdd(a.count, (unsigned long long)total);
-            basei = __shfl_sync(0xffffffffu, basei, 0) + (incl - mine);
+        // every pattern of the request is evaluated on the registers of this tile: the planes are read once
+#pragma unroll 1
+        for (int pi = 0; pi < a.npat; pi++) {
+            const ExactPat &pt = a.pat[pi];
+            unsigned M[EX_WPL];
+#pragma unroll
+            for (int w = 0; w < EX_WPL; w++) M[w] = ~0u;
+            unsigned P[EX_WPL + 2];
+            if (pt.npos[0]) {
+#pragma unroll
+                for (int w = 0; w < EX_WPL + 2; w++) P[w] = ~(H[w] | Lw[w] | X[w]);
+                exact_apply_group<LONG>(M, P, pt.shift[0], pt.npos[0]);
+            }
+            if (pt.npos[1]) {
+#pragma unroll
+                for (int w = 0; w < EX_WPL + 2; w++) P[w] = Lw[w] & ~H[w];
+                exact_apply_group<LONG>(M, P, pt.shift[1], pt.npos[1]);
+            }
+            if (pt.npos[2]) {
+#pragma unroll
+                for (int w = 0; w < EX_WPL + 2; w++) P[w] = H[w] & Lw[w];
+                exact_apply_group<LONG>(M, P, pt.shift[2], pt.npos[2]);
+            }
+            if (pt.npos[3]) {
+#pragma unroll
+                for (int w = 0; w < EX_WPL + 2; w++) P[w] = H[w] & ~Lw[w];
+                exact_apply_group<LONG>(M, P, pt.shift[3], pt.npos[3]);
+            }
+            if (pt.npos[4]) {
+                exact_apply_group<LONG>(M, X, pt.shift[4], pt.npos[4]);
+            }
+            for (int e = 0; e < pt.npos[5]; e++) {
+                sp_plane_dyn(pt.cls[e], P, H, Lw, X);
+                exact_apply<LONG>(M, P, pt.shift[5][e]);
+            }
+            // ---- hits of this warp tile: buffered in shared memory, no per-hit global atomics ----
+            unsigned mine = 0;
+#pragma unroll
+            for (int w = 0; w < EX_WPL; w++) mine += __popc(M[w]);
+            const unsigned have = __ballot_sync(0xffffffffu, mine != 0);
+            if (!have) continue;
+            // offsets: one ballot when no lane holds more than one hit (the usual case), a shuffle scan otherwise
+            unsigned incl, total;
+            if (!__any_sync(0xffffffffu, mine > 1)) {
+                incl = __popc(have & (0xffffffffu >> (31 - lane)));
+                total = __popc(have);
+            } else {
+                incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                total = __shfl_sync(0xffffffffu, incl, 31);
+            }
+            // only the first / last tiles of the scanned range need the per-hit range test
+            const long long pa0 = pt.a0, pa1 = pt.a1;
+            const bool inside = wbase >= pa0 && wbase + 32 * 32 * EX_WPL <= pa1;
+            const unsigned long long tag = pt.keytag;
+            if (total > EX_HITBUF) {
+                // dense tile: straight to global memory
+                flush();
+                unsigned long long basei = 0;
+                if (lane == 0) basei = atomicAdd(a.count, (unsigned long long)total);
+                basei = __shfl_sync(0xffffffffu, basei, 0) + (incl - mine);
+#pragma unroll
+                for (int w = 0; w < EX_WPL; w++) {
+                    unsigned c = M[w];
+                    while (c) {
+                        const int b = __ffs(c) - 1;
+                        c &= c - 1;
+                        const long long p = wbase + (lrel + w * 32 + b);
+                        const bool ok = inside || (p >= pa0 && p < pa1);
+                        if ((long long)basei < a.cap) a.keys[basei] = ok ? (tag | ((unsigned long long)p << 4)) : a.bad;
+                        if (!ok) atomicAdd(a.count + 1, 1ULL);          // placeholders sort last and are cut off afterwards
+                        basei++;
+                    }
+                }
+                continue;
+            }
+            if (nbuf + total > EX_HITBUF) flush();
+            unsigned slot = nbuf + (incl - mine);
 #pragma unroll
             for (int w = 0; w < EX_WPL; w++) {
                 unsigned c = M[w];
@@ -442,30 +473,14 @@ __global__ void __launch_bounds__((EX_WARPS + 1) * 32, 5) k_scan_packed_exact(co
                     const int b = __ffs(c) - 1;
                     c &= c - 1;
                     const long long p = wbase + (lrel + w * 32 + b);
-                    const bool ok = inside || (p >= a.a0 && p < a.a1 && p + a.L <= a.n);
-                    if ((long long)basei < a.cap) a.keys[basei] = ok ? (unsigned long long)p << 4 : bad;
-                    if (!ok) atomicAdd(a.count + 1, 1ULL);          // placeholders sort last and are cut off by the host
-                    basei++;
+                    const bool ok = inside || (p >= pa0 && p < pa1);
+                    hitbuf[slot++] = ok ? (tag | ((unsigned long long)p << 4)) : a.bad;
+                    if (!ok) atomicAdd(a.count + 1, 1ULL);              // placeholders sort last and are cut off afterwards
                 }
             }
-            continue;
+            nbuf += total;
+            __syncwarp();
         }
-        if (nbuf + total > EX_HITBUF) flush();
-        unsigned slot = nbuf + (incl - mine);
-#pragma unroll
-        for (int w = 0; w < EX_WPL; w++) {
-            unsigned c = M[w];
-            while (c) {
-                const int b = __ffs(c) - 1;
-                c &= c - 1;
-                const long long p = wbase + (lrel + w * 32 + b);
-                const bool ok = inside || (p >= a.a0 && p < a.a1 && p + a.L <= a.n);
-                hitbuf[slot++] = ok ? (unsigned long long)p << 4 : bad;
-                if (!ok) atomicAdd(a.count + 1, 1ULL);              // placeholders sort last and are cut off by the host
-            }
-        }
-        nbuf += total;
-        __syncwarp();
     }
     flush();
 }
@@ -610,7 +625,7 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
                     if (slot < BK_QUEUE) queue[i][slot] = rel;
                     else {                                                          // not filtered: decided by k_verify
                         const unsigned long long idx = atomicAdd(a.count, 1ULL);
-                        if ((long long)idx < a.cap) a.keys[idx] = ((unsigned long long)p << 4) | (unsigned)i;
+                        if ((long long)idx < a.cap) a.keys[idx] = a.keytag | ((unsigned long long)p << 4) | (unsigned)i;
                     }
                 }
             }
@@ -696,7 +711,7 @@ __global__ void __launch_bounds__(256) k_scan_packed(const PackedArgs<NP> a, con
                 if (minL + minR <= v.k) {
                     const long long p = qb * 32 + (rel0 - PK_HALO * 32);
                     const unsigned long long idx = atomicAdd(a.count, 1ULL);
-                    if ((long long)idx < a.cap) a.keys[idx] = ((unsigned long long)p << 4) | (unsigned)i;
+                    if ((long long)idx < a.cap) a.keys[idx] = a.keytag | ((unsigned long long)p << 4) | (unsigned)i;
                 }
             }
         }
@@ -738,7 +753,8 @@ template <typename W>
 __device__ __noinline__ void sp_round(const unsigned long long *__restrict__ qkey, unsigned head, unsigned cnt,
                                       const unsigned *__restrict__ hi, const unsigned *__restrict__ lo, const unsigned *__restrict__ xx,
                                       const W *__restrict__ tabs, const SpParams *__restrict__ par, int k,
-                                      unsigned long long *__restrict__ keys, unsigned long long *__restrict__ count, long long cap)
+                                      unsigned long long *__restrict__ keys, unsigned long long *__restrict__ count, long long cap,
+                                      unsigned long long keytag)
 {
     const int lane = threadIdx.x & 31;
     unsigned long long key[2];
@@ -831,8 +847,8 @@ __device__ __noinline__ void sp_round(const unsigned long long *__restrict__ qke
         basei = __shfl_sync(0xffffffffu, basei, 0);
         const unsigned below = (1u << lane) - 1u;
         const unsigned long long i0 = basei + __popc(bal0 & below), i1 = basei + __popc(bal0) + __popc(bal1 & below);
-        if (keep[0] && (long long)i0 < cap) keys[i0] = key[0];
-        if (keep[1] && (long long)i1 < cap) keys[i1] = key[1];
+        if (keep[0] && (long long)i0 < cap) keys[i0] = key[0] | keytag;
+        if (keep[1] && (long long)i1 < cap) keys[i1] = key[1] | keytag;
     }
     __syncwarp();
 }
@@ -882,7 +898,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32, SP_CTAS) k_scan_split(const Pac
             for (long long p = 0; p < v.k + v.V[i]; p++) {
                 if (p < a.a0 || p >= a.a1 || p + a.L > a.n) continue;
                 const unsigned long long idx = atomicAdd(a.count, 1ULL);
-                if ((long long)idx < a.cap) a.keys[idx] = ((unsigned long long)p << 4) | (unsigned)i;
+                if ((long long)idx < a.cap) a.keys[idx] = a.keytag | ((unsigned long long)p << 4) | (unsigned)i;
             }
     }
     unsigned long long *qk = q_key[wib];
@@ -1025,7 +1041,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32, SP_CTAS) k_scan_split(const Pac
                 qcnt += total;
                 __syncwarp();
                 while (qcnt >= 64) {
-                    sp_round<W>(qk, qhead, 64, a.hi, a.lo, a.xx, sT, spar, v.k, a.keys, a.count, a.cap);
+                    sp_round<W>(qk, qhead, 64, a.hi, a.lo, a.xx, sT, spar, v.k, a.keys, a.count, a.cap, a.keytag);
                     qhead = (qhead + 64) & (SP_QUEUE - 1);
                     qcnt -= 64;
                 }
@@ -1045,7 +1061,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32, SP_CTAS) k_scan_split(const Pac
                         qcnt += __popc(bal);
                         __syncwarp();
                         if (qcnt >= 64) {
-                            sp_round<W>(qk, qhead, 64, a.hi, a.lo, a.xx, sT, spar, v.k, a.keys, a.count, a.cap);
+                            sp_round<W>(qk, qhead, 64, a.hi, a.lo, a.xx, sT, spar, v.k, a.keys, a.count, a.cap, a.keytag);
                             qhead = (qhead + 64) & (SP_QUEUE - 1);
                             qcnt -= 64;
                         }
@@ -1054,7 +1070,390 @@ __global__ void __launch_bounds__(EX_WARPS * 32, SP_CTAS) k_scan_split(const Pac
             }
         }
     }
-    if (qcnt) sp_round<W>(qk, qhead, qcnt, a.hi, a.lo, a.xx, sT, spar, v.k, a.keys, a.count, a.cap);
+    if (qcnt) sp_round<W>(qk, qhead, qcnt, a.hi, a.lo, a.xx, sT, spar, v.k, a.keys, a.count, a.cap, a.keytag);
+}
+
+// ---------------------------------------------------------------------------------------
+// SPLIT scan, second generation (k_scan_apx): one pass over the planes for every pattern of a request (a motif and
+// its reverse complement), m + 2k <= 64, k <= 3.  Same TMA ring, warp tiles and pattern-start coordinates
+// b = anchor - V[i] - k as k_scan_split, but
+//   * the k+1 exact pieces are not evaluated position by position: the host picks q-gram chunks that refine the
+//     pieces, and a piece plane is the AND of the (undilated) planes of its chunks -- every pattern position is
+//     turned into a class plane once per tile;
+//   * the per-anchor filter is not a symbol-by-symbol Myers loop but Landau-Vishkin over the 2k+1 diagonals of the
+//     64-symbol window: D_d = pattern positions that match on diagonal d (ten logic operations per diagonal from the
+//     one-hot symbol planes and per-symbol position masks), then the furthest-reaching pattern index per (errors,
+//     diagonal) with a count-trailing-ones slide.  Straight-line code, no loop over text symbols, one check per
+//     pattern start b whatever the number of pieces that fired there.  "P aligns to text[b + d0 ...] with at most k
+//     errors for some start diagonal d0 in [0, 2k]" is necessary for checkMatch1 @414190 to accept any anchor whose
+//     pattern start is b (its alignment stays within k diagonals of the nominal one, d = k, which it crosses at the
+//     exact piece); record ends, fill cuts, line anchors and the scan start only remove alignments.  Which pieces
+//     matched exactly comes for free from the nominal diagonal D_k.
+// Survivors are decided on the raw bytes by k_verify as before.
+#define AX_MAXCH 12
+#define AX_MAXLEN 12
+#define AX_MAXDENSE 64
+#define AX_QUEUE 128                     // per-warp queue of pattern starts (b << 1 | pattern)
+struct ApxChunk {
+    unsigned char off;                   // first bit of the (dilated) window, relative to b
+    unsigned char npos;                  // constrained positions of the chunk
+    unsigned char piece;                 // piece the chunk is part of (its plane is ANDed into that piece), 0xff = none
+    unsigned char poff;                  // k + start of the chunk: bit b of (plane >> poff) <=> the chunk sits at its nominal place
+    unsigned char first, last;           // first / last chunk of its piece
+    unsigned char counted;               // takes part in the q-gram count (0: too unselective, only builds its piece)
+    unsigned char pad;
+    unsigned char t[AX_MAXLEN];          // offsets of the constrained positions inside the chunk
+    unsigned char cls[AX_MAXLEN];        // their classes (bits A,C,G,T,X)
+};
+struct ApxPat {
+    long long a0, a1;                    // anchors a0 <= p < a1
+    unsigned long long keytag;
+    unsigned long long posmask[5];       // pattern positions accepting A, C, T, G (code = hi<<1|lo) and some non-ACGT byte
+    int m, k, L, npieces, indel;
+    int V[4];
+    int nch, win, ncounted;
+    ApxChunk ch[AX_MAXCH];
+    unsigned char dn[4];                 // per piece: positions evaluated one by one (pieces not covered by chunks)
+    unsigned char dwild[4];              // piece without any constrained position: matches everywhere
+    unsigned char dshift[AX_MAXDENSE], dcls[AX_MAXDENSE];
+};
+struct ApxArgs {
+    const unsigned *hi, *lo, *xx;
+    long long nwords, n, tile0, ntiles;
+    int npat;
+    ApxPat pat[EX_MAXPAT];
+    unsigned long long *keys, *count;
+    long long cap;
+};
+struct ApxSparse {                       // what the per-anchor check needs, copied to shared memory
+    long long a0, a1;
+    unsigned long long keytag;
+    unsigned long long posmask[5];
+    int m, L, npieces, indel;
+    int V[4];
+};
+
+__device__ __forceinline__ int ax_tz(unsigned x) { return __clz(__brev(x)); }
+__device__ __forceinline__ int ax_tz(unsigned long long x) { return __clzll(__brevll(x)); }
+
+template <int K, typename DW>
+__device__ __noinline__ void apx_round(const unsigned long long *__restrict__ qk, unsigned head, unsigned cnt,
+                                       const unsigned *__restrict__ hi, const unsigned *__restrict__ lo, const unsigned *__restrict__ xx,
+                                       const ApxSparse *__restrict__ sp, long long n,
+                                       unsigned long long *__restrict__ keys, unsigned long long *__restrict__ count, long long cap)
+{
+    constexpr int ND = 2 * K + 1;
+    const int lane = threadIdx.x & 31;
+    const bool act = (unsigned)lane < cnt;
+    const unsigned long long ent = qk[(head + lane) & (AX_QUEUE - 1)];
+    const ApxSparse &pt = sp[act ? (int)(ent & 1) : 0];
+    const long long b = act ? (long long)(ent >> 1) : 0;
+    DW A, C, T, G, X;
+    if (sizeof(DW) == 8) {
+        const unsigned long long h = sp_window(hi, b), l = sp_window(lo, b), x = sp_window(xx, b);
+        A = (DW)~(h | l | x); C = (DW)(l & ~h); T = (DW)(h & ~l); G = (DW)(h & l); X = (DW)x;
+    } else {
+        const long long wi = b >> 5;
+        const int bi = (int)(b & 31);
+        const unsigned h = __funnelshift_r(__ldg(hi + wi), __ldg(hi + wi + 1), bi), l = __funnelshift_r(__ldg(lo + wi), __ldg(lo + wi + 1), bi),
+                       x = __funnelshift_r(__ldg(xx + wi), __ldg(xx + wi + 1), bi);
+        A = (DW)~(h | l | x); C = (DW)(l & ~h); T = (DW)(h & ~l); G = (DW)(h & l); X = (DW)x;
+    }
+    const DW mA = (DW)pt.posmask[0], mC = (DW)pt.posmask[1], mT = (DW)pt.posmask[2], mG = (DW)pt.posmask[3], mX = (DW)pt.posmask[4];
+    DW D[ND];
+#pragma unroll
+    for (int d = 0; d < ND; d++) D[d] = (DW)((mA & (A >> d)) | (mC & (C >> d)) | (mT & (T >> d)) | (mG & (G >> d)) | (mX & (X >> d)));
+    const int m = pt.m;
+    const bool indel = pt.indel != 0;
+    int f[ND];
+    bool pass = false;
+#pragma unroll
+    for (int d = 0; d < ND; d++) {
+        f[d] = (indel || d == K) ? ax_tz((DW)~D[d]) : -1000;
+        pass |= f[d] >= m;
+    }
+#pragma unroll
+    for (int e = 1; e <= K; e++) {
+        int g[ND];
+#pragma unroll
+        for (int d = 0; d < ND; d++) {
+            int v = f[d] + 1;
+            if (indel) {
+                if (d > 0) v = max(v, f[d - 1]);
+                if (d < ND - 1) v = max(v, f[d + 1] + 1);
+            }
+            if (v >= m) { v = m; pass = true; }
+            else if (v >= 0) {
+                v += ax_tz((DW)~(DW)(D[d] >> v));
+                pass |= v >= m;
+            }
+            g[d] = v;
+        }
+#pragma unroll
+        for (int d = 0; d < ND; d++) f[d] = g[d];
+    }
+    // pieces that match exactly at their nominal place (diagonal k), restricted to the anchors asked for
+    unsigned pieces = 0;
+    if (act && pass) {
+        const DW Lm = (DW)(((DW)1 << pt.L) - 1);       // L <= 31: a SPLIT plan has at least two pieces
+        for (int i = 0; i < pt.npieces; i++) {
+            const long long p = b + K + pt.V[i];
+            if ((DW)((D[K] >> pt.V[i]) & Lm) == Lm && p >= pt.a0 && p < pt.a1 && p + pt.L <= n) pieces |= 1u << i;
+        }
+    }
+    const unsigned np = __popc(pieces);
+    if (__any_sync(0xffffffffu, np != 0)) {
+        unsigned incl = np;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned long long basei = 0;
+        if (lane == 0) basei = atomicAdd(count, (unsigned long long)total);
+        basei = __shfl_sync(0xffffffffu, basei, 0) + (incl - np);
+        unsigned c = pieces;
+        while (c) {
+            const int i = __ffs(c) - 1;
+            c &= c - 1;
+            if ((long long)basei < cap) keys[basei] = pt.keytag | ((unsigned long long)(b + K + pt.V[i]) << 4) | (unsigned)i;
+            basei++;
+        }
+    }
+    __syncwarp();
+}
+
+template <int ROWS, typename DW>
+__global__ void __launch_bounds__(EX_WARPS * 32, SP_CTAS) k_scan_apx(const ApxArgs a)
+{
+    constexpr int K = ROWS - 1;
+    extern __shared__ __align__(128) unsigned char ex_smem[];
+    __shared__ unsigned long long q_key[EX_WARPS][AX_QUEUE];
+    __shared__ unsigned s_cand[EX_WARPS][EX_WPL * 32];     // dense tiles only: candidate bits, [word][lane]
+    __shared__ ApxSparse s_sp[EX_MAXPAT];
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    if (tid < a.npat) {
+        const ApxPat &pt = a.pat[tid];
+        ApxSparse &o = s_sp[tid];
+        o.a0 = pt.a0; o.a1 = pt.a1; o.keytag = pt.keytag;
+        for (int q = 0; q < 5; q++) o.posmask[q] = pt.posmask[q];
+        o.m = pt.m; o.L = pt.L; o.npieces = pt.npieces; o.indel = pt.indel;
+        for (int q = 0; q < 4; q++) o.V[q] = pt.V[q];
+    }
+    unsigned *stage_base = reinterpret_cast<unsigned *>(ex_smem);
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(ex_smem + SP_STAGES * EX_STAGE_BYTES);
+    unsigned long long *empty = full + SP_STAGES;
+    const long long nbt = (a.ntiles + 7) / 8;
+    const long long my = blockIdx.x < nbt ? (nbt - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (tid == 0) {
+        for (int s = 0; s < SP_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], EX_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](long long it) {
+        const int s = (int)(it % SP_STAGES);
+        if (it >= SP_STAGES) mbar_wait(&empty[s], (unsigned)(((it / SP_STAGES) - 1) & 1));
+        const long long q = (a.tile0 * 128) + (blockIdx.x + it * gridDim.x) * EX_WORDS;
+        unsigned *dst = stage_base + (size_t)s * (3 * EX_ROW);
+        mbar_expect_tx(&full[s], EX_STAGE_BYTES);
+        tma_load_1d(dst, a.hi + q, EX_ROW * 4, &full[s]);
+        tma_load_1d(dst + EX_ROW, a.lo + q, EX_ROW * 4, &full[s]);
+        tma_load_1d(dst + 2 * EX_ROW, a.xx + q, EX_ROW * 4, &full[s]);
+    };
+    if (tid == 0)
+        for (long long it = 0; it < SP_STAGES - 1 && it < my; it++) issue(it);
+    if (tid == 32 && blockIdx.x == 0 && a.tile0 == 0) {
+        // anchors closer than k + V[i] to the start of the text have no pattern start b >= 0:
+        // they go to k_verify unfiltered (it re-checks the trigger on the raw bytes)
+        for (int pi = 0; pi < a.npat; pi++) {
+            const ApxPat &pt = a.pat[pi];
+            for (int i = 0; i < pt.npieces; i++)
+                for (long long p = 0; p < pt.k + pt.V[i]; p++) {
+                    if (p < pt.a0 || p >= pt.a1 || p + pt.L > a.n) continue;
+                    const unsigned long long idx = atomicAdd(a.count, 1ULL);
+                    if ((long long)idx < a.cap) a.keys[idx] = pt.keytag | ((unsigned long long)p << 4) | (unsigned)i;
+                }
+        }
+    }
+    unsigned long long *qk = q_key[wib];
+    unsigned *sC = s_cand[wib];
+    unsigned qhead = 0, qcnt = 0;                       // warp-uniform ring state
+    for (long long it = 0; it < my; it++) {
+        const int s = (int)(it % SP_STAGES);
+        const unsigned ph = (unsigned)((it / SP_STAGES) & 1);
+        if (tid == 0 && it + SP_STAGES - 1 < my) issue(it + SP_STAGES - 1);
+        __syncwarp();
+        mbar_wait(&full[s], ph);
+        const unsigned *sp = stage_base + (size_t)s * (3 * EX_ROW) + wib * (32 * EX_WPL) + EX_WPL * lane;
+        unsigned H[EX_WPL + 2], Lw[EX_WPL + 2], X[EX_WPL + 2];
+#pragma unroll
+        for (int v4 = 0; v4 < EX_WPL / 4; v4++) {
+            const uint4 h4 = *reinterpret_cast<const uint4 *>(sp + 4 * v4), l4 = *reinterpret_cast<const uint4 *>(sp + EX_ROW + 4 * v4),
+                        x4 = *reinterpret_cast<const uint4 *>(sp + 2 * EX_ROW + 4 * v4);
+            H[4 * v4] = h4.x; H[4 * v4 + 1] = h4.y; H[4 * v4 + 2] = h4.z; H[4 * v4 + 3] = h4.w;
+            Lw[4 * v4] = l4.x; Lw[4 * v4 + 1] = l4.y; Lw[4 * v4 + 2] = l4.z; Lw[4 * v4 + 3] = l4.w;
+            X[4 * v4] = x4.x; X[4 * v4 + 1] = x4.y; X[4 * v4 + 2] = x4.z; X[4 * v4 + 3] = x4.w;
+        }
+        {
+            const uint2 h2 = *reinterpret_cast<const uint2 *>(sp + EX_WPL), l2 = *reinterpret_cast<const uint2 *>(sp + EX_ROW + EX_WPL),
+                        x2 = *reinterpret_cast<const uint2 *>(sp + 2 * EX_ROW + EX_WPL);
+            H[EX_WPL] = h2.x; H[EX_WPL + 1] = h2.y; Lw[EX_WPL] = l2.x; Lw[EX_WPL + 1] = l2.y; X[EX_WPL] = x2.x; X[EX_WPL + 1] = x2.y;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);            // this warp's slice is in registers
+        const long long bt = blockIdx.x + it * gridDim.x;
+        const long long wbase = ((a.tile0 * 128) + bt * EX_WORDS + wib * (32 * EX_WPL)) * 32;   // first pattern start of the warp tile
+        const unsigned lrel = (unsigned)(EX_WPL * lane) * 32;
+#pragma unroll 1
+        for (int pi = 0; pi < a.npat; pi++) {
+            const ApxPat &pt = a.pat[pi];
+            unsigned P[EX_WPL + 2];
+            unsigned U[EX_WPL], M[EX_WPL];
+            unsigned miss[ROWS][EX_WPL];                  // miss[r] : more than r counted chunks missing
+#pragma unroll
+            for (int w = 0; w < EX_WPL; w++) { U[w] = 0; M[w] = 0; }
+#pragma unroll
+            for (int r = 0; r < ROWS; r++)
+#pragma unroll
+                for (int w = 0; w < EX_WPL; w++) miss[r][w] = 0;
+            const int nch = pt.nch, win = pt.win;
+#pragma unroll 1
+            for (int g = 0; g < nch; g++) {
+                const ApxChunk &ch = pt.ch[g];
+                unsigned G[EX_WPL + 2];
+#pragma unroll
+                for (int w = 0; w < EX_WPL + 2; w++) G[w] = 0xffffffffu;
+                const int npos = ch.npos;
+                for (int c = 0; c < npos; c++) {
+                    const int t = ch.t[c];
+                    sp_plane_dyn(ch.cls[c], P, H, Lw, X);
+#pragma unroll
+                    for (int w = 0; w < EX_WPL + 1; w++) G[w] &= __funnelshift_r(P[w], P[w + 1], t);
+                    G[EX_WPL + 1] &= P[EX_WPL + 1] >> t;
+                }
+                if (ch.piece != 0xff) {                   // the undilated chunk plane is a factor of its piece
+                    if (ch.first) {
+#pragma unroll
+                        for (int w = 0; w < EX_WPL; w++) M[w] = 0xffffffffu;
+                    }
+                    exact_apply<true>(M, G, ch.poff);
+                    if (ch.last) {
+#pragma unroll
+                        for (int w = 0; w < EX_WPL; w++) U[w] |= M[w];
+                    }
+                }
+                if (ch.counted) {
+                    // dilate: G[x] |= G[x+1] | ... | G[x+win-1]   (doubling)
+                    int cw = 1;
+                    while (cw < win) {
+                        const int sft = min(cw, win - cw);
+#pragma unroll
+                        for (int w = 0; w < EX_WPL + 1; w++) G[w] |= __funnelshift_r(G[w], G[w + 1], sft);
+                        G[EX_WPL + 1] |= G[EX_WPL + 1] >> sft;
+                        cw += sft;
+                    }
+                    unsigned x[EX_WPL];
+#pragma unroll
+                    for (int w = 0; w < EX_WPL; w++) x[w] = 0xffffffffu;
+                    exact_apply<true>(x, G, ch.off);
+#pragma unroll
+                    for (int w = 0; w < EX_WPL; w++) {
+                        const unsigned ms = ~x[w];
+#pragma unroll
+                        for (int r = ROWS - 1; r > 0; r--) miss[r][w] |= miss[r - 1][w] & ms;
+                        miss[0][w] |= ms;
+                    }
+                }
+            }
+            // pieces that the chunks do not cover: position by position
+            {
+                int dp = 0;
+#pragma unroll 1
+                for (int i = 0; i < pt.npieces; i++) {
+                    const int nd = pt.dn[i];
+                    if (pt.dwild[i]) {
+#pragma unroll
+                        for (int w = 0; w < EX_WPL; w++) U[w] = 0xffffffffu;
+                    }
+                    if (nd == 0) continue;
+#pragma unroll
+                    for (int w = 0; w < EX_WPL; w++) M[w] = 0xffffffffu;
+                    for (int j = 0; j < nd; j++) {
+                        sp_plane_dyn(pt.dcls[dp + j], P, H, Lw, X);
+                        exact_apply<true>(M, P, pt.dshift[dp + j]);
+                    }
+                    dp += nd;
+#pragma unroll
+                    for (int w = 0; w < EX_WPL; w++) U[w] |= M[w];
+                }
+            }
+            unsigned mine = 0;
+#pragma unroll
+            for (int w = 0; w < EX_WPL; w++) { U[w] &= ~miss[ROWS - 1][w]; mine += __popc(U[w]); }
+            const unsigned have = __ballot_sync(0xffffffffu, mine != 0);
+            if (!have) continue;
+            unsigned incl, total;
+            if (!__any_sync(0xffffffffu, mine > 1)) {
+                incl = __popc(have & (0xffffffffu >> (31 - lane)));
+                total = __popc(have);
+            } else {
+                incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                total = __shfl_sync(0xffffffffu, incl, 31);
+            }
+            const unsigned long long b0 = (unsigned long long)(wbase + lrel);
+            if (qcnt + total <= AX_QUEUE) {
+                // sparse: every lane appends its pattern starts at its own offset, then full rounds are drained
+                unsigned slot = qhead + qcnt + (incl - mine);
+#pragma unroll
+                for (int w = 0; w < EX_WPL; w++) {
+                    unsigned c = U[w];
+                    while (c) {
+                        const int bb = __ffs(c) - 1;
+                        c &= c - 1;
+                        qk[slot++ & (AX_QUEUE - 1)] = ((b0 + (unsigned)(w * 32 + bb)) << 1) | (unsigned)pi;
+                    }
+                }
+                qcnt += total;
+                __syncwarp();
+                while (qcnt >= 32) {
+                    apx_round<K, DW>(qk, qhead, 32, a.hi, a.lo, a.xx, s_sp, a.n, a.keys, a.count, a.cap);
+                    qhead = (qhead + 32) & (AX_QUEUE - 1);
+                    qcnt -= 32;
+                }
+            } else {
+                // dense: one pattern start per lane and step, a round as soon as 32 are queued
+#pragma unroll
+                for (int w = 0; w < EX_WPL; w++) sC[w * 32 + lane] = U[w];
+#pragma unroll 1
+                for (int w = 0; w < EX_WPL; w++) {
+                    unsigned c = sC[w * 32 + lane];
+                    while (__any_sync(0xffffffffu, c != 0)) {
+                        const bool hv = c != 0;
+                        const unsigned bal = __ballot_sync(0xffffffffu, hv);
+                        if (hv) {
+                            const int bb = __ffs(c) - 1;
+                            c &= c - 1;
+                            qk[(qhead + qcnt + __popc(bal & ((1u << lane) - 1u))) & (AX_QUEUE - 1)] = ((b0 + (unsigned)(w * 32 + bb)) << 1) | (unsigned)pi;
+                        }
+                        qcnt += __popc(bal);
+                        __syncwarp();
+                        while (qcnt >= 32) {
+                            apx_round<K, DW>(qk, qhead, 32, a.hi, a.lo, a.xx, s_sp, a.n, a.keys, a.count, a.cap);
+                            qhead = (qhead + 32) & (AX_QUEUE - 1);
+                            qcnt -= 32;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (qcnt) apx_round<K, DW>(qk, qhead, qcnt, a.hi, a.lo, a.xx, s_sp, a.n, a.keys, a.count, a.cap);
 }
 
 // ---------------------------------------------------------------------------------------

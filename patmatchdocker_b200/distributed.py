@@ -83,7 +83,77 @@ class DeviceShardedSearch:
         import torch
         self.engine, self.rank, self.world, self.device, self.group = engine, rank, world, device, group
         self.torch = torch
+        if str(device) != "cpu":
+            # torch (NCCL collectives, copy_) and the engine must work on ONE stream: the engine reads buffers that
+            # torch has only enqueued writes for, and vice versa.  Without this the engine would launch on its own
+            # non-blocking stream and race with them.
+            engine.use_torch_stream(torch.cuda.current_stream(torch.device(device)))
         self._alloc(cap)
+
+    def request_fills(self, dataset, patterns, kopt):
+        """One PatMatch request (all patterns, e.g. motif + reverse complement) over `world` ranks with ONE collective:
+        every rank runs pm_request_fills_device on the buffer fills that start in its position range -- a single
+        pass over its part of the planes, one sort / verify / chain / select, no host synchronisation -- and the
+        per-rank [header | hits] blocks are all-gathered over NVLink.  Rank 0 copies the gathered buffer to the
+        host once and returns the per-pattern hit lists (== Engine.search_request); the other ranks read only the
+        header rows (to agree on a retry when some rank needed more room) and return None."""
+        import torch.distributed as dist
+        from ._native import HIT_DTYPE, request_header_rows
+        torch = self.torch
+        npat = len(patterns)
+        hr = request_header_rows(npat)
+        on_gpu = str(self.device) != "cpu"
+        if not hasattr(self, "rq_rows"):
+            self.rq_rows, self.rq_cap, self.rq_alloc = 1 << 14, 1 << 16, 0
+        beg, end = shard_ranges(len(dataset), self.world)[self.rank]
+        while True:
+            rows = max(self.rq_rows, hr + 16)
+            if rows > self.rq_alloc:
+                self.rq_alloc = rows + rows // 2
+                self.rq_mine = torch.zeros((self.rq_alloc, 2), dtype=torch.int64, device=self.device)
+                self.rq_all = torch.empty((self.rq_alloc * self.world, 2), dtype=torch.int64, device=self.device)
+                self.rq_host = torch.empty((self.rq_alloc * self.world, 2), dtype=torch.int64, pin_memory=on_gpu) if self.rank == 0 else None
+                self.rq_hdr = torch.empty((self.world, hr, 2), dtype=torch.int64, pin_memory=on_gpu)
+            if self.rq_hdr.shape[1] != hr:
+                self.rq_hdr = torch.empty((self.world, hr, 2), dtype=torch.int64, pin_memory=on_gpu)
+            mine = self.rq_mine[:rows]
+            self.engine.request_fills_device(dataset, patterns, kopt, beg, end, self.rq_cap, mine.data_ptr(), rows)
+            flat = self.rq_all[: self.world * rows]
+            if self.world > 1:
+                dist.all_gather_into_tensor(flat, mine, group=self.group)
+            else:
+                flat.copy_(mine)
+            view = flat.view(self.world, rows, 2)
+            if self.rank == 0:                                     # one D2H of everything gathered, one synchronisation
+                hview = self.rq_host[: self.world * rows]
+                hview.copy_(flat, non_blocking=True)
+                if on_gpu:
+                    torch.cuda.current_stream().synchronize()
+                h = hview.numpy().reshape(self.world, rows, 2)
+                hdrs = h[:, :hr]
+            else:
+                self.rq_hdr.copy_(view[:, :hr], non_blocking=True)
+                if on_gpu:
+                    torch.cuda.current_stream().synchronize()
+                hdrs = self.rq_hdr.numpy()
+            nh = hdrs[:, 0, 0]
+            ncand = hdrs[:, 0, 1]
+            ok = int(ncand.max()) <= self.rq_cap and int(nh.max()) + hr <= rows
+            # agreed by construction: every rank saw the same headers
+            self.rq_cap = max(1 << 12, int(int(ncand.max()) * 1.25) + 1024)
+            self.rq_rows = max(256, int((int(nh.max()) + hr) * 1.25) + 16)
+            if ok:
+                break
+        if self.rank != 0:
+            return None
+        out = []
+        counts = hdrs[:, 2:hr].reshape(self.world, -1)[:, :npat]
+        offs = np.zeros((self.world, npat + 1), dtype=np.int64)
+        offs[:, 1:] = np.cumsum(counts, axis=1)
+        for p in range(npat):
+            parts = [h[r, hr + offs[r, p]: hr + offs[r, p + 1]] for r in range(self.world)]
+            out.append(np.ascontiguousarray(np.concatenate(parts) if self.world > 1 else parts[0].copy()).view(HIT_DTYPE).reshape(-1))
+        return out
 
     def _alloc(self, cap):
         torch = self.torch

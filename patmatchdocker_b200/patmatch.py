@@ -11,6 +11,7 @@ Out of scope (not on the search path): S3 upload / download URLs, temp-file clea
 Flask routing, get_config / get_sequence.
 """
 import re
+import threading
 
 import numpy as np
 
@@ -301,13 +302,22 @@ class PatMatch:
     def __init__(self, device=0, engine=None):
         self.engine = engine or Engine(device)
         self.datasets = {}
+        self._lock = threading.RLock()       # request threads of one WSGI process share the engine and the dataset table
 
     def add_dataset(self, name, data, locus=None):
         """name as the reference's '<dataset>.seq' file name; data = file bytes."""
         raw = bytes(data) if not isinstance(data, bytes) else data
         offsets, names = get_record_offset(raw)
-        self.datasets[name] = {"ds": self.engine.load_dataset(raw), "raw": raw, "offsets": offsets,
-                               "names": names, "locus": locus, "text": None}
+        with self._lock:
+            self.datasets[name] = {"ds": self.engine.load_dataset(raw), "raw": raw, "offsets": offsets,
+                                   "names": names, "locus": locus, "text": None}
+
+    def _nrgrep_request(self, entry, patterns, option):
+        """Both nrgrep_coords runs of a request (patmatch.py:733-735 and :739-743) in ONE pass over the dataset
+        (pm_search_request): the stdout texts the reference would have read, in the order it concatenates them."""
+        banner = "SIMPLE search" if int(re.match(r"\d+", option).group()) == 0 else "ESIMPLE search"
+        lists = self.engine.search_request(entry["ds"], patterns, option)
+        return [format_output([(int(b), int(e)) for b, e in hits], entry["raw"], banner) for hits in lists]
 
     def _nrgrep(self, entry, pattern, option):
         """One nrgrep_coords run: (stdout text the reference would have read, hit array)."""
@@ -336,10 +346,9 @@ class PatMatch:
             return {"error": error}
         conv, comp, option = process_pattern(pattern, seqtype, strand, insertion, deletion, substitution, mismatch)
         try:
-            output, _ = self._nrgrep(entry, conv, option)
-            if comp:
-                output2, _ = self._nrgrep(entry, comp, option)
-                output = output + "\n" + output2
+            with self._lock:
+                outs = self._nrgrep_request(entry, [conv, comp] if comp else [conv], option)
+            output = outs[0] if len(outs) == 1 else outs[0] + "\n" + outs[1]
         except NativeError as e:
             return {"error": str(e)}
         if (endMatch == 1 or 'Not' in dataset) and entry["text"] is None:

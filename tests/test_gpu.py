@@ -217,7 +217,10 @@ def test_scan_kernel_selection_and_equivalence(engine):
     ds.close()
 
 
-def test_qgram_prefilter_keeps_every_hit(engine):
+@pytest.mark.parametrize("filter_mode", [1, 4])
+def test_qgram_prefilter_keeps_every_hit(engine, filter_mode):
+    # filter_mode 1: k_scan_apx (pieces built from q-gram chunks, Landau-Vishkin check per pattern start);
+    # filter_mode 4: the first-generation k_scan_split (q-gram count + Myers filter).
     # low-selectivity pieces (many wildcards / wide classes) switch the bit-sliced q-gram pre-filter on; it
     # may only drop candidates whose verification fails: hit lists equal the oracle's and the unfiltered scan's
     rng = random.Random(77)
@@ -241,7 +244,7 @@ def test_qgram_prefilter_keeps_every_hit(engine):
                 text = s0[rng.randint(0, k):] + text[text.index("\n") + 1:]
             raw = text.encode("latin-1")
             ds = engine.load_dataset(raw)
-            engine.set_fused_filter(1)
+            engine.set_fused_filter(filter_mode)
             a = engine.search(ds, pat, kopt)
             st = engine.stats()
             used += 1 if st["qgram_chunks"] > 0 else 0
@@ -724,4 +727,149 @@ def test_large_genome_properties(engine):
         inner = lambda hs: [h for h in hs if h[0] >= lo + 200 and h[1] <= hi - 200]
         mine = [(int(x), int(y)) for x, y in zip(b, e) if x >= lo and y <= hi]
         assert inner(mine) == inner(local), c
+    ds.close()
+
+
+def _request_case(rng, it):
+    """(patterns, kopt, text): what one PatMatch request hands to the engine -- a pattern and a second one of the same
+    length (for DNA the reference sends the reverse complement), random plan types, line anchors, EXTENDED plans"""
+    if it % 5 == 4:
+        pat, members, ops = extended_pattern(rng, DNA, rng.randint(4, 14))
+        pat2, members2, ops2 = extended_pattern(rng, DNA, rng.randint(4, 14))
+        text = extended_text(rng, DNA, members, ops, rng.randint(1, 3), 100, 2500) + extended_text(rng, DNA, members2, ops2, rng.randint(1, 3), 100, 2500)
+        return [pat, pat2], "0ids", text
+    m = rng.randint(3, 24) if rng.random() < 0.85 else rng.randint(25, 50)
+    k = min(rng.choice([0, 0, 1, 1, 2, 2, 3]), m - 1)
+    kopt = "%d%s" % (k, rng.choice(["ids", "ids", "s", "id", "is", "d"]))
+    pat, members = random_pattern(rng, DNA, m)
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    members2 = [[comp[c] for c in cls] for cls in reversed(members)]
+    pat2 = "(" + "".join(c[0] if len(c) == 1 else "." if len(c) == 4 else "[" + "".join(c) + "]" for c in members2) + ")"
+    if it % 7 == 0:
+        pat, pat2 = "^" + pat, pat2 + "$"
+    text = (random_text(rng, members, DNA, k, nrec=rng.randint(1, 3), lo=80, hi=3000) +
+            random_text(rng, members2, DNA, k, nrec=rng.randint(1, 3), lo=80, hi=3000)).encode("latin-1")
+    return [pat, pat2], kopt, text
+
+
+def test_request_one_pass_equals_two_searches(engine, scan_mode):
+    # pm_search_request: both patterns of a request in one pass and one pipeline; each hit list must equal the
+    # single-pattern search and the oracle (the reference runs nrgrep_coords once per pattern, patmatch.py:733-743)
+    rng = random.Random(20262)
+    types = set()
+    for it in range(160):
+        pats, kopt, text = _request_case(rng, it)
+        bufsize = rng.choice([1600000, 1600000, 100, 700])
+        engine.set_buffer_size(bufsize)
+        try:
+            ds = engine.load_dataset(text)
+            got = engine.search_request(ds, pats, kopt)
+            single = [engine.search(ds, p, kopt) for p in pats]
+            ds.close()
+        finally:
+            engine.set_buffer_size(1600000)
+        for p, g, s in zip(pats, got, single):
+            want = O.search(p, text, kopt, bufsize=bufsize)
+            assert [(int(b), int(e)) for b, e in g] == want, (p, kopt, bufsize)
+            assert np.array_equal(g, s), (p, kopt, bufsize)
+            types.add(pm.plan(p, kopt)["type"])
+    assert {"SIMPLE", "SPLIT", "EXT_BEG"} <= types, types
+
+
+def test_request_on_genome_both_strands(engine):
+    # the bench request on a 6 Mb genome with planted copies: one pass for motif + reverse complement, one host
+    # synchronisation; a page-locked result buffer is filled directly
+    from patmatchdocker_b200._native import pinned_empty, HIT_DTYPE
+    g = bytearray(genome(31, 6, 6_000_000))
+    rng = random.Random(9)
+    conv, comp, opt = host.process_pattern("TGASTCANNNRYGATAAG", "dna", "Both strands", None, None, None, 2)
+    site = "TGAGTCATTTACGATAAG"
+    for _ in range(300):
+        p = rng.randrange(100, len(g) - 100)
+        if b"\n" in g[p - 30:p + 60] or b">" in g[p - 30:p + 60]:
+            continue
+        s = list(site)
+        for _e in range(rng.randint(0, 2)):
+            q = rng.randrange(len(s))
+            r = rng.randint(0, 2)
+            if r == 0:
+                s[q] = rng.choice("ACGT")
+            elif r == 1:
+                del s[q]
+            else:
+                s.insert(q, rng.choice("ACGT"))
+        s = "".join(s)
+        if rng.random() < 0.5:
+            s = s[::-1].translate(str.maketrans("ACGT", "TGCA"))
+        g[p:p + len(s)] = s.encode()
+    g = bytes(g)
+    ds = engine.load_dataset(g)
+    out, keep = pinned_empty(1 << 16, HIT_DTYPE)
+    for kopt, pats in ((opt, [conv, comp]), ("0ids", ["(GATAAG)", "(CTTATC)"])):
+        lists = engine.search_request(ds, pats, kopt, out=out)
+        st = engine.stats()
+        assert st["packed"] == 1
+        lists2 = engine.search_request(ds, pats, kopt, out=out)        # capacity hints are warm now: one synchronisation
+        assert engine.stats()["syncs"] == 1, engine.stats()
+        for p, a, b in zip(pats, lists, lists2):
+            want = O.search(p, g, kopt)
+            assert len(want) > 100
+            assert [(int(x), int(y)) for x, y in a] == want, (p, kopt)
+            assert [(int(x), int(y)) for x, y in b] == want, (p, kopt)
+    ds.close()
+    del keep
+
+
+def test_request_fills_device_equals_search(engine, scan_mode):
+    # pm_request_fills_device (the multi-GPU path): asynchronous, header + hits of both patterns in device memory;
+    # contiguous position ranges concatenate to the full per-pattern hit lists
+    import torch
+    from patmatchdocker_b200._native import request_header_rows
+    rng = random.Random(515)
+    rows = 1 << 15
+    buf = torch.zeros((rows, 2), dtype=torch.int64, device="cuda")
+    engine.use_torch_stream()
+    try:
+        for it in range(40):
+            pats, kopt, text = _request_case(rng, it)
+            bufsize = rng.choice([1600000, 64, 200, 1000])
+            engine.set_buffer_size(bufsize)
+            ds = engine.load_dataset(text)
+            world = rng.randint(2, 5)
+            cuts = sorted(rng.randint(0, len(text) + 1) for _ in range(world - 1))
+            edges = [0] + cuts + [len(text) + 1]
+            hr = request_header_rows(len(pats))
+            got = [[] for _ in pats]
+            for r in range(world):
+                engine.request_fills_device(ds, pats, kopt, edges[r], edges[r + 1], 1 << 13, buf.data_ptr(), rows)
+                h = buf.cpu().numpy()
+                nh, ncand = int(h[0, 0]), int(h[0, 1])
+                assert ncand <= (1 << 13) and nh + hr <= rows
+                counts = [int(x) for x in h[2:hr].reshape(-1)[:len(pats)]]
+                assert sum(counts) == nh
+                off = hr
+                for i, c in enumerate(counts):
+                    got[i] += [(int(b), int(e)) for b, e in h[off:off + c]]
+                    off += c
+            ds.close()
+            for p, gl in zip(pats, got):
+                assert gl == O.search(p, text, kopt, bufsize=bufsize), (p, kopt, bufsize, edges)
+    finally:
+        engine.set_buffer_size(1600000)
+        engine.set_stream(0)
+
+
+def test_batch_with_errors_equals_single(engine):
+    # pm_search_batch with k > 0: groups of patterns through the request pipeline
+    rng = random.Random(99)
+    g = genome(41, 4, 400_000)
+    ds = engine.load_dataset(g)
+    pats = []
+    for _ in range(70):
+        p, _m = random_pattern(rng, DNA, rng.randint(8, 16), cls_pct=0.1, dot_pct=0.05, neg_pct=0.0)
+        pats.append(p)
+    hits, off = engine.search_batch(ds, pats, "1ids")
+    for i in (0, 1, 31, 32, 33, 69):
+        want = O.search(pats[i], g, "1ids")
+        assert [(int(b), int(e)) for b, e in hits[off[i]:off[i + 1]]] == want, pats[i]
     ds.close()

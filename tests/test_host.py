@@ -78,6 +78,9 @@ class _OracleEngine:
         hits = O.search(pattern, ds.raw, kopt)
         return np.array(hits, dtype=_native.HIT_DTYPE)
 
+    def search_request(self, ds, patterns, kopt):
+        return [self.search(ds, p, kopt) for p in patterns]
+
 
 def _locus(text):
     out = {}
