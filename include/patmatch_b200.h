@@ -72,6 +72,7 @@ typedef struct {
     int packed;                  /* 1: 2-bit packed bit-sliced scan, 0: byte Shift-And / dense */
     int qgram_chunks;            /* pattern chunks of the bit-sliced q-gram pre-filter (0 = not used) */
     int syncs;                   /* host synchronisations of the last pm_search_request */
+    int jit;                     /* 1: the scan ran as a kernel specialised for the request (NVRTC), 0: generic kernels */
 } pm_stats;
 
 const char *pm_last_error(void);
@@ -93,6 +94,14 @@ int pm_engine_set_scan_mode(pm_engine *e, int mode);
  * that surely fail.  1 (default) = q-gram pre-filter + Myers filter, 2 = Myers filter only,
  * 0 = off: every exact piece hit goes through k_verify */
 int pm_engine_set_fused_filter(pm_engine *e, int on);
+/* Specialised scan kernels: for approximate (SPLIT) searches the engine can write the dense part of the scan as
+ * straight-line CUDA for exactly the request's patterns and compile it with NVRTC for sm_100a (about 0.2 s, cached
+ * per process and request text).  0 = never, 1 (default) = when the request covers at least 2^28 pattern x bases and
+ * libnvrtc is present, 2 = always (error when NVRTC is missing).  Results are identical either way. */
+int pm_engine_set_jit(pm_engine *e, int mode);
+/* host-only: the CUDA source the engine would compile for this request (debugging, SASS inspection).
+ * Returns the number of bytes needed (including the terminating 0) or a negative PM_ERR_*. */
+int64_t pm_jit_source(int npat, const char *const *patterns, const char *kopt, char *buf, int64_t cap);
 /* the reference's -b buffer size in BYTES (patmatch.py:37,733 pass 1600000, the default here):
  * nrgrep_coords scans the file one buffer fill at a time and no hit crosses a fill. 0 = one fill. */
 int pm_engine_set_buffer_size(pm_engine *e, int64_t bytes);

@@ -36,7 +36,7 @@ class PmStats(ctypes.Structure):
                 ("chain_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
                 ("candidates", ctypes.c_int64), ("verified", ctypes.c_int64), ("hits", ctypes.c_int64),
                 ("scan_bytes", ctypes.c_int64), ("scan_bases", ctypes.c_int64), ("launches", ctypes.c_int),
-                ("packed", ctypes.c_int), ("qgram_chunks", ctypes.c_int), ("syncs", ctypes.c_int)]
+                ("packed", ctypes.c_int), ("qgram_chunks", ctypes.c_int), ("syncs", ctypes.c_int), ("jit", ctypes.c_int)]
 
 
 HIT_DTYPE = np.dtype([("beg", "<i8"), ("end", "<i8")])
@@ -70,6 +70,9 @@ def load():
     L.pm_engine_set_scan_mode.argtypes = [vp, ctypes.c_int]
     L.pm_engine_set_buffer_size.argtypes = [vp, i64]
     L.pm_engine_set_fused_filter.argtypes = [vp, ctypes.c_int]
+    L.pm_engine_set_jit.argtypes = [vp, ctypes.c_int]
+    L.pm_jit_source.restype = ctypes.c_int64
+    L.pm_jit_source.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int64]
     L.pm_search_fills_device.argtypes = [vp, vp, ctypes.c_char_p, ctypes.c_char_p, i64, i64, vp, i64, ctypes.POINTER(i64), vp]
     L.pm_search_stream.argtypes = [vp, vp, i64, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_char_p, i64, vp, i64,
                                    ctypes.POINTER(i64), ctypes.POINTER(vp)]
@@ -278,6 +281,10 @@ class Engine:
     def set_fused_filter(self, on):
         """True/1 = q-gram pre-filter + Myers filter (default), 2 = Myers filter only, False/0 = off"""
         _check(load().pm_engine_set_fused_filter(self._h, int(on)))
+
+    def set_jit(self, mode):
+        """'off' | 'auto' | 'always' -- per-request specialised scan kernels (NVRTC); results are identical"""
+        _check(load().pm_engine_set_jit(self._h, {"off": 0, "auto": 1, "always": 2}[mode]))
 
     def set_buffer_size(self, nbytes):
         """the reference's -b (bytes); patmatch.py uses 1600000, the default"""

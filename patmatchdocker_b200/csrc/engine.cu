@@ -20,6 +20,7 @@
 #include <cub/device/device_select.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -29,6 +30,8 @@
 #include <mutex>
 #include "../../include/patmatch_b200.h"
 #include "plan.hpp"
+#include "apx_jit.hpp"
+#include <map>
 
 #define PM_MAXK 15
 
@@ -735,6 +738,7 @@ struct pm_engine {
     int fused_filter = 1;                           // packed scan drops candidates whose verification surely fails
     int qgram_filter = 1;                           // bit-sliced q-gram pre-filter in front of the Myers filter
     int split_kernel = 1;                           // 1: k_scan_apx (chunk-built pieces + Landau-Vishkin check), 2: k_scan_split (first generation), 0: block-tile kernel
+    int jit_mode = 1;                               // 0: never, 1: auto (genome-scale requests), 2: always -- specialised scan kernels (apx_jit.cpp)
     bool attr_exact = false, attr_split = false, attr_apx = false;   // cudaFuncSetAttribute is per device: kept per engine
     // one spare text buffer and one spare plane buffer, so that re-creating a dataset of the same size
     // (a request that uploads its file every time) does not pay cudaMalloc/cudaFree of gigabytes
@@ -905,6 +909,7 @@ int pm_engine_create(int device, pm_engine **out)
     e->stream = e->own;
     for (auto &ev : e->ev) CK(cudaEventCreate(&ev));
     CK(cudaMallocHost((void **)&e->h_count, 64));
+    if (const char *j = getenv("PM_JIT")) { const int m = atoi(j); if (m >= 0 && m <= 2) e->jit_mode = m; }   // test hook: force / forbid the specialised kernels
     *out = e;
     return PM_OK;
 }
@@ -948,6 +953,14 @@ int pm_engine_set_fused_filter(pm_engine *e, int on)
     e->fused_filter = on ? 1 : 0;
     e->qgram_filter = (on == 1 || on == 4) ? 1 : 0;
     e->split_kernel = on == 3 ? 0 : (on == 4 || on == 5) ? 2 : 1;   // 4 / 5: first-generation k_scan_split with / without the q-gram count
+    return PM_OK;
+}
+
+int pm_engine_set_jit(pm_engine *e, int mode)
+{
+    if (!e || mode < 0 || mode > 2) { g_err = "bad argument"; return PM_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
+    e->jit_mode = mode;
     return PM_OK;
 }
 
@@ -1281,7 +1294,7 @@ static bool apx_eligible(const pm_engine *e, const pm_dataset *d, const Compiled
 // tilings and equal-information segmentations that ignore the piece borders (pieces evaluated position by position),
 // (C) no q-gram count at all.  Cost in warp instructions per 8192-base warp tile: dense work + expected pattern starts
 // that reach the per-anchor check.
-static void build_apx_pat(const pm_engine *e, const Compiled &c, long long a0, long long a1, unsigned long long tag, ApxPat &out)
+static void build_apx_pat(bool qgram, const Compiled &c, long long a0, long long a1, unsigned long long tag, ApxPat &out)
 {
     const DevPlan &dp = c.dp;
     const int m = dp.m, k = dp.k, L = dp.L, np = dp.npieces;
@@ -1427,7 +1440,7 @@ static void build_apx_pat(const pm_engine *e, const Compiled &c, long long a0, l
     };
     // (C) no count, pieces position by position
     evaluate({}, false);
-    if (e->qgram_filter) {
+    if (qgram) {
         // (A) pieces cut into 1..3 sub-chunks of about equal information
         {
             std::vector<int> parts((size_t)np, 1);
@@ -1489,6 +1502,59 @@ static void build_apx_pat(const pm_engine *e, const Compiled &c, long long a0, l
     out = best;
 }
 
+// ---- specialised kernels (NVRTC): compiled once per request text, shared by all engines of the process ----
+#define PM_JIT_MIN_WORK (1LL << 28)     // pattern x bases from which a ~0.2 s compilation pays off within a few requests
+struct JitEntry {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t kern = nullptr;
+    int rc = PM_OK;
+    std::string err;
+    unsigned long long attr_devices = 0;   // devices on which the shared-memory attribute has been set
+};
+static std::mutex g_jit_mu;
+static std::map<std::string, JitEntry> g_jit_cache;
+
+static int launch_apx_jit(pm_engine *e, const ApxArgs &a, int grid, size_t smem)
+{
+    const std::string prefix = apx_generate_prefix(a.pat, a.npat);
+    cudaKernel_t kern = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_jit_mu);
+        auto it = g_jit_cache.find(prefix);
+        if (it == g_jit_cache.end()) {
+            JitEntry en;
+            std::vector<char> cubin;
+            std::string log;
+            if (apx_jit_compile(apx_full_source(prefix), cubin, log)) {
+                en.rc = log.find("libnvrtc") != std::string::npos ? PM_ERR_UNSUPPORTED : PM_ERR_CUDA;
+                en.err = "specialised scan kernel: " + log;
+            } else {
+                cudaError_t ce = cudaLibraryLoadData(&en.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+                if (ce == cudaSuccess) ce = cudaLibraryGetKernel(&en.kern, en.lib, "k_scan_apx_jit");
+                if (ce != cudaSuccess) { en.rc = PM_ERR_CUDA; en.err = std::string("loading the specialised scan kernel: ") + cudaGetErrorString(ce); (void)cudaGetLastError(); }
+            }
+            it = g_jit_cache.emplace(prefix, en).first;
+        }
+        JitEntry &en = it->second;
+        if (en.rc) { g_err = en.err; return en.rc; }
+        if (!(en.attr_devices >> (e->device & 63) & 1ULL)) {
+            CK(cudaFuncSetAttribute((const void *)en.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            en.attr_devices |= 1ULL << (e->device & 63);
+        }
+        kern = en.kern;
+    }
+    JitArgs ja;
+    memset(&ja, 0, sizeof ja);
+    ja.hi = a.hi; ja.lo = a.lo; ja.xx = a.xx; ja.nwords = a.nwords; ja.n = a.n; ja.tile0 = a.tile0; ja.ntiles = a.ntiles;
+    ja.keys = a.keys; ja.count = a.count; ja.cap = a.cap;
+    for (int p = 0; p < a.npat; p++) { ja.a0[p] = a.pat[p].a0; ja.a1[p] = a.pat[p].a1; ja.keytag[p] = a.pat[p].keytag; }
+    void *params[] = {&ja};
+    CK(cudaLaunchKernel((const void *)kern, dim3((unsigned)grid), dim3(EX_WARPS * 32), params, smem, e->stream));
+    e->stats.launches++;
+    e->stats.jit = 1;
+    return PM_OK;
+}
+
 static int launch_apx(pm_engine *e, pm_dataset *d, const ApxPat *pats, int npat, const ScanTarget &t)
 {
     ApxArgs a;
@@ -1521,16 +1587,22 @@ static int launch_apx(pm_engine *e, pm_dataset *d, const ApxPat *pats, int npat,
     }
     const long long nbt = (a.ntiles + 7) / 8;
     const int grid = std::max((int)std::min<long long>(nbt, (long long)e->sms * SP_CTAS), 1);
+    e->stats.scan_bytes += a.ntiles * 128 * 4 * 3;
+    e->stats.scan_bases += (hi - lo) * a.npat;
+    e->stats.packed = 1;
+    e->stats.qgram_chunks = a.pat[0].ncounted;
+    // genome-scale requests: straight-line kernel compiled for exactly these patterns (apx_jit.cpp)
+    if (e->jit_mode == 2 || (e->jit_mode == 1 && (hi - lo) * a.npat >= PM_JIT_MIN_WORK)) {
+        int rc = launch_apx_jit(e, a, grid, smem);
+        if (rc == PM_OK) return PM_OK;
+        if (e->jit_mode == 2 || rc != PM_ERR_UNSUPPORTED) return rc;   // auto mode: no NVRTC on this machine -> generic kernel
+    }
 #define PM_LAUNCH(R, W) k_scan_apx<R, W><<<grid, EX_WARPS * 32, smem, e->stream>>>(a)
     if (narrow) { if (k == 1) PM_LAUNCH(2, unsigned); else if (k == 2) PM_LAUNCH(3, unsigned); else PM_LAUNCH(4, unsigned); }
     else { if (k == 1) PM_LAUNCH(2, unsigned long long); else if (k == 2) PM_LAUNCH(3, unsigned long long); else PM_LAUNCH(4, unsigned long long); }
 #undef PM_LAUNCH
     CK(cudaGetLastError());
     e->stats.launches++;
-    e->stats.scan_bytes += a.ntiles * 128 * 4 * 3;
-    e->stats.scan_bases += (hi - lo) * a.npat;
-    e->stats.packed = 1;
-    e->stats.qgram_chunks = a.pat[0].ncounted;
     return PM_OK;
 }
 
@@ -1557,7 +1629,7 @@ static int launch_scan(pm_engine *e, pm_dataset *d, const Compiled &c_full, long
                     return launch_exact(e, d, &pt, 1, bad, t);
                 } else if (apx_eligible(e, d, c)) {
                     ApxPat ap;
-                    build_apx_pat(e, c, a0, wend, tag, ap);
+                    build_apx_pat(e->qgram_filter != 0, c, a0, wend, tag, ap);
                     return launch_apx(e, d, &ap, 1, t);
                 } else {
                     PackedArgs<4> a;

@@ -14,6 +14,7 @@
 // accepts only SOME non-ACGT bytes are treated as accepting all of them; k_verify then
 // re-checks every candidate against the raw bytes, so the candidate set stays exact.
 #pragma once
+#include "apx.hpp"
 
 struct PackedPos { unsigned char sel; unsigned char cls; };   // sel 0..4 = plane A,C,G,T,X ; 5 = class `cls` (bits A,C,G,T,X)
 
@@ -164,7 +165,6 @@ struct PackedVerify {
 // Exact (k = 0, SIMPLE) scan: one piece, registers only, next tile prefetched while the current
 // one is evaluated.  Positions are grouped by the plane they read so that no per-position
 // dispatch is needed.
-#define EX_MAXPAT 2                     // patterns evaluated per staged tile: a motif and its reverse complement (one PatMatch request)
 struct ExactPat {
     long long a0, a1;                     // window starts a0 <= w < a1 (already cut to n - L + 1)
     unsigned long long keytag;            // pid << PM_PID_SHIFT
@@ -1090,33 +1090,6 @@ __global__ void __launch_bounds__(EX_WARPS * 32, SP_CTAS) k_scan_split(const Pac
 //     exact piece); record ends, fill cuts, line anchors and the scan start only remove alignments.  Which pieces
 //     matched exactly comes for free from the nominal diagonal D_k.
 // Survivors are decided on the raw bytes by k_verify as before.
-#define AX_MAXCH 12
-#define AX_MAXLEN 12
-#define AX_MAXDENSE 64
-#define AX_QUEUE 128                     // per-warp queue of pattern starts (b << 1 | pattern)
-struct ApxChunk {
-    unsigned char off;                   // first bit of the (dilated) window, relative to b
-    unsigned char npos;                  // constrained positions of the chunk
-    unsigned char piece;                 // piece the chunk is part of (its plane is ANDed into that piece), 0xff = none
-    unsigned char poff;                  // k + start of the chunk: bit b of (plane >> poff) <=> the chunk sits at its nominal place
-    unsigned char first, last;           // first / last chunk of its piece
-    unsigned char counted;               // takes part in the q-gram count (0: too unselective, only builds its piece)
-    unsigned char pad;
-    unsigned char t[AX_MAXLEN];          // offsets of the constrained positions inside the chunk
-    unsigned char cls[AX_MAXLEN];        // their classes (bits A,C,G,T,X)
-};
-struct ApxPat {
-    long long a0, a1;                    // anchors a0 <= p < a1
-    unsigned long long keytag;
-    unsigned long long posmask[5];       // pattern positions accepting A, C, T, G (code = hi<<1|lo) and some non-ACGT byte
-    int m, k, L, npieces, indel;
-    int V[4];
-    int nch, win, ncounted;
-    ApxChunk ch[AX_MAXCH];
-    unsigned char dn[4];                 // per piece: positions evaluated one by one (pieces not covered by chunks)
-    unsigned char dwild[4];              // piece without any constrained position: matches everywhere
-    unsigned char dshift[AX_MAXDENSE], dcls[AX_MAXDENSE];
-};
 struct ApxArgs {
     const unsigned *hi, *lo, *xx;
     long long nwords, n, tile0, ntiles;

@@ -240,7 +240,7 @@ static int scan_request(pm_engine *e, pm_dataset *d, const Request &rq, const Fi
             if ((int)ex.size() == EX_MAXPAT && (rc = flush_exact())) return rc;
         } else if (apx_eligible(e, d, c)) {
             ApxPat ap;
-            build_apx_pat(e, c, a0, std::min(a1, d->n - c.dp.L + 1), tag, ap);
+            build_apx_pat(e->qgram_filter != 0, c, a0, std::min(a1, d->n - c.dp.L + 1), tag, ap);
             ax.push_back(ap);
             if ((int)ax.size() == EX_MAXPAT && (rc = flush_apx())) return rc;
         } else {
@@ -462,4 +462,29 @@ int pm_request_fills_device(pm_engine *e, pm_dataset *d, int npat, const char *c
     const long long rows = std::min<long long>(out_rows, cap + req_hdr_rows(npat));
     CK(cudaMemcpyAsync(dev_out, e->hits2.p, (size_t)rows * sizeof(pm_hit), cudaMemcpyDeviceToDevice, e->stream));
     return PM_OK;
+}
+
+// host-only: the source apx_jit.cpp would hand to NVRTC for this request
+int64_t pm_jit_source(int npat, const char *const *patterns, const char *kopt, char *buf, int64_t cap)
+{
+    if (npat < 1 || npat > EX_MAXPAT || !patterns || !kopt) { g_err = "bad argument"; return PM_ERR_ARG; }
+    Request rq;
+    int rc = compile_request(npat, patterns, kopt, rq);
+    if (rc) return rc;
+    std::vector<ApxPat> ax((size_t)npat);
+    for (int p = 0; p < npat; p++) {
+        const Compiled &c = rq.comp[p];
+        const DevPlan &dp = c.dp;
+        if (c.scan || dp.type != PM_PLAN_SPLIT || dp.k < 1 || dp.k > 3 || dp.m + 2 * dp.k > 64 || dp.npieces > 4 || !plain_triggers(dp)) {
+            g_err = "no specialised kernel for this plan"; return PM_ERR_UNSUPPORTED;
+        }
+        build_apx_pat(true, c, 0, 1LL << 40, (unsigned long long)p << PM_PID_SHIFT, ax[(size_t)p]);
+    }
+    const std::string src = apx_full_source(apx_generate_prefix(ax.data(), npat));
+    if (buf && cap > 0) {
+        const size_t ncopy = std::min<size_t>(src.size(), (size_t)cap - 1);
+        memcpy(buf, src.data(), ncopy);
+        buf[ncopy] = 0;
+    }
+    return (int64_t)src.size() + 1;
 }

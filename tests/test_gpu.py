@@ -873,3 +873,57 @@ def test_batch_with_errors_equals_single(engine):
         want = O.search(pats[i], g, "1ids")
         assert [(int(b), int(e)) for b, e in hits[off[i]:off[i + 1]]] == want, pats[i]
     ds.close()
+
+
+def test_specialised_kernels_equal_generic_and_oracle(engine):
+    # pm_engine_set_jit: SPLIT requests as straight-line kernels compiled by NVRTC for exactly the request's patterns
+    # (apx_jit.cpp).  Same candidates, same hits as the generic kernel and as the oracle; one and two patterns per
+    # launch, 32- and 64-symbol windows, substitutions only and indels, texts with N runs / lower case / IUPAC letters.
+    rng = random.Random(4242)
+    engine.set_scan_mode("packed")
+    used = 0
+    try:
+        for it in range(36):
+            k = rng.randint(1, 3)
+            m = rng.randint(max(2 * k + 2, 6), 26 if it % 3 else 56)
+            pat, members = random_pattern(rng, DNA, m, cls_pct=0.3, dot_pct=0.25)
+            kopt = "%d%s" % (k, rng.choice(["ids", "ids", "s", "id", "is", "ds"]))
+            try:
+                if pm.plan(pat, kopt)["type"] != "SPLIT":
+                    continue
+            except pm.NativeError:
+                continue
+            comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+            members2 = [[comp[c] for c in cls] for cls in reversed(members)]
+            pat2 = "(" + "".join(c[0] if len(c) == 1 else "." if len(c) == 4 else "[" + "".join(c) + "]" for c in members2) + ")"
+            text = bytearray((random_text(rng, members, DNA, k, nrec=rng.randint(1, 3), lo=2000, hi=60000 if it % 4 == 0 else 9000, plant=0.02) +
+                              random_text(rng, members2, DNA, k, nrec=rng.randint(1, 2), lo=2000, hi=9000, plant=0.02)).encode("latin-1"))
+            for _ in range(6):
+                p = rng.randrange(0, len(text) - 40)
+                if b"\n" in text[p:p + 40] or b">" in text[p:p + 40]:
+                    continue
+                text[p:p + rng.randint(1, 30)] = rng.choice([b"N" * 30, b"RYKMSW" * 5, bytes(text[p:p + 30]).lower()])[:30]
+            text = bytes(text)
+            if it % 5 == 0:
+                engine.set_buffer_size(rng.choice([300, 2000]))
+            ds = engine.load_dataset(text)
+            pats = [pat, pat2] if it % 2 == 0 else [pat]
+            engine.set_jit("always")
+            a = engine.search_request(ds, pats, kopt)
+            used += engine.stats()["jit"]
+            engine.set_jit("off")
+            b = engine.search_request(ds, pats, kopt)
+            assert engine.stats()["jit"] == 0
+            bufsize = 1600000
+            ds.close()
+            for p_, x, y in zip(pats, a, b):
+                assert np.array_equal(x, y), (p_, kopt)
+            if it % 5 != 0:
+                for p_, x in zip(pats, a):
+                    assert [(int(s), int(e)) for s, e in x] == O.search(p_, text, kopt, bufsize=bufsize), (p_, kopt)
+            engine.set_buffer_size(1600000)
+        assert used >= 10, used
+    finally:
+        engine.set_jit("auto")
+        engine.set_buffer_size(1600000)
+        engine.set_scan_mode("auto")
