@@ -102,6 +102,8 @@ int pm_engine_set_jit(pm_engine *e, int mode);
 /* host-only: the CUDA source the engine would compile for this request (debugging, SASS inspection).
  * Returns the number of bytes needed (including the terminating 0) or a negative PM_ERR_*. */
 int64_t pm_jit_source(int npat, const char *const *patterns, const char *kopt, char *buf, int64_t cap);
+/* drops the per-process caches of compiled patterns and chunk plans (experiments that change PM_APX_* environment knobs) */
+int pm_debug_reset_caches(void);
 /* the reference's -b buffer size in BYTES (patmatch.py:37,733 pass 1600000, the default here):
  * nrgrep_coords scans the file one buffer fill at a time and no hit crosses a fill. 0 = one fill. */
 int pm_engine_set_buffer_size(pm_engine *e, int64_t bytes);

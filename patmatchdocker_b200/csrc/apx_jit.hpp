@@ -6,6 +6,19 @@
 
 // The request-specific part of the CUDA source (constants + straight-line dense_<p> functions).  It doubles as the
 // cache key of the compiled kernel: two requests with the same text here run the same code.
+// resident CTAs per SM the kernel is compiled for (register budget); the launch grid is sms x this
+int apx_jit_ctas();
+// words of 32 pattern starts a lane holds (8: 4 warps per CTA, 4: 8 warps per CTA with half the registers each)
+int apx_jit_wpl();
+// launch geometry of the kernel apx_generate_prefix writes (environment knobs PM_JIT_* are for experiments)
+struct ApxJitShape {
+    int stream;          // 1: streaming form (jit_stream_kernel.inc), 0: unrolled tile form (jit_apx_kernel.inc)
+    int w;               // words of 32 bases per lane (segment length / words per lane of a warp tile)
+    int warps, stages, ctas;
+    int tile_words;      // words per plane of a block tile
+    size_t smem;         // dynamic shared memory per CTA
+};
+ApxJitShape apx_jit_shape();
 std::string apx_generate_prefix(const ApxPat *pats, int npat);
 // prefix + the constant kernel body
 std::string apx_full_source(const std::string &prefix);

@@ -747,6 +747,8 @@ struct pm_engine {
     pm_stats stats{};
 };
 
+// words of padding in front of the hi plane: the streaming scan kernels stage tiles together with the words before them
+#define PM_PLANE_FRONT 128
 struct pm_dataset {
     pm_engine *e = nullptr;
     const unsigned char *d_text = nullptr;
@@ -755,6 +757,7 @@ struct pm_dataset {
     long long n = 0;
     // 2-bit packed planes (packed.cuh)
     unsigned *hi = nullptr, *lo = nullptr, *xx = nullptr;
+    void *planes_base = nullptr;   // allocation that holds the planes: PM_PLANE_FRONT words of padding, then hi | lo | xx
     long long nwords = 0;
     long long nexc = 0;            // bytes that are not ACGTacgt
     bool dna_like = false;         // few enough exceptions for the packed scan to pay off
@@ -778,7 +781,7 @@ static int pack_dataset(pm_engine *e, pm_dataset *d)
     nw = (nw + 1023) / 1024 * 1024 + 1024;          // whole block tiles of the TMA-staged scan + halo
     d->nwords = nw;
     void *p = nullptr;
-    const size_t need = (size_t)nw * 4 * 3;
+    const size_t need = ((size_t)nw * 3 + PM_PLANE_FRONT) * 4;
     if (e->pool_planes && e->pool_planes_cap >= need) {
         p = e->pool_planes; d->planes_cap = e->pool_planes_cap;
         e->pool_planes = nullptr; e->pool_planes_cap = 0;
@@ -786,7 +789,9 @@ static int pack_dataset(pm_engine *e, pm_dataset *d)
         CK(cudaMalloc(&p, need));
         d->planes_cap = need;
     }
-    d->hi = (unsigned *)p; d->lo = d->hi + nw; d->xx = d->lo + nw;
+    d->planes_base = p;
+    d->hi = (unsigned *)p + PM_PLANE_FRONT; d->lo = d->hi + nw; d->xx = d->lo + nw;
+    CK(cudaMemsetAsync(p, 0, PM_PLANE_FRONT * 4, e->stream));
     int rc;
     if ((rc = e->counters.reserve(64))) return rc;
     unsigned long long *d_exc = (unsigned long long *)((char *)e->counters.p + 32);
@@ -1042,8 +1047,8 @@ void pm_dataset_destroy(pm_dataset *d)
     if (d->hi) {
         if (!e->pool_planes || e->pool_planes_cap < d->planes_cap) {
             if (e->pool_planes) cudaFree(e->pool_planes);
-            e->pool_planes = d->hi; e->pool_planes_cap = d->planes_cap;
-        } else cudaFree(d->hi);
+            e->pool_planes = d->planes_base; e->pool_planes_cap = d->planes_cap;
+        } else cudaFree(d->planes_base);
     }
     if (d->d_fills) cudaFree(d->d_fills);
     delete d;
@@ -1091,9 +1096,34 @@ struct Compiled {
     pm::VerifyTables vt;
     // EXTENDED plans: the exact scan runs on the window of plain positions around the anchor, compiled as a SIMPLE pattern
     std::shared_ptr<Compiled> scan;
+    std::string key;                  // (pattern, -k) text this was compiled from: key of the per-process caches
 };
 
+static int compile_uncached(const char *pattern, const char *kopt, Compiled &c, bool need_tables);
+
+// Parsing, the reference's cost model (esimplePreproc @415540) and the verification tables are pure functions of
+// (pattern, -k): the results are kept per process, so that a repeated request costs a map lookup and a copy.
+static std::mutex g_compile_mu;
+static std::map<std::string, std::shared_ptr<const Compiled>> g_compile_cache;
+
 static int compile(const char *pattern, const char *kopt, Compiled &c, bool need_tables)
+{
+    std::string key = std::string(need_tables ? "T" : "P") + kopt + '\x01' + pattern;
+    {
+        std::lock_guard<std::mutex> lock(g_compile_mu);
+        auto it = g_compile_cache.find(key);
+        if (it != g_compile_cache.end()) { c = *it->second; return PM_OK; }
+    }
+    int rc = compile_uncached(pattern, kopt, c, need_tables);
+    if (rc) return rc;
+    c.key = key;
+    std::lock_guard<std::mutex> lock(g_compile_mu);
+    if (g_compile_cache.size() >= 4096) g_compile_cache.clear();
+    g_compile_cache[key] = std::make_shared<const Compiled>(c);
+    return PM_OK;
+}
+
+static int compile_uncached(const char *pattern, const char *kopt, Compiled &c, bool need_tables)
 {
     std::string err;
     int rc = pm::parse_kopt(kopt, c.o, err);
@@ -1294,14 +1324,59 @@ static bool apx_eligible(const pm_engine *e, const pm_dataset *d, const Compiled
 // tilings and equal-information segmentations that ignore the piece borders (pieces evaluated position by position),
 // (C) no q-gram count at all.  Cost in warp instructions per 8192-base warp tile: dense work + expected pattern starts
 // that reach the per-anchor check.
-static void build_apx_pat(bool qgram, const Compiled &c, long long a0, long long a1, unsigned long long tag, ApxPat &out)
+// Cost constants of the two kernels that execute an ApxPat, in warp instructions per 8192-base warp tile.
+struct ApxCost {
+    double pos;            // one constrained position ANDed into its chunk plane (shift + AND)
+    double cls;            // one class plane (per run of equal classes inside a chunk)
+    double derive;         // chunk plane shifted to the nominal diagonal and ANDed into its piece
+    double dense_pos;      // one position of a piece evaluated directly at the nominal diagonal
+    double dense_piece;    // per piece evaluated directly
+    double dil_step;       // one dilation step (generic kernel: doubling; specialised: see dil[])
+    double dil[4];         // specialised kernel: whole dilation for win = 1, 3, 5, 7
+    double count_fix, count_row;
+    double survivor;       // one pattern start that reaches the sparse stage (extraction + 1/32 Landau-Vishkin round)
+};
+static const ApxCost kCostGeneric = {45.0, 0.0, 18.0, 43.0, 12.0, 20.0, {0, 0, 0, 0}, 26.0, 16.0, 0.0};
+static const ApxCost kCostJit = {13.5, 9.0, 12.0, 13.5, 4.0, 0.0, {8.0, 24.0, 43.0, 51.0}, 0.0, 8.0, 28.0};
+
+static void build_apx_pat_uncached(bool qgram, bool jit, const Compiled &c, ApxPat &out);
+
+static std::mutex g_apx_mu;
+static std::map<std::string, ApxPat> g_apx_cache;
+
+static void build_apx_pat(bool qgram, bool jit, const Compiled &c, long long a0, long long a1, unsigned long long tag, ApxPat &out)
 {
+    const std::string key = std::string(qgram ? "Q" : "N") + (jit ? "J" : "G") + c.key;
+    bool hit = false;
+    if (!c.key.empty()) {
+        std::lock_guard<std::mutex> lock(g_apx_mu);
+        auto it = g_apx_cache.find(key);
+        if (it != g_apx_cache.end()) { out = it->second; hit = true; }
+    }
+    if (!hit) {
+        build_apx_pat_uncached(qgram, jit, c, out);
+        if (!c.key.empty()) {
+            std::lock_guard<std::mutex> lock(g_apx_mu);
+            if (g_apx_cache.size() >= 4096) g_apx_cache.clear();
+            g_apx_cache[key] = out;
+        }
+    }
+    out.a0 = a0; out.a1 = a1; out.keytag = tag;
+}
+
+// Chunk selection.  Candidate chunk sets: (A) every piece cut into 1..3 sub-chunks of about equal information and the
+// stretches between / around the pieces cut into 1..2 chunks (then piece planes are ANDs of chunk planes and every
+// pattern position is evaluated once), (B) uniform tilings and equal-information segmentations that ignore the piece
+// borders (pieces evaluated position by position), (C) no q-gram count at all.  Cost: dense work + expected pattern
+// starts that reach the per-anchor check, with the constants of the kernel that will run the plan.
+static void build_apx_pat_uncached(bool qgram, bool jit, const Compiled &c, ApxPat &out)
+{
+    const ApxCost &K = jit ? kCostJit : kCostGeneric;
     const DevPlan &dp = c.dp;
     const int m = dp.m, k = dp.k, L = dp.L, np = dp.npieces;
     const int win = (dp.ins || dp.del) ? 2 * k + 1 : 1;
     const int rows = k + 1;
     memset(&out, 0, sizeof out);
-    out.a0 = a0; out.a1 = a1; out.keytag = tag;
     out.m = m; out.k = k; out.L = L; out.npieces = np; out.indel = (dp.ins || dp.del) ? 1 : 0;
     for (int i = 0; i < np; i++) out.V[i] = dp.V[i];
     out.win = win;
@@ -1323,16 +1398,22 @@ static void build_apx_pat(bool qgram, const Compiled &c, long long a0, long long
     }
     int steps = 0;
     for (int cw = 1; cw < win; cw += std::min(cw, win - cw)) steps++;
-    // per pattern start that reaches the sparse stage: extraction + 1/32 of a Landau-Vishkin round
-    const double anchor_ops = (m + 2 * k <= 32 ? 1.0 : 1.6) * (4.0 + 1.2 * (2 * k + 1) * (k + 1)) + 3.0;
+    const double dil_cost = jit ? K.dil[std::min(win / 2, 3)] : K.dil_step * steps;
+    const double count_cost = dil_cost + K.count_fix + K.count_row * rows;
+    // per pattern start that reaches the sparse stage
+    const double anchor_ops = jit ? K.survivor : (m + 2 * k <= 32 ? 1.0 : 1.6) * (4.0 + 1.2 * (2 * k + 1) * (k + 1)) + 3.0;
     struct Seg { int b, e, piece; };
     ApxPat best = out;
-    double best_cost = -1;
+    double best_cost = -1, best_ops = 0, best_surv = 0;
+    const char *fam_env = getenv("PM_APX_FAMILY");                     // experiments: restrict the candidate families (A, B, C)
+    const bool dbg = getenv("PM_APX_DEBUG") != nullptr;
+    auto fam_ok = [&](char f) { return !fam_env || strchr(fam_env, f) != nullptr; };
     auto evaluate = [&](const std::vector<Seg> &segs, bool derive) {
         ApxPat cur = out;
         double ops = 0;
         std::vector<std::pair<int, int>> span;                         // constrained positions of each COUNTED chunk: [first, last]
         std::vector<int> covered((size_t)m, 0);
+        std::vector<double> chunk_ops;                                 // evaluation cost of each kept chunk (to undo it)
         for (const Seg &sg : segs) {
             if (cur.nch >= AX_MAXCH) { if (derive) return; break; }
             ApxChunk ch;
@@ -1341,6 +1422,8 @@ static void build_apx_pat(bool qgram, const Compiled &c, long long a0, long long
             double pr = 1;
             int first = -1, last = -1;
             bool cut = false;
+            unsigned seen_cls = 0;
+            int ncls = 0;
             for (int j = sg.b; j < sg.e; j++) {
                 if (pcls[j] == 31u) continue;
                 if (first < 0) first = j;
@@ -1348,27 +1431,31 @@ static void build_apx_pat(bool qgram, const Compiled &c, long long a0, long long
                 ch.t[ch.npos] = (unsigned char)(j - first);
                 ch.cls[ch.npos] = (unsigned char)pcls[j];
                 ch.npos++;
+                if (!(seen_cls >> pcls[j] & 1u)) { seen_cls |= 1u << pcls[j]; ncls++; }
                 pr *= pprob[j];
                 last = j;
             }
             if (first < 0) continue;
-            if (cut && derive) return;                                 // a derived piece needs all its positions in chunks
+            if (cut && derive && sg.piece >= 0) return;                // a derived piece needs all its positions in chunks
             pr = std::min(pr * win, 1.0);
             ch.counted = pr <= 0.6 ? 1 : 0;                            // hardly ever missing: not worth counting
-            if (!ch.counted && !derive) continue;
+            const bool builds = derive && sg.piece >= 0;
+            if (!ch.counted && !builds) continue;
             ch.off = (unsigned char)(first + (win > 1 ? 0 : k));
             ch.poff = (unsigned char)(first + k);
-            if (derive) ch.piece = (unsigned char)sg.piece;
-            ops += 45.0 * ch.npos + (derive ? 18.0 : 0.0);
-            if (ch.counted) { ops += 20.0 * steps + 26.0 + 16.0 * rows; span.push_back({first, last}); }
+            if (builds) ch.piece = (unsigned char)sg.piece;
+            const double ev = K.pos * ch.npos + K.cls * ncls;
+            ops += ev + (builds ? (ch.counted || !jit ? K.derive : K.dense_piece) : 0.0);
+            if (ch.counted) { ops += count_cost; span.push_back({first, last}); }
             for (int t = 0; t < ch.npos; t++) covered[first + ch.t[t]] = 1;
+            chunk_ops.push_back(ev);
             cur.ch[cur.nch++] = ch;
         }
         int ncounted = (int)span.size();
         if (ncounted <= k) {                                           // k missing chunks are always allowed: no count
-            if (!derive) { cur.nch = 0; ops = 0; }
+            if (!derive) { cur.nch = 0; ops = 0; chunk_ops.clear(); }
             else for (int g = 0; g < cur.nch; g++) {
-                if (cur.ch[g].counted) ops -= 20.0 * steps + 26.0 + 16.0 * rows;
+                if (cur.ch[g].counted) ops -= count_cost;
                 cur.ch[g].counted = 0;
             }
             ncounted = 0;
@@ -1389,7 +1476,8 @@ static void build_apx_pat(bool qgram, const Compiled &c, long long a0, long long
                 else { cur.ch[gf].first = 1; cur.ch[gl].last = 1; }
             }
             if (!derived) {
-                for (int g = 0; g < cur.nch; g++) if (cur.ch[g].piece == i) { cur.ch[g].piece = 0xff; ops -= 18.0; }
+                for (int g = 0; g < cur.nch; g++) if (cur.ch[g].piece == i) { cur.ch[g].piece = 0xff; ops -= K.derive; }
+                unsigned seen_cls = 0;
                 for (int j = dp.V[i]; j < dp.V[i] + L; j++) {
                     if (pcls[j] == 31u) continue;
                     if (dp_n >= AX_MAXDENSE) return;
@@ -1397,16 +1485,17 @@ static void build_apx_pat(bool qgram, const Compiled &c, long long a0, long long
                     cur.dcls[dp_n] = (unsigned char)pcls[j];
                     dp_n++;
                     cur.dn[i]++;
-                    ops += 43.0;
+                    ops += K.dense_pos;
+                    if (!(seen_cls >> pcls[j] & 1u)) { seen_cls |= 1u << pcls[j]; ops += K.cls; }
                 }
-                ops += 12.0;
+                ops += K.dense_piece;
             }
         }
         // uncounted chunks that build no piece are useless
         {
             int w = 0;
             for (int g = 0; g < cur.nch; g++) {
-                if (!cur.ch[g].counted && cur.ch[g].piece == 0xff) { ops -= 45.0 * cur.ch[g].npos; continue; }
+                if (!cur.ch[g].counted && cur.ch[g].piece == 0xff) { ops -= chunk_ops[(size_t)g]; continue; }
                 cur.ch[w++] = cur.ch[g];
             }
             cur.nch = w;
@@ -1436,41 +1525,75 @@ static void build_apx_pat(bool qgram, const Compiled &c, long long a0, long long
             survivors += piece_rate[i] * pass;
         }
         const double cost = ops + std::min(survivors, 1.0) * 8192.0 * anchor_ops;
-        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = cur; }
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = cur; best_ops = ops; best_surv = survivors; }
     };
     // (C) no count, pieces position by position
     evaluate({}, false);
     if (qgram) {
-        // (A) pieces cut into 1..3 sub-chunks of about equal information
+        if (fam_ok('A'))
+        // (A) pieces cut into 1..3 sub-chunks of about equal information; the stretches outside the pieces into 0..2
         {
-            std::vector<int> parts((size_t)np, 1);
+            // equal-information split of [pb, pe) into `parts` segments
+            auto split = [&](int pb, int pe, int parts, int piece, std::vector<Seg> &segs) {
+                double tot = 0;
+                for (int j = pb; j < pe; j++) tot += info[j];
+                int jb = pb;
+                double acc = 0;
+                for (int r = 1; r <= parts && jb < pe; r++) {
+                    const double target = tot * r / parts;
+                    int je = jb;
+                    double a2 = acc;
+                    while (je < pe && (je == jb || std::fabs(a2 + info[je] - target) <= std::fabs(a2 - target))) { a2 += info[je]; je++; }
+                    if (r == parts) je = pe;
+                    segs.push_back({jb, je, piece});
+                    acc = 0;
+                    for (int j = pb; j < je; j++) acc += info[j];
+                    jb = je;
+                }
+            };
+            // stretches not covered by pieces (pieces are sorted by V and disjoint)
+            std::vector<std::pair<int, int>> gaps;
+            {
+                int pos = 0;
+                for (int i = 0; i < np; i++) {
+                    if (dp.V[i] > pos) gaps.push_back({pos, dp.V[i]});
+                    pos = std::max(pos, dp.V[i] + L);
+                }
+                if (pos < m) gaps.push_back({pos, m});
+                std::vector<std::pair<int, int>> keep;
+                for (auto &g : gaps) {
+                    double t = 0;
+                    for (int j = g.first; j < g.second; j++) t += info[j];
+                    if (t > 0) keep.push_back(g);
+                }
+                gaps.swap(keep);
+            }
+            const int ng = std::min((int)gaps.size(), 4);
+            std::vector<int> parts((size_t)np, 1), gparts((size_t)ng, 0);
             for (;;) {
                 std::vector<Seg> segs;
-                for (int i = 0; i < np; i++) {
-                    const int pb = dp.V[i], pe = dp.V[i] + L;
-                    double tot = 0;
-                    for (int j = pb; j < pe; j++) tot += info[j];
-                    int jb = pb;
-                    double acc = 0;
-                    for (int r = 1; r <= parts[i] && jb < pe; r++) {
-                        const double target = tot * r / parts[i];
-                        int je = jb;
-                        double a2 = acc;
-                        while (je < pe && (je == jb || std::fabs(a2 + info[je] - target) <= std::fabs(a2 - target))) { a2 += info[je]; je++; }
-                        if (r == parts[i]) { je = pe; }
-                        segs.push_back({jb, je, i});
-                        acc = 0;
-                        for (int j = pb; j < je; j++) acc += info[j];
-                        jb = je;
+                {
+                    // in pattern order, so that the chunks of a piece stay consecutive
+                    size_t gi = 0;
+                    for (int i = 0; i < np; i++) {
+                        while (gi < (size_t)ng && gaps[gi].first < dp.V[i]) { if (gparts[gi]) split(gaps[gi].first, gaps[gi].second, gparts[gi], -1, segs); gi++; }
+                        split(dp.V[i], dp.V[i] + L, parts[i], i, segs);
                     }
+                    while (gi < (size_t)ng) { if (gparts[gi]) split(gaps[gi].first, gaps[gi].second, gparts[gi], -1, segs); gi++; }
                 }
                 evaluate(segs, true);
                 int q = 0;
                 while (q < np && ++parts[q] > 3) parts[q++] = 1;
-                if (q == np) break;
+                if (q == np) {
+                    int g = 0;
+                    const int gmax = np + ng > 6 ? 1 : 2;              // keeps the enumeration below ~2000 evaluations
+                    while (g < ng && ++gparts[g] > gmax) gparts[g++] = 0;
+                    if (g == ng) break;
+                }
             }
         }
         // (B1) uniform tilings of every length and phase
+        if (fam_ok('B'))
         for (int q = 2; q <= AX_MAXLEN; q++)
             for (int a_off = 0; a_off < q; a_off++) {
                 std::vector<Seg> segs;
@@ -1481,7 +1604,7 @@ static void build_apx_pat(bool qgram, const Compiled &c, long long a0, long long
                 evaluate(segs, false);
             }
         // (B2) T segments of (nearly) equal information: wildcards carry none, so chunks stretch over them
-        {
+        if (fam_ok('B')) {
             std::vector<double> cum((size_t)m + 1, 0.0);
             for (int j = 0; j < m; j++) cum[j + 1] = cum[j] + info[j];
             for (int T = k + 1; T <= std::min(2 * k + 3, AX_MAXCH); T++) {
@@ -1500,10 +1623,21 @@ static void build_apx_pat(bool qgram, const Compiled &c, long long a0, long long
         }
     }
     out = best;
+    if (dbg) fprintf(stderr, "[apx plan] jit=%d nch=%d counted=%d derived-pieces=%d dense ops=%.0f survivors/start=%.5f cost=%.0f\n", (int)jit, best.nch,
+                     best.ncounted, (int)std::count_if(best.ch, best.ch + best.nch, [](const ApxChunk &ch) { return ch.piece != 0xff && ch.first; }),
+                     best_ops, best_surv, best_cost);
+}
+
+int pm_debug_reset_caches(void)
+{
+    { std::lock_guard<std::mutex> lock(g_compile_mu); g_compile_cache.clear(); }
+    { std::lock_guard<std::mutex> lock(g_apx_mu); g_apx_cache.clear(); }
+    return PM_OK;
 }
 
 // ---- specialised kernels (NVRTC): compiled once per request text, shared by all engines of the process ----
-#define PM_JIT_MIN_WORK (1LL << 28)     // pattern x bases from which a ~0.2 s compilation pays off within a few requests
+#define PM_JIT_MIN_WORK (1LL << 27)     // bases per pattern from which a ~0.3 s compilation pays off within a few requests
+static bool jit_wanted(const pm_engine *e, long long bases) { return e->jit_mode == 2 || (e->jit_mode == 1 && bases >= PM_JIT_MIN_WORK); }
 struct JitEntry {
     cudaLibrary_t lib = nullptr;
     cudaKernel_t kern = nullptr;
@@ -1514,14 +1648,28 @@ struct JitEntry {
 static std::mutex g_jit_mu;
 static std::map<std::string, JitEntry> g_jit_cache;
 
-static int launch_apx_jit(pm_engine *e, const ApxArgs &a, int grid, size_t smem)
+static int launch_apx_jit(pm_engine *e, const ApxArgs &a, long long lo, long long hi)
 {
-    const std::string prefix = apx_generate_prefix(a.pat, a.npat);
+    const ApxJitShape shp = apx_jit_shape();
+    // key: the pattern descriptions without what stays a run-time argument (ranges, key tags) + the launch geometry
+    std::string key((size_t)a.npat * sizeof(ApxPat) + sizeof shp, '\0');
+    for (int p = 0; p < a.npat; p++) {
+        ApxPat t = a.pat[p];
+        t.a0 = t.a1 = 0; t.keytag = 0;
+        memcpy(&key[(size_t)p * sizeof(ApxPat)], &t, sizeof t);
+    }
+    {
+        ApxJitShape t;
+        memset(&t, 0, sizeof t);
+        t.stream = shp.stream; t.w = shp.w; t.warps = shp.warps; t.stages = shp.stages; t.ctas = shp.ctas; t.tile_words = shp.tile_words; t.smem = shp.smem;
+        memcpy(&key[(size_t)a.npat * sizeof(ApxPat)], &t, sizeof t);
+    }
     cudaKernel_t kern = nullptr;
     {
         std::lock_guard<std::mutex> lock(g_jit_mu);
-        auto it = g_jit_cache.find(prefix);
+        auto it = g_jit_cache.find(key);
         if (it == g_jit_cache.end()) {
+            const std::string prefix = apx_generate_prefix(a.pat, a.npat);
             JitEntry en;
             std::vector<char> cubin;
             std::string log;
@@ -1533,25 +1681,38 @@ static int launch_apx_jit(pm_engine *e, const ApxArgs &a, int grid, size_t smem)
                 if (ce == cudaSuccess) ce = cudaLibraryGetKernel(&en.kern, en.lib, "k_scan_apx_jit");
                 if (ce != cudaSuccess) { en.rc = PM_ERR_CUDA; en.err = std::string("loading the specialised scan kernel: ") + cudaGetErrorString(ce); (void)cudaGetLastError(); }
             }
-            it = g_jit_cache.emplace(prefix, en).first;
+            it = g_jit_cache.emplace(key, en).first;
         }
         JitEntry &en = it->second;
         if (en.rc) { g_err = en.err; return en.rc; }
         if (!(en.attr_devices >> (e->device & 63) & 1ULL)) {
-            CK(cudaFuncSetAttribute((const void *)en.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute((const void *)en.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shp.smem));
             en.attr_devices |= 1ULL << (e->device & 63);
         }
         kern = en.kern;
     }
     JitArgs ja;
     memset(&ja, 0, sizeof ja);
-    ja.hi = a.hi; ja.lo = a.lo; ja.xx = a.xx; ja.nwords = a.nwords; ja.n = a.n; ja.tile0 = a.tile0; ja.ntiles = a.ntiles;
+    ja.hi = a.hi; ja.lo = a.lo; ja.xx = a.xx; ja.nwords = a.nwords; ja.n = a.n;
     ja.keys = a.keys; ja.count = a.count; ja.cap = a.cap;
     for (int p = 0; p < a.npat; p++) { ja.a0[p] = a.pat[p].a0; ja.a1[p] = a.pat[p].a1; ja.keytag[p] = a.pat[p].keytag; }
+    long long nblk;
+    if (shp.stream) {
+        // pattern starts lo <= b < hi; the kernel works in end coordinates e = b + span <= b + 63
+        const long long w0 = (lo / 32) & ~3LL;
+        const long long w1 = std::min((hi + 63) / 32 + 1, a.nwords);
+        nblk = std::max<long long>((w1 - w0 + shp.tile_words - 1) / shp.tile_words, 1);
+        ja.tile0 = w0; ja.ntiles = nblk;
+    } else {
+        ja.tile0 = a.tile0; ja.ntiles = a.ntiles;
+        nblk = (a.ntiles + 7) / 8;
+    }
+    const int grid = std::max((int)std::min<long long>(nblk, (long long)e->sms * shp.ctas), 1);
     void *params[] = {&ja};
-    CK(cudaLaunchKernel((const void *)kern, dim3((unsigned)grid), dim3(EX_WARPS * 32), params, smem, e->stream));
+    CK(cudaLaunchKernel((const void *)kern, dim3((unsigned)grid), dim3((unsigned)shp.warps * 32), params, shp.smem, e->stream));
     e->stats.launches++;
     e->stats.jit = 1;
+    e->stats.scan_bytes += nblk * (shp.stream ? shp.tile_words : 1024) * 4 * 3;
     return PM_OK;
 }
 
@@ -1587,16 +1748,16 @@ static int launch_apx(pm_engine *e, pm_dataset *d, const ApxPat *pats, int npat,
     }
     const long long nbt = (a.ntiles + 7) / 8;
     const int grid = std::max((int)std::min<long long>(nbt, (long long)e->sms * SP_CTAS), 1);
-    e->stats.scan_bytes += a.ntiles * 128 * 4 * 3;
     e->stats.scan_bases += (hi - lo) * a.npat;
     e->stats.packed = 1;
     e->stats.qgram_chunks = a.pat[0].ncounted;
-    // genome-scale requests: straight-line kernel compiled for exactly these patterns (apx_jit.cpp)
-    if (e->jit_mode == 2 || (e->jit_mode == 1 && (hi - lo) * a.npat >= PM_JIT_MIN_WORK)) {
-        int rc = launch_apx_jit(e, a, grid, smem);
+    // genome-scale requests: kernel compiled for exactly the request's patterns (apx_jit.cpp)
+    if (jit_wanted(e, hi - lo)) {
+        int rc = launch_apx_jit(e, a, lo, hi);
         if (rc == PM_OK) return PM_OK;
         if (e->jit_mode == 2 || rc != PM_ERR_UNSUPPORTED) return rc;   // auto mode: no NVRTC on this machine -> generic kernel
     }
+    e->stats.scan_bytes += a.ntiles * 128 * 4 * 3;
 #define PM_LAUNCH(R, W) k_scan_apx<R, W><<<grid, EX_WARPS * 32, smem, e->stream>>>(a)
     if (narrow) { if (k == 1) PM_LAUNCH(2, unsigned); else if (k == 2) PM_LAUNCH(3, unsigned); else PM_LAUNCH(4, unsigned); }
     else { if (k == 1) PM_LAUNCH(2, unsigned long long); else if (k == 2) PM_LAUNCH(3, unsigned long long); else PM_LAUNCH(4, unsigned long long); }
@@ -1629,7 +1790,7 @@ static int launch_scan(pm_engine *e, pm_dataset *d, const Compiled &c_full, long
                     return launch_exact(e, d, &pt, 1, bad, t);
                 } else if (apx_eligible(e, d, c)) {
                     ApxPat ap;
-                    build_apx_pat(e->qgram_filter != 0, c, a0, wend, tag, ap);
+                    build_apx_pat(e->qgram_filter != 0, jit_wanted(e, wend - a0), c, a0, wend, tag, ap);
                     return launch_apx(e, d, &ap, 1, t);
                 } else {
                     PackedArgs<4> a;
@@ -2155,7 +2316,7 @@ int pm_search_stream(pm_engine *e, const uint8_t *host, int64_t n, int npat, con
     d->nwords = nw;
     {
         void *p = nullptr;
-        const size_t need = (size_t)nw * 4 * 3;
+        const size_t need = ((size_t)nw * 3 + PM_PLANE_FRONT) * 4;
         if (e->pool_planes && e->pool_planes_cap >= need) {
             p = e->pool_planes; d->planes_cap = e->pool_planes_cap;
             e->pool_planes = nullptr; e->pool_planes_cap = 0;
@@ -2163,7 +2324,9 @@ int pm_search_stream(pm_engine *e, const uint8_t *host, int64_t n, int npat, con
             CKD(cudaMalloc(&p, need));
             d->planes_cap = need;
         }
-        d->hi = (unsigned *)p; d->lo = d->hi + nw; d->xx = d->lo + nw;
+        d->planes_base = p;
+        d->hi = (unsigned *)p + PM_PLANE_FRONT; d->lo = d->hi + nw; d->xx = d->lo + nw;
+        CKD(cudaMemsetAsync(p, 0, PM_PLANE_FRONT * 4, e->stream));
     }
     // all copies are queued at once on their own stream; one event per chunk
     if (!e->copy_stream) CKD(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));

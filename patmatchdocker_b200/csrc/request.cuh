@@ -240,7 +240,7 @@ static int scan_request(pm_engine *e, pm_dataset *d, const Request &rq, const Fi
             if ((int)ex.size() == EX_MAXPAT && (rc = flush_exact())) return rc;
         } else if (apx_eligible(e, d, c)) {
             ApxPat ap;
-            build_apx_pat(e->qgram_filter != 0, c, a0, std::min(a1, d->n - c.dp.L + 1), tag, ap);
+            build_apx_pat(e->qgram_filter != 0, jit_wanted(e, a1 - a0), c, a0, std::min(a1, d->n - c.dp.L + 1), tag, ap);
             ax.push_back(ap);
             if ((int)ax.size() == EX_MAXPAT && (rc = flush_apx())) return rc;
         } else {
@@ -478,7 +478,7 @@ int64_t pm_jit_source(int npat, const char *const *patterns, const char *kopt, c
         if (c.scan || dp.type != PM_PLAN_SPLIT || dp.k < 1 || dp.k > 3 || dp.m + 2 * dp.k > 64 || dp.npieces > 4 || !plain_triggers(dp)) {
             g_err = "no specialised kernel for this plan"; return PM_ERR_UNSUPPORTED;
         }
-        build_apx_pat(true, c, 0, 1LL << 40, (unsigned long long)p << PM_PID_SHIFT, ax[(size_t)p]);
+        build_apx_pat(true, true, c, 0, 1LL << 40, (unsigned long long)p << PM_PID_SHIFT, ax[(size_t)p]);
     }
     const std::string src = apx_full_source(apx_generate_prefix(ax.data(), npat));
     if (buf && cap > 0) {

@@ -923,6 +923,21 @@ def test_specialised_kernels_equal_generic_and_oracle(engine):
                     assert [(int(s), int(e)) for s, e in x] == O.search(p_, text, kopt, bufsize=bufsize), (p_, kopt)
             engine.set_buffer_size(1600000)
         assert used >= 10, used
+        # low-complexity text: every start survives the dense filter, the per-lane survivor lists overflow and the
+        # kernel falls back to unfiltered candidates for the rest (jx_unfiltered); hit lists must not change
+        motif = "ACACACACACACACAC"
+        text = (">r1\n" + "AC" * 30000 + "\n>r2\n" + "A" * 40000 + "\n>r3\n" + ("ACACACACTCACACAC" + "GT") * 3000 + "\n").encode()
+        ds = engine.load_dataset(text)
+        for pats, kopt in (([f"({motif})", "(GTGTGTGTGTGTGTGT)"], "2ids"), (["(AAAAAAAAAAAA)"], "1ids"), (["(ACACAC[AC]CAC.CAC)"], "2s")):
+            engine.set_jit("always")
+            a = engine.search_request(ds, pats, kopt)
+            assert engine.stats()["jit"] == 1
+            engine.set_jit("off")
+            b = engine.search_request(ds, pats, kopt)
+            for p_, x, y in zip(pats, a, b):
+                assert np.array_equal(x, y), (p_, kopt)
+                assert [(int(s), int(e)) for s, e in x] == O.search(p_, text, kopt), (p_, kopt)
+        ds.close()
     finally:
         engine.set_jit("auto")
         engine.set_buffer_size(1600000)
