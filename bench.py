@@ -12,6 +12,11 @@ patmatch.py:733-743) over the whole genome.  metric = pattern.Gbases/s = 2 * gen
   value : dataset resident in HBM, device time by CUDA events on the launching stream
   e2e   : same request through the C ABI from pinned HOST buffers: the genome is copied
           host->device inside the timed region every step and the hit list comes back to the host
+
+Outside the timed region the benched hit list is checked against the CPU oracle in sampled windows (around planted
+copies of the motif and around random hits, both strands): `parity_windows_ok`; a disagreement aborts the run.
+`secondary` carries the other BASELINE configs (configs[0] on 12 Mb and on 3.1 Gb, [1], [2], [3]), each with its own
+kernel time and roofline fraction; with N > 1 ranks only configs[3] (pattern-sharded) is repeated.
 """
 import argparse
 import json
@@ -134,6 +139,270 @@ def make_genome_torch(lengths, mine, device):
     return torch.cat(parts)
 
 
+def python_fills(newlines, n, bufsize=1600000):
+    """Buffer fills [S, E) of the reference for a file of n bytes (engine.cu: compute_fills; bufLoad @41bbf0):
+    a fill that does not reach EOF ends at its last newline and the next one starts AT that newline; without a usable
+    newline the fill is scanned whole and the next starts right after it."""
+    import bisect
+    S, E = [], []
+    s0 = 0
+    while n - s0 > 0:
+        dsize = min(bufsize, n - s0)
+        if dsize < bufsize:
+            en, nxt = s0 + dsize, n
+        else:
+            i = bisect.bisect_right(newlines, s0 + dsize - 1)
+            p = newlines[i - 1] if i > 0 else -1
+            if p > s0:
+                en, nxt = p + 1, p
+            else:
+                en, nxt = s0 + dsize, s0 + dsize
+        S.append(s0); E.append(en)
+        s0 = nxt
+    return S, E
+
+
+def genome_layout(lengths):
+    """(sequence start, sequence end) of every chromosome line and the newline positions of make_genome_torch's file"""
+    pos, lines, newlines = 0, [], []
+    for i, ln in enumerate(lengths):
+        head = len(">chr%d synthetic human-shaped\n" % (i + 1))
+        newlines.append(pos + head - 1)
+        lines.append((pos + head, pos + head + ln))
+        pos += head + ln + 1
+        newlines.append(pos - 1)
+    return lines, newlines, pos
+
+
+def plant_sites(genome, lines, site, count, seed, maxerr=2):
+    """Overwrite `count` random places of the device genome with copies of `site` carrying 0..maxerr random edits
+    (substitutions, insertions, deletions), half of them reverse-complemented.  Returns the positions."""
+    import random
+    import torch
+    rng = random.Random(seed)
+    comp = str.maketrans("ACGT", "TGCA")
+    where = []
+    for _ in range(count):
+        a, b = lines[rng.randrange(len(lines))]
+        p = rng.randrange(a + 4000, b - 4000)
+        s = list(site)
+        for _e in range(rng.randint(0, maxerr)):
+            q = rng.randrange(len(s))
+            r = rng.randint(0, 2)
+            if r == 0:
+                s[q] = rng.choice("ACGT")
+            elif r == 1:
+                del s[q]
+            else:
+                s.insert(q, rng.choice("ACGT"))
+        s = "".join(s)
+        if rng.random() < 0.5:
+            s = s[::-1].translate(comp)
+        genome[p:p + len(s)] = torch.tensor(list(s.encode()), dtype=torch.uint8, device=genome.device)
+        where.append(p)
+    return where
+
+
+def parity_windows(genome, lines, newlines, n, hit_lists, pats, kopt, centers, half=3000, margin=200):
+    """The benched hit lists against the CPU oracle inside windows of +-half bytes around `centers`: a window stays
+    inside one sequence line and one buffer fill; hits are compared away from the window edges (the oracle's scan
+    starts at the window start, the product's wherever the previous hit ended).  -> (windows checked, windows equal)"""
+    import bisect
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    S, _E = python_fills(newlines, n)
+    checked = ok = 0
+    for c in centers:
+        li = bisect.bisect_right([a for a, _ in lines], c) - 1
+        if li < 0:
+            continue
+        a, b = lines[li]
+        lo, hi = max(a, c - half), min(b, c + half)
+        k = bisect.bisect_right(S, lo)                         # first fill that starts after lo
+        if k < len(S) and S[k] < hi:                           # a fill boundary inside: shrink to the side that holds c
+            if S[k] <= c:
+                lo = S[k]
+            else:
+                hi = S[k]
+        if hi - lo < 4 * margin:
+            continue
+        text = genome[lo:hi].cpu().numpy().tobytes()
+        good = True
+        for pat, hits in zip(pats, hit_lists):
+            want = [(x + lo, y + lo) for x, y in oracle_lib.search(pat, text, kopt)]
+            i0, i1 = np.searchsorted(hits["beg"], lo), np.searchsorted(hits["beg"], hi)
+            mine = [(int(x), int(y)) for x, y in zip(hits["beg"][i0:i1], hits["end"][i0:i1]) if y <= hi]
+            inner = lambda hs: [h for h in hs if h[0] >= lo + margin and h[1] <= hi - margin]
+            good = good and inner(mine) == inner(want)
+        checked += 1
+        ok += 1 if good else 0
+    return checked, ok
+
+
+def profile_constants():
+    """Per-launch counters of the headline scan kernel from the committed ncu capture (profiles/r02_traffic.json):
+    DRAM bytes and executed warp instructions per scanned base.  They cannot be measured without a profiler, so the
+    bench line scales them to the launch it timed and says where they come from."""
+    tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(tp):
+        return None
+    return json.load(open(tp)).get("k_scan_apx_jit")
+
+
+def synth_lines(nlines, total, seed, alphabet=b"ACGT", name="chr"):
+    """a .seq file of nlines sequences (one per line, '>name' header lines) as bytes, and its hosts numpy RNG"""
+    rng = np.random.default_rng(seed)
+    lut = np.frombuffer(alphabet, dtype=np.uint8)
+    per = max(total // nlines, 8)
+    parts = []
+    for i in range(nlines):
+        ln = int(per * (0.5 + rng.random())) if nlines > 64 else per
+        parts.append((">%s%d\n" % (name, i + 1)).encode())
+        parts.append(lut[rng.integers(0, len(lut), size=ln, dtype=np.uint8)].tobytes())
+        parts.append(b"\n")
+    return b"".join(parts)
+
+
+def timed_requests(torch, eng, fn, steps, warmup):
+    """wall-clock per step of fn() (each call synchronises on its own result copy), scan kernel ms and bytes per step"""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    scan_ms = scan_bytes = 0
+    out = None
+    for _ in range(steps):
+        out = fn()
+        st = eng.stats()
+        scan_ms += st["scan_ms"]; scan_bytes += st["scan_bytes"]
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    return ms, scan_ms / steps, scan_bytes // steps, out, st
+
+
+def secondary_configs(args, torch, dist, pm, eng, dev, rank, world, big_ds, big_bases, peak):
+    """The other BASELINE configs, each a whole request through the C ABI with the dataset resident, checked against the
+    CPU oracle.  Returns the `secondary` object of the bench line."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from patmatchdocker_b200 import patmatch as host
+    sec = {}
+
+    def entry(workload, bases, npat, ms, kms, kbytes, kernel, hits, parity, bytes_per_base):
+        ach = kbytes / (kms / 1e3) / 1e9 if kms > 0 else 0.0
+        return {"workload": workload, "value": round(npat * bases / (ms / 1e3) / 1e9, 3), "unit": "pattern*Gbases/s", "ms_per_step": round(ms, 4),
+                "kernel": kernel, "kernel_ms": round(kms, 4), "algorithmic_bytes": int(kbytes), "bytes_per_base": bytes_per_base,
+                "achieved_GBps": round(ach, 1), "frac": round(ach / peak, 4), "hits_per_step": int(hits), "parity": parity}
+
+    if rank == 0 and world == 1:
+        # configs[0]: exact IUPAC motif, both strands, 12 Mb 16-chromosome genome -- whole hit list against the oracle
+        text = synth_lines(16, 12_000_000, 100)
+        ds = eng.load_dataset(text)
+        conv, comp, opt = host.process_pattern("GATAAG", "dna", "Both strands", None, None, None, 0)
+        ms, kms, kb, out, st = timed_requests(torch, eng, lambda: eng.search_request(ds, [conv, comp], opt, cap=1 << 20), args.steps, args.warmup)
+        ok = all([(int(x), int(y)) for x, y in h] == oracle_lib.search(p, text, opt, cap=1 << 22) for p, h in zip((conv, comp), out))
+        if not ok:
+            raise SystemExit("bench: configs[0] hit list differs from the oracle")
+        sec["configs[0]"] = entry("GATAAG exact, both strands, synthetic 12 Mb 16-chromosome genome (one request = 2 patterns, one pass)", len(text), 2, ms, kms, kb,
+                                  "k_scan_packed_exact (TMA ring, both patterns per staged tile)", sum(len(h) for h in out), "whole hit list == CPU oracle", 0.375)
+        ds.close()
+        # the same request on the 3.1 Gb genome: the single-pattern-scan roofline the north star names
+        ms, kms, kb, out, st = timed_requests(torch, eng, lambda: eng.search_request(big_ds, [conv, comp], opt, cap=1 << 22), args.steps, args.warmup)
+        sec["configs[0]@3.1Gb"] = entry("GATAAG exact, both strands, the 3.1 Gb genome of the headline (one request = 2 patterns, one pass over the planes)", big_bases, 2, ms, kms, kb,
+                                        "k_scan_packed_exact (TMA ring, both patterns per staged tile)", sum(len(h) for h in out), "sorted, non-overlapping; count == sum over single searches (tests)", 0.375)
+        # configs[1]: peptide pattern with degenerate classes, 1 substitution, ~6000-ORF proteome
+        prot = synth_lines(6000, 2_900_000, 101, alphabet=b"ACDEFGHIKLMNPQRSTVWY", name="YORF")
+        ds = eng.load_dataset(prot)
+        conv, _, opt = host.process_pattern("CXXC[ILVM]XXHXXXH", "pep", None, None, None, "substitution", 1)
+        ms, kms, kb, out, st = timed_requests(torch, eng, lambda: eng.search_request(ds, [conv], opt), args.steps, args.warmup)
+        if [(int(x), int(y)) for x, y in out[0]] != oracle_lib.search(conv, prot, opt):
+            raise SystemExit("bench: configs[1] hit list differs from the oracle")
+        sec["configs[1]"] = entry("peptide CXXC[ILVM]XXHXXXH, 1 substitution, synthetic 6000-ORF proteome (%.1f M residues)" % (len(prot) / 1e6), len(prot), 1, ms, kms, kb,
+                                  "k_scan_pep (5-bit residue planes)" if st["packed"] else "k_scan_bytes (1 B/residue Shift-And)", len(out[0]), "whole hit list == CPU oracle", 0.625 if st["packed"] else 1.0)
+        ds.close()
+        # configs[2]: 20-nt pattern, 2 errors with indels, both strands, 12 Mb
+        text = bytearray(synth_lines(16, 12_000_000, 102))
+        rng = np.random.default_rng(8)
+        motif = "TGACGTCAGATAAGCCGATT"
+        for _ in range(300):
+            q = int(rng.integers(1000, len(text) - 1000))
+            if b"\n" in text[q - 40:q + 60] or b">" in text[q - 40:q + 60]:
+                continue
+            text[q:q + len(motif)] = motif.encode()
+        text = bytes(text)
+        ds = eng.load_dataset(text)
+        conv, comp, opt = host.process_pattern(motif, "dna", "Both strands", None, None, None, 2)
+        ms, kms, kb, out, st = timed_requests(torch, eng, lambda: eng.search_request(ds, [conv, comp], opt), args.steps, args.warmup)
+        ok = all([(int(x), int(y)) for x, y in h] == oracle_lib.search(p, text, opt) for p, h in zip((conv, comp), out))
+        if not ok:
+            raise SystemExit("bench: configs[2] hit list differs from the oracle")
+        sec["configs[2]"] = entry("20-nt TGACGTCAGATAAGCCGATT, -k 2ids, both strands, synthetic 12 Mb genome", len(text), 2, ms, kms, kb,
+                                  "k_scan_apx (generic; the specialised kernel is compiled from 2^27 bases per pattern)", sum(len(h) for h in out), "whole hit list == CPU oracle", 0.375)
+        ds.close()
+
+    # configs[3]: 10,000 IUPAC motifs x 50 fungal-sized genomes (600 Mb), motifs sharded over the ranks, no collective on the data path
+    import random
+    rng = random.Random(5)
+    iupac = {"R": "[AG]", "Y": "[CT]", "S": "[GC]", "W": "[AT]", "M": "[AC]", "K": "[GT]", "N": ".", "B": "[CGT]", "D": "[AGT]"}
+    npat = args.batch_patterns
+    pats = []
+    for _ in range(npat):
+        m = rng.randint(8, 14)
+        pats.append("(" + "".join(rng.choice("ACGT") if rng.random() < 0.75 else iupac[rng.choice(list(iupac))] for _ in range(m)) + ")")
+    mine = pats[rank::world]
+    lengths = [args.batch_bases // 800] * 800
+    genome = make_genome_torch(lengths, list(range(len(lengths))), dev)
+    ds = eng.wrap_device(genome.data_ptr(), genome.numel())
+    best, kms, kb, nh = 1e18, 0.0, 0, 0
+    hits = off = None
+    for rep in range(3):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        hits, off = eng.search_batch(ds, mine, "0ids", cap=1 << 24, copy=False)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        if rep > 0 and float(dt) < best:
+            best = float(dt)
+            st = eng.stats()
+            kms, kb = st["scan_ms"], st["scan_bytes"]
+    tot = torch.tensor([int(off[-1])], device=dev)
+    if world > 1:
+        dist.all_reduce(tot)
+    parity = None
+    if rank == 0:
+        # three sampled motifs against the oracle on a prefix of the file that ends at a buffer-fill boundary
+        lines_, newlines_, n_ = [], [], 0
+        pos = 0
+        for i, ln in enumerate(lengths):
+            head = len(">chr%d synthetic human-shaped\n" % (i + 1))
+            newlines_.append(pos + head - 1); pos += head + ln + 1; newlines_.append(pos - 1)
+        S, _E = python_fills(newlines_, pos)
+        cut = S[min(24, len(S) - 1)]
+        prefix = genome[:cut + 1].cpu().numpy().tobytes()
+        okc = 0
+        for i in (0, len(mine) // 2, len(mine) - 1):
+            want = [h for h in oracle_lib.search(mine[i], prefix, "0ids", cap=1 << 22) if h[1] <= cut]
+            got = [(int(x), int(y)) for x, y in hits[off[i]:off[i + 1]] if y <= cut]
+            okc += 1 if got == want else 0
+        if okc != 3:
+            raise SystemExit("bench: configs[3] hit lists differ from the oracle")
+        parity = "3 sampled motifs == CPU oracle on the first %.0f Mb" % (cut / 1e6)
+        ach = kb / (kms / 1e3) / 1e9 if kms > 0 else 0.0
+        sec["configs[3]"] = {"workload": "%d IUPAC motifs (8-14 nt, 25%% degenerate positions) x synthetic %.0f Mb in 800 chromosomes (50 genomes x 16), exact, motifs sharded over %d rank(s)" % (npat, genome.numel() / 1e6, world),
+                             "value": round(npat * genome.numel() / best / 1e9, 1), "unit": "pattern*Gbases/s", "ms_per_step": round(best * 1e3, 2),
+                             "kernel": "k_scan_packed_multi (tile staged once, every motif of the batch evaluated from registers)", "kernel_ms": round(kms, 3),
+                             "kernel_pattern_Gbases_per_s_per_gpu": round(len(mine) * genome.numel() / (kms / 1e3) / 1e9, 1) if kms > 0 else None,
+                             "algorithmic_bytes": int(kb), "hits_per_step": int(tot), "d2h_bytes_per_step": int(tot) * 16, "parity": parity,
+                             "note": "integer-pipe bound (no HBM roofline: the planes are read once per batch of patterns); wall time includes sort, chain and the D2H copy of every hit"}
+    ds.close()
+    del genome
+    return sec
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -151,13 +420,16 @@ def run_ours(args):
     from patmatchdocker_b200 import distributed as pmd
     lengths = chrom_lengths(args.bases)
     # every rank holds the whole genome (3.1 GB of 180 GB) and scans its share of the positions;
-    # only verified candidates travel (patmatchdocker_b200/distributed.py)
+    # only hit lists travel (patmatchdocker_b200/distributed.py)
     mine = list(range(len(lengths)))
     total_bases = sum(lengths)
     pats, kopt = patterns()
 
     genome = make_genome_torch(lengths, mine, dev)
+    lines, newlines, nfile = genome_layout(lengths)
+    planted = plant_sites(genome, lines, "TGAGTCATTTACGATAAG", 256, seed=77)      # same on every rank
     nbytes = genome.numel()
+    assert nbytes == nfile
     host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
     host.copy_(genome)
     torch.cuda.synchronize()
@@ -168,7 +440,7 @@ def run_ours(args):
     ds = eng.wrap_device(genome.data_ptr(), nbytes)
     host_np = host.numpy()                                 # pinned host buffer holding the .seq file bytes
 
-    stats_acc = {"scan_ms": 0.0, "scan_bytes": 0, "launches": 0, "searches": 0, "total_ms": 0.0, "packed": 0, "syncs": 0, "last": None}
+    stats_acc = {"scan_ms": 0.0, "scan_bytes": 0, "launches": 0, "searches": 0, "total_ms": 0.0, "packed": 0, "syncs": 0, "jit": 0, "last": None}
 
     sharded = pmd.DeviceShardedSearch(eng, rank, world, dev, cap=1 << 19) if world > 1 else None
 
@@ -192,20 +464,21 @@ def run_ours(args):
         stats_acc["searches"] += 1
         stats_acc["packed"] = s["packed"]
         stats_acc["syncs"] = s["syncs"]
+        stats_acc["jit"] = s["jit"]
         stats_acc["last"] = s
         return sum(len(h) for h in hits) if hits is not None else 0
 
     def step_e2e():
         # the call a user makes: file bytes in HOST memory -> dataset (H2D copy, 2-bit packing and record
-        # index on the device) -> the two searches of the request -> hit lists back in host memory
-        # (N > 1: every rank uploads 1/N of the file over its own PCIe link, NCCL all-gathers the slices over NVLink)
+        # index on the device) -> the request -> hit lists back in host memory
         if world == 1:
             # streaming: chunks are packed and searched while the next ones are still crossing PCIe (pm_search_stream)
             d, hits = eng.search_stream(host_np, pats, kopt)
             s = eng.stats()
             stats_acc["e2e_launches"] = s["launches"]
         else:
-            d = sharded.load_dataset(host)
+            # every rank uploads and packs only the bytes its own buffer fills need (windowed dataset)
+            d = sharded.load_window(host)
             hits = run_request(d)
         d.close()
         return (sum(len(h) for h in hits), sum(h.nbytes for h in hits)) if hits is not None else (0, 0)
@@ -231,6 +504,29 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         step_resident()
+    # ---- parity of the benched hit list (outside the timed region) ----
+    parity = None
+    hit_lists = run_request(ds)
+    if rank == 0:
+        hit_lists = [np.array(h, copy=True) for h in hit_lists]
+        for h in hit_lists:
+            assert np.all(h["beg"][1:] >= h["end"][:-1]) and np.all(h["end"] > h["beg"]), "hit list not sorted / overlapping"
+        rs = np.random.default_rng(3)
+        centers = list(planted[:48])
+        for h in hit_lists:
+            centers += [int(h["beg"][i]) for i in rs.integers(0, len(h), size=24)]
+        checked, okw = parity_windows(genome, lines, newlines, nbytes, hit_lists, pats, kopt, centers)
+        covered = 0
+        for p_ in planted:
+            hit = False
+            for h in hit_lists:
+                j = np.searchsorted(h["end"], p_, side="right")
+                hit = hit or (j < len(h) and h["beg"][j] < p_ + 18)
+            covered += 1 if hit else 0
+        parity = {"windows_checked": checked, "windows_ok": okw, "planted": len(planted), "planted_covered_by_a_hit": covered}
+        if okw != checked or checked < 60 or covered != len(planted):
+            print(json.dumps({"error": "benched hit list disagrees with the CPU oracle", "parity": parity}), flush=True)
+            raise SystemExit(2)
     for k in stats_acc:
         stats_acc[k] = 0 if k != "last" else None
     sampler = ClockSampler(local)
@@ -247,20 +543,26 @@ def run_ours(args):
     value = 2 * total_bases / (ms_step / 1e3) / 1e9
     e2e = 2 * total_bases / (ms_e2e / 1e3) / 1e9
     peak, peak_src = peaks()
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tp) and stats_acc["packed"]:
-        tr = json.load(open(tp)).get("k_scan_split")
-        if tr:                                             # DRAM bytes of one launch from the committed ncu capture,
-            per_base = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["scan_bases"]   # scaled to this launch's bases
-            traffic = int(per_base * total_bases / world)
-    achieved = (scan_bytes / nsearch) / (scan_ms / nsearch / 1e3) / 1e9 if scan_ms > 0 else 0.0
+    kms = scan_ms / max(nsearch, 1)
+    achieved = (scan_bytes / nsearch) / (kms / 1e3) / 1e9 if scan_ms > 0 else 0.0
+    prof = profile_constants() if stats_acc["jit"] else None
+    traffic = inst = None
+    int_pipe_frac = alu_pipe_frac = None
+    sms, f_sm = 148, (clocks or {}).get("sm_mhz") or 1965
+    if prof:
+        share = (total_bases / world) / prof["scan_bases"]
+        traffic = int((prof["dram_bytes_read"] + prof["dram_bytes_write"]) * share)
+        inst = prof["warp_instructions"] * share
+        issue_peak = sms * 4 * f_sm * 1e6                      # warp instructions per second, all schedulers
+        int_pipe_frac = round(inst / (kms / 1e3) / issue_peak, 4)
+        alu_pipe_frac = round(prof["alu_pipe_warp_instructions"] * share / (kms / 1e3) / (issue_peak / 2), 4)
+    secondary = secondary_configs(args, torch, dist, pm, eng, dev, rank, world, ds, total_bases, peak) if args.secondary else None
     line = {
         "metric": "pattern.Gbases/s scanned (2-error degenerate motif, both strands)",
         "value": round(value, 3), "unit": "pattern*Gbases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "configs[4]: single 2-mismatch degenerate motif %s (-k %s), both strands, synthetic %.2f Gb 24-chromosome genome, chromosome-sharded" % (MOTIF, kopt, total_bases / 1e9),
+        "config": {"workload": "configs[4]: single 2-mismatch degenerate motif %s (-k %s), both strands, synthetic %.2f Gb 24-chromosome genome with 256 planted copies, chromosome-sharded" % (MOTIF, kopt, total_bases / 1e9),
                    "bases": total_bases, "patterns_per_step": 2, "plan": pm.plan(pats[0], kopt)["type"],
                    "l2_policy": "inputs (>= %.1f GB per rank) larger than the 126 MB L2" % (nbytes / 1e9),
                    "parallelism": "buffer fills (1.6 MB, independent by the reference's own restart rule) split over %d rank(s) by position; one NCCL all-gather of the per-rank hit lists" % world},
@@ -268,18 +570,25 @@ def run_ours(args):
                 "ms_per_step": round(ms_e2e, 3),
                 "path": ("pm_search_stream: file in pinned host memory -> 256 MiB chunks over PCIe, each packed and its completed buffer fills searched (both strands) while the next chunk is in flight -> hit lists in host memory"
                          if world == 1 else
-                         "every rank uploads 1/N of the pinned host file, NCCL all-gather over NVLink, pack, fill-sharded search of both strands, all-gather of hit lists, one D2H on rank 0")},
+                         "every rank uploads only the bytes of its own buffer fills (1/N of the pinned host file + one fill of overlap) over its own PCIe link, packs them, exchanges newline positions (one small all-gather), fill-sharded request, all-gather of hit lists, one D2H on rank 0; h2d_bytes_per_step is the whole job")},
         "gpu_launches": int(launches),
         "hits_per_step": int(nhits),
-        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": traffic, "kernel": "k_scan_apx<3,u32> (both strands in one launch: 2-bit planes via TMA ring, pieces built from bit-sliced q-gram chunks, Landau-Vishkin check per surviving pattern start; integer-pipe bound)" if stats_acc["packed"] else "k_scan_bytes",
+        "parity_windows_ok": (parity["windows_ok"] == parity["windows_checked"]) if parity else None, "parity": parity,
+        "roofline": {"bound": "alu_pipe" if stats_acc["jit"] else "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                     "traffic": traffic, "traffic_source": "profiles/r02_traffic.json (ncu --set full of this kernel on this workload, scaled to the bases of this launch)" if prof else None,
+                     "kernel": ("k_scan_apx_jit (NVRTC-specialised for the request: both strands in one launch, 2-bit planes via TMA ring, streaming bit-sliced q-gram chunks + pieces, Landau-Vishkin check per surviving pattern start)"
+                                if stats_acc["jit"] else "k_scan_apx (generic)") if stats_acc["packed"] else "k_scan_bytes",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(scan_bytes / max(nsearch, 1)),
-                     "kernel_ms": round(scan_ms / max(nsearch, 1), 4),
-                     "kernel_share_of_step": round(scan_ms / max(nsearch, 1) / ms_step, 3)},
+                     "kernel_ms": round(kms, 4),
+                     "kernel_share_of_step": round(kms / ms_step, 3),
+                     "warp_instructions_per_launch": int(inst) if inst else None,
+                     "int_pipe_frac": int_pipe_frac, "alu_pipe_frac": alu_pipe_frac,
+                     "int_pipe_note": "int_pipe_frac = executed warp instructions / (148 SMs x 4 schedulers x f_SM x kernel time); alu_pipe_frac = LOP3/SHF/IADD-class instructions / the ALU pipe's issue rate (one warp instruction per 2 clocks and scheduler, tools/pipe_bench.cu); instruction counts from the committed ncu capture" if prof else None},
         "host_syncs_per_step": stats_acc["syncs"], "stage_ms": {k: round(stats_acc["last"][k], 4) for k in ("scan_ms", "sort_ms", "verify_ms", "chain_ms", "total_ms")} if stats_acc["last"] else None,
         "candidates_per_step": int(stats_acc["last"]["candidates"]) if stats_acc["last"] else None,
         "clocks": clocks,
+        "secondary": secondary,
     }
     if rank == 0:
         line["cpu_baseline"] = cpu_baseline(pats, kopt, sample_bytes=args.cpu_sample, procs=1)
@@ -375,6 +684,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--bases", type=int, default=3_100_000_000)
     ap.add_argument("--cpu-sample", type=int, default=800_000, help="bases per process of the CPU baseline sample")
+    ap.add_argument("--no-secondary", dest="secondary", action="store_false", help="skip the other BASELINE configs")
+    ap.add_argument("--batch-patterns", type=int, default=10_000, help="configs[3]: motifs in the batch")
+    ap.add_argument("--batch-bases", type=int, default=600_000_000, help="configs[3]: bases of the multi-genome dataset")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

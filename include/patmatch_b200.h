@@ -113,6 +113,17 @@ int pm_engine_set_buffer_size(pm_engine *e, int64_t bytes);
 int pm_dataset_create(pm_engine *e, const uint8_t *host_bytes, int64_t n, pm_dataset **out);
 /* same, bytes already on the device (pointer stays owned by the caller) */
 int pm_dataset_wrap_device(pm_engine *e, const uint8_t *device_bytes, int64_t n, pm_dataset **out);
+/* Multi-GPU cold request (replaces the part of the file a rank would read; the reference reads the whole file per run,
+ * patmatch.py:733-743): a rank that searches only the buffer fills starting in [pos_beg, pos_end) needs only the bytes
+ * of those fills.  host_bytes points at the WHOLE file in host memory (pinned for an asynchronous copy); only
+ * [win_lo, win_hi) is copied and packed, positions stay absolute.  dev_newlines (device memory, nl_rows x int64)
+ * receives [0] = the number of record delimiters in the window and [1..] their positions (unordered, at most
+ * nl_rows - 1 stored).  No host synchronisation.  Before searching, the caller installs the newline index of the whole
+ * file (gathered from all ranks) with pm_dataset_set_newlines; pm_request_fills_device then works on fills inside
+ * the window. */
+int pm_dataset_create_window(pm_engine *e, const uint8_t *host_bytes, int64_t n, int64_t win_lo, int64_t win_hi,
+                             void *dev_newlines, int64_t nl_rows, pm_dataset **out);
+int pm_dataset_set_newlines(pm_engine *e, pm_dataset *d, const int64_t *sorted_positions, int64_t count);
 void pm_dataset_destroy(pm_dataset *d);
 int64_t pm_dataset_size(const pm_dataset *d);
 

@@ -71,6 +71,8 @@ def load():
     L.pm_engine_set_buffer_size.argtypes = [vp, i64]
     L.pm_engine_set_fused_filter.argtypes = [vp, ctypes.c_int]
     L.pm_engine_set_jit.argtypes = [vp, ctypes.c_int]
+    L.pm_dataset_create_window.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, vp, ctypes.c_int64, ctypes.POINTER(vp)]
+    L.pm_dataset_set_newlines.argtypes = [vp, vp, vp, ctypes.c_int64]
     L.pm_jit_source.restype = ctypes.c_int64
     L.pm_jit_source.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int64]
     L.pm_search_fills_device.argtypes = [vp, vp, ctypes.c_char_p, ctypes.c_char_p, i64, i64, vp, i64, ctypes.POINTER(i64), vp]
@@ -293,6 +295,21 @@ class Engine:
     def synchronize(self):
         _check(load().pm_engine_synchronize(self._h))
 
+    def load_window(self, data, win_lo, win_hi, dev_newlines_ptr, nl_rows):
+        """pm_dataset_create_window: `data` = the whole file in host memory (numpy uint8, pinned for an asynchronous
+        copy); only [win_lo, win_hi) is uploaded and packed.  dev_newlines_ptr: device memory (nl_rows x int64) that
+        receives the count and the positions of the window's newlines.  Asynchronous."""
+        arr = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
+        h = ctypes.c_void_p()
+        _check(load().pm_dataset_create_window(self._h, ctypes.c_void_p(arr.ctypes.data), arr.size, int(win_lo), int(win_hi),
+                                               ctypes.c_void_p(dev_newlines_ptr), int(nl_rows), ctypes.byref(h)))
+        return Dataset(self, h, arr)
+
+    def set_newlines(self, dataset, positions):
+        """pm_dataset_set_newlines: sorted newline positions of the whole file (numpy int64)"""
+        pos = np.ascontiguousarray(positions, dtype=np.int64)
+        _check(load().pm_dataset_set_newlines(self._h, dataset._h, ctypes.c_void_p(pos.ctypes.data), pos.size))
+
     def load_dataset(self, data):
         """data: bytes / bytearray / numpy uint8 array with the .seq file contents (host memory)."""
         arr = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
@@ -325,9 +342,10 @@ class Engine:
         return n.value
 
     @_locked
-    def search_batch(self, dataset, patterns, kopt="0ids", cap=1 << 20):
+    def search_batch(self, dataset, patterns, kopt="0ids", cap=1 << 20, copy=True):
         """-> (hits, offsets): hits[offsets[i]:offsets[i+1]] is the hit list of patterns[i].  Large results
-        cross PCIe into a page-locked staging buffer owned by the engine; the caller always receives its own copy."""
+        cross PCIe into a page-locked staging buffer owned by the engine; the caller receives its own copy unless it
+        passes copy=False (then the array is a view of that buffer and only valid until the next search_batch)."""
         L = load()
         arr = (ctypes.c_char_p * len(patterns))(*[_b(p) for p in patterns])
         offsets = (ctypes.c_int64 * (len(patterns) + 1))()
@@ -350,7 +368,7 @@ class Engine:
                     rc = L.pm_search_batch(self._h, dataset._h, len(patterns), arr, _b(kopt), ctypes.c_void_p(hits.ctypes.data), cap, offsets)
         _check(rc)
         off = np.array(list(offsets), dtype=np.int64)
-        if hits is getattr(getattr(self, "_keep", None), "array", None):
+        if copy and hits is getattr(getattr(self, "_keep", None), "array", None):
             return hits[: off[-1]].copy(), off          # the pinned staging buffer is reused by the next call: hand out a copy
         return hits[: off[-1]], off
 

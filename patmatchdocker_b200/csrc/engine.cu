@@ -771,6 +771,10 @@ struct pm_dataset {
     size_t fills_cap = 0;              // entries allocated at d_fills
     int nfills = 0;
     int ncuts = 0;                     // fill boundaries that do not fall on a '\n'
+    // windowed datasets (pm_dataset_create_window): only the bytes / plane words of [win_lo, win_hi) exist on the device
+    bool windowed = false;
+    long long win_lo = 0, win_hi = 0;
+    unsigned long long *d_wcount = nullptr;   // [0] non-ACGT bytes, [1] newlines of the window (device)
 
 };
 
@@ -1031,6 +1035,88 @@ int pm_dataset_wrap_device(pm_engine *e, const uint8_t *dev, int64_t n, pm_datas
     return PM_OK;
 }
 
+// Windowed dataset for multi-GPU cold requests: text and planes are allocated for the whole file, so positions stay
+// absolute everywhere, but only the window is copied and packed.  No host synchronisation.
+int pm_dataset_create_window(pm_engine *e, const uint8_t *host, int64_t n, int64_t win_lo, int64_t win_hi, void *dev_newlines, int64_t nl_rows,
+                             pm_dataset **out)
+{
+    if (!e || !out || !host || n <= 0 || win_lo < 0 || win_hi > n || win_lo >= win_hi || !dev_newlines || nl_rows < 2) { g_err = "bad argument"; return PM_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
+    if (n >= (1LL << PM_POS_BITS) - 4096) { g_err = "dataset too large (candidate keys hold 36-bit positions)"; return PM_ERR_UNSUPPORTED; }
+    CK(cudaSetDevice(e->device));
+    pm_dataset *d = new pm_dataset();
+    d->e = e; d->n = n;
+    auto fail = [&](int rc) { pm_dataset_destroy(d); return rc; };
+#define CKW(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { g_err = std::string(#x) + " (engine.cu:" + std::to_string(__LINE__) + "): " + cudaGetErrorString(e_); return fail(PM_ERR_CUDA); } } while (0)
+    {
+        void *p = nullptr;
+        if (e->pool_text && e->pool_text_cap >= (size_t)n + 256) {
+            p = e->pool_text; d->owned_cap = e->pool_text_cap;
+            e->pool_text = nullptr; e->pool_text_cap = 0;
+        } else {
+            CKW(cudaMalloc(&p, (size_t)n + 256));
+            d->owned_cap = (size_t)n + 256;
+        }
+        d->owned = p; d->d_text = (const unsigned char *)p;
+    }
+    long long nw = (n + 31) / 32;
+    nw = (nw + 1023) / 1024 * 1024 + 1024;
+    d->nwords = nw;
+    {
+        void *p = nullptr;
+        const size_t need = ((size_t)nw * 3 + PM_PLANE_FRONT) * 4;
+        if (e->pool_planes && e->pool_planes_cap >= need) {
+            p = e->pool_planes; d->planes_cap = e->pool_planes_cap;
+            e->pool_planes = nullptr; e->pool_planes_cap = 0;
+        } else {
+            CKW(cudaMalloc(&p, need));
+            d->planes_cap = need;
+        }
+        d->planes_base = p;
+        d->hi = (unsigned *)p + PM_PLANE_FRONT; d->lo = d->hi + nw; d->xx = d->lo + nw;
+        CKW(cudaMemsetAsync(p, 0, PM_PLANE_FRONT * 4, e->stream));
+    }
+    // whole words: [lo32, hi32)
+    const long long lo32 = win_lo & ~31LL, hi32 = std::min<long long>((win_hi + 31) & ~31LL, n);
+    d->windowed = true; d->win_lo = lo32; d->win_hi = hi32;
+    CKW(cudaMemcpyAsync((char *)d->owned + lo32, host + lo32, (size_t)(hi32 - lo32), cudaMemcpyHostToDevice, e->stream));
+    if (hi32 == n) CKW(cudaMemsetAsync((char *)d->owned + n, 0, 256, e->stream));
+    CKW(cudaMalloc((void **)&d->d_wcount, 32));
+    CKW(cudaMemsetAsync(d->d_wcount, 0, 32, e->stream));
+    {
+        const long long q0 = lo32 / 32, q1 = hi32 == n ? std::min<long long>((n + 31) / 32 + 8, nw) : hi32 / 32;
+        const int grid = (int)std::min<long long>((q1 - q0 + 255) / 256, (long long)e->sms * 16);
+        k_pack<<<std::max(grid, 1), 256, 0, e->stream>>>(d->d_text + lo32, n - lo32, q1 - q0, d->hi + q0, d->lo + q0, d->xx + q0, d->d_wcount,
+                                                         (unsigned long long *)dev_newlines + 1, nl_rows - 1, lo32);
+        CKW(cudaGetLastError());
+        CKW(cudaMemcpyAsync(dev_newlines, d->d_wcount + 1, 8, cudaMemcpyDeviceToDevice, e->stream));
+    }
+#undef CKW
+    d->fills_complete = false;
+    *out = d;
+    return PM_OK;
+}
+
+// installs the newline index of the WHOLE file (sorted positions), e.g. gathered from the ranks' windows; the buffer
+// fills follow from it.  Synchronises the engine's stream once to learn how DNA-like the window is.
+int pm_dataset_set_newlines(pm_engine *e, pm_dataset *d, const int64_t *pos, int64_t count)
+{
+    if (!e || !d || d->e != e || count < 0 || (count > 0 && !pos)) { g_err = "bad argument"; return PM_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
+    CK(cudaSetDevice(e->device));
+    d->newlines.assign(pos, pos + count);
+    if (!std::is_sorted(d->newlines.begin(), d->newlines.end())) std::sort(d->newlines.begin(), d->newlines.end());
+    d->fills_bufsize = -1;
+    d->fills_complete = true;
+    if (d->windowed && d->d_wcount) {
+        CK(cudaMemcpyAsync(e->h_count + 4, d->d_wcount, 16, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        d->nexc = (long long)e->h_count[4];
+        d->dna_like = d->nexc * 8 <= (d->win_hi - d->win_lo);
+    }
+    return PM_OK;
+}
+
 void pm_dataset_destroy(pm_dataset *d)
 {
     if (!d) return;
@@ -1051,6 +1137,7 @@ void pm_dataset_destroy(pm_dataset *d)
         } else cudaFree(d->planes_base);
     }
     if (d->d_fills) cudaFree(d->d_fills);
+    if (d->d_wcount) cudaFree(d->d_wcount);
     delete d;
 }
 

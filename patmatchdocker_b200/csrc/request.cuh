@@ -423,6 +423,7 @@ int pm_search_request(pm_engine *e, pm_dataset *d, int npat, const char *const *
     Request rq;
     int rc = compile_request(npat, patterns, kopt, rq);
     if (rc) return rc;
+    if (d->windowed) { g_err = "windowed dataset: only pm_request_fills_device can search it"; return PM_ERR_ARG; }
     for (int p = 0; p < npat; p++) { rq.a0[p] = 0; rq.a1[p] = d->n + 1; }
     return run_request_host(e, d, rq, hits, cap, offsets);
 }
@@ -455,6 +456,10 @@ int pm_request_fills_device(pm_engine *e, pm_dataset *d, int npat, const char *c
     const std::vector<long long> &S = d->fill_starts;
     const long long f0 = std::lower_bound(S.begin(), S.end(), (long long)pos_beg) - S.begin();
     const long long f1 = std::lower_bound(S.begin(), S.end(), (long long)pos_end) - S.begin();
+    if (d->windowed && f1 > f0 && (S[(size_t)f0] < d->win_lo || d->fill_ends[(size_t)f1 - 1] > d->win_hi)) {
+        g_err = "the buffer fills of this position range are not inside the dataset's window";
+        return PM_ERR_ARG;
+    }
     for (int p = 0; p < npat; p++) fill_anchor_range(d, rq.comp[p], f0, f1, &rq.a0[p], &rq.a1[p]);
     const long long cap = std::max<long long>(sort_cap > 0 ? sort_cap : e->req_cap_hint, 1 << 12);
     e->stats = pm_stats{};

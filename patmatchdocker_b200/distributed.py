@@ -169,6 +169,36 @@ class DeviceShardedSearch:
         self.full = assemble_from_host(host, self.rank, self.world, self.device, getattr(self, "full", None), self.group)
         return self.engine.wrap_device(self.full.data_ptr(), int(host.numel()))
 
+    def load_window(self, host, bufsize=1600000, nl_rows=1 << 16):
+        """Cold multi-GPU request: every rank uploads and packs only the bytes its own buffer fills can touch -- its
+        position range plus one buffer fill of overlap -- over its own PCIe link (pm_dataset_create_window); nothing
+        but the newline positions (a few KB, one all-gather) is exchanged, because the fill table of the reference
+        depends on every newline of the file.  `host`: 1-D uint8 torch tensor holding the file, pinned, identical on
+        all ranks.  Returns a windowed Dataset that request_fills() can search."""
+        import torch.distributed as dist
+        torch = self.torch
+        n = int(host.numel())
+        beg, end = shard_ranges(n, self.world)[self.rank]
+        lo, hi = max(beg - 4096, 0), min(n, end + bufsize + 4096)
+        if getattr(self, "nl_mine", None) is None or self.nl_mine.shape[0] != nl_rows:
+            self.nl_mine = torch.zeros(nl_rows, dtype=torch.int64, device=self.device)
+            self.nl_all = torch.zeros(nl_rows * self.world, dtype=torch.int64, device=self.device)
+            self.nl_host = torch.zeros(nl_rows * self.world, dtype=torch.int64, pin_memory=str(self.device) != "cpu")
+        ds = self.engine.load_window(host.numpy(), lo, hi, self.nl_mine.data_ptr(), nl_rows)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.nl_all, self.nl_mine, group=self.group)
+        else:
+            self.nl_all.copy_(self.nl_mine)
+        self.nl_host.copy_(self.nl_all, non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+        h = self.nl_host.numpy().reshape(self.world, nl_rows)
+        if int(h[:, 0].max()) > nl_rows - 1:
+            ds.close()
+            raise RuntimeError("more than %d newlines in one rank's window: pass a larger nl_rows" % (nl_rows - 1))
+        allnl = np.unique(np.concatenate([h[r, 1:1 + int(h[r, 0])] for r in range(self.world)]))     # windows overlap: unique
+        self.engine.set_newlines(ds, allnl)
+        return ds
+
     def search_fills(self, dataset, pattern, kopt):
         """Fill-sharded search (pm_search_fills_device): the reference restarts its scan at every buffer fill, so
         every rank searches the fills that start in its position range completely, chain stage included, and

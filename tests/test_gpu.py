@@ -859,6 +859,60 @@ def test_request_fills_device_equals_search(engine, scan_mode):
         engine.set_stream(0)
 
 
+def test_windowed_datasets_equal_whole_dataset(engine, scan_mode):
+    # pm_dataset_create_window (the multi-GPU cold path): every "rank" uploads and packs only its position range plus
+    # one buffer fill of overlap; the newline index of the whole file is the union of what the windows found.  The
+    # fill-sharded request on the windows must give the hit lists of the whole dataset (and of the oracle).
+    import torch
+    from patmatchdocker_b200._native import request_header_rows
+    from patmatchdocker_b200.distributed import shard_ranges
+    rng = random.Random(616)
+    rows = 1 << 15
+    buf = torch.zeros((rows, 2), dtype=torch.int64, device="cuda")
+    nl_rows = 4096
+    engine.use_torch_stream()
+    try:
+        for it in range(24):
+            pats, kopt, text = _request_case(rng, it)
+            if isinstance(text, str):
+                text = text.encode("latin-1")
+            bufsize = rng.choice([1600000, 90, 300, 1000])
+            engine.set_buffer_size(bufsize)
+            world = rng.randint(2, 4)
+            data = np.frombuffer(text, dtype=np.uint8)
+            n = len(text)
+            ranges = shard_ranges(n, world)
+            wins, nls = [], []
+            for r in range(world):
+                beg, end = ranges[r]
+                lo, hi = max(beg - 64, 0), min(n, end + min(bufsize, n) + 64)
+                nl = torch.zeros(nl_rows, dtype=torch.int64, device="cuda")
+                wins.append(engine.load_window(data, lo, hi, nl.data_ptr(), nl_rows))
+                h = nl.cpu().numpy()
+                nls.append(h[1:1 + int(h[0])])
+            allnl = np.unique(np.concatenate(nls))
+            assert [int(x) for x in allnl] == [i for i, c in enumerate(text) if c == 10]
+            hr = request_header_rows(len(pats))
+            got = [[] for _ in pats]
+            for r in range(world):
+                engine.set_newlines(wins[r], allnl)
+                engine.request_fills_device(wins[r], pats, kopt, ranges[r][0], ranges[r][1], 1 << 13, buf.data_ptr(), rows)
+                h = buf.cpu().numpy()
+                nh = int(h[0, 0])
+                counts = [int(x) for x in h[2:hr].reshape(-1)[:len(pats)]]
+                assert sum(counts) == nh
+                off = hr
+                for i, c in enumerate(counts):
+                    got[i] += [(int(b), int(e)) for b, e in h[off:off + c]]
+                    off += c
+                wins[r].close()
+            for p, gl in zip(pats, got):
+                assert gl == O.search(p, text, kopt, bufsize=bufsize), (p, kopt, bufsize, world)
+    finally:
+        engine.set_buffer_size(1600000)
+        engine.set_stream(0)
+
+
 def test_batch_with_errors_equals_single(engine):
     # pm_search_batch with k > 0: groups of patterns through the request pipeline
     rng = random.Random(99)
