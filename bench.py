@@ -318,7 +318,7 @@ def secondary_configs(args, torch, dist, pm, eng, dev, rank, world, big_ds, big_
         if [(int(x), int(y)) for x, y in out[0]] != oracle_lib.search(conv, prot, opt):
             raise SystemExit("bench: configs[1] hit list differs from the oracle")
         sec["configs[1]"] = entry("peptide CXXC[ILVM]XXHXXXH, 1 substitution, synthetic 6000-ORF proteome (%.1f M residues)" % (len(prot) / 1e6), len(prot), 1, ms, kms, kb,
-                                  "k_scan_pep (5-bit residue planes)" if st["packed"] else "k_scan_bytes (1 B/residue Shift-And)", len(out[0]), "whole hit list == CPU oracle", 0.625 if st["packed"] else 1.0)
+                                  "k_scan_bytes over 5-bit residue codes (six per word, k_pack5)" if st["packed"] == 2 else "k_scan_bytes (1 B/residue Shift-And)", len(out[0]), "whole hit list == CPU oracle", 0.667 if st["packed"] == 2 else 1.0)
         ds.close()
         # configs[2]: 20-nt pattern, 2 errors with indels, both strands, 12 Mb
         text = bytearray(synth_lines(16, 12_000_000, 102))

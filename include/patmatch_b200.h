@@ -69,7 +69,7 @@ typedef struct {
     int64_t scan_bytes;          /* HBM bytes the scan kernel had to read (its algorithmic bytes) */
     int64_t scan_bases;          /* text positions the scan kernel covered */
     int launches;                /* kernels launched by the last search */
-    int packed;                  /* 1: 2-bit packed bit-sliced scan, 0: byte Shift-And / dense */
+    int packed;                  /* 1: 2-bit packed bit-sliced scan, 2: Shift-And over 5-bit residue codes, 0: byte Shift-And / dense */
     int qgram_chunks;            /* pattern chunks of the bit-sliced q-gram pre-filter (0 = not used) */
     int syncs;                   /* host synchronisations of the last pm_search_request */
     int jit;                     /* 1: the scan ran as a kernel specialised for the request (NVRTC), 0: generic kernels */
@@ -94,6 +94,10 @@ int pm_engine_set_scan_mode(pm_engine *e, int mode);
  * that surely fail.  1 (default) = q-gram pre-filter + Myers filter, 2 = Myers filter only,
  * 0 = off: every exact piece hit goes through k_verify */
 int pm_engine_set_fused_filter(pm_engine *e, int on);
+/* Datasets that are not DNA-like (proteomes) are also kept as 5-bit residue codes (letters of either case -> 0..25,
+ * every other byte -> 31; six codes per 32-bit word) and the Shift-And scan reads those instead of the raw bytes:
+ * 0.667 B per residue.  Candidates are re-checked on the raw bytes, results do not change.  1 (default) / 0. */
+int pm_engine_set_peptide_codes(pm_engine *e, int on);
 /* Specialised scan kernels: for approximate (SPLIT) searches the engine can write the dense part of the scan as
  * straight-line CUDA for exactly the request's patterns and compile it with NVRTC for sm_100a (about 0.2 s, cached
  * per process and request text).  0 = never, 1 (default) = when the request covers at least 2^28 pattern x bases and

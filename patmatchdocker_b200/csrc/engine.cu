@@ -428,6 +428,28 @@ __device__ int check_match_ext(const DevPlan &pl, const unsigned char *__restric
 // One block stages TILE bytes (+64 bytes of left halo) into shared memory with coalesced
 // 128-bit loads; every thread then walks its own SEG-byte run.  Rows are padded by 16
 // bytes so that the per-thread 128-bit shared loads of a quarter-warp hit distinct banks.
+// 5-bit residue codes for peptide datasets: letters (either case) -> 0..25, every other byte -> PEP_OTHER; six codes
+// per 32-bit word, 0.667 B per residue instead of 1.  Replaces the bytes nrgrep_coords reads for proteome searches.
+#define PEP_OTHER 31
+__global__ void __launch_bounds__(256) k_pack5(const unsigned char *__restrict__ text, long long n, long long nwords, unsigned *__restrict__ codes)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += stride) {
+        unsigned v = 0;
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            const long long i = w * 6 + r;
+            unsigned code = PEP_OTHER;
+            if (i < n) {
+                const unsigned c = text[i] | 0x20u;
+                if (c >= 'a' && c <= 'z') code = c - 'a';
+            }
+            v |= code << (5 * r);
+        }
+        codes[w] = v;
+    }
+}
+
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_SEG = 128;                              // bytes per thread per tile
 constexpr int SCAN_ROW = SCAN_SEG + 16;                    // padded row
@@ -437,6 +459,7 @@ constexpr int SCAN_HALO = 64;
 template <typename T>
 struct ScanArgs {
     const unsigned char *text;
+    const unsigned *codes;       // non-null: scan the 5-bit residue codes (6 per 32-bit word, k_pack5) instead of the raw bytes
     long long n;
     long long p0, p1;            // end positions p handled: p0 <= p < p1
     long long tile0;             // first tile index (tile = p / SCAN_TILE)
@@ -471,13 +494,39 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_bytes(const ScanArgs<T> a
     __shared__ __align__(16) unsigned char srow[SCAN_THREADS * SCAN_ROW];
     __shared__ __align__(16) unsigned char shalo[SCAN_HALO];
     const int tid = threadIdx.x;
-    sB[tid] = (T)a.B[tid];
+    if (a.codes) {
+        // table over the 32 residue codes: a letter code collects both cases, code 31 every other byte (an
+        // over-approximation that k_verify's re-check on the raw bytes removes)
+        unsigned long long m = 0;
+        if (tid < 26) m = a.B['A' + tid] | a.B['a' + tid];
+        else if (tid == PEP_OTHER) {
+            for (int c = 0; c < 256; c++)
+                if (!((c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z'))) m |= a.B[c];
+        }
+        sB[tid] = (T)m;
+    } else sB[tid] = (T)a.B[tid];
     const bool aligned = ((size_t)a.text & 15) == 0;
 
     for (long long t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
         const long long tstart = (a.tile0 + t) * SCAN_TILE;
         __syncthreads();
         // ---- stage tile ----
+        if (a.codes) {
+            // 5-bit codes: every word carries 6 residues; they are unpacked into the byte rows the run below reads
+            const long long w0 = (tstart - SCAN_HALO) / 6 - (tstart < SCAN_HALO ? 1 : 0);
+            const long long w1 = (tstart + SCAN_TILE + 5) / 6;
+            for (long long w = w0 + tid; w < w1; w += SCAN_THREADS) {
+                if (w < 0) continue;
+                const unsigned v = (w * 6 < a.n) ? __ldg(a.codes + w) : 0x3fffffffu;
+#pragma unroll
+                for (int r = 0; r < 6; r++) {
+                    const long long o = w * 6 + r - tstart;              // offset of this residue relative to the tile start
+                    const unsigned char code = (unsigned char)((v >> (5 * r)) & 31u);
+                    if (o >= 0 && o < SCAN_TILE) srow[(o / SCAN_SEG) * SCAN_ROW + (o % SCAN_SEG)] = code;
+                    else if (o < 0 && o >= -SCAN_HALO) shalo[SCAN_HALO + o] = code;
+                }
+            }
+        } else {
 #pragma unroll
         for (int it = 0; it < SCAN_TILE / 16 / SCAN_THREADS; it++) {
             const int c = it * SCAN_THREADS + tid;              // 16-byte chunk in tile
@@ -496,6 +545,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_bytes(const ScanArgs<T> a
         if (tid < SCAN_HALO) {
             const long long g = tstart - SCAN_HALO + tid;
             shalo[tid] = (g >= 0 && g < a.n) ? a.text[g] : 0;
+        }
         }
         __syncthreads();
         // ---- per-thread run ----
@@ -738,6 +788,7 @@ struct pm_engine {
     int fused_filter = 1;                           // packed scan drops candidates whose verification surely fails
     int qgram_filter = 1;                           // bit-sliced q-gram pre-filter in front of the Myers filter
     int split_kernel = 1;                           // 1: k_scan_apx (chunk-built pieces + Landau-Vishkin check), 2: k_scan_split (first generation), 0: block-tile kernel
+    int pep5 = 1;                                   // non-DNA datasets: scan the 5-bit residue codes (0: raw bytes)
     int jit_mode = 1;                               // 0: never, 1: auto (genome-scale requests), 2: always -- specialised scan kernels (apx_jit.cpp)
     bool attr_exact = false, attr_split = false, attr_apx = false;   // cudaFuncSetAttribute is per device: kept per engine
     // one spare text buffer and one spare plane buffer, so that re-creating a dataset of the same size
@@ -757,6 +808,7 @@ struct pm_dataset {
     long long n = 0;
     // 2-bit packed planes (packed.cuh)
     unsigned *hi = nullptr, *lo = nullptr, *xx = nullptr;
+    unsigned *codes = nullptr;     // 5-bit residue codes (k_pack5): datasets that are not DNA-like
     void *planes_base = nullptr;   // allocation that holds the planes: PM_PLANE_FRONT words of padding, then hi | lo | xx
     long long nwords = 0;
     long long nexc = 0;            // bytes that are not ACGTacgt
@@ -812,6 +864,14 @@ static int pack_dataset(pm_engine *e, pm_dataset *d)
     CK(cudaStreamSynchronize(e->stream));
     d->nexc = (long long)e->h_count[4];
     d->dna_like = n > 0 && d->nexc * 8 <= n;
+    if (!d->dna_like && n > 0) {
+        // proteomes: 5-bit residue codes for the Shift-And scan
+        const long long ncw = (n + 5) / 6 + 16;
+        CK(cudaMalloc((void **)&d->codes, (size_t)ncw * 4));
+        const int g5 = (int)std::min<long long>((ncw + 255) / 256, (long long)e->sms * 16);
+        k_pack5<<<std::max(g5, 1), 256, 0, e->stream>>>(d->d_text, n, ncw, d->codes);
+        CK(cudaGetLastError());
+    }
     const long long nnl = (long long)e->h_count[5];
     d->newlines.resize((size_t)nnl);
     if (nnl > 0 && nnl <= nl_cap) {
@@ -962,6 +1022,14 @@ int pm_engine_set_fused_filter(pm_engine *e, int on)
     e->fused_filter = on ? 1 : 0;
     e->qgram_filter = (on == 1 || on == 4) ? 1 : 0;
     e->split_kernel = on == 3 ? 0 : (on == 4 || on == 5) ? 2 : 1;   // 4 / 5: first-generation k_scan_split with / without the q-gram count
+    return PM_OK;
+}
+
+int pm_engine_set_peptide_codes(pm_engine *e, int on)
+{
+    if (!e) { g_err = "bad argument"; return PM_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
+    e->pep5 = on ? 1 : 0;
     return PM_OK;
 }
 
@@ -1137,6 +1205,7 @@ void pm_dataset_destroy(pm_dataset *d)
         } else cudaFree(d->planes_base);
     }
     if (d->d_fills) cudaFree(d->d_fills);
+    if (d->codes) cudaFree(d->codes);
     if (d->d_wcount) cudaFree(d->d_wcount);
     delete d;
 }
@@ -1337,6 +1406,14 @@ static bool scan_uses_packed(const pm_engine *e, const pm_dataset *d, const Comp
     const Compiled &c = c_full.scan ? *c_full.scan : c_full;
     const bool packable = (c.dp.type == PM_PLAN_SIMPLE || c.dp.type == PM_PLAN_SPLIT) && c.dp.npieces <= 4 && d->hi != nullptr;
     return packable && (e->scan_mode == 2 || (e->scan_mode == 0 && d->dna_like));
+}
+
+// does the byte Shift-And scan of this pattern read the 5-bit residue codes?  (its candidates are re-checked on the raw bytes)
+static bool scan_uses_pep5(const pm_engine *e, const pm_dataset *d, const Compiled &c_full)
+{
+    const Compiled &c = c_full.scan ? *c_full.scan : c_full;
+    return d->codes != nullptr && e->pep5 && e->scan_mode != 2 && !scan_uses_packed(e, d, c_full) &&
+           (c.dp.type == PM_PLAN_SIMPLE || c.dp.type == PM_PLAN_SPLIT);
 }
 
 // ---- exact scan (k_scan_packed_exact): up to EX_MAXPAT patterns per pass over the planes ----
@@ -2072,22 +2149,23 @@ static int launch_scan(pm_engine *e, pm_dataset *d, const Compiled &c_full, long
                 const int grid = (int)std::min<long long>(ntiles, (long long)e->sms * 8);
                 if (dp.npieces * dp.L <= 32) {
                     ScanArgs<unsigned> a;
-                    a.text = d->d_text; a.n = n; a.p0 = p0; a.p1 = p1; a.tile0 = tile0; a.ntiles = ntiles; a.B = dB;
+                    a.text = d->d_text; a.codes = scan_uses_pep5(e, d, c_full) ? d->codes : nullptr; a.n = n; a.p0 = p0; a.p1 = p1; a.tile0 = tile0; a.ntiles = ntiles; a.B = dB;
                     a.init = (unsigned)dp.init; a.fin = (unsigned)dp.fin;
                     for (int i = 0; i < PM_MAX_PIECES; i++) a.trig[i] = (unsigned)dp.trig[i];
                     a.L = dp.L; a.npieces = dp.npieces; a.keys = t.keys; a.count = t.count; a.cap = t.cap; a.keytag = tag;
                     k_scan_bytes<unsigned><<<grid, SCAN_THREADS, 0, e->stream>>>(a);
                 } else {
                     ScanArgs<unsigned long long> a;
-                    a.text = d->d_text; a.n = n; a.p0 = p0; a.p1 = p1; a.tile0 = tile0; a.ntiles = ntiles; a.B = dB;
+                    a.text = d->d_text; a.codes = scan_uses_pep5(e, d, c_full) ? d->codes : nullptr; a.n = n; a.p0 = p0; a.p1 = p1; a.tile0 = tile0; a.ntiles = ntiles; a.B = dB;
                     a.init = dp.init; a.fin = dp.fin;
                     for (int i = 0; i < PM_MAX_PIECES; i++) a.trig[i] = dp.trig[i];
                     a.L = dp.L; a.npieces = dp.npieces; a.keys = t.keys; a.count = t.count; a.cap = t.cap; a.keytag = tag;
                     k_scan_bytes<unsigned long long><<<grid, SCAN_THREADS, 0, e->stream>>>(a);
                 }
                 e->stats.launches++;
-                e->stats.scan_bytes += p1 - p0;
+                e->stats.scan_bytes += scan_uses_pep5(e, d, c_full) ? (p1 - p0 + 5) / 6 * 4 : p1 - p0;
                 e->stats.scan_bases += p1 - p0;
+                e->stats.packed = scan_uses_pep5(e, d, c_full) ? 2 : 0;
             }
         } else {
             // BWD: anchors w with w + (L - k) <= n ; FWD: anchors pos in [1, n]
@@ -2170,7 +2248,7 @@ static int produce_candidates(pm_engine *e, pm_dataset *d, const Compiled &c_ful
     if (ncand > 0) {
         if ((rc = e->cands.reserve((size_t)ncand * sizeof(Cand)))) return rc;
         k_verify<<<(unsigned)((ncand + 127) / 128), 128, 0, e->stream>>>(vdp, d->d_text, n, dB, dTL, dTR, keys, ncand, (Cand *)e->cands.p,
-                                                                        use_packed ? 1 : 0, fills);
+                                                                        (use_packed || scan_uses_pep5(e, d, c_full)) ? 1 : 0, fills);
         CK(cudaGetLastError());
         e->stats.launches++;
     }

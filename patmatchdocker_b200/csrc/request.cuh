@@ -200,7 +200,7 @@ static int upload_request(pm_engine *e, pm_dataset *d, const Request &rq, const 
         memset(&rp, 0, sizeof rp);
         rp.pl = c.dp;
         rp.B = base + off; rp.TL = base + off + 256; rp.TR = base + off + 256 + nv;
-        rp.recheck = scan_uses_packed(e, d, c) ? 1 : 0;
+        rp.recheck = (scan_uses_packed(e, d, c) || scan_uses_pep5(e, d, c)) ? 1 : 0;
         memcpy(blob.data() + pats_off + (size_t)p * sizeof(ReqPat), &rp, sizeof rp);
         off += 256 + 2 * nv;
     }

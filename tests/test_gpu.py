@@ -656,6 +656,38 @@ def test_config1_peptide_one_substitution(engine):
     ds.close()
 
 
+def test_peptide_codes_equal_raw_bytes_and_oracle(engine):
+    # proteomes are scanned as 5-bit residue codes (six per word); lower case, 'X', '*', digits and header lines map to
+    # codes that over-approximate -- the re-check on the raw bytes must remove every difference
+    rng = random.Random(31)
+    text = bytearray(genome(23, 800, 400_000, alphabet=PEP.encode(), name="YORF"))
+    for _ in range(300):
+        p = rng.randrange(50, len(text) - 50)
+        if b"\n" in text[p - 2:p + 12] or b">" in text[p - 2:p + 12]:
+            continue
+        text[p:p + 8] = rng.choice([b"xxxxXXXX", b"cqqc*mqh", b"ACDEFGHI".lower(), b"C12C3L4H", b"BJOUZbjz"])
+    text = bytes(text)
+    ds = engine.load_dataset(text)
+    cases = [("(CAAC[ILVM]QQH)", "1s"), ("(C..C[ILVM]..H...H)", "1s"), ("(C..C)", "0ids"), ("([^C]Q[ILVM].K)", "0ids"), ("(MKV.L)", "1ids"),
+             ("(xxXX)", "0ids"), ("(C.?.?C[ILVM])", "0ids"), ("^(MK)", "0ids"), ("(W.W[FY]..[DE])", "2ids"), ("(BJOUZ)", "1s")]
+    used = 0
+    try:
+        for pat, kopt in cases:
+            engine.set_peptide_codes(True)
+            a = engine.search(ds, pat, kopt)
+            used += 1 if engine.stats()["packed"] == 2 else 0
+            r = engine.search_request(ds, [pat], kopt)[0]
+            engine.set_peptide_codes(False)
+            b = engine.search(ds, pat, kopt)
+            assert engine.stats()["packed"] == 0
+            assert np.array_equal(a, b) and np.array_equal(a, r), (pat, kopt)
+            assert [(int(x), int(y)) for x, y in a] == O.search(pat, text, kopt), (pat, kopt)
+        assert used >= 7, used
+    finally:
+        engine.set_peptide_codes(True)
+        ds.close()
+
+
 def test_config2_20nt_two_errors_with_indels(engine, scan_mode):
     text = bytearray(genome(2, 16, 12_000_000))
     motif = b"TGACGTCAGATAAGCCGATT"
