@@ -94,6 +94,10 @@ int pm_engine_set_scan_mode(pm_engine *e, int mode);
  * that surely fail.  1 (default) = q-gram pre-filter + Myers filter, 2 = Myers filter only,
  * 0 = off: every exact piece hit goes through k_verify */
 int pm_engine_set_fused_filter(pm_engine *e, int on);
+/* pm_search_batch with 64 or more exact motifs hashes every text position once (8-mer code -> the motifs whose most
+ * selective 8-position window accepts it) and verifies only those motifs, instead of evaluating every motif at every
+ * position.  1 (default) / 0 = always the dense multi-pattern kernel.  Results are identical. */
+int pm_engine_set_batch_lookup(pm_engine *e, int on);
 /* Datasets that are not DNA-like (proteomes) are also kept as 5-bit residue codes (letters of either case -> 0..25,
  * every other byte -> 31; six codes per 32-bit word) and the Shift-And scan reads those instead of the raw bytes:
  * 0.667 B per residue.  Candidates are re-checked on the raw bytes, results do not change.  1 (default) / 0. */

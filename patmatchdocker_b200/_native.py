@@ -72,6 +72,7 @@ def load():
     L.pm_engine_set_fused_filter.argtypes = [vp, ctypes.c_int]
     L.pm_engine_set_jit.argtypes = [vp, ctypes.c_int]
     L.pm_engine_set_peptide_codes.argtypes = [vp, ctypes.c_int]
+    L.pm_engine_set_batch_lookup.argtypes = [vp, ctypes.c_int]
     L.pm_dataset_create_window.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, vp, ctypes.c_int64, ctypes.POINTER(vp)]
     L.pm_dataset_set_newlines.argtypes = [vp, vp, vp, ctypes.c_int64]
     L.pm_jit_source.restype = ctypes.c_int64
@@ -284,6 +285,10 @@ class Engine:
     def set_fused_filter(self, on):
         """True/1 = q-gram pre-filter + Myers filter (default), 2 = Myers filter only, False/0 = off"""
         _check(load().pm_engine_set_fused_filter(self._h, int(on)))
+
+    def set_batch_lookup(self, on):
+        """batches of >= 64 exact motifs: q-gram lookup kernel (default) or the dense multi-pattern kernel"""
+        _check(load().pm_engine_set_batch_lookup(self._h, 1 if on else 0))
 
     def set_peptide_codes(self, on):
         """proteomes: scan the 5-bit residue codes (default) or the raw bytes"""

@@ -790,6 +790,8 @@ struct pm_engine {
     int split_kernel = 1;                           // 1: k_scan_apx (chunk-built pieces + Landau-Vishkin check), 2: k_scan_split (first generation), 0: block-tile kernel
     int pep5 = 1;                                   // non-DNA datasets: scan the 5-bit residue codes (0: raw bytes)
     int jit_mode = 1;                               // 0: never, 1: auto (genome-scale requests), 2: always -- specialised scan kernels (apx_jit.cpp)
+    int batch_hash = 1;                             // batches of >= 64 exact motifs: q-gram lookup kernel (0: always the dense multi-pattern kernel)
+    bool attr_hash = false;
     bool attr_exact = false, attr_split = false, attr_apx = false;   // cudaFuncSetAttribute is per device: kept per engine
     // one spare text buffer and one spare plane buffer, so that re-creating a dataset of the same size
     // (a request that uploads its file every time) does not pay cudaMalloc/cudaFree of gigabytes
@@ -1022,6 +1024,14 @@ int pm_engine_set_fused_filter(pm_engine *e, int on)
     e->fused_filter = on ? 1 : 0;
     e->qgram_filter = (on == 1 || on == 4) ? 1 : 0;
     e->split_kernel = on == 3 ? 0 : (on == 4 || on == 5) ? 2 : 1;   // 4 / 5: first-generation k_scan_split with / without the q-gram count
+    return PM_OK;
+}
+
+int pm_engine_set_batch_lookup(pm_engine *e, int on)
+{
+    if (!e) { g_err = "bad argument"; return PM_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
+    e->batch_hash = on ? 1 : 0;
     return PM_OK;
 }
 
@@ -2660,6 +2670,80 @@ static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char 
                 m.ent[m.nent++] = (unsigned short)(sel | (j << 3) | (cls << 8));
             }
     }
+    // ---- large batches: q-gram lookup (packed.cuh: k_scan_multi_hash).  Every motif with an 8-position window whose
+    // classes stay inside ACGT is indexed by the 8-mers that window accepts; the others keep the dense kernel.
+    std::vector<HashPat> hpat;
+    std::vector<unsigned> hoffs, hents, dense_map;
+    std::vector<MultiPat> dense_mp;
+    const bool use_hash = npat >= 64 && e->batch_hash;
+    if (use_hash) {
+        std::vector<std::pair<unsigned, unsigned>> pairs;       // (code, entry)
+        std::vector<unsigned> clsv;
+        for (int b = 0; b < npat; b++) {
+            pm::Pattern P;
+            pm::parse_pattern(patterns[b], true, P, err);
+            const int m = P.m();
+            clsv.assign((size_t)m, 0);
+            for (int j = 0; j < m; j++) clsv[(size_t)j] = packed_class_of(P.pos[j], nullptr);
+            int best_o = -1;
+            double best_cost = 0;
+            for (int o = 0; o + MH_Q <= m; o++) {
+                double cost = 1;
+                bool ok = true;
+                for (int t = 0; t < MH_Q && ok; t++) {
+                    const unsigned c = clsv[(size_t)(o + t)];
+                    if ((c & 16u) || !(c & 15u)) ok = false;
+                    cost *= __builtin_popcount(c & 15u);
+                }
+                if (ok && cost <= 64 && (best_o < 0 || cost < best_cost)) { best_o = o; best_cost = cost; }
+            }
+            if (best_o < 0) { dense_mp.push_back(mp[(size_t)b]); dense_map.push_back((unsigned)b); continue; }
+            HashPat hp;
+            memset(&hp, 0, sizeof hp);
+            for (int j = 0; j < m; j++) {
+                const unsigned c = clsv[(size_t)j];
+                if (c & 1u) hp.ma |= 1u << j;
+                if (c & 2u) hp.mc |= 1u << j;
+                if (c & 4u) hp.mg |= 1u << j;
+                if (c & 8u) hp.mt |= 1u << j;
+                if (c & 16u) hp.mx |= 1u << j;
+            }
+            hp.lenmask = m >= 32 ? 0xffffffffu : ((1u << m) - 1u);
+            hp.m = (unsigned)m; hp.pid = (unsigned)b;
+            const unsigned hidx = (unsigned)hpat.size();
+            hpat.push_back(hp);
+            // every concrete 8-mer of the window: letters as (hi, lo) = A 00, C 01, G 11, T 10
+            static const unsigned hi_of[4] = {0, 0, 1, 1}, lo_of[4] = {0, 1, 1, 0};      // by class bit index A, C, G, T
+            unsigned idx[MH_Q] = {0};
+            for (;;) {
+                unsigned code = 0;
+                bool valid = true;
+                for (int t = 0; t < MH_Q; t++) {
+                    const unsigned c = clsv[(size_t)(best_o + t)] & 15u;
+                    // idx[t]-th set bit of c
+                    unsigned cc = c, bit = 0;
+                    for (unsigned q = 0; q <= idx[t]; q++) { bit = (unsigned)__builtin_ctz(cc); cc &= cc - 1; }
+                    (void)valid;
+                    code |= (hi_of[bit] << (8 + t)) | (lo_of[bit] << t);
+                }
+                pairs.push_back({code, ((unsigned)best_o << 20) | hidx});
+                int t = 0;
+                while (t < MH_Q) {
+                    if (++idx[t] < (unsigned)__builtin_popcount(clsv[(size_t)(best_o + t)] & 15u)) break;
+                    idx[t] = 0;
+                    t++;
+                }
+                if (t == MH_Q) break;
+            }
+        }
+        hoffs.assign(65537, 0);
+        for (const auto &pr : pairs) hoffs[pr.first + 1]++;
+        for (int c = 0; c < 65536; c++) hoffs[(size_t)c + 1] += hoffs[(size_t)c];
+        hents.resize(pairs.size() + 1);
+        std::vector<unsigned> fillp(hoffs.begin(), hoffs.end() - 1);
+        for (const auto &pr : pairs) hents[fillp[pr.first]++] = pr.second;
+    }
+    const int ndense = use_hash ? (int)dense_mp.size() : npat;
     CK(cudaSetDevice(e->device));
     (void)cudaGetLastError();
     e->stats = pm_stats{};
@@ -2667,10 +2751,25 @@ static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char 
     Fills fills;
     if ((rc = ensure_fills(e, d, &fills))) return rc;
     if ((rc = e->tables.reserve((size_t)npat * (sizeof(MultiPat) + 2 + 8) + 256))) return rc;
+    const unsigned *d_hoffs = nullptr, *d_hents = nullptr, *d_dmap = nullptr;
+    const HashPat *d_hpat = nullptr;
+    if (use_hash) {
+        const size_t b0 = 65537 * 4, b1 = hents.size() * 4, b2 = (hpat.size() + 1) * sizeof(HashPat), b3 = (dense_map.size() + 1) * 4;
+        auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        if ((rc = e->scanbuf.reserve(al(b0) + al(b1) + al(b2) + al(b3)))) return rc;
+        char *base = (char *)e->scanbuf.p;
+        CK(cudaMemcpyAsync(base, hoffs.data(), b0, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(base + al(b0), hents.data(), b1, cudaMemcpyHostToDevice, e->stream));
+        if (!hpat.empty()) CK(cudaMemcpyAsync(base + al(b0) + al(b1), hpat.data(), hpat.size() * sizeof(HashPat), cudaMemcpyHostToDevice, e->stream));
+        if (!dense_map.empty()) CK(cudaMemcpyAsync(base + al(b0) + al(b1) + al(b2), dense_map.data(), dense_map.size() * 4, cudaMemcpyHostToDevice, e->stream));
+        d_hoffs = (const unsigned *)base; d_hents = (const unsigned *)(base + al(b0));
+        d_hpat = (const HashPat *)(base + al(b0) + al(b1)); d_dmap = (const unsigned *)(base + al(b0) + al(b1) + al(b2));
+        if (ndense) mp.assign(dense_mp.begin(), dense_mp.end());
+    }
     MultiPat *d_pats = (MultiPat *)e->tables.p;
     unsigned short *d_mlen = (unsigned short *)((char *)e->tables.p + (((size_t)npat * sizeof(MultiPat) + 15) & ~(size_t)15));
     unsigned long long *d_perpat = (unsigned long long *)((char *)d_mlen + (((size_t)npat * 2 + 15) & ~(size_t)15));
-    CK(cudaMemcpyAsync(d_pats, mp.data(), (size_t)npat * sizeof(MultiPat), cudaMemcpyHostToDevice, e->stream));
+    if (ndense) CK(cudaMemcpyAsync(d_pats, mp.data(), (size_t)ndense * sizeof(MultiPat), cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(d_mlen, mlen.data(), (size_t)npat * 2, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemsetAsync(d_perpat, 0, (size_t)npat * 8, e->stream));
     if ((rc = e->counters.reserve(64))) return rc;
@@ -2683,12 +2782,32 @@ static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char 
         if ((rc = e->keys.reserve((size_t)capk * 8))) return rc;
         CK(cudaMemsetAsync(d_count, 0, 16, e->stream));
         CK(cudaEventRecord(e->ev[0], e->stream));
+        if (use_hash && !hpat.empty()) {
+            HashArgs h;
+            h.hi = d->hi; h.lo = d->lo; h.xx = d->xx; h.nwords = d->nwords; h.n = n;
+            h.ntiles = (((n > 0 ? n - 1 : 0) / 32) + MH_WORDS) / MH_WORDS;
+            h.offs = d_hoffs; h.ents = d_hents; h.pats = d_hpat;
+            h.keys = (unsigned long long *)e->keys.p; h.count = d_count; h.cap = capk;
+            const size_t smem = MH_STAGES * MH_STAGE_BYTES + 2 * MH_STAGES * 8;
+            if (!e->attr_hash) {
+                CK(cudaFuncSetAttribute(k_scan_multi_hash, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                e->attr_hash = true;
+            }
+            const int gridh = std::max((int)std::min<long long>(h.ntiles, (long long)e->sms * 4), 1);
+            k_scan_multi_hash<<<gridh, (MH_WARPS + 1) * 32, smem, e->stream>>>(h);
+            CK(cudaGetLastError());
+            e->stats.launches++;
+        }
+        if (ndense) {
         MultiArgs a;
         a.hi = d->hi; a.lo = d->lo; a.xx = d->xx; a.nwords = d->nwords; a.n = n; a.a0 = 0; a.a1 = n + 1; a.tile0 = 0; a.ntiles = ntiles;
-        a.pats = d_pats; a.npat = npat; a.keys = (unsigned long long *)e->keys.p; a.count = d_count; a.cap = capk;
+        a.pats = d_pats; a.npat = ndense; a.keys = (unsigned long long *)e->keys.p; a.count = d_count; a.cap = capk;
+        a.pid_map = use_hash ? d_dmap : nullptr;
+        a.bad = (unsigned long long)npat << 40;
         const int grid = std::max((int)std::min<long long>((ntiles + 7) / 8, (long long)e->sms * 4), 1);
         k_scan_packed_multi<<<grid, 256, 0, e->stream>>>(a);
         CK(cudaGetLastError());
+        }
         CK(cudaEventRecord(e->ev[1], e->stream));
         CK(cudaMemcpyAsync(e->h_count, d_count, 16, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
@@ -2698,9 +2817,10 @@ static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char 
         capk = nkeys + 4096;
     }
     const long long nplace = (long long)e->h_count[1];
-    e->stats.scan_bytes = ntiles * 128 * 4 * 3;
+    e->stats.scan_bytes = ntiles * 128 * 4 * 3 * ((use_hash && !hpat.empty() ? 1 : 0) + (ndense ? 1 : 0));
     e->stats.scan_bases = n * (long long)npat;
     e->stats.packed = 1;
+    e->stats.qgram_chunks = use_hash ? (int)hpat.size() : 0;      // batches: motifs served by the q-gram lookup kernel
     unsigned long long *keys = (unsigned long long *)e->keys.p;
     if (nkeys > 1) {
         if ((rc = e->keys2.reserve((size_t)nkeys * 8))) return rc;

@@ -1447,6 +1447,8 @@ struct MultiArgs {
     int npat;
     unsigned long long *keys, *count;
     long long cap;
+    const unsigned *pid_map;             // index in the caller's batch of every pattern handed to this launch (nullptr: identity)
+    unsigned long long bad;              // placeholder key of out-of-range hits: sorts after every real key
 };
 
 #define MP_CHUNK 32                      // pattern descriptors staged in shared memory at a time
@@ -1553,8 +1555,8 @@ __global__ void __launch_bounds__(256) k_scan_packed_multi(const MultiArgs a)
                     if (lane >= o) incl += vv;
                 }
                 const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-                const unsigned long long pidbits = (unsigned long long)(c0 + pb) << 40;
-                const unsigned long long bad = (unsigned long long)a.npat << 40;   // sorts after every real key, cut off by the host
+                const unsigned long long pidbits = (unsigned long long)(a.pid_map ? __ldg(a.pid_map + c0 + pb) : (unsigned)(c0 + pb)) << 40;
+                const unsigned long long bad = a.bad;      // sorts after every real key, cut off by the host
                 const unsigned Mw[4] = {M0, M1, M2, M3};
                 if (total > MP_HITBUF) {
                     flush();
@@ -1592,6 +1594,140 @@ __global__ void __launch_bounds__(256) k_scan_packed_multi(const MultiArgs a)
                 }
                 nbuf += total;
                 __syncwarp();
+            }
+        }
+    }
+    flush();
+}
+
+// ---------------------------------------------------------------------------------------
+// Multi-pattern exact scan by q-gram lookup (large batches).  Evaluating every motif at every position costs
+// npat x positions operations; here every text position is hashed ONCE: the 8 bases starting at it form a 16-bit code
+// (8 bits of the hi plane | 8 bits of the lo plane), a CSR table built on the host maps the code to the motifs whose
+// most selective 8-position window (all of its classes inside ACGT) accepts that 8-mer, and only those motifs are
+// verified -- on the packed planes, all positions at once:  ((A & ma) | (C & mc) | (G & mg) | (T & mt) | (X & mx))
+// must cover the motif's length.  With 10 000 IUPAC motifs that is < 1 candidate per text position instead of
+// 10 000 evaluations.  Text windows that contain a non-ACGT symbol cannot match such a window and are skipped.  Motifs
+// without a usable window (shorter than 8, wildcards everywhere, too many expansions) stay with k_scan_packed_multi.
+// Same keys as there: pid << 40 | window start << 4.   Staging: 1-D bulk TMA copies, 3-stage ring, producer warp.
+#define MH_Q 8
+#define MH_WORDS 1024
+#define MH_FRONT 4
+#define MH_ROW (MH_FRONT + MH_WORDS + 4)
+#define MH_STAGES 3
+#define MH_STAGE_BYTES (3 * MH_ROW * 4)
+#define MH_WPL 8
+#define MH_WARPS 4
+#define MH_HITBUF 256
+struct HashPat { unsigned ma, mc, mg, mt, mx, lenmask, m, pid; };   // position masks per symbol; pid = index in the caller's batch
+struct HashArgs {
+    const unsigned *hi, *lo, *xx;
+    long long nwords, n, ntiles;           // ntiles = block tiles of MH_WORDS words
+    const unsigned *offs;                  // 65537 CSR offsets by 8-mer code
+    const unsigned *ents;                  // entries: window offset inside the motif << 20 | index into pats
+    const HashPat *pats;
+    unsigned long long *keys, *count;
+    long long cap;
+};
+
+__global__ void __launch_bounds__((MH_WARPS + 1) * 32, 4) k_scan_multi_hash(const HashArgs a)
+{
+    extern __shared__ __align__(128) unsigned char ex_smem[];
+    __shared__ unsigned long long hitbuf_all[MH_WARPS + 1][MH_HITBUF];
+    unsigned long long *hitbuf = hitbuf_all[threadIdx.x >> 5];
+    unsigned nbuf = 0;                                      // warp-uniform fill of hitbuf
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    auto flush = [&]() {
+        if (nbuf == 0) return;
+        unsigned long long basei = 0;
+        if (lane == 0) basei = atomicAdd(a.count, (unsigned long long)nbuf);
+        basei = __shfl_sync(0xffffffffu, basei, 0);
+        for (unsigned e = lane; e < nbuf; e += 32)
+            if ((long long)(basei + e) < a.cap) a.keys[basei + e] = hitbuf[e];
+        __syncwarp();
+        nbuf = 0;
+    };
+    unsigned *stage_base = reinterpret_cast<unsigned *>(ex_smem);
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(ex_smem + MH_STAGES * MH_STAGE_BYTES);
+    unsigned long long *empty = full + MH_STAGES;
+    const long long my = blockIdx.x < a.ntiles ? (a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < MH_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], MH_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (wib == MH_WARPS) {
+        if (lane == 0) {
+            int s = 0;
+            unsigned ph = 1;
+            for (long long it = 0; it < my; it++) {
+                if (it >= MH_STAGES) mbar_wait(&empty[s], ph);
+                const long long q = (blockIdx.x + it * gridDim.x) * (long long)MH_WORDS;
+                long long words = MH_ROW;
+                if (q + MH_WORDS + 4 > a.nwords) words = a.nwords - q + MH_FRONT;
+                const unsigned bytes = (unsigned)words * 4u;
+                unsigned *dst = stage_base + (size_t)s * (3 * MH_ROW);
+                mbar_expect_tx(&full[s], 3u * bytes);
+                tma_load_1d(dst, a.hi + q - MH_FRONT, bytes, &full[s]);
+                tma_load_1d(dst + MH_ROW, a.lo + q - MH_FRONT, bytes, &full[s]);
+                tma_load_1d(dst + 2 * MH_ROW, a.xx + q - MH_FRONT, bytes, &full[s]);
+                if (++s == MH_STAGES) { s = 0; ph ^= 1u; }
+            }
+        }
+        return;
+    }
+    int s = 0;
+    unsigned ph = 0;
+    for (long long it = 0; it < my; it++) {
+        mbar_wait(&full[s], ph);
+        // lane segment: words [seg, seg + 8) of the tile; index 0 of the register arrays is the word before it
+        const int seg = (wib * 32 + lane) * MH_WPL;
+        const unsigned *sp = stage_base + (size_t)s * (3 * MH_ROW) + MH_FRONT + seg - 1;
+        unsigned H[MH_WPL + 2], L[MH_WPL + 2], X[MH_WPL + 2];
+#pragma unroll
+        for (int w = 0; w < MH_WPL + 2; w++) { H[w] = sp[w]; L[w] = sp[MH_ROW + w]; X[w] = sp[2 * MH_ROW + w]; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (++s == MH_STAGES) { s = 0; ph ^= 1u; }
+        const long long q = (blockIdx.x + it * gridDim.x) * (long long)MH_WORDS;
+        const long long segpos = (q + seg) * 32;                 // text position of bit 0 of H[1]
+#pragma unroll
+        for (int t = 0; t < MH_WPL; t++) {
+            const unsigned h0 = H[t], h1 = H[t + 1], h2 = H[t + 2], l0 = L[t], l1 = L[t + 1], l2 = L[t + 2], x0 = X[t], x1 = X[t + 1], x2 = X[t + 2];
+#pragma unroll 1
+            for (int r = 0; r < 32; r++) {
+                // 8-mer that starts at bit r of word t + 1
+                const unsigned xs = __funnelshift_r(x1, x2, r) & 0xffu;
+                const unsigned code = ((__funnelshift_r(h1, h2, r) & 0xffu) << 8) | (__funnelshift_r(l1, l2, r) & 0xffu);
+                unsigned e0 = 0, e1 = 0;
+                if (xs == 0) { e0 = __ldg(a.offs + code); e1 = __ldg(a.offs + code + 1); }
+                while (__any_sync(0xffffffffu, e0 < e1)) {
+                    bool ok = false;
+                    unsigned long long key = 0;
+                    if (e0 < e1) {
+                        const unsigned ent = __ldg(a.ents + e0);
+                        e0++;
+                        const uint4 pa = __ldg(reinterpret_cast<const uint4 *>(a.pats + (ent & 0xfffffu)));
+                        const uint4 pb = __ldg(reinterpret_cast<const uint4 *>(a.pats + (ent & 0xfffffu)) + 1);
+                        const int sh = 32 + r - (int)(ent >> 20);            // window start relative to bit 0 of word t: 8 .. 63
+                        unsigned hw, lw, xw;
+                        if (sh < 32) { hw = __funnelshift_r(h0, h1, sh); lw = __funnelshift_r(l0, l1, sh); xw = __funnelshift_r(x0, x1, sh); }
+                        else { hw = __funnelshift_r(h1, h2, sh - 32); lw = __funnelshift_r(l1, l2, sh - 32); xw = __funnelshift_r(x1, x2, sh - 32); }
+                        const unsigned A = ~(hw | lw | xw), C = lw & ~hw, G = hw & lw, T = hw & ~lw;
+                        const unsigned acc = (A & pa.x) | (C & pa.y) | (G & pa.z) | (T & pa.w) | (xw & pb.x);
+                        const long long w = segpos + t * 32 + r - (long long)(ent >> 20);
+                        ok = (acc & pb.y) == pb.y && w >= 0 && w + (long long)pb.z <= a.n;
+                        key = ((unsigned long long)pb.w << 40) | ((unsigned long long)w << 4);
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+                    if (bal) {
+                        const unsigned cnt = __popc(bal);
+                        if (nbuf + cnt > MH_HITBUF) flush();
+                        if (ok) hitbuf[nbuf + __popc(bal & ((1u << lane) - 1u))] = key;
+                        nbuf += cnt;
+                        __syncwarp();
+                    }
+                }
             }
         }
     }

@@ -632,6 +632,54 @@ def test_batch_of_iupac_motifs_against_oracle(engine):
         ds.close()
 
 
+def test_batch_lookup_kernel_equals_dense_kernel(engine):
+    # batches of >= 64 motifs: k_scan_multi_hash (8-mer lookup, then verification of the listed motifs) against the
+    # dense multi-pattern kernel and the oracle, on a genome with N runs, lower case and IUPAC letters; motifs shorter
+    # than 8 or without an ACGT-only window stay on the dense kernel inside the same call
+    rng = random.Random(99)
+    iupac = {"R": "[AG]", "Y": "[CT]", "S": "[GC]", "W": "[AT]", "M": "[AC]", "K": "[GT]", "N": ".", "B": "[CGT]", "V": "[^T]", "H": "[ACT]"}
+    pats = []
+    for i in range(700):
+        m = rng.randint(4, 32) if i % 7 == 0 else rng.randint(8, 14)
+        pats.append("(" + "".join(rng.choice("ACGT") if rng.random() < 0.72 else iupac[rng.choice(list(iupac))] for _ in range(m)) + ")")
+    pats += ["(ACGTACGT)", "(NNNNNNNNNN)".replace("N", "."), "(ACGTAC.TACGTACGTAC.TACGTACGTACGT)", "(.CGTACGTA)", "(ACGTACGT.)"]
+    g = bytearray(genome(41, 9, 900_000))
+    for _ in range(120):
+        p = rng.randrange(100, len(g) - 3000)
+        if b"\n" in g[p - 5:p + 2100] or b">" in g[p - 5:p + 2100]:
+            continue
+        kind = rng.randint(0, 2)
+        ln = rng.randint(1, 2000)
+        if kind == 0:
+            g[p:p + ln] = b"N" * ln
+        elif kind == 1:
+            g[p:p + ln] = bytes(g[p:p + ln]).lower()
+        else:
+            g[p:p + 6] = b"RYKMSW"
+    g[0:8] = b"ACGTACGT"                       # a hit at the very start of the file (header line replaced)
+    g = bytes(g)
+    ds = engine.load_dataset(g)
+    try:
+        for bs in (1600000, 50000):
+            engine.set_buffer_size(bs)
+            engine.set_batch_lookup(True)
+            hits, off = engine.search_batch(ds, pats, "0ids", cap=1 << 22)
+            st = engine.stats()
+            assert 500 < st["qgram_chunks"] < len(pats), st          # most motifs indexed, some left to the dense kernel
+            engine.set_batch_lookup(False)
+            hits2, off2 = engine.search_batch(ds, pats, "0ids", cap=1 << 22)
+            assert engine.stats()["qgram_chunks"] == 0
+            assert np.array_equal(off, off2) and np.array_equal(hits, hits2)
+            for i in rng.sample(range(len(pats)), 30) + list(range(len(pats) - 5, len(pats))):
+                want = O.search(pats[i], g, "0ids", bufsize=bs, cap=1 << 22)
+                got = [(int(b), int(e)) for b, e in hits[off[i]:off[i + 1]]]
+                assert got == want, (pats[i], bs)
+    finally:
+        engine.set_batch_lookup(True)
+        engine.set_buffer_size(1600000)
+        ds.close()
+
+
 def test_request_level_parity_with_reference_python(engine, request_golden):
     check_requests(engine, request_golden)
 
