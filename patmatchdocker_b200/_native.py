@@ -2,6 +2,7 @@
 import ctypes
 import os
 import threading
+import weakref
 
 import numpy as np
 
@@ -152,13 +153,15 @@ class Dataset:
 
     def __init__(self, engine, handle, host_bytes=None):
         self.engine, self._h, self.host_bytes = engine, handle, host_bytes
+        engine._datasets.add(self)             # an engine closes its datasets before it goes away (pm_dataset holds a pointer to it)
 
     def __len__(self):
         return load().pm_dataset_size(self._h)
 
     def close(self):
         if self._h:
-            load().pm_dataset_destroy(self._h)
+            if self.engine._h:                  # engine already destroyed: the handle points into freed memory
+                load().pm_dataset_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -192,6 +195,7 @@ class Engine:
     def __init__(self, device=0):
         self._h = ctypes.c_void_p()
         self._lock = threading.RLock()
+        self._datasets = weakref.WeakSet()
         _check(load().pm_engine_create(int(device), ctypes.byref(self._h)))
         self.device = device
 
@@ -223,6 +227,8 @@ class Engine:
 
     def close(self):
         if self._h:
+            for d in list(self._datasets):
+                d.close()
             load().pm_engine_destroy(self._h)
             self._h = None
 

@@ -2650,6 +2650,7 @@ static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char 
     if (!d->hi || e->scan_mode == 1 || (e->scan_mode == 0 && !d->dna_like) || npat < 2 || npat >= (1 << 20) || d->n >= (1LL << 36)) return 1;
     std::vector<MultiPat> mp((size_t)npat);
     std::vector<unsigned short> mlen((size_t)npat);
+    std::vector<unsigned char> allcls((size_t)npat * 32, 0);       // packed class of every position of every motif
     for (int b = 0; b < npat; b++) {
         pm::Pattern P;
         if (pm::parse_pattern(patterns[b], true, P, err)) return 1;
@@ -2658,6 +2659,7 @@ static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char 
         memset(&m, 0, sizeof m);
         m.m = (unsigned short)P.m();
         mlen[b] = m.m;
+        for (int j = 0; j < P.m(); j++) allcls[(size_t)b * 32 + j] = (unsigned char)packed_class_of(P.pos[j], nullptr);
         // entries grouped by plane so that consecutive entries tend to take the same branch
         for (int s = 0; s < 6; s++)
             for (int j = 0; j < P.m(); j++) {
@@ -2680,24 +2682,26 @@ static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char 
         std::vector<std::pair<unsigned, unsigned>> pairs;       // (code, entry)
         std::vector<unsigned> clsv;
         for (int b = 0; b < npat; b++) {
-            pm::Pattern P;
-            pm::parse_pattern(patterns[b], true, P, err);
-            const int m = P.m();
+            const int m = mlen[(size_t)b];
             clsv.assign((size_t)m, 0);
-            for (int j = 0; j < m; j++) clsv[(size_t)j] = packed_class_of(P.pos[j], nullptr);
-            int best_o = -1;
+            for (int j = 0; j < m; j++) clsv[(size_t)j] = allcls[(size_t)b * 32 + j];
+            int best_o = -1, best_lev = -1;
             double best_cost = 0;
-            for (int o = 0; o + MH_Q <= m; o++) {
-                double cost = 1;
-                bool ok = true;
-                for (int t = 0; t < MH_Q && ok; t++) {
-                    const unsigned c = clsv[(size_t)(o + t)];
-                    if ((c & 16u) || !(c & 15u)) ok = false;
-                    cost *= __builtin_popcount(c & 15u);
+            for (int lev = 0; lev < MH_NLEV && best_o < 0; lev++) {
+                const int Q = mh_q(lev);
+                for (int o = 0; o + Q <= m; o++) {
+                    double cost = 1;
+                    bool ok = true;
+                    for (int t = 0; t < Q && ok; t++) {
+                        const unsigned c = clsv[(size_t)(o + t)];
+                        if ((c & 16u) || !(c & 15u)) ok = false;
+                        cost *= __builtin_popcount(c & 15u);
+                    }
+                    if (ok && cost <= (lev == 0 ? 64 : 16) && (best_o < 0 || cost < best_cost)) { best_o = o; best_cost = cost; best_lev = lev; }
                 }
-                if (ok && cost <= 64 && (best_o < 0 || cost < best_cost)) { best_o = o; best_cost = cost; }
             }
             if (best_o < 0) { dense_mp.push_back(mp[(size_t)b]); dense_map.push_back((unsigned)b); continue; }
+            const int Q = mh_q(best_lev);
             HashPat hp;
             memset(&hp, 0, sizeof hp);
             for (int j = 0; j < m; j++) {
@@ -2712,33 +2716,30 @@ static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char 
             hp.m = (unsigned)m; hp.pid = (unsigned)b;
             const unsigned hidx = (unsigned)hpat.size();
             hpat.push_back(hp);
-            // every concrete 8-mer of the window: letters as (hi, lo) = A 00, C 01, G 11, T 10
+            // every concrete q-mer of the window: letters as (hi, lo) = A 00, C 01, G 11, T 10
             static const unsigned hi_of[4] = {0, 0, 1, 1}, lo_of[4] = {0, 1, 1, 0};      // by class bit index A, C, G, T
             unsigned idx[MH_Q] = {0};
             for (;;) {
                 unsigned code = 0;
-                bool valid = true;
-                for (int t = 0; t < MH_Q; t++) {
+                for (int t = 0; t < Q; t++) {
                     const unsigned c = clsv[(size_t)(best_o + t)] & 15u;
-                    // idx[t]-th set bit of c
-                    unsigned cc = c, bit = 0;
+                    unsigned cc = c, bit = 0;                        // idx[t]-th set bit of c
                     for (unsigned q = 0; q <= idx[t]; q++) { bit = (unsigned)__builtin_ctz(cc); cc &= cc - 1; }
-                    (void)valid;
-                    code |= (hi_of[bit] << (8 + t)) | (lo_of[bit] << t);
+                    code |= (hi_of[bit] << (Q + t)) | (lo_of[bit] << t);
                 }
-                pairs.push_back({code, ((unsigned)best_o << 20) | hidx});
+                pairs.push_back({mh_base(best_lev) + code, ((unsigned)best_o << 20) | hidx});
                 int t = 0;
-                while (t < MH_Q) {
+                while (t < Q) {
                     if (++idx[t] < (unsigned)__builtin_popcount(clsv[(size_t)(best_o + t)] & 15u)) break;
                     idx[t] = 0;
                     t++;
                 }
-                if (t == MH_Q) break;
+                if (t == Q) break;
             }
         }
-        hoffs.assign(65537, 0);
+        hoffs.assign(MH_BUCKETS + 1, 0);
         for (const auto &pr : pairs) hoffs[pr.first + 1]++;
-        for (int c = 0; c < 65536; c++) hoffs[(size_t)c + 1] += hoffs[(size_t)c];
+        for (int c = 0; c < MH_BUCKETS; c++) hoffs[(size_t)c + 1] += hoffs[(size_t)c];
         hents.resize(pairs.size() + 1);
         std::vector<unsigned> fillp(hoffs.begin(), hoffs.end() - 1);
         for (const auto &pr : pairs) hents[fillp[pr.first]++] = pr.second;
@@ -2754,7 +2755,7 @@ static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char 
     const unsigned *d_hoffs = nullptr, *d_hents = nullptr, *d_dmap = nullptr;
     const HashPat *d_hpat = nullptr;
     if (use_hash) {
-        const size_t b0 = 65537 * 4, b1 = hents.size() * 4, b2 = (hpat.size() + 1) * sizeof(HashPat), b3 = (dense_map.size() + 1) * 4;
+        const size_t b0 = (MH_BUCKETS + 1) * 4, b1 = hents.size() * 4, b2 = (hpat.size() + 1) * sizeof(HashPat), b3 = (dense_map.size() + 1) * 4;
         auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
         if ((rc = e->scanbuf.reserve(al(b0) + al(b1) + al(b2) + al(b3)))) return rc;
         char *base = (char *)e->scanbuf.p;
@@ -2776,6 +2777,7 @@ static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char 
     unsigned long long *d_count = (unsigned long long *)e->counters.p;
     const long long n = d->n;
     long long capk = std::max<long long>((long long)(e->keys.cap / 8), 1 << 20);
+    if (const char *dbg = getenv("PM_BATCH_CAP")) capk = std::max<long long>(atoll(dbg), 1024);     // experiments: initial key capacity
     long long nkeys = 0;
     const long long ntiles = ((n > 0 ? n - 1 : 0) / 32) / 128 + 1;
     for (int attempt = 0; attempt < 3; attempt++) {

@@ -213,6 +213,15 @@ __device__ __forceinline__ void mbar_arrive_addr(unsigned bar_addr)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
 }
+// Release of a staged tile that has just been copied to registers.  The shared-memory loads are only ISSUED at this
+// point: measured on B200 (k_scan_multi_hash with the release right behind its loads, lookups slowing the consumers
+// down), the producer saw the arrive, refilled the stage by TMA and the refill landed before queued loads of the same
+// warp had read the old tile.  `dep` must depend on the destination registers of every load: the arrive then cannot
+// issue before their data has come back (dep is stored to a scratch word first: a store ptxas cannot drop).
+__device__ __forceinline__ void mbar_arrive_after_loads(unsigned bar_addr, unsigned dep, unsigned sink_addr)
+{
+    asm volatile("st.volatile.shared.u32 [%2], %1;\n\tmbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr), "r"(dep), "r"(sink_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_addr(unsigned bar_addr, unsigned parity)
 {
     asm volatile(
@@ -312,6 +321,7 @@ __global__ void __launch_bounds__((EX_WARPS + 1) * 32, 5) k_scan_packed_exact(co
 {
     extern __shared__ __align__(128) unsigned char ex_smem[];
     __shared__ unsigned long long hitbuf_all[EX_WARPS + 1][EX_HITBUF];
+    __shared__ unsigned dep_sink[EX_WARPS + 1];
     unsigned long long *hitbuf = hitbuf_all[threadIdx.x >> 5];
     unsigned nbuf = 0;                                      // warp-uniform fill of hitbuf
     auto flush = [&]() {
@@ -380,7 +390,11 @@ __global__ void __launch_bounds__((EX_WARPS + 1) * 32, 5) k_scan_packed_exact(co
             H[EX_WPL] = h2.x; H[EX_WPL + 1] = h2.y; Lw[EX_WPL] = l2.x; Lw[EX_WPL + 1] = l2.y; X[EX_WPL] = x2.x; X[EX_WPL + 1] = x2.y;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive_addr(empty_base + 8u * s);   // this warp's slice is in registers
+        {
+            // one register of every load instruction above (uint4 / uint2 per plane)
+            const unsigned dep = (H[0] ^ H[4] ^ H[EX_WPL]) ^ (Lw[0] ^ Lw[4] ^ Lw[EX_WPL]) ^ (X[0] ^ X[4] ^ X[EX_WPL]);
+            if (lane == 0) mbar_arrive_after_loads(empty_base + 8u * s, dep, smem_u32(&dep_sink[wib]));   // this warp's slice is in registers
+        }
         const long long bt = blockIdx.x + it * gridDim.x;
         const long long wbase = ((a.tile0 * 128) + bt * EX_WORDS + wib * (32 * EX_WPL)) * 32;   // text position of the warp tile
         const unsigned lrel = (unsigned)(EX_WPL * lane) * 32;
@@ -858,6 +872,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32, SP_CTAS) k_scan_split(const Pac
 {
     extern __shared__ __align__(128) unsigned char ex_smem[];
     __shared__ unsigned long long q_key[EX_WARPS][SP_QUEUE];
+    __shared__ unsigned dep_sink[EX_WARPS];
     __shared__ unsigned s_anchor[EX_WARPS][EX_WPL * 32];   // anchor bits of the piece being extracted, [word][lane]
     __shared__ W sT[NP * 16];                           // match masks by symbol (A,C,T,G,X): [piece][left | right][8]
     __shared__ SpParams spar[NP];
@@ -926,7 +941,10 @@ __global__ void __launch_bounds__(EX_WARPS * 32, SP_CTAS) k_scan_split(const Pac
             H[EX_WPL] = h2.x; H[EX_WPL + 1] = h2.y; Lw[EX_WPL] = l2.x; Lw[EX_WPL + 1] = l2.y; X[EX_WPL] = x2.x; X[EX_WPL + 1] = x2.y;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);            // this warp's slice is in registers
+        {
+            const unsigned dep = (H[0] ^ H[4] ^ H[EX_WPL]) ^ (Lw[0] ^ Lw[4] ^ Lw[EX_WPL]) ^ (X[0] ^ X[4] ^ X[EX_WPL]);
+            if (lane == 0) mbar_arrive_after_loads(smem_u32(&empty[s]), dep, smem_u32(&dep_sink[wib]));   // this warp's slice is in registers
+        }
         const long long bt = blockIdx.x + it * gridDim.x;
         unsigned P[EX_WPL + 2];
         // ---- q-gram pre-filter: pass[w] bit b <=> at most k chunks are missing for pattern start b ----
@@ -1203,6 +1221,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32, SP_CTAS) k_scan_apx(const ApxAr
     constexpr int K = ROWS - 1;
     extern __shared__ __align__(128) unsigned char ex_smem[];
     __shared__ unsigned long long q_key[EX_WARPS][AX_QUEUE];
+    __shared__ unsigned dep_sink[EX_WARPS];
     __shared__ unsigned s_cand[EX_WARPS][EX_WPL * 32];     // dense tiles only: candidate bits, [word][lane]
     __shared__ ApxSparse s_sp[EX_MAXPAT];
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
@@ -1274,7 +1293,10 @@ __global__ void __launch_bounds__(EX_WARPS * 32, SP_CTAS) k_scan_apx(const ApxAr
             H[EX_WPL] = h2.x; H[EX_WPL + 1] = h2.y; Lw[EX_WPL] = l2.x; Lw[EX_WPL + 1] = l2.y; X[EX_WPL] = x2.x; X[EX_WPL + 1] = x2.y;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);            // this warp's slice is in registers
+        {
+            const unsigned dep = (H[0] ^ H[4] ^ H[EX_WPL]) ^ (Lw[0] ^ Lw[4] ^ Lw[EX_WPL]) ^ (X[0] ^ X[4] ^ X[EX_WPL]);
+            if (lane == 0) mbar_arrive_after_loads(smem_u32(&empty[s]), dep, smem_u32(&dep_sink[wib]));   // this warp's slice is in registers
+        }
         const long long bt = blockIdx.x + it * gridDim.x;
         const long long wbase = ((a.tile0 * 128) + bt * EX_WORDS + wib * (32 * EX_WPL)) * 32;   // first pattern start of the warp tile
         const unsigned lrel = (unsigned)(EX_WPL * lane) * 32;
@@ -1611,6 +1633,10 @@ __global__ void __launch_bounds__(256) k_scan_packed_multi(const MultiArgs a)
 // without a usable window (shorter than 8, wildcards everywhere, too many expansions) stay with k_scan_packed_multi.
 // Same keys as there: pid << 40 | window start << 4.   Staging: 1-D bulk TMA copies, 3-stage ring, producer warp.
 #define MH_Q 8
+#define MH_NLEV 3                       // lookup tables by window length 8, 6, 4 (motifs without a longer wildcard-free window)
+#define MH_BUCKETS (65536 + 4096 + 256)
+__host__ __device__ __forceinline__ int mh_q(int lev) { return lev == 0 ? 8 : lev == 1 ? 6 : 4; }
+__host__ __device__ __forceinline__ unsigned mh_base(int lev) { return lev == 0 ? 0u : lev == 1 ? 65536u : 65536u + 4096u; }
 #define MH_WORDS 1024
 #define MH_FRONT 4
 #define MH_ROW (MH_FRONT + MH_WORDS + 4)
@@ -1623,7 +1649,7 @@ struct HashPat { unsigned ma, mc, mg, mt, mx, lenmask, m, pid; };   // position 
 struct HashArgs {
     const unsigned *hi, *lo, *xx;
     long long nwords, n, ntiles;           // ntiles = block tiles of MH_WORDS words
-    const unsigned *offs;                  // 65537 CSR offsets by 8-mer code
+    const unsigned *offs;                  // MH_BUCKETS + 1 CSR offsets by (level, q-mer code)
     const unsigned *ents;                  // entries: window offset inside the motif << 20 | index into pats
     const HashPat *pats;
     unsigned long long *keys, *count;
@@ -1684,23 +1710,26 @@ __global__ void __launch_bounds__((MH_WARPS + 1) * 32, 4) k_scan_multi_hash(cons
         const int seg = (wib * 32 + lane) * MH_WPL;
         const unsigned *sp = stage_base + (size_t)s * (3 * MH_ROW) + MH_FRONT + seg - 1;
         unsigned H[MH_WPL + 2], L[MH_WPL + 2], X[MH_WPL + 2];
+        const long long q = (blockIdx.x + it * gridDim.x) * (long long)MH_WORDS;
 #pragma unroll
         for (int w = 0; w < MH_WPL + 2; w++) { H[w] = sp[w]; L[w] = sp[MH_ROW + w]; X[w] = sp[2 * MH_ROW + w]; }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
+        const int s_rel = s;                             // released after the tile has been processed (see mbar_arrive_after_loads)
         if (++s == MH_STAGES) { s = 0; ph ^= 1u; }
-        const long long q = (blockIdx.x + it * gridDim.x) * (long long)MH_WORDS;
         const long long segpos = (q + seg) * 32;                 // text position of bit 0 of H[1]
 #pragma unroll
         for (int t = 0; t < MH_WPL; t++) {
             const unsigned h0 = H[t], h1 = H[t + 1], h2 = H[t + 2], l0 = L[t], l1 = L[t + 1], l2 = L[t + 2], x0 = X[t], x1 = X[t + 1], x2 = X[t + 2];
 #pragma unroll 1
             for (int r = 0; r < 32; r++) {
-                // 8-mer that starts at bit r of word t + 1
-                const unsigned xs = __funnelshift_r(x1, x2, r) & 0xffu;
-                const unsigned code = ((__funnelshift_r(h1, h2, r) & 0xffu) << 8) | (__funnelshift_r(l1, l2, r) & 0xffu);
+                // q-mers that start at bit r of word t + 1
+                const unsigned xs8 = __funnelshift_r(x1, x2, r) & 0xffu, hs8 = __funnelshift_r(h1, h2, r) & 0xffu, ls8 = __funnelshift_r(l1, l2, r) & 0xffu;
+#pragma unroll 1
+                for (int lev = 0; lev < MH_NLEV; lev++) {
+                const int qq = mh_q(lev);
+                const unsigned qm = (1u << qq) - 1u;
+                const unsigned code = mh_base(lev) + (((hs8 & qm) << qq) | (ls8 & qm));
                 unsigned e0 = 0, e1 = 0;
-                if (xs == 0) { e0 = __ldg(a.offs + code); e1 = __ldg(a.offs + code + 1); }
+                if ((xs8 & qm) == 0) { e0 = __ldg(a.offs + code); e1 = __ldg(a.offs + code + 1); }
                 while (__any_sync(0xffffffffu, e0 < e1)) {
                     bool ok = false;
                     unsigned long long key = 0;
@@ -1728,8 +1757,11 @@ __global__ void __launch_bounds__((MH_WARPS + 1) * 32, 4) k_scan_multi_hash(cons
                         __syncwarp();
                     }
                 }
+                }
             }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s_rel]);
     }
     flush();
 }
@@ -1772,7 +1804,12 @@ __global__ void __launch_bounds__(128) k_chain_multi(const unsigned long long *_
         hits[2 * t] = p;
         hits[2 * t + 1] = p + m;
         sel[t] = 1;
-        atomicAdd(&per_pattern[pid], 1ULL);
+        // per-pattern counts: keys are sorted by pattern, so the lanes of a warp mostly count for the same one --
+        // one atomic per group of lanes instead of one per hit
+        {
+            const unsigned grp = __match_any_sync(__activemask(), pid);
+            if ((int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&per_pattern[pid], (unsigned long long)__popc(grp));
+        }
         pos = p + m;
     }
 }
