@@ -2628,12 +2628,8 @@ int pm_last_hits(pm_engine *e, pm_hit *hits, int64_t cap, int64_t *nhits)
 static unsigned packed_class_of(const pm::ByteSet &bs, bool *mixed)
 {
     unsigned cls = (bs.has('A') ? 1u : 0u) | (bs.has('C') ? 2u : 0u) | (bs.has('G') ? 4u : 0u) | (bs.has('T') ? 8u : 0u);
-    int other = 0;
-    for (unsigned ch = 0; ch < 256; ch++) {
-        const unsigned f = ch | 0x20u;
-        if (f == 'a' || f == 'c' || f == 'g' || f == 't') continue;
-        other += bs.has(ch) ? 1 : 0;
-    }
+    int other = __builtin_popcountll(bs.w[0]) + __builtin_popcountll(bs.w[1]) + __builtin_popcountll(bs.w[2]) + __builtin_popcountll(bs.w[3]);
+    for (const char *q = "ACGTacgt"; *q; q++) other -= bs.has((unsigned char)*q) ? 1 : 0;      // bytes outside ACGTacgt the class accepts
     if (other) cls |= 16u;
     if (mixed) *mixed = other != 0 && other != 248;
     return cls;
@@ -2659,13 +2655,17 @@ static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char 
         memset(&m, 0, sizeof m);
         m.m = (unsigned short)P.m();
         mlen[b] = m.m;
-        for (int j = 0; j < P.m(); j++) allcls[(size_t)b * 32 + j] = (unsigned char)packed_class_of(P.pos[j], nullptr);
+        unsigned char mixedv[32];
+        for (int j = 0; j < P.m(); j++) {
+            bool mixed = false;
+            allcls[(size_t)b * 32 + j] = (unsigned char)packed_class_of(P.pos[j], &mixed);
+            mixedv[j] = mixed ? 1 : 0;
+        }
         // entries grouped by plane so that consecutive entries tend to take the same branch
         for (int s = 0; s < 6; s++)
             for (int j = 0; j < P.m(); j++) {
-                bool mixed = false;
-                const unsigned cls = packed_class_of(P.pos[j], &mixed);
-                if (mixed) return 1;
+                const unsigned cls = allcls[(size_t)b * 32 + j];
+                if (mixedv[j]) return 1;
                 const int sel = cls == 1 ? 0 : cls == 2 ? 1 : cls == 4 ? 2 : cls == 8 ? 3 : cls == 16 ? 4 : 5;
                 if (sel != s) continue;
                 if (cls == 31) continue;                     // accepts everything: no constraint (window validity is checked separately)
@@ -2818,6 +2818,8 @@ static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char 
         if (nkeys <= capk) break;
         capk = nkeys + 4096;
     }
+    if (nkeys > capk) { g_err = "hit buffer keeps overflowing"; return PM_ERR_CUDA; }
+    if (nkeys >= (1LL << 31) - 1) { g_err = "more than 2^31 hits in one batch: split the batch"; return PM_ERR_UNSUPPORTED; }
     const long long nplace = (long long)e->h_count[1];
     e->stats.scan_bytes = ntiles * 128 * 4 * 3 * ((use_hash && !hpat.empty() ? 1 : 0) + (ndense ? 1 : 0));
     e->stats.scan_bases = n * (long long)npat;
