@@ -96,7 +96,8 @@ class DeviceShardedSearch:
         pass over its part of the planes, one sort / verify / chain / select, no host synchronisation -- and the
         per-rank [header | hits] blocks are all-gathered over NVLink.  Rank 0 copies the gathered buffer to the
         host once and returns the per-pattern hit lists (== Engine.search_request); the other ranks read only the
-        header rows (to agree on a retry when some rank needed more room) and return None."""
+        header rows (to agree on a retry when some rank needed more room) and return None.  The arrays returned on
+        rank 0 are views of a page-locked buffer that the next call reuses: copy them to keep them."""
         import torch.distributed as dist
         from ._native import HIT_DTYPE, request_header_rows
         torch = self.torch
@@ -112,7 +113,6 @@ class DeviceShardedSearch:
                 self.rq_alloc = rows + rows // 2
                 self.rq_mine = torch.zeros((self.rq_alloc, 2), dtype=torch.int64, device=self.device)
                 self.rq_all = torch.empty((self.rq_alloc * self.world, 2), dtype=torch.int64, device=self.device)
-                self.rq_host = torch.empty((self.rq_alloc * self.world, 2), dtype=torch.int64, pin_memory=on_gpu) if self.rank == 0 else None
                 self.rq_hdr = torch.empty((self.world, hr, 2), dtype=torch.int64, pin_memory=on_gpu)
             if self.rq_hdr.shape[1] != hr:
                 self.rq_hdr = torch.empty((self.world, hr, 2), dtype=torch.int64, pin_memory=on_gpu)
@@ -124,18 +124,11 @@ class DeviceShardedSearch:
             else:
                 flat.copy_(mine)
             view = flat.view(self.world, rows, 2)
-            if self.rank == 0:                                     # one D2H of everything gathered, one synchronisation
-                hview = self.rq_host[: self.world * rows]
-                hview.copy_(flat, non_blocking=True)
-                if on_gpu:
-                    torch.cuda.current_stream().synchronize()
-                h = hview.numpy().reshape(self.world, rows, 2)
-                hdrs = h[:, :hr]
-            else:
-                self.rq_hdr.copy_(view[:, :hr], non_blocking=True)
-                if on_gpu:
-                    torch.cuda.current_stream().synchronize()
-                hdrs = self.rq_hdr.numpy()
+            # every rank reads the header rows (a few hundred bytes): they agree on a retry and on the next sizes
+            self.rq_hdr.copy_(view[:, :hr], non_blocking=True)
+            if on_gpu:
+                torch.cuda.current_stream().synchronize()
+            hdrs = self.rq_hdr.numpy()
             nh = hdrs[:, 0, 0]
             ncand = hdrs[:, 0, 1]
             ok = int(ncand.max()) <= self.rq_cap and int(nh.max()) + hr <= rows
@@ -146,13 +139,28 @@ class DeviceShardedSearch:
                 break
         if self.rank != 0:
             return None
-        out = []
+        # rank 0: the per-pattern lists are put together ON THE DEVICE (pattern-major, ranks in file order) and cross PCIe
+        # once, exactly sized; the returned arrays are views of a pinned buffer that the next call reuses
         counts = hdrs[:, 2:hr].reshape(self.world, -1)[:, :npat]
         offs = np.zeros((self.world, npat + 1), dtype=np.int64)
         offs[:, 1:] = np.cumsum(counts, axis=1)
+        total = int(counts.sum())
+        if total == 0:
+            return [np.zeros(0, dtype=HIT_DTYPE) for _ in range(npat)]
+        parts = [view[r, hr + int(offs[r, p]): hr + int(offs[r, p + 1])] for p in range(npat) for r in range(self.world)]
+        merged = torch.cat(parts)
+        if getattr(self, "rq_out", None) is None or self.rq_out.shape[0] < total:
+            self.rq_out = torch.empty((total + total // 4 + 256, 2), dtype=torch.int64, pin_memory=on_gpu)
+        hout = self.rq_out[:total]
+        hout.copy_(merged, non_blocking=True)
+        if on_gpu:
+            torch.cuda.current_stream().synchronize()
+        flat_np = hout.numpy().view(HIT_DTYPE).reshape(-1)
+        out, at = [], 0
         for p in range(npat):
-            parts = [h[r, hr + offs[r, p]: hr + offs[r, p + 1]] for r in range(self.world)]
-            out.append(np.ascontiguousarray(np.concatenate(parts) if self.world > 1 else parts[0].copy()).view(HIT_DTYPE).reshape(-1))
+            c = int(counts[:, p].sum())
+            out.append(flat_np[at:at + c])
+            at += c
         return out
 
     def _alloc(self, cap):

@@ -993,6 +993,34 @@ def test_windowed_datasets_equal_whole_dataset(engine, scan_mode):
         engine.set_stream(0)
 
 
+def test_sharded_request_class_world_1(engine):
+    # DeviceShardedSearch.request_fills / load_window with one rank (no process group): the code path bench.py runs
+    # per rank -- device-side merge of the per-pattern lists, pinned result views, windowed cold dataset
+    import torch
+    from patmatchdocker_b200.distributed import DeviceShardedSearch
+    rng = random.Random(717)
+    sh = DeviceShardedSearch(engine, 0, 1, torch.device("cuda", 0))
+    try:
+        for it in range(12):
+            pats, kopt, text = _request_case(rng, it)
+            if isinstance(text, str):
+                text = text.encode("latin-1")
+            ds = engine.load_dataset(text)
+            want = [np.array(h, copy=True) for h in engine.search_request(ds, pats, kopt)]
+            got = sh.request_fills(ds, pats, kopt)
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b), (pats, kopt)
+            ds.close()
+            host = torch.from_numpy(np.frombuffer(text, dtype=np.uint8).copy()).pin_memory()
+            dw = sh.load_window(host)
+            got = sh.request_fills(dw, pats, kopt)
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b), (pats, kopt, "window")
+            dw.close()
+    finally:
+        engine.set_stream(0)
+
+
 def test_batch_with_errors_equals_single(engine):
     # pm_search_batch with k > 0: groups of patterns through the request pipeline
     rng = random.Random(99)
