@@ -82,6 +82,15 @@ const char *pm_version(void);
  * -k argument ("2ids", "1s", "0ids", ...) and report the plan the reference would choose. */
 int pm_plan(const char *pattern, const char *kopt, pm_plan_info *info);
 
+/* Approximate searches of the reference read never-written scratch cells while choosing their k+1 pieces
+ * (esimplePreproc @415a68), so the DEPLOYED binary's piece choice -- and through it some hit boundaries -- depends on
+ * what glibc's malloc hands back.  Default (0): the defined behaviour, the cells read as +0.0 (the stock binary under
+ * GLIBC_TUNABLES=glibc.malloc.tcache_count=0:glibc.malloc.perturb=255).  1: what the cells hold in the stock CLI
+ * process with the default glibc 2.39 allocator (the table simpleFindBest @416a10 has just freed, at the offset its
+ * chunk is split at); reproduces the deployed binary on 2 000 of 2 000 random searches (tools/deployed_gap.py).
+ * Process-wide; affects patterns of 11 or more positions with k > 0 only. */
+int pm_set_compat_deployed_glibc(int on);
+
 int pm_engine_create(int device, pm_engine **out);
 void pm_engine_destroy(pm_engine *e);
 /* launch on this cudaStream_t instead of the engine's own (non-blocking) stream; 0 = back to own.  To share the

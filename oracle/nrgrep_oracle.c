@@ -137,6 +137,13 @@ static void class_probs(const nro_pattern *P, double *prob)
 
 /* simpleFindBest @416a10: best BNDM sub-pattern [beg,end) under the cost     */
 /* model, for a search with k errors; returns its cost (1.0 if >= 0.8).       */
+/* Deployed-allocator compatibility (see nro_set_compat): the table simpleFindBest frees is what glibc hands back,
+ * unzeroed, when esimplePreproc allocates its scratch rows a moment later. */
+static int g_compat_deployed = 0;
+static double *g_sfb_pp = NULL;          /* copy of simpleFindBest's table as it is when freed, (m+1) x (m+1) */
+static int g_sfb_m = 0;
+void nro_set_compat(int deployed_glibc) { g_compat_deployed = deployed_glibc; }
+
 static double simple_find_best(const nro_pattern *P, int k, int *flag, int *beg, int *end)
 {
     int m = P->m, S = m + 1;
@@ -210,6 +217,12 @@ static double simple_find_best(const nro_pattern *P, int k, int *flag, int *beg,
             if ((unsigned)(j - i) > 64u) break;
         }
     }
+    if (g_compat_deployed) {
+        free(g_sfb_pp);
+        g_sfb_pp = malloc(sizeof(double) * (size_t)S * (size_t)S);
+        memcpy(g_sfb_pp, pp, sizeof(double) * (size_t)S * (size_t)S);
+        g_sfb_m = m;
+    }
     free(pp); free(mprob); free(last);
     if (*end - *beg <= K1) { *end = 0; *beg = 0; }
     *flag = (*end != 0);
@@ -251,6 +264,42 @@ int nro_plan_make(const nro_pattern *P, int k, int ins, int del, int subs, nro_p
      * i.e. +0.0, in the CLI process); calloc reproduces that. */
     double *A = calloc((size_t)(Lmax + 1) * (size_t)(Lmax ? Lmax : 1), sizeof(double));
     double *Bm = calloc((size_t)m * (size_t)(Lmax ? Lmax : 1), sizeof(double));
+    if (g_compat_deployed && Lmax > 1 && g_sfb_pp && g_sfb_m == m) {
+        /* What the never-written cells A[l][l] hold in the deployed CLI process (glibc 2.39 malloc, traced with an
+         * LD_PRELOAD shim, tools/deployed_gap.py): simpleFindBest's (m+1)^2 table is too large for the tcache once
+         * m >= 11, so its freed chunk is split from the front by esimplePreproc's allocations -- the V array
+         * (4(k+1) bytes, a 32-byte chunk), the (m+1) x (Lmax+1) table, then these scratch rows -- and the rows see
+         * the old table's doubles at that offset.  Smaller tables go to the tcache and the rows come from fresh
+         * (zero) memory; rows whose chunk size equals that of the 8m-byte probability array reuse that array. */
+#define NRO_CS(n) ((((size_t)(n) + 8 + 15) & ~(size_t)15) < 32 ? (size_t)32 : (((size_t)(n) + 8 + 15) & ~(size_t)15))
+        const size_t szpp0 = 8 * (size_t)(m + 1) * (size_t)(m + 1);
+        const size_t szA = 8 * (size_t)(Lmax + 1) * (size_t)Lmax;
+        if (NRO_CS(szA) == NRO_CS(8 * (size_t)m)) {
+            /* the probability array esimplePreproc has just freed sits in the tcache bin of this size (first 16
+             * bytes clobbered by the tcache) */
+            double *prob2 = malloc(sizeof(double) * (size_t)m);
+            class_probs(P, prob2);
+            for (int l = 1; l < Lmax; l++) {
+                const size_t idx = (size_t)l * (size_t)Lmax + (size_t)l;
+                A[idx] = (idx >= 2 && idx < (size_t)m) ? prob2[idx] : 0.0;
+            }
+            free(prob2);
+        } else if (NRO_CS(szA) == NRO_CS(4 * (size_t)m)) {
+            /* simpleFindBest's int array: as doubles, denormals that vanish in 1.0 - x */
+        } else if (szpp0 <= 1032) {
+            if (NRO_CS(szA) == NRO_CS(szpp0))                      /* the old table itself, from the tcache */
+                for (int l = 1; l < Lmax; l++) {
+                    const size_t idx = (size_t)l * (size_t)Lmax + (size_t)l;
+                    A[idx] = (idx >= 2 && idx < (size_t)(m + 1) * (size_t)(m + 1)) ? g_sfb_pp[idx] : 0.0;
+                }
+        } else {
+            const size_t off = (NRO_CS(4 * (size_t)K1) + NRO_CS(8 * (size_t)(m + 1) * (size_t)S)) / 8;
+            for (int l = 1; l < Lmax; l++) {
+                const size_t idx = off + (size_t)l * (size_t)Lmax + (size_t)l;
+                A[(size_t)l * (size_t)Lmax + (size_t)l] = idx < (size_t)(m + 1) * (size_t)(m + 1) ? g_sfb_pp[idx] : 0.0;
+            }
+        }
+    }
     for (int i = 0; i < m && Lmax > 0; i++) {
         memset(A, 0, sizeof(double) * (size_t)Lmax);
         double *prev = A;

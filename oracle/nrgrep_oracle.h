@@ -63,6 +63,10 @@ typedef struct { int64_t beg, end; } nro_hit;
 
 int nro_parse(const char *pattern, int icase, nro_pattern *P);
 int nro_plan_make(const nro_pattern *P, int k, int ins, int del, int subs, nro_plan *plan);
+/* 1: nro_plan_make reproduces the piece choice of the DEPLOYED binary (default glibc 2.39 allocator: esimplePreproc's
+ * never-written scratch cells hold the table simpleFindBest has just freed); 0 (default): the defined behaviour, the
+ * cells read as +0.0 (what the binary does with zero-filled malloc).  Not thread-safe (test infrastructure). */
+void nro_set_compat(int deployed_glibc);
 
 /* Whole-file search exactly as recSearchFile @402250 drives searchScan: returns the
  * number of hits (may exceed cap; only the first cap are stored). Offsets are

@@ -139,6 +139,12 @@ def pinned_empty(count, dtype):
     return p.array, p
 
 
+def set_compat_deployed_glibc(on):
+    """pm_set_compat_deployed_glibc: piece choice of the deployed binary (default glibc allocator) instead of the
+    defined zero-scratch behaviour; process-wide."""
+    _check(load().pm_set_compat_deployed_glibc(1 if on else 0))
+
+
 def plan(pattern, kopt):
     """Host-only: the search plan the reference's esimplePreproc picks for (pattern, -k kopt)."""
     info = PmPlanInfo()

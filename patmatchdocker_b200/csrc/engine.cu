@@ -1274,7 +1274,7 @@ static std::map<std::string, std::shared_ptr<const Compiled>> g_compile_cache;
 
 static int compile(const char *pattern, const char *kopt, Compiled &c, bool need_tables)
 {
-    std::string key = std::string(need_tables ? "T" : "P") + kopt + '\x01' + pattern;
+    std::string key = std::string(need_tables ? "T" : "P") + (pm::compat_deployed() ? "D" : "Z") + kopt + '\x01' + pattern;
     {
         std::lock_guard<std::mutex> lock(g_compile_mu);
         auto it = g_compile_cache.find(key);
@@ -1370,6 +1370,12 @@ static int compile_uncached(const char *pattern, const char *kopt, Compiled &c, 
         d.maxleft = vmax + c.plan.k;                        // the left walk reads at most V + k bytes
     }
     if (c.plan.type != pm::SIMPLE) pm::build_verify(c.P, c.plan, c.vt);
+    return PM_OK;
+}
+
+int pm_set_compat_deployed_glibc(int on)
+{
+    pm::set_compat_deployed(on);
     return PM_OK;
 }
 

@@ -350,6 +350,10 @@ static int make_plan_extended(const Pattern &P, const Options &o, Plan &plan, st
     return PM_OK;
 }
 
+static int g_compat_deployed = 0;
+void set_compat_deployed(int on) { g_compat_deployed = on ? 1 : 0; }
+int compat_deployed() { return g_compat_deployed; }
+
 int make_plan(const Pattern &P, const Options &o, Plan &plan, std::string &err)
 {
     plan = Plan();
@@ -370,8 +374,44 @@ int make_plan(const Pattern &P, const Options &o, Plan &plan, std::string &err)
     // scratch rows start from zero (the defined behaviour of the reference, see DESIGN.md "UB").
     std::vector<double> work((size_t)m * (lmax ? lmax : 1), 0.0);
     std::vector<double> rows((size_t)(lmax + 1) * (lmax ? lmax : 1), 0.0);
+    // The reference never writes the cells rows[l][l] and reads them.  Opt-in (pm_set_compat_deployed_glibc): what they
+    // hold in the DEPLOYED process -- simpleFindBest's (m+1)^2 table is too large for glibc's tcache once m >= 11, its
+    // freed chunk is split from the front by esimplePreproc's allocations (V: a 32-byte chunk, the (m+1) x (lmax+1)
+    // table, then these rows), so the rows see the old table's doubles at that offset; rows whose chunk size equals
+    // that of the 8m-byte probability array reuse that array; everything else is fresh zero memory.  Traced with an
+    // LD_PRELOAD shim and checked against the stock binary on 2 000 random searches (tools/deployed_gap.py).
+    std::vector<double> stale((size_t)(lmax > 0 ? lmax : 1), 0.0);
+    if (g_compat_deployed && lmax > 1) {
+        auto cs = [](size_t n) { const size_t c = (n + 8 + 15) & ~(size_t)15; return c < 32 ? (size_t)32 : c; };
+        const size_t szpp0 = 8 * (size_t)(m + 1) * (size_t)(m + 1), szA = 8 * (size_t)(lmax + 1) * (size_t)lmax;
+        if (cs(szA) == cs(8 * (size_t)m)) {                    // the probability array just freed, from the tcache
+            const std::vector<double> prob = class_probs(P);
+            for (int l = 1; l < lmax; l++) {
+                const size_t idx = (size_t)l * lmax + l;
+                stale[(size_t)l] = (idx >= 2 && idx < (size_t)m) ? prob[idx] : 0.0;
+            }
+        } else if (cs(szA) == cs(4 * (size_t)m)) {
+            // simpleFindBest's int array: as doubles, denormals that vanish in 1.0 - x
+        } else if (szpp0 <= 1032) {
+            if (cs(szA) == cs(szpp0)) {                           // the old table itself, from the tcache
+                const std::vector<double> old = prefix_products(class_probs(P), m, m);
+                for (int l = 1; l < lmax; l++) {
+                    const size_t idx = (size_t)l * lmax + l;
+                    stale[(size_t)l] = (idx >= 2 && idx < old.size()) ? old[idx] : 0.0;
+                }
+            }
+        } else {
+            const std::vector<double> old = prefix_products(class_probs(P), m, m);          // simpleFindBest's table
+            const size_t off = (cs(4 * (size_t)K1) + cs(8 * (size_t)(m + 1) * (size_t)S)) / 8;
+            for (int l = 1; l < lmax; l++) {
+                const size_t idx = off + (size_t)l * lmax + l;
+                stale[(size_t)l] = idx < old.size() ? old[idx] : 0.0;
+            }
+        }
+    }
     for (int i = 0; i < m && lmax > 0; i++) {
         std::fill(rows.begin(), rows.end(), 0.0);
+        for (int l = 1; l < lmax; l++) rows[(size_t)l * lmax + l] = stale[(size_t)l];
         double *prev = rows.data();
         for (int l = 1; l <= lmax; l++) {
             double *cur = prev + lmax;

@@ -64,6 +64,9 @@ struct Plan {
 int parse_kopt(const char *kopt, Options &o, std::string &err);
 int parse_pattern(const char *pattern, bool icase, Pattern &P, std::string &err);
 int make_plan(const Pattern &P, const Options &o, Plan &plan, std::string &err);
+// process-wide: piece choice of the deployed binary (default glibc allocator) instead of the defined zero-scratch behaviour
+void set_compat_deployed(int on);
+int compat_deployed();
 
 // Device tables ---------------------------------------------------------------
 struct FilterTables {                  // byte Shift-And over the superimposed pieces

@@ -103,6 +103,11 @@ def plan(pattern, kopt="0ids", icase=True):
     return P, pl
 
 
+def set_compat(deployed):
+    """piece choice of the deployed binary (default allocator) instead of the defined zero-scratch behaviour"""
+    lib().nro_set_compat(1 if deployed else 0)
+
+
 BUFSIZE = 1600000          # patmatch.py:37 MAX_BUFFER_SIZE, passed as -b
 
 

@@ -1104,3 +1104,23 @@ def test_specialised_kernels_equal_generic_and_oracle(engine):
         engine.set_jit("auto")
         engine.set_buffer_size(1600000)
         engine.set_scan_mode("auto")
+
+
+def test_deployed_compat_mode_reproduces_the_stock_binary(engine, scan_mode):
+    # pm_set_compat_deployed_glibc(1): hit lists of the unmodified nrgrep_coords with its DEFAULT allocator
+    # (tests/golden/deployed_golden.json, 60 cases where they differ from the zero-scratch behaviour + 30 where not)
+    import json, os
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "deployed_golden.json")))["cases"]
+    try:
+        for c in cases:
+            text = c["text"].encode("latin-1")
+            ds = engine.load_dataset(text)
+            pm.set_compat_deployed_glibc(False)
+            a = [(int(x), int(y)) for x, y in engine.search(ds, c["pattern"], c["kopt"])]
+            pm.set_compat_deployed_glibc(True)
+            b = [(int(x), int(y)) for x, y in engine.search(ds, c["pattern"], c["kopt"])]
+            ds.close()
+            assert a == [tuple(h) for h in c["zero_fill"]], (c["pattern"], c["kopt"])
+            assert b == [tuple(h) for h in c["deployed"]], (c["pattern"], c["kopt"])
+    finally:
+        pm.set_compat_deployed_glibc(False)

@@ -45,6 +45,32 @@ def test_plan_is_bit_exact_with_oracle():
         assert mine["split_cost"] == pl.split_cost and mine["fb_cost"] == pl.fb_cost, (pat, kopt)
 
 
+def test_deployed_compat_plan_is_bit_exact_with_oracle():
+    # pm_set_compat_deployed_glibc: the piece choice of the DEPLOYED binary (default glibc allocator).  Product
+    # (plan.cpp) and oracle model the stale scratch cells independently; they must agree, and the mode must change
+    # some plans of patterns with >= 11 positions and none of the shorter exact-arithmetic cases it does not touch.
+    rng = random.Random(12)
+    changed = 0
+    try:
+        for it in range(1200):
+            m = rng.randint(5, 30)
+            k = min(rng.choice([1, 1, 2, 2, 3]), m - 1)
+            pat, _ = random_pattern(rng, DNA, m, neg_pct=0.0)
+            kopt = "%d%s" % (k, rng.choice(["ids", "s", "id"]))
+            pm.set_compat_deployed_glibc(False); O.set_compat(False)
+            zero = pm.plan(pat, kopt)
+            pm.set_compat_deployed_glibc(True); O.set_compat(True)
+            mine = pm.plan(pat, kopt)
+            _, pl = O.plan(pat, kopt)
+            assert mine["type"] == O.TYPE_NAMES[pl.type], (pat, kopt)
+            assert mine["L"] == pl.L and mine["V"] == list(pl.V)[: pl.npieces], (pat, kopt)
+            assert mine["split_cost"] == pl.split_cost, (pat, kopt)
+            changed += 1 if (mine["type"], mine["L"], mine["V"]) != (zero["type"], zero["L"], zero["V"]) else 0
+        assert changed > 20, changed
+    finally:
+        pm.set_compat_deployed_glibc(False); O.set_compat(False)
+
+
 def test_unsupported_patterns_fail_loudly():
     for pat in ("(GA(TA)*AG)", "(GA(TA)?AG)", "(GAT|AAG)", "(G(AT)+AAG)"):
         with pytest.raises(pm.NativeError) as ei:

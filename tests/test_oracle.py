@@ -54,3 +54,25 @@ def test_32bit_piece_test_quirk():
     assert (pl.type, pl.L, list(pl.V)[:4]) == (1, 11, [1, 12, 23, 35])
     text = ">s\nCTCCCTACCCGTGCGGCTACTAATTCCCCCAAAGGTCTAGCGGGAACTGGTCCAAACCGAGTGCG\n"
     assert O.search(pat, text, "3id") == []
+
+
+def test_deployed_compat_reproduces_the_stock_binary_with_its_default_allocator():
+    # tests/golden/deployed_golden.json (tools/deployed_gap.py --emit): hit lists printed by the unmodified
+    # nrgrep_coords with the default glibc allocator ("deployed") and with zero-filled malloc ("zero_fill").  The
+    # oracle's default is the zero-fill behaviour; with nro_set_compat(1) it must print the deployed lists, including
+    # the cases where the two differ.
+    import json, os
+    path = os.path.join(os.path.dirname(__file__), "golden", "deployed_golden.json")
+    cases = json.load(open(path))["cases"]
+    differing = 0
+    try:
+        for c in cases:
+            text = c["text"].encode("latin-1")
+            O.set_compat(False)
+            assert O.search(c["pattern"], text, c["kopt"]) == [tuple(h) for h in c["zero_fill"]], (c["pattern"], c["kopt"])
+            O.set_compat(True)
+            assert O.search(c["pattern"], text, c["kopt"]) == [tuple(h) for h in c["deployed"]], (c["pattern"], c["kopt"])
+            differing += 1 if c["deployed"] != c["zero_fill"] else 0
+    finally:
+        O.set_compat(False)
+    assert differing >= 40 and len(cases) - differing >= 20, (differing, len(cases))
