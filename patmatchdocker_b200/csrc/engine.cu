@@ -677,6 +677,106 @@ __device__ __forceinline__ long long dep_lo(const DevPlan &pl, const Cand &c)
     return c.reach < a ? c.reach : a;
 }
 
+// ---------------------------------------------------------------------------------------
+// Chain stage: the reference restarts its scan at the end of every reported hit (recSearchFile @402250), so whether a
+// verified candidate is reported depends on where the previous hit ended.  Candidates are cut into dependency clusters
+// (cand_opens_cluster) and a cluster is resolved by ONE WARP: it loads 32 candidates at a time, coalesced, and walks them
+// in order with ballots -- the first candidate that is still eligible under the current scan start is examined by its
+// lane (re-verified with the scan start clipped when its unclipped verification had looked left of it), everything in
+// front of it is settled in the same step.  A step is taken per candidate that gets examined, not per candidate, so
+// dense searches (a short motif with many errors: hundreds of thousands of overlapping candidates per buffer fill) cost
+// a few instructions per skipped candidate instead of a dependent global load each (3.1 Gb, (GATAAGC) -k 3ids, 836 M
+// candidates: the one-thread-per-cluster walk took 1.02 s).
+//
+// Candidate j opens a cluster when nothing before it can influence it OR ANY LATER candidate: every hit of an
+// earlier candidate ends at or before the leftmost byte that j and its successors can examine.  Bounded plans:
+// a hit ends within `span` of its anchor and a verification looks at most maxleft (+ the '^' context byte, + the
+// one-byte locus offset of end-anchored plans) to the left.  '*' / '+' patterns: prefix maxima of the hit ends
+// against suffix minima of the examined ranges.  Another pattern of the request or another buffer fill always does.
+__device__ __forceinline__ bool cand_opens_cluster(const DevPlan &pl, const Cand *__restrict__ cands, long long ncand, long long j, const Fills &fills,
+                                                   const long long *__restrict__ maxend, const long long *__restrict__ mindep_rev)
+{
+    if (j == 0) return true;
+    const unsigned long long ka = (unsigned long long)cands[j - 1].key, kb = (unsigned long long)cands[j].key;
+    if (key_pid(ka) != key_pid(kb)) return true;
+    if ((maxend && mindep_rev && pl.ext_repeats) ? maxend[j - 1] <= mindep_rev[ncand - 1 - j]
+                                                 : anchor_of(pl, (long long)ka) + (pl.m + pl.k) + pl.maxleft + 2 <= anchor_of(pl, (long long)kb)) return true;
+    return fill_of(fills, locus_of(pl, anchor_of(pl, (long long)ka))) != fill_of(fills, locus_of(pl, anchor_of(pl, (long long)kb)));
+}
+
+// Resolves the cluster that starts at candidate j0; called by all 32 lanes of a warp with the same arguments.
+// use_scan: decide cluster borders with the maxend / mindep_rev arrays (patterns with '*' / '+').  Returns the hits chosen.
+__device__ unsigned long long chain_cluster_warp(const DevPlan &pl, const unsigned char *__restrict__ text,
+                                                 const unsigned long long *__restrict__ TL, const unsigned long long *__restrict__ TR,
+                                                 const Cand *__restrict__ cands, long long ncand, long long j0,
+                                                 pm_hit *__restrict__ hits, unsigned char *__restrict__ sel, const Fills &fills,
+                                                 const long long *__restrict__ maxend, const long long *__restrict__ mindep_rev)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned below = (1u << lane) - 1u;
+    const int cur = fill_of(fills, locus_of(pl, anchor_of(pl, cands[j0].key)));
+    const long long n_fill = fills.E[cur];
+    long long pos = fills.S[cur];
+    unsigned long long nsel = 0;
+    bool stop = false;
+    for (long long t0 = j0; t0 < ncand && !stop; t0 += 32) {
+        const long long t = t0 + lane;
+        const bool exists = t < ncand;
+        // the cluster ends in front of the first later candidate that opens a new one
+        const bool opens = exists && t > j0 && cand_opens_cluster(pl, cands, ncand, t, fills, maxend, mindep_rev);
+        const unsigned endm = __ballot_sync(0xffffffffu, opens || !exists);
+        const int nin = endm ? __ffs(endm) - 1 : 32;            // lanes 0 .. nin-1 belong to the cluster
+        const bool incl = lane < nin;
+        Cand c;
+        c.key = 0; c.beg = -1; c.end = -1; c.reach = 0;
+        long long anchor = 0, p = 0, dl = 0;
+        if (incl) {
+            c = cands[t];
+            sel[t] = 0;
+            anchor = anchor_of(pl, c.key);
+            p = locus_of(pl, anchor);
+            dl = dep_lo(pl, c);
+        }
+        unsigned todo = incl ? 0xffffffffu : 0u;                 // per lane: all ones while the candidate is not settled
+        for (;;) {
+            // a failed verification is final unless '^' is in play: then a scan start inside the examined bytes can
+            // turn it into a match (the left context is satisfied AT the scan start), so it is redone clipped below
+            const bool elig = todo && p >= pos && (c.beg >= 0 || (pl.start_line && pl.type != PM_PLAN_SIMPLE && dl < pos));
+            const unsigned em = __ballot_sync(0xffffffffu, elig);
+            if (!em) break;
+            const int L = __ffs(em) - 1;
+            if (lane <= L) todo = 0;                              // everything in front of L is settled under this scan start
+            long long b = c.beg, e = c.end;
+            int ok = 0;
+            if (lane == L) {
+                ok = 1;
+                if (pl.type == PM_PLAN_SIMPLE) {
+                    // simple checkMatch @416790: '^' / '$' look at the byte next to the match unless it touches the scan range
+                    if (pl.start_line && anchor > pos && text[anchor - 1] != '\n') ok = 0;
+                    if (ok && pl.end_line && e < n_fill && text[e] != '\n') ok = 0;
+                } else if (dl < pos) {
+                    // the unclipped verification looked left of the new scan start: redo it clipped
+                    long long r;
+                    if (plan_is_ext(pl)) ok = check_match_ext(pl, text, n_fill, TL, TR, anchor, pos, &b, &e, &r) ? 1 : 0;
+                    else ok = check_match(pl, text, n_fill, TL, TR, (int)(c.key & 15), anchor, pos, &b, &e, &r) ? 1 : 0;
+                }
+                if (ok) { hits[t].beg = b; hits[t].end = e; sel[t] = 1; }
+            }
+            ok = __shfl_sync(0xffffffffu, ok, L);
+            if (ok) {
+                const long long ne = __shfl_sync(0xffffffffu, e, L), nb = __shfl_sync(0xffffffffu, b, L);
+                nsel++;
+                if (ne <= pos && nb == ne) { stop = true; break; }   // zero-length hit: the reference would not advance either
+                pos = ne;
+            }
+        }
+        if (nin < 32) break;
+    }
+    (void)below;
+    return nsel;
+}
+
+// one warp per 32 consecutive candidates: the lanes find the cluster heads among them, the warp resolves those clusters
 __global__ void __launch_bounds__(128) k_chain(const DevPlan pl, const unsigned char *__restrict__ text, long long n,
                                                const unsigned long long *__restrict__ TL, const unsigned long long *__restrict__ TR,
                                                const Cand *__restrict__ cands, long long ncand,
@@ -684,54 +784,16 @@ __global__ void __launch_bounds__(128) k_chain(const DevPlan pl, const unsigned 
                                                const long long *__restrict__ maxend,        // prefix maxima of Cand.end, or null
                                                const long long *__restrict__ mindep_rev)    // prefix minima of dep_lo over the REVERSED list
 {
-    const long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j0 >= ncand) return;
-    const long long span = pl.m + pl.k;
-    auto fill_at = [&](long long j) -> int {
-        return fill_of(fills, locus_of(pl, anchor_of(pl, cands[j].key)));
-    };
-    // Candidate j opens a cluster when nothing before it can influence it OR ANY LATER candidate: every hit of an
-    // earlier candidate ends at or before the leftmost byte that j and its successors can examine.  Bounded plans:
-    // a hit ends within `span` of its anchor and a verification looks at most maxleft (+ the '^' context byte, + the
-    // one-byte locus offset of end-anchored plans) to the left.  '*' / '+' patterns: prefix maxima of the hit ends
-    // against suffix minima of the examined ranges.
-    auto independent = [&](long long j) -> bool {
-        if (j == 0) return true;
-        if (maxend ? maxend[j - 1] <= mindep_rev[ncand - 1 - j]
-                   : anchor_of(pl, cands[j - 1].key) + span + pl.maxleft + 2 <= anchor_of(pl, cands[j].key)) return true;
-        return fill_at(j) != fill_at(j - 1);               // a new fill restarts the scan
-    };
-    if (!independent(j0)) return;
-    int cur = fill_at(j0);
-    long long pos = fills.S[cur];
-    for (long long t = j0; t < ncand; t++) {
-        if (t > j0 && independent(t)) break;
-        sel[t] = 0;
-        const Cand c = cands[t];
-        // a failed verification is final unless '^' is in play: then a scan start inside the examined bytes can
-        // turn it into a match (the left context is satisfied AT the scan start), so it is redone clipped below
-        if (c.beg < 0 && !(pl.start_line && pl.type != PM_PLAN_SIMPLE && dep_lo(pl, c) < pos)) continue;
-        const long long anchor = anchor_of(pl, c.key);
-        const long long p = locus_of(pl, anchor);
-        if (p < pos) continue;
-        const long long n_fill = fills.E[cur];
-        long long b = c.beg, e = c.end;
-        if (pl.type == PM_PLAN_SIMPLE) {
-            // simple checkMatch @416790: '^' / '$' look at the byte next to the match unless it touches the scan range
-            if (pl.start_line && anchor > pos && text[anchor - 1] != '\n') continue;
-            if (pl.end_line && e < n_fill && text[e] != '\n') continue;
-        } else if (dep_lo(pl, c) < pos) {
-            // the unclipped verification looked left of the new scan start: redo it clipped
-            long long r;
-            if (plan_is_ext(pl)) { if (!check_match_ext(pl, text, n_fill, TL, TR, anchor, pos, &b, &e, &r)) continue; }
-            else if (!check_match(pl, text, n_fill, TL, TR, (int)(c.key & 15), anchor, pos, &b, &e, &r)) continue;
-        }
-        hits[t].beg = b;
-        hits[t].end = e;
-        sel[t] = 1;
-        if (e <= pos && b == e) break;                      // zero-length hit: the reference would not advance either
-        pos = e;
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool head = j < ncand && cand_opens_cluster(pl, cands, ncand, j, fills, maxend, mindep_rev);
+    unsigned heads = __ballot_sync(0xffffffffu, head);
+    const long long wbase = j - (threadIdx.x & 31);
+    while (heads) {
+        const int h = __ffs(heads) - 1;
+        heads &= heads - 1;
+        chain_cluster_warp(pl, text, TL, TR, cands, ncand, wbase + h, hits, sel, fills, maxend, mindep_rev);
     }
+    (void)n;
 }
 
 struct MaxLL { __host__ __device__ long long operator()(long long a, long long b) const { return a > b ? a : b; } };

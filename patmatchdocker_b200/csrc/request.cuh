@@ -99,57 +99,30 @@ __global__ void k_cand_ends_req(const ReqPat *__restrict__ pats, const Cand *__r
     deps_rev[nv - 1 - j] = dl + pid * REQ_SEG;
 }
 
+// one warp per 32 consecutive candidates: the lanes find the cluster heads among them, the warp resolves those clusters
+// (engine.cu: chain_cluster_warp); clusters never span patterns
 __global__ void __launch_bounds__(128) k_chain_req(const ReqPat *__restrict__ pats, const unsigned char *__restrict__ text, long long n,
                                                    const Cand *__restrict__ cands, unsigned long long *__restrict__ hdr, long long cap,
                                                    pm_hit *__restrict__ hits, unsigned char *__restrict__ sel, const Fills fills,
                                                    const long long *__restrict__ maxend, const long long *__restrict__ mindep_rev)
 {
-    const long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long ncand = req_nvalid(hdr, cap);
-    if (j0 >= ncand) return;
-    const int pid = key_pid((unsigned long long)cands[j0].key);
-    const ReqPat &rp = pats[pid];
-    const DevPlan &pl = rp.pl;
-    const long long span = pl.m + pl.k;
-    auto fill_at = [&](long long j) -> int {
-        return fill_of(fills, locus_of(pl, anchor_of(pl, cands[j].key)));
-    };
-    auto independent = [&](long long j) -> bool {
-        if (j == 0) return true;
-        if (key_pid((unsigned long long)cands[j - 1].key) != pid) return true;            // another pattern: its own search
-        if ((maxend && pl.ext_repeats) ? maxend[j - 1] <= mindep_rev[ncand - 1 - j]
-                                       : anchor_of(pl, cands[j - 1].key) + span + pl.maxleft + 2 <= anchor_of(pl, cands[j].key)) return true;
-        return fill_at(j) != fill_at(j - 1);               // a new fill restarts the scan
-    };
-    if (!independent(j0)) return;
-    int cur = fill_at(j0);
-    long long pos = fills.S[cur];
-    unsigned long long nsel = 0;
-    for (long long t = j0; t < ncand; t++) {
-        if (t > j0 && (key_pid((unsigned long long)cands[t].key) != pid || independent(t))) break;
-        const Cand c = cands[t];
-        if (c.beg < 0 && !(pl.start_line && pl.type != PM_PLAN_SIMPLE && dep_lo(pl, c) < pos)) continue;
-        const long long anchor = anchor_of(pl, c.key);
-        const long long p = locus_of(pl, anchor);
-        if (p < pos) continue;
-        const long long n_fill = fills.E[cur];
-        long long b = c.beg, e = c.end;
-        if (pl.type == PM_PLAN_SIMPLE) {
-            if (pl.start_line && anchor > pos && text[anchor - 1] != '\n') continue;
-            if (pl.end_line && e < n_fill && text[e] != '\n') continue;
-        } else if (dep_lo(pl, c) < pos) {
-            long long r;
-            if (plan_is_ext(pl)) { if (!check_match_ext(pl, text, n_fill, rp.TL, rp.TR, anchor, pos, &b, &e, &r)) continue; }
-            else if (!check_match(pl, text, n_fill, rp.TL, rp.TR, (int)(c.key & 15), anchor, pos, &b, &e, &r)) continue;
-        }
-        hits[t].beg = b;
-        hits[t].end = e;
-        sel[t] = 1;
-        nsel++;
-        if (e <= pos && b == e) break;                      // zero-length hit: the reference would not advance either
-        pos = e;
+    const long long wbase = j - (threadIdx.x & 31);
+    if (wbase >= ncand) return;                               // warp-uniform
+    bool head = false;
+    if (j < ncand) head = cand_opens_cluster(pats[key_pid((unsigned long long)cands[j].key)].pl, cands, ncand, j, fills, maxend, mindep_rev);
+    unsigned heads = __ballot_sync(0xffffffffu, head);
+    while (heads) {
+        const int h = __ffs(heads) - 1;
+        heads &= heads - 1;
+        const long long j0 = wbase + h;
+        const int pid = key_pid((unsigned long long)cands[j0].key);
+        const ReqPat &rp = pats[pid];
+        const unsigned long long nsel = chain_cluster_warp(rp.pl, text, rp.TL, rp.TR, cands, ncand, j0, hits, sel, fills, maxend, mindep_rev);
+        if (nsel && (threadIdx.x & 31) == 0) atomicAdd(hdr + REQ_HDR_FIXED + pid, nsel);
     }
-    if (nsel) atomicAdd(hdr + REQ_HDR_FIXED + pid, nsel);
+    (void)n;
 }
 
 // ---------------------------------------------------------------------------------------
