@@ -376,10 +376,10 @@ static int env_int(const char *name, int dflt, int lo, int hi)
     return dflt;
 }
 
-ApxJitShape apx_jit_shape()
+ApxJitShape apx_jit_shape(bool force_stream)
 {
     ApxJitShape sh;
-    sh.stream = env_int("PM_JIT_STREAM", 1, 0, 1);
+    sh.stream = force_stream ? 1 : env_int("PM_JIT_STREAM", 1, 0, 1);
     if (sh.stream) {
         sh.w = env_int("PM_JIT_W", 9, 1, 63) | 1;           // odd: conflict-free 32-bit shared-memory reads
         sh.warps = env_int("PM_JIT_WARPS", 8, 1, 16);
@@ -398,14 +398,15 @@ ApxJitShape apx_jit_shape()
     return sh;
 }
 
-std::string apx_generate_prefix(const ApxPat *pats, int npat)
+std::string apx_generate_prefix(const ApxPat *pats, int npat, bool exact)
 {
-    const ApxJitShape shp = apx_jit_shape();
-    if (shp.stream) {
+    const ApxJitShape shp = apx_jit_shape(exact);
+    if (shp.stream || exact) {
         Emit o;
         bool wide = false;
         for (int p = 0; p < npat; p++) wide = wide || pats[p].m + 2 * pats[p].k > 32;
-        o.f("#define AX_STREAM 1\n#define AX_K %d\n#define AX_WIDE %d\n#define AX_NPAT %d\n#define AX_CTAS %d\n#define AX_W %d\n#define AX_WARPS %d\n#define AX_STAGES %d\n",
+        o.f("#define AX_STREAM 1\n#define AX_EXACT %d\n", exact ? 1 : 0);
+        o.f("#define AX_K %d\n#define AX_WIDE %d\n#define AX_NPAT %d\n#define AX_CTAS %d\n#define AX_W %d\n#define AX_WARPS %d\n#define AX_STAGES %d\n",
             pats[0].k, wide ? 1 : 0, npat, shp.ctas, shp.w, shp.warps, shp.stages);
         for (int p = 0; p < 2; p++) {
             const ApxPat &pt = pats[p < npat ? p : 0];

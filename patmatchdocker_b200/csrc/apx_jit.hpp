@@ -18,8 +18,10 @@ struct ApxJitShape {
     int tile_words;      // words per plane of a block tile
     size_t smem;         // dynamic shared memory per CTA
 };
-ApxJitShape apx_jit_shape();
-std::string apx_generate_prefix(const ApxPat *pats, int npat);
+ApxJitShape apx_jit_shape(bool force_stream = false);
+// exact = true: k = 0 patterns described as ApxPat with one piece evaluated position by position (dn / dshift / dcls);
+// the kernel then writes hit keys directly instead of running the Landau-Vishkin check
+std::string apx_generate_prefix(const ApxPat *pats, int npat, bool exact = false);
 // prefix + the constant kernel body
 std::string apx_full_source(const std::string &prefix);
 // NVRTC (loaded with dlopen on first use) -> cubin for sm_100a.  Returns 0 on success; `log` carries the reason otherwise.

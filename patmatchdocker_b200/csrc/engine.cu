@@ -776,7 +776,51 @@ __device__ unsigned long long chain_cluster_warp(const DevPlan &pl, const unsign
     return nsel;
 }
 
-// one warp per 32 consecutive candidates: the lanes find the cluster heads among them, the warp resolves those clusters
+// Short clusters (the usual case of a selective search: the few pieces that fire at one site) are walked by the lane of
+// their first candidate, up to CHAIN_SHORT candidates; returns the hits chosen, or -1 when the cluster is longer than
+// that (the warp then resolves it from the start, chain_cluster_warp).
+#define CHAIN_SHORT 24
+__device__ __forceinline__ int chain_cluster_thread(const DevPlan &pl, const unsigned char *__restrict__ text,
+                                                    const unsigned long long *__restrict__ TL, const unsigned long long *__restrict__ TR,
+                                                    const Cand *__restrict__ cands, long long ncand, long long j0,
+                                                    pm_hit *__restrict__ hits, unsigned char *__restrict__ sel, const Fills &fills,
+                                                    const long long *__restrict__ maxend, const long long *__restrict__ mindep_rev)
+{
+    const int cur = fill_of(fills, locus_of(pl, anchor_of(pl, cands[j0].key)));
+    const long long n_fill = fills.E[cur];
+    long long pos = fills.S[cur];
+    int nsel = 0;
+    for (long long t = j0; t < ncand; t++) {
+        if (t > j0 && cand_opens_cluster(pl, cands, ncand, t, fills, maxend, mindep_rev)) break;
+        if (t - j0 >= CHAIN_SHORT) return -1;
+        sel[t] = 0;
+        const Cand c = cands[t];
+        const long long dl = dep_lo(pl, c);
+        if (c.beg < 0 && !(pl.start_line && pl.type != PM_PLAN_SIMPLE && dl < pos)) continue;
+        const long long anchor = anchor_of(pl, c.key);
+        const long long p = locus_of(pl, anchor);
+        if (p < pos) continue;
+        long long b = c.beg, e = c.end;
+        if (pl.type == PM_PLAN_SIMPLE) {
+            if (pl.start_line && anchor > pos && text[anchor - 1] != '\n') continue;
+            if (pl.end_line && e < n_fill && text[e] != '\n') continue;
+        } else if (dl < pos) {
+            long long r;
+            if (plan_is_ext(pl)) { if (!check_match_ext(pl, text, n_fill, TL, TR, anchor, pos, &b, &e, &r)) continue; }
+            else if (!check_match(pl, text, n_fill, TL, TR, (int)(c.key & 15), anchor, pos, &b, &e, &r)) continue;
+        }
+        hits[t].beg = b;
+        hits[t].end = e;
+        sel[t] = 1;
+        nsel++;
+        if (e <= pos && b == e) break;                      // zero-length hit: the reference would not advance either
+        pos = e;
+    }
+    return nsel;
+}
+
+// one warp per 32 consecutive candidates: the lanes find the cluster heads among them; short clusters are walked by
+// the lane of their head (all in parallel), clusters longer than CHAIN_SHORT by the whole warp, one after the other
 __global__ void __launch_bounds__(128) k_chain(const DevPlan pl, const unsigned char *__restrict__ text, long long n,
                                                const unsigned long long *__restrict__ TL, const unsigned long long *__restrict__ TR,
                                                const Cand *__restrict__ cands, long long ncand,
@@ -785,9 +829,12 @@ __global__ void __launch_bounds__(128) k_chain(const DevPlan pl, const unsigned 
                                                const long long *__restrict__ mindep_rev)    // prefix minima of dep_lo over the REVERSED list
 {
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const bool head = j < ncand && cand_opens_cluster(pl, cands, ncand, j, fills, maxend, mindep_rev);
-    unsigned heads = __ballot_sync(0xffffffffu, head);
-    const long long wbase = j - (threadIdx.x & 31);
+    bool longc = false;
+    if (head) longc = chain_cluster_thread(pl, text, TL, TR, cands, ncand, j, hits, sel, fills, maxend, mindep_rev) < 0;
+    unsigned heads = __ballot_sync(0xffffffffu, longc);
+    const long long wbase = j - lane;
     while (heads) {
         const int h = __ffs(heads) - 1;
         heads &= heads - 1;
@@ -1509,6 +1556,9 @@ static void fill_exact_pat(const Compiled &c, long long a0, long long a1, long l
     }
 }
 
+static bool jit_wanted(const pm_engine *e, long long bases);
+static int launch_apx_jit(pm_engine *e, const ApxArgs &a, long long lo, long long hi, bool exact);
+
 static int launch_exact(pm_engine *e, pm_dataset *d, const ExactPat *pats, int npat, unsigned long long bad, const ScanTarget &t)
 {
     ExactArgs a;
@@ -1528,6 +1578,41 @@ static int launch_exact(pm_engine *e, pm_dataset *d, const ExactPat *pats, int n
     a.ntiles = ((hi - 1) / 32) / 128 + 1 - a.tile0;
     a.bad = bad;
     a.keys = t.keys; a.count = t.count; a.cap = t.cap;
+    // genome-scale requests: the streaming kernel compiled for exactly these patterns (apx_jit.cpp, exact mode)
+    if (jit_wanted(e, hi - lo)) {
+        ApxArgs ja;
+        memset(&ja, 0, sizeof ja);
+        ja.hi = d->hi; ja.lo = d->lo; ja.xx = d->xx; ja.nwords = d->nwords; ja.n = d->n;
+        ja.keys = t.keys; ja.count = t.count; ja.cap = t.cap;
+        ja.npat = a.npat;
+        bool fits = true;
+        for (int p = 0; p < a.npat; p++) {
+            const ExactPat &xp = a.pat[p];
+            ApxPat &ap = ja.pat[p];
+            ap.a0 = xp.a0; ap.a1 = xp.a1; ap.keytag = xp.keytag;
+            ap.m = xp.L; ap.k = 0; ap.L = xp.L; ap.npieces = 1; ap.indel = 0; ap.win = 1;
+            int nd = 0;
+            static const unsigned char plane_cls[5] = {1, 2, 4, 8, 16};
+            for (int sidx = 0; sidx < 6; sidx++)
+                for (int q = 0; q < xp.npos[sidx]; q++) {
+                    if (nd >= AX_MAXDENSE) { fits = false; break; }
+                    ap.dshift[nd] = xp.shift[sidx][q];                       // k + j with k = 0
+                    ap.dcls[nd] = sidx < 5 ? plane_cls[sidx] : xp.cls[q];
+                    nd++;
+                }
+            ap.dn[0] = (unsigned char)nd;
+            if (nd == 0) ap.dwild[0] = 1;
+        }
+        if (fits) {
+            int rc = launch_apx_jit(e, ja, lo, hi, true);
+            if (rc == PM_OK) {
+                e->stats.scan_bases += (hi - lo) * a.npat;
+                e->stats.packed = 1;
+                return PM_OK;
+            }
+            if (e->jit_mode == 2 || rc != PM_ERR_UNSUPPORTED) return rc;   // auto mode: no NVRTC on this machine -> generic kernel
+        }
+    }
     const size_t smem = EX_STAGES * EX_STAGE_BYTES + 2 * EX_STAGES * 8;
     if (!e->attr_exact) {
         CK(cudaFuncSetAttribute(k_scan_packed_exact<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1890,9 +1975,9 @@ struct JitEntry {
 static std::mutex g_jit_mu;
 static std::map<std::string, JitEntry> g_jit_cache;
 
-static int launch_apx_jit(pm_engine *e, const ApxArgs &a, long long lo, long long hi)
+static int launch_apx_jit(pm_engine *e, const ApxArgs &a, long long lo, long long hi, bool exact)
 {
-    const ApxJitShape shp = apx_jit_shape();
+    const ApxJitShape shp = apx_jit_shape(exact);
     // key: the pattern descriptions without what stays a run-time argument (ranges, key tags) + the launch geometry
     std::string key((size_t)a.npat * sizeof(ApxPat) + sizeof shp, '\0');
     for (int p = 0; p < a.npat; p++) {
@@ -1903,7 +1988,7 @@ static int launch_apx_jit(pm_engine *e, const ApxArgs &a, long long lo, long lon
     {
         ApxJitShape t;
         memset(&t, 0, sizeof t);
-        t.stream = shp.stream; t.w = shp.w; t.warps = shp.warps; t.stages = shp.stages; t.ctas = shp.ctas; t.tile_words = shp.tile_words; t.smem = shp.smem;
+        t.stream = shp.stream + (exact ? 2 : 0); t.w = shp.w; t.warps = shp.warps; t.stages = shp.stages; t.ctas = shp.ctas; t.tile_words = shp.tile_words; t.smem = shp.smem;
         memcpy(&key[(size_t)a.npat * sizeof(ApxPat)], &t, sizeof t);
     }
     cudaKernel_t kern = nullptr;
@@ -1911,7 +1996,7 @@ static int launch_apx_jit(pm_engine *e, const ApxArgs &a, long long lo, long lon
         std::lock_guard<std::mutex> lock(g_jit_mu);
         auto it = g_jit_cache.find(key);
         if (it == g_jit_cache.end()) {
-            const std::string prefix = apx_generate_prefix(a.pat, a.npat);
+            const std::string prefix = apx_generate_prefix(a.pat, a.npat, exact);
             JitEntry en;
             std::vector<char> cubin;
             std::string log;
@@ -1995,7 +2080,7 @@ static int launch_apx(pm_engine *e, pm_dataset *d, const ApxPat *pats, int npat,
     e->stats.qgram_chunks = a.pat[0].ncounted;
     // genome-scale requests: kernel compiled for exactly the request's patterns (apx_jit.cpp)
     if (jit_wanted(e, hi - lo)) {
-        int rc = launch_apx_jit(e, a, lo, hi);
+        int rc = launch_apx_jit(e, a, lo, hi, false);
         if (rc == PM_OK) return PM_OK;
         if (e->jit_mode == 2 || rc != PM_ERR_UNSUPPORTED) return rc;   // auto mode: no NVRTC on this machine -> generic kernel
     }

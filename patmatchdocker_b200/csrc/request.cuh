@@ -110,9 +110,22 @@ __global__ void __launch_bounds__(128) k_chain_req(const ReqPat *__restrict__ pa
     const long long ncand = req_nvalid(hdr, cap);
     const long long wbase = j - (threadIdx.x & 31);
     if (wbase >= ncand) return;                               // warp-uniform
+    const int lane = threadIdx.x & 31;
     bool head = false;
     if (j < ncand) head = cand_opens_cluster(pats[key_pid((unsigned long long)cands[j].key)].pl, cands, ncand, j, fills, maxend, mindep_rev);
-    unsigned heads = __ballot_sync(0xffffffffu, head);
+    bool longc = false;
+    {
+        // short clusters: walked by the lane of their first candidate
+        int pid = 0, nsel = 0;
+        if (head) {
+            pid = key_pid((unsigned long long)cands[j].key);
+            const ReqPat &rp = pats[pid];
+            nsel = chain_cluster_thread(rp.pl, text, rp.TL, rp.TR, cands, ncand, j, hits, sel, fills, maxend, mindep_rev);
+            longc = nsel < 0;
+        }
+        if (head && nsel > 0) atomicAdd(hdr + REQ_HDR_FIXED + pid, (unsigned long long)nsel);
+    }
+    unsigned heads = __ballot_sync(0xffffffffu, longc);
     while (heads) {
         const int h = __ffs(heads) - 1;
         heads &= heads - 1;

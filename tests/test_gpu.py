@@ -1085,12 +1085,37 @@ def test_specialised_kernels_equal_generic_and_oracle(engine):
                     assert [(int(s), int(e)) for s, e in x] == O.search(p_, text, kopt, bufsize=bufsize), (p_, kopt)
             engine.set_buffer_size(1600000)
         assert used >= 10, used
+        # exact requests (k = 0) through the same streaming kernel in exact mode: one or two patterns per launch,
+        # IUPAC classes, a class that accepts non-ACGT bytes, line anchors, 33..70 positions (two halo words / tail compare)
+        g = bytearray(genome(77, 5, 400_000))
+        for _ in range(60):
+            p = rng.randrange(100, len(g) - 200)
+            if b"\n" in g[p - 5:p + 120] or b">" in g[p - 5:p + 120]:
+                continue
+            g[p:p + rng.randint(1, 60)] = rng.choice([b"N" * 60, b"RYKMSW" * 10, bytes(g[p:p + 60]).lower()])[:rng.randint(1, 60)]
+        long_pat = "".join(rng.choice("ACGT") for _ in range(70))
+        g[5000:5070] = long_pat.encode(); g[90000:90040] = long_pat[:40].encode()
+        g = bytes(g)
+        ds = engine.load_dataset(g)
+        for pats, kopt in ((["(GATAAG)", "(CTTATC)"], "0ids"), (["(GAT[AG]AG)"], "0ids"), (["(GA.AAG[^C])", "(NNGATAAG)".replace("N", ".")], "0ids"),
+                           (["^(>chr)", "(ACGT)$"], "0ids"), (["(" + long_pat + ")", "(" + long_pat[:40] + ")"], "0ids"), (["(" + long_pat[:33] + ")"], "0ids")):
+            engine.set_jit("always")
+            a = engine.search_request(ds, pats, kopt, cap=1 << 20)
+            assert engine.stats()["jit"] == 1, pats
+            engine.set_jit("off")
+            b = engine.search_request(ds, pats, kopt, cap=1 << 20)
+            assert engine.stats()["jit"] == 0
+            for p_, x, y in zip(pats, a, b):
+                assert np.array_equal(x, y), (p_, kopt)
+                assert [(int(s), int(e)) for s, e in x] == O.search(p_, g, kopt, cap=1 << 22), (p_, kopt)
+        ds.close()
         # low-complexity text: every start survives the dense filter, the per-lane survivor lists overflow and the
         # kernel falls back to unfiltered candidates for the rest (jx_unfiltered); hit lists must not change
         motif = "ACACACACACACACAC"
         text = (">r1\n" + "AC" * 30000 + "\n>r2\n" + "A" * 40000 + "\n>r3\n" + ("ACACACACTCACACAC" + "GT") * 3000 + "\n").encode()
         ds = engine.load_dataset(text)
-        for pats, kopt in (([f"({motif})", "(GTGTGTGTGTGTGTGT)"], "2ids"), (["(AAAAAAAAAAAA)"], "1ids"), (["(ACACAC[AC]CAC.CAC)"], "2s")):
+        for pats, kopt in (([f"({motif})", "(GTGTGTGTGTGTGTGT)"], "2ids"), (["(AAAAAAAAAAAA)"], "1ids"), (["(ACACAC[AC]CAC.CAC)"], "2s"),
+                           (["(ACAC)", "(AAAA)"], "0ids"), (["(A)"], "0ids")):
             engine.set_jit("always")
             a = engine.search_request(ds, pats, kopt)
             assert engine.stats()["jit"] == 1
