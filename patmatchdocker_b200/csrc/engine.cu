@@ -899,6 +899,10 @@ struct pm_engine {
     int split_kernel = 1;                           // 1: k_scan_apx (chunk-built pieces + Landau-Vishkin check), 2: k_scan_split (first generation), 0: block-tile kernel
     int pep5 = 1;                                   // non-DNA datasets: scan the 5-bit residue codes (0: raw bytes)
     int jit_mode = 1;                               // 0: never, 1: auto (genome-scale requests), 2: always -- specialised scan kernels (apx_jit.cpp)
+    struct BatchCache;                               // host-side index of the last motif batch (search_batch_fused)
+    std::shared_ptr<BatchCache> bcache;
+    DevBuf batch_tab;                               // its lookup tables on the device
+    std::string batch_tab_key;
     int batch_hash = 1;                             // batches of >= 64 exact motifs: q-gram lookup kernel (0: always the dense multi-pattern kernel)
     bool attr_hash = false;
     bool attr_exact = false, attr_split = false, attr_apx = false;   // cudaFuncSetAttribute is per device: kept per engine
@@ -1101,7 +1105,7 @@ void pm_engine_destroy(pm_engine *e)
     cudaStreamSynchronize(e->stream);
     if (e->pool_text) cudaFree(e->pool_text);
     if (e->pool_planes) cudaFree(e->pool_planes);
-    for (DevBuf *b : {&e->keys, &e->keys2, &e->cands, &e->hits, &e->hits2, &e->sel, &e->tables, &e->counters, &e->cubtmp, &e->scanbuf}) b->release();
+    for (DevBuf *b : {&e->keys, &e->keys2, &e->cands, &e->hits, &e->hits2, &e->sel, &e->tables, &e->counters, &e->cubtmp, &e->scanbuf, &e->batch_tab}) b->release();
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     if (e->h_count) cudaFreeHost(e->h_count);
     if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -2790,13 +2794,22 @@ static unsigned packed_class_of(const pm::ByteSet &bs, bool *mixed)
 
 // Batched exact motifs on a packed dataset: one scan launch evaluates every pattern on each staged tile.
 // Returns 1 when the fast path does not apply (caller falls back to one search per pattern).
-static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
-                              pm_hit *hits, int64_t cap, int64_t *offsets)
+// everything search_batch_fused derives from the motif list alone: kept for the next call with the same list (a motif
+// library searched against many datasets), device tables included
+struct pm_engine::BatchCache {
+    std::string key;
+    std::vector<MultiPat> mp;            // dense-kernel descriptors (all motifs, or the ones without a lookup window)
+    std::vector<unsigned short> mlen;
+    std::vector<HashPat> hpat;
+    std::vector<unsigned> hoffs, hents, dense_map;
+    int ndense = 0;
+    bool use_hash = false;
+};
+
+// parses the motifs and builds the dense descriptors and the lookup index; 1 = the fused path does not apply
+static int build_batch_cache(const pm_engine *e, int npat, const char *const *patterns, pm_engine::BatchCache &bc)
 {
-    pm::Options o;
     std::string err;
-    if (pm::parse_kopt(kopt, o, err) || o.k != 0) return 1;
-    if (!d->hi || e->scan_mode == 1 || (e->scan_mode == 0 && !d->dna_like) || npat < 2 || npat >= (1 << 20) || d->n >= (1LL << 36)) return 1;
     std::vector<MultiPat> mp((size_t)npat);
     std::vector<unsigned short> mlen((size_t)npat);
     std::vector<unsigned char> allcls((size_t)npat * 32, 0);       // packed class of every position of every motif
@@ -2897,7 +2910,36 @@ static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char 
         std::vector<unsigned> fillp(hoffs.begin(), hoffs.end() - 1);
         for (const auto &pr : pairs) hents[fillp[pr.first]++] = pr.second;
     }
-    const int ndense = use_hash ? (int)dense_mp.size() : npat;
+    bc.use_hash = use_hash;
+    bc.ndense = use_hash ? (int)dense_mp.size() : npat;
+    bc.mp = use_hash ? dense_mp : mp;
+    bc.mlen = mlen;
+    bc.hpat = hpat; bc.hoffs = hoffs; bc.hents = hents; bc.dense_map = dense_map;
+    return 0;
+}
+
+static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
+                              pm_hit *hits, int64_t cap, int64_t *offsets)
+{
+    pm::Options o;
+    std::string err;
+    if (pm::parse_kopt(kopt, o, err) || o.k != 0) return 1;
+    if (!d->hi || e->scan_mode == 1 || (e->scan_mode == 0 && !d->dna_like) || npat < 2 || npat >= (1 << 20) || d->n >= (1LL << 36)) return 1;
+    std::string bkey = std::string(kopt) + (e->batch_hash ? "\x01H" : "\x01D");
+    for (int b = 0; b < npat; b++) { if (!patterns[b]) return 1; bkey += '\n'; bkey += patterns[b]; }
+    std::shared_ptr<pm_engine::BatchCache> bc = e->bcache;
+    if (!bc || bc->key != bkey) {
+        bc = std::make_shared<pm_engine::BatchCache>();
+        if (build_batch_cache(e, npat, patterns, *bc)) return 1;
+        bc->key = bkey;
+        e->bcache = bc;
+    }
+    const std::vector<MultiPat> &mp = bc->mp;
+    const std::vector<unsigned short> &mlen = bc->mlen;
+    const std::vector<HashPat> &hpat = bc->hpat;
+    const std::vector<unsigned> &hoffs = bc->hoffs, &hents = bc->hents, &dense_map = bc->dense_map;
+    const bool use_hash = bc->use_hash;
+    const int ndense = bc->ndense;
     CK(cudaSetDevice(e->device));
     (void)cudaGetLastError();
     e->stats = pm_stats{};
@@ -2910,15 +2952,18 @@ static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char 
     if (use_hash) {
         const size_t b0 = (MH_BUCKETS + 1) * 4, b1 = hents.size() * 4, b2 = (hpat.size() + 1) * sizeof(HashPat), b3 = (dense_map.size() + 1) * 4;
         auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-        if ((rc = e->scanbuf.reserve(al(b0) + al(b1) + al(b2) + al(b3)))) return rc;
-        char *base = (char *)e->scanbuf.p;
-        CK(cudaMemcpyAsync(base, hoffs.data(), b0, cudaMemcpyHostToDevice, e->stream));
-        CK(cudaMemcpyAsync(base + al(b0), hents.data(), b1, cudaMemcpyHostToDevice, e->stream));
-        if (!hpat.empty()) CK(cudaMemcpyAsync(base + al(b0) + al(b1), hpat.data(), hpat.size() * sizeof(HashPat), cudaMemcpyHostToDevice, e->stream));
-        if (!dense_map.empty()) CK(cudaMemcpyAsync(base + al(b0) + al(b1) + al(b2), dense_map.data(), dense_map.size() * 4, cudaMemcpyHostToDevice, e->stream));
+        if (e->batch_tab.cap < al(b0) + al(b1) + al(b2) + al(b3)) e->batch_tab_key.clear();
+        if ((rc = e->batch_tab.reserve(al(b0) + al(b1) + al(b2) + al(b3)))) return rc;
+        char *base = (char *)e->batch_tab.p;
+        if (e->batch_tab_key != bkey) {
+            CK(cudaMemcpyAsync(base, hoffs.data(), b0, cudaMemcpyHostToDevice, e->stream));
+            CK(cudaMemcpyAsync(base + al(b0), hents.data(), b1, cudaMemcpyHostToDevice, e->stream));
+            if (!hpat.empty()) CK(cudaMemcpyAsync(base + al(b0) + al(b1), hpat.data(), hpat.size() * sizeof(HashPat), cudaMemcpyHostToDevice, e->stream));
+            if (!dense_map.empty()) CK(cudaMemcpyAsync(base + al(b0) + al(b1) + al(b2), dense_map.data(), dense_map.size() * 4, cudaMemcpyHostToDevice, e->stream));
+            e->batch_tab_key = bkey;
+        }
         d_hoffs = (const unsigned *)base; d_hents = (const unsigned *)(base + al(b0));
         d_hpat = (const HashPat *)(base + al(b0) + al(b1)); d_dmap = (const unsigned *)(base + al(b0) + al(b1) + al(b2));
-        if (ndense) mp.assign(dense_mp.begin(), dense_mp.end());
     }
     MultiPat *d_pats = (MultiPat *)e->tables.p;
     unsigned short *d_mlen = (unsigned short *)((char *)e->tables.p + (((size_t)npat * sizeof(MultiPat) + 15) & ~(size_t)15));

@@ -1687,7 +1687,16 @@ __global__ void __launch_bounds__((MH_WARPS + 1) * 32, 4) k_scan_multi_hash(cons
             int s = 0;
             unsigned ph = 1;
             for (long long it = 0; it < my; it++) {
-                if (it >= MH_STAGES) mbar_wait(&empty[s], ph);
+                if (it >= MH_STAGES) {
+                    // the consumers hold a stage for a whole tile: poll at leisure instead of burning issue slots
+                    const unsigned bar = smem_u32(&empty[s]);
+                    for (;;) {
+                        unsigned done;
+                        asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar), "r"(ph) : "memory");
+                        if (done) break;
+                        __nanosleep(400);
+                    }
+                }
                 const long long q = (blockIdx.x + it * gridDim.x) * (long long)MH_WORDS;
                 long long words = MH_ROW;
                 if (q + MH_WORDS + 4 > a.nwords) words = a.nwords - q + MH_FRONT;
