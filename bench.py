@@ -265,8 +265,11 @@ def synth_lines(nlines, total, seed, alphabet=b"ACGT", name="chr"):
 
 def timed_requests(torch, eng, fn, steps, warmup):
     """wall-clock per step of fn() (each call synchronises on its own result copy), scan kernel ms and bytes per step"""
-    for _ in range(warmup):
+    import patmatchdocker_b200 as pm
+    for i in range(max(warmup, 1)):
         fn()
+        if i == 0:
+            pm.jit_wait()            # the first request started the background compilation of its specialised kernel (if any)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     scan_ms = scan_bytes = 0
@@ -519,8 +522,10 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps, out
 
-    for _ in range(args.warmup):
+    for i in range(max(args.warmup, 1)):
         step_resident()
+        if i == 0:
+            pm.jit_wait()            # specialised kernel of this request: compiled beside the first (generic) pass, used from here on
     # ---- parity of the benched hit list (outside the timed region) ----
     parity = None
     hit_lists = run_request(ds)
@@ -552,8 +557,10 @@ def run_ours(args):
     ms_step, nhits = timed(step_resident, args.steps)
     scan_ms, scan_bytes, nsearch = stats_acc["scan_ms"], stats_acc["scan_bytes"], stats_acc["searches"]
     launches = stats_acc["launches"]
-    for _ in range(max(1, args.warmup // 2)):
+    for i in range(max(1, args.warmup // 2)):
         step_e2e()
+        if i == 0:
+            pm.jit_wait()
     ms_e2e, (nhits2, d2h) = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -591,7 +598,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "hits_per_step": int(nhits),
         "parity_windows_ok": (parity["windows_ok"] == parity["windows_checked"]) if parity else None, "parity": parity,
-        "roofline": {"bound": "alu_pipe" if stats_acc["jit"] else "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+        "roofline": {"bound": "hbm", "limiter": "alu_pipe" if stats_acc["jit"] else None, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                      "traffic": traffic, "traffic_source": "profiles/r02_traffic.json (ncu --set full of this kernel on this workload, scaled to the bases of this launch)" if prof else None,
                      "kernel": ("k_scan_apx_jit (NVRTC-specialised for the request: both strands in one launch, 2-bit planes via TMA ring, streaming bit-sliced q-gram chunks + pieces, Landau-Vishkin check per surviving pattern start)"
                                 if stats_acc["jit"] else "k_scan_apx (generic)") if stats_acc["packed"] else "k_scan_bytes",

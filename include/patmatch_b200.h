@@ -113,9 +113,14 @@ int pm_engine_set_batch_lookup(pm_engine *e, int on);
 int pm_engine_set_peptide_codes(pm_engine *e, int on);
 /* Specialised scan kernels: for approximate (SPLIT) searches the engine can write the dense part of the scan as
  * straight-line CUDA for exactly the request's patterns and compile it with NVRTC for sm_100a (about 0.2 s, cached
- * per process and request text).  0 = never, 1 (default) = when the request covers at least 2^28 pattern x bases and
- * libnvrtc is present, 2 = always (error when NVRTC is missing).  Results are identical either way. */
+ * per process and request text).  0 = never; 1 (default) = for requests that cover at least 2^27 bases per pattern,
+ * when libnvrtc is present: the compilation runs on a background thread and the generic kernel answers until the
+ * specialised one is there, so no request ever waits for the compiler; 2 = always, compiled synchronously (error when
+ * NVRTC is missing).  Results are identical either way. */
 int pm_engine_set_jit(pm_engine *e, int mode);
+/* Blocks until no background compilation (mode 1 above) is in flight: a service calls it after warming up its common
+ * motifs, a benchmark before its timed region. */
+int pm_jit_wait(void);
 /* host-only: the CUDA source the engine would compile for this request (debugging, SASS inspection).
  * Returns the number of bytes needed (including the terminating 0) or a negative PM_ERR_*. */
 int64_t pm_jit_source(int npat, const char *const *patterns, const char *kopt, char *buf, int64_t cap);

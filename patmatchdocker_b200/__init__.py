@@ -7,7 +7,7 @@ There is no CPU fallback: importing the native layer without the built library, 
 creating an engine without a CUDA device, raises.
 """
 from .pattern import convert, reverse_complement, PatternError            # noqa: F401
-from ._native import Engine, Dataset, NativeError, plan, lib_path, load, set_compat_deployed_glibc    # noqa: F401
+from ._native import Engine, Dataset, NativeError, plan, lib_path, load, set_compat_deployed_glibc, jit_wait    # noqa: F401
 from . import patmatch                                                     # noqa: F401
 
 __all__ = ["Engine", "Dataset", "NativeError", "plan", "convert", "reverse_complement",

@@ -72,6 +72,7 @@ def load():
     L.pm_engine_set_buffer_size.argtypes = [vp, i64]
     L.pm_engine_set_fused_filter.argtypes = [vp, ctypes.c_int]
     L.pm_engine_set_jit.argtypes = [vp, ctypes.c_int]
+    L.pm_jit_wait.argtypes = []
     L.pm_engine_set_peptide_codes.argtypes = [vp, ctypes.c_int]
     L.pm_engine_set_batch_lookup.argtypes = [vp, ctypes.c_int]
     L.pm_dataset_create_window.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, vp, ctypes.c_int64, ctypes.POINTER(vp)]
@@ -444,3 +445,8 @@ class Engine:
         s = PmStats()
         _check(load().pm_get_stats(self._h, ctypes.byref(s)))
         return {f: getattr(s, f) for f, _ in PmStats._fields_}
+
+
+def jit_wait():
+    """pm_jit_wait: blocks until the background compilations of specialised scan kernels (Engine.set_jit("auto")) are done."""
+    _check(load().pm_jit_wait())

@@ -28,6 +28,8 @@
 #include <cmath>
 #include <memory>
 #include <mutex>
+#include <thread>
+#include <condition_variable>
 #include "../../include/patmatch_b200.h"
 #include "plan.hpp"
 #include "apx_jit.hpp"
@@ -1970,14 +1972,49 @@ int pm_debug_reset_caches(void)
 #define PM_JIT_MIN_WORK (1LL << 27)     // bases per pattern from which a ~0.3 s compilation pays off within a few requests
 static bool jit_wanted(const pm_engine *e, long long bases) { return e->jit_mode == 2 || (e->jit_mode == 1 && bases >= PM_JIT_MIN_WORK); }
 struct JitEntry {
+    enum State { COMPILING, COMPILED, READY, FAILED } state = COMPILING;
+    std::vector<char> cubin;               // COMPILED: the image, not yet loaded (loading needs the caller's CUDA context)
     cudaLibrary_t lib = nullptr;
     cudaKernel_t kern = nullptr;
     int rc = PM_OK;
     std::string err;
     unsigned long long attr_devices = 0;   // devices on which the shared-memory attribute has been set
 };
-static std::mutex g_jit_mu;
-static std::map<std::string, JitEntry> g_jit_cache;
+// never destroyed: a background compilation may still be running when the process exits
+static std::mutex &g_jit_mu = *new std::mutex;
+static std::condition_variable &g_jit_cv = *new std::condition_variable;
+static std::map<std::string, JitEntry> &g_jit_cache = *new std::map<std::string, JitEntry>;
+static int g_jit_pending = 0;              // compilations in flight (g_jit_mu)
+
+// NVRTC only (host work): runs on the caller's thread in mode 2, on its own thread in auto mode
+static void jit_compile_entry(const std::string &key, const std::string &source)
+{
+    std::vector<char> cubin;
+    std::string log;
+    const int bad = apx_jit_compile(source, cubin, log);
+    std::lock_guard<std::mutex> lock(g_jit_mu);
+    auto it = g_jit_cache.find(key);
+    if (it != g_jit_cache.end() && it->second.state == JitEntry::COMPILING) {     // (the caches may have been reset meanwhile)
+        JitEntry &en = it->second;
+        if (bad) {
+            en.state = JitEntry::FAILED;
+            en.rc = log.find("libnvrtc") != std::string::npos ? PM_ERR_UNSUPPORTED : PM_ERR_CUDA;
+            en.err = "specialised scan kernel: " + log;
+        } else {
+            en.cubin.swap(cubin);
+            en.state = JitEntry::COMPILED;
+        }
+    }
+    g_jit_pending--;
+    g_jit_cv.notify_all();
+}
+
+int pm_jit_wait(void)
+{
+    std::unique_lock<std::mutex> lock(g_jit_mu);
+    g_jit_cv.wait(lock, [] { return g_jit_pending == 0; });
+    return PM_OK;
+}
 
 static int launch_apx_jit(pm_engine *e, const ApxArgs &a, long long lo, long long hi, bool exact)
 {
@@ -1997,25 +2034,42 @@ static int launch_apx_jit(pm_engine *e, const ApxArgs &a, long long lo, long lon
     }
     cudaKernel_t kern = nullptr;
     {
-        std::lock_guard<std::mutex> lock(g_jit_mu);
+        std::unique_lock<std::mutex> lock(g_jit_mu);
         auto it = g_jit_cache.find(key);
         if (it == g_jit_cache.end()) {
-            const std::string prefix = apx_generate_prefix(a.pat, a.npat, exact);
-            JitEntry en;
-            std::vector<char> cubin;
-            std::string log;
-            if (apx_jit_compile(apx_full_source(prefix), cubin, log)) {
-                en.rc = log.find("libnvrtc") != std::string::npos ? PM_ERR_UNSUPPORTED : PM_ERR_CUDA;
-                en.err = "specialised scan kernel: " + log;
+            it = g_jit_cache.emplace(key, JitEntry()).first;
+            g_jit_pending++;
+            std::string source = apx_full_source(apx_generate_prefix(a.pat, a.npat, exact));
+            if (e->jit_mode == 2) {
+                lock.unlock();
+                jit_compile_entry(key, source);
+                lock.lock();
             } else {
-                cudaError_t ce = cudaLibraryLoadData(&en.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-                if (ce == cudaSuccess) ce = cudaLibraryGetKernel(&en.kern, en.lib, "k_scan_apx_jit");
-                if (ce != cudaSuccess) { en.rc = PM_ERR_CUDA; en.err = std::string("loading the specialised scan kernel: ") + cudaGetErrorString(ce); (void)cudaGetLastError(); }
+                // auto mode: the compilation (about 0.2 s) runs beside the requests; until it is there the generic
+                // kernel answers (the caller falls back on PM_ERR_UNSUPPORTED)
+                std::thread(jit_compile_entry, key, std::move(source)).detach();
             }
-            it = g_jit_cache.emplace(key, en).first;
+            it = g_jit_cache.find(key);
+            if (it == g_jit_cache.end()) { g_err = "specialised scan kernel: caches were reset during the compilation"; return PM_ERR_UNSUPPORTED; }
+        }
+        if (it->second.state == JitEntry::COMPILING) {
+            if (e->jit_mode != 2) { g_err = "specialised scan kernel: still compiling"; return PM_ERR_UNSUPPORTED; }
+            g_jit_cv.wait(lock, [&] { auto i2 = g_jit_cache.find(key); return i2 == g_jit_cache.end() || i2->second.state != JitEntry::COMPILING; });
+            it = g_jit_cache.find(key);
+            if (it == g_jit_cache.end()) { g_err = "specialised scan kernel: caches were reset during the compilation"; return PM_ERR_CUDA; }
         }
         JitEntry &en = it->second;
-        if (en.rc) { g_err = en.err; return en.rc; }
+        if (en.state == JitEntry::COMPILED) {
+            cudaError_t ce = cudaLibraryLoadData(&en.lib, en.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+            if (ce == cudaSuccess) ce = cudaLibraryGetKernel(&en.kern, en.lib, "k_scan_apx_jit");
+            if (ce != cudaSuccess) {
+                en.state = JitEntry::FAILED; en.rc = PM_ERR_CUDA;
+                en.err = std::string("loading the specialised scan kernel: ") + cudaGetErrorString(ce);
+                (void)cudaGetLastError();
+            } else en.state = JitEntry::READY;
+            std::vector<char>().swap(en.cubin);
+        }
+        if (en.state == JitEntry::FAILED) { g_err = en.err; return en.rc; }
         if (!(en.attr_devices >> (e->device & 63) & 1ULL)) {
             CK(cudaFuncSetAttribute((const void *)en.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shp.smem));
             en.attr_devices |= 1ULL << (e->device & 63);

@@ -110,7 +110,6 @@ __global__ void __launch_bounds__(128) k_chain_req(const ReqPat *__restrict__ pa
     const long long ncand = req_nvalid(hdr, cap);
     const long long wbase = j - (threadIdx.x & 31);
     if (wbase >= ncand) return;                               // warp-uniform
-    const int lane = threadIdx.x & 31;
     bool head = false;
     if (j < ncand) head = cand_opens_cluster(pats[key_pid((unsigned long long)cands[j].key)].pl, cands, ncand, j, fills, maxend, mindep_rev);
     bool longc = false;

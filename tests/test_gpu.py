@@ -787,6 +787,12 @@ def test_large_genome_properties(engine):
     ds = engine.load_dataset(text)
     hits = engine.search(ds, "(GATTACAGATTACA)", "2ids")
     assert engine.stats()["packed"] == 1                       # auto mode picks the packed scan for DNA
+    # a request of this size has its specialised kernel compiled in the background (pm_engine_set_jit, mode 1): the
+    # generic kernel answers meanwhile; once pm_jit_wait returns the specialised one runs -- same hit list
+    pm.jit_wait()
+    hits_jit = engine.search(ds, "(GATTACAGATTACA)", "2ids")
+    assert engine.stats()["jit"] == 1
+    assert np.array_equal(hits, hits_jit)
     b, e = hits["beg"], hits["end"]
     assert len(hits) > len(planted_at)
     assert np.all(b[1:] >= e[:-1]) and np.all(e > b)
@@ -1149,3 +1155,44 @@ def test_deployed_compat_mode_reproduces_the_stock_binary(engine, scan_mode):
             assert b == [tuple(h) for h in c["deployed"]], (c["pattern"], c["kopt"])
     finally:
         pm.set_compat_deployed_glibc(False)
+
+
+def test_engine_is_safe_to_share_between_threads(engine):
+    # mod_wsgi runs the Flask app with 15 request threads per process: every pm_* entry point holds
+    # the engine's mutex, and the Python methods that combine calls hold Engine._lock, so concurrent requests on ONE
+    # engine are serialised and each gets its own, correct hit list
+    import threading
+    rng = random.Random(818)
+    cases = []
+    for it in range(10):
+        pats, kopt, text = _request_case(rng, it)
+        if isinstance(text, str):
+            text = text.encode("latin-1")
+        cases.append((pats, kopt, text, [O.search(p_, text, kopt) for p_ in pats]))
+    datasets = [engine.load_dataset(c[2]) for c in cases]
+    errors = []
+
+    def worker(tid):
+        try:
+            r = random.Random(tid)
+            for _ in range(25):
+                i = r.randrange(len(cases))
+                pats, kopt, text, want = cases[i]
+                if r.random() < 0.5:
+                    got = engine.search_request(datasets[i], pats, kopt)
+                else:
+                    got = [engine.search(datasets[i], p_, kopt) for p_ in pats]
+                for g, w in zip(got, want):
+                    if [(int(b), int(e)) for b, e in g] != w:
+                        errors.append((tid, pats, kopt))
+        except Exception as ex:                              # noqa: BLE001
+            errors.append((tid, repr(ex)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for d in datasets:
+        d.close()
+    assert not errors, errors[:3]

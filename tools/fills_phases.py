@@ -12,6 +12,7 @@ torch.cuda.set_device(local); dev = torch.device("cuda", local)
 lengths = bench.chrom_lengths(3_100_000_000)
 g = bench.make_genome_torch(lengths, list(range(len(lengths))), dev)
 eng = pm.Engine(local); eng.set_stream(torch.cuda.current_stream().cuda_stream)
+eng.set_jit("always")      # profiling: compile the specialised kernel synchronously (the default compiles in the background)
 ds = eng.wrap_device(g.data_ptr(), g.numel())
 pats, kopt = bench.patterns()
 sh = pmd.DeviceShardedSearch(eng, rank, world, dev, cap=1 << 19)

@@ -17,6 +17,7 @@ kind = sys.argv[1] if len(sys.argv) > 1 else "request"
 bases = int(float(sys.argv[2])) if len(sys.argv) > 2 else 3_100_000_000
 dev = torch.device("cuda", 0)
 eng = pm.Engine(0)
+eng.set_jit("always")      # profiling: compile the specialised kernel synchronously (the default compiles in the background)
 if kind == "pep":
     prot = bench.synth_lines(60000, bases if len(sys.argv) > 2 else 30_000_000, 101, alphabet=b"ACDEFGHIKLMNPQRSTVWY", name="YORF")
     ds = eng.load_dataset(prot)

@@ -12,6 +12,7 @@ dev = torch.device("cuda", 0)
 lengths = bench.chrom_lengths(bases)
 g = bench.make_genome_torch(lengths, list(range(len(lengths))), dev)
 eng = pm.Engine(0)
+eng.set_jit("always")      # profiling: compile the specialised kernel synchronously (the default compiles in the background)
 sh = pmd.DeviceShardedSearch(eng, 0, 1, dev)
 ds = eng.wrap_device(g.data_ptr(), g.numel())
 pats, kopt = bench.patterns()

@@ -13,6 +13,7 @@ dev = torch.device("cuda", 0)
 lengths = bench.chrom_lengths(bases)
 g = bench.make_genome_torch(lengths, list(range(len(lengths))), dev)
 eng = pm.Engine(0); eng.use_torch_stream()
+eng.set_jit("always")      # profiling: compile the specialised kernel synchronously (the default compiles in the background)
 ds = eng.wrap_device(g.data_ptr(), g.numel())
 pats, kopt = bench.patterns()
 rows = 1 << 18

@@ -27,6 +27,7 @@ def main():
     host.copy_(g)
     torch.cuda.synchronize()
     eng = pm.Engine(local)
+    eng.set_jit("always")      # profiling: compile the specialised kernel synchronously (the default compiles in the background)
     sh = pmd.DeviceShardedSearch(eng, rank, world, dev)
     ds = eng.wrap_device(g.data_ptr(), g.numel())
     pats, kopt = bench.patterns()

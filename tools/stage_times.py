@@ -16,6 +16,7 @@ dev = torch.device("cuda", 0)
 lengths = bench.chrom_lengths(bases)
 genome = bench.make_genome_torch(lengths, list(range(len(lengths))), dev)
 eng = pm.Engine(0)
+eng.set_jit("always")      # profiling: compile the specialised kernel synchronously (the default compiles in the background)
 ds = eng.wrap_device(genome.data_ptr(), genome.numel())
 for mode in ("packed", "bytes"):
     eng.set_scan_mode(mode)
