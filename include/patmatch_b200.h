@@ -169,6 +169,14 @@ int pm_last_hits(pm_engine *e, pm_hit *hits, int64_t cap, int64_t *nhits);
  * delimit pattern i.  offsets has npat+1 entries. */
 int pm_search_batch(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns,
                     const char *kopt, pm_hit *hits, int64_t cap, int64_t *offsets);
+/* The same batch over the buffer fills that START in [pos_beg, pos_end) only (whole or windowed dataset; positions are
+ * file offsets).  Buffer fills are independent by the reference's own restart rule (bufLoad @41bbf0 hands whole
+ * fills to the scan), so the lists of a partition of the file into position ranges concatenate, motif by motif, to the
+ * lists of pm_search_batch: this is how a batch is TEXT-sharded over the GPUs of a box (every rank: all motifs, 1/N of
+ * the genomes) -- the lookup kernel hashes every position once whatever the number of motifs, so sharding the text
+ * scales where sharding the motif list does not. */
+int pm_search_batch_fills(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
+                          int64_t pos_beg, int64_t pos_end, pm_hit *hits, int64_t cap, int64_t *offsets);
 
 /* One PatMatch request in ONE pass (replaces BOTH nrgrep_coords runs of patmatch.py:733-735 and :739-743: the pattern
  * and its reverse complement; any number of patterns with the same -k works).  All patterns are evaluated on each

@@ -91,6 +91,7 @@ def load():
     L.pm_search.argtypes = [vp, vp, cp, cp, vp, i64, ctypes.POINTER(i64)]
     L.pm_last_hits.argtypes = [vp, vp, i64, ctypes.POINTER(i64)]
     L.pm_search_batch.argtypes = [vp, vp, ctypes.c_int, ctypes.POINTER(cp), cp, vp, i64, ctypes.POINTER(i64)]
+    L.pm_search_batch_fills.argtypes = [vp, vp, ctypes.c_int, ctypes.POINTER(cp), cp, i64, i64, vp, i64, ctypes.POINTER(i64)]
     L.pm_search_request.argtypes = [vp, vp, ctypes.c_int, ctypes.POINTER(cp), cp, vp, i64, ctypes.POINTER(i64)]
     L.pm_request_fills_device.argtypes = [vp, vp, ctypes.c_int, ctypes.POINTER(cp), cp, i64, i64, i64, vp, i64]
     L.pm_candidates.argtypes = [vp, vp, cp, cp, i64, i64, vp, i64, ctypes.POINTER(i64)]
@@ -365,16 +366,24 @@ class Engine:
         return n.value
 
     @_locked
-    def search_batch(self, dataset, patterns, kopt="0ids", cap=1 << 20, copy=True):
+    def search_batch(self, dataset, patterns, kopt="0ids", cap=1 << 20, copy=True, pos_range=None):
         """-> (hits, offsets): hits[offsets[i]:offsets[i+1]] is the hit list of patterns[i].  Large results
         cross PCIe into a page-locked staging buffer owned by the engine; the caller receives its own copy unless it
-        passes copy=False (then the array is a view of that buffer and only valid until the next search_batch)."""
+        passes copy=False (then the array is a view of that buffer and only valid until the next search_batch).
+        pos_range=(beg, end): pm_search_batch_fills -- only the buffer fills that START in that position range (a
+        text-sharded batch: the per-range lists of a partition of the file concatenate to the whole-file lists)."""
         L = load()
         arr = (ctypes.c_char_p * len(patterns))(*[_b(p) for p in patterns])
         offsets = (ctypes.c_int64 * (len(patterns) + 1))()
         n = ctypes.c_int64()
         hits = np.empty(cap, dtype=HIT_DTYPE)
-        rc = L.pm_search_batch(self._h, dataset._h, len(patterns), arr, _b(kopt), ctypes.c_void_p(hits.ctypes.data), cap, offsets)
+
+        def run(buf, room):
+            if pos_range is None:
+                return L.pm_search_batch(self._h, dataset._h, len(patterns), arr, _b(kopt), ctypes.c_void_p(buf.ctypes.data), room, offsets)
+            return L.pm_search_batch_fills(self._h, dataset._h, len(patterns), arr, _b(kopt), int(pos_range[0]), int(pos_range[1]),
+                                           ctypes.c_void_p(buf.ctypes.data), room, offsets)
+        rc = run(hits, cap)
         if rc == PM_ERR_OVERFLOW:
             total = int(offsets[len(patterns)])
             if total > 0 and self.stats()["hits"] == total:      # fused batch: the list is still on the device
@@ -388,7 +397,7 @@ class Engine:
                 while rc == PM_ERR_OVERFLOW:
                     cap *= 4
                     hits = np.empty(cap, dtype=HIT_DTYPE)
-                    rc = L.pm_search_batch(self._h, dataset._h, len(patterns), arr, _b(kopt), ctypes.c_void_p(hits.ctypes.data), cap, offsets)
+                    rc = run(hits, cap)
         _check(rc)
         off = np.array(list(offsets), dtype=np.int64)
         if copy and hits is getattr(getattr(self, "_keep", None), "array", None):

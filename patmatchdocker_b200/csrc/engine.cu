@@ -2973,7 +2973,7 @@ static int build_batch_cache(const pm_engine *e, int npat, const char *const *pa
 }
 
 static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
-                              pm_hit *hits, int64_t cap, int64_t *offsets)
+                              long long a0, long long a1, pm_hit *hits, int64_t cap, int64_t *offsets)
 {
     pm::Options o;
     std::string err;
@@ -3031,15 +3031,20 @@ static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char 
     long long capk = std::max<long long>((long long)(e->keys.cap / 8), 1 << 20);
     if (const char *dbg = getenv("PM_BATCH_CAP")) capk = std::max<long long>(atoll(dbg), 1024);     // experiments: initial key capacity
     long long nkeys = 0;
-    const long long ntiles = ((n > 0 ? n - 1 : 0) / 32) / 128 + 1;
-    for (int attempt = 0; attempt < 3; attempt++) {
+    // motif starts a0 <= w < a1 (whole buffer fills; the whole dataset: 0 .. n + 1)
+    const long long last = std::max<long long>(std::min<long long>(a1, n) - 1, a0);
+    const long long tile0 = (a0 / 32) / 128;
+    const long long ntiles = (last / 32) / 128 + 1 - tile0;
+    for (int attempt = 0; attempt < 3 && a1 > a0; attempt++) {
         if ((rc = e->keys.reserve((size_t)capk * 8))) return rc;
         CK(cudaMemsetAsync(d_count, 0, 16, e->stream));
         CK(cudaEventRecord(e->ev[0], e->stream));
         if (use_hash && !hpat.empty()) {
             HashArgs h;
             h.hi = d->hi; h.lo = d->lo; h.xx = d->xx; h.nwords = d->nwords; h.n = n;
-            h.ntiles = (((n > 0 ? n - 1 : 0) / 32) + MH_WORDS) / MH_WORDS;
+            h.tile0 = (a0 / 32) / MH_WORDS;
+            h.ntiles = (last / 32) / MH_WORDS + 1 - h.tile0;
+            h.a0 = a0; h.a1 = a1;
             h.offs = d_hoffs; h.ents = d_hents; h.pats = d_hpat;
             h.keys = (unsigned long long *)e->keys.p; h.count = d_count; h.cap = capk;
             const size_t smem = MH_STAGES * MH_STAGE_BYTES + 2 * MH_STAGES * 8;
@@ -3054,7 +3059,7 @@ static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char 
         }
         if (ndense) {
         MultiArgs a;
-        a.hi = d->hi; a.lo = d->lo; a.xx = d->xx; a.nwords = d->nwords; a.n = n; a.a0 = 0; a.a1 = n + 1; a.tile0 = 0; a.ntiles = ntiles;
+        a.hi = d->hi; a.lo = d->lo; a.xx = d->xx; a.nwords = d->nwords; a.n = n; a.a0 = a0; a.a1 = a1; a.tile0 = tile0; a.ntiles = ntiles;
         a.pats = d_pats; a.npat = ndense; a.keys = (unsigned long long *)e->keys.p; a.count = d_count; a.cap = capk;
         a.pid_map = use_hash ? d_dmap : nullptr;
         a.bad = (unsigned long long)npat << 40;
@@ -3072,9 +3077,9 @@ static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char 
     }
     if (nkeys > capk) { g_err = "hit buffer keeps overflowing"; return PM_ERR_CUDA; }
     if (nkeys >= (1LL << 31) - 1) { g_err = "more than 2^31 hits in one batch: split the batch"; return PM_ERR_UNSUPPORTED; }
-    const long long nplace = (long long)e->h_count[1];
-    e->stats.scan_bytes = ntiles * 128 * 4 * 3 * ((use_hash && !hpat.empty() ? 1 : 0) + (ndense ? 1 : 0));
-    e->stats.scan_bases = n * (long long)npat;
+    const long long nplace = a1 > a0 ? (long long)e->h_count[1] : 0;
+    e->stats.scan_bytes = (a1 > a0 ? ntiles : 0) * 128 * 4 * 3 * ((use_hash && !hpat.empty() ? 1 : 0) + (ndense ? 1 : 0));
+    e->stats.scan_bases = (std::min<long long>(a1, n) - a0) * (long long)npat;
     e->stats.packed = 1;
     e->stats.qgram_chunks = use_hash ? (int)hpat.size() : 0;      // batches: motifs served by the q-gram lookup kernel
     unsigned long long *keys = (unsigned long long *)e->keys.p;
@@ -3135,13 +3140,18 @@ static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char 
 int pm_search_request(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
                       pm_hit *hits, int64_t cap, int64_t *offsets);
 
-int pm_search_batch(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
-                    pm_hit *hits, int64_t cap, int64_t *offsets)
+static int search_request_range(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
+                                long long f0, long long f1, pm_hit *hits, int64_t cap, int64_t *offsets);
+
+// batch over the buffer fills f0 .. f1-1 of the dataset (the whole dataset: 0 .. number of fills)
+static int search_batch_range(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
+                              long long f0, long long f1, pm_hit *hits, int64_t cap, int64_t *offsets)
 {
-    if (!e || !d || npat < 0 || !patterns || !offsets || !kopt) { g_err = "bad argument"; return PM_ERR_ARG; }
-    std::lock_guard<std::recursive_mutex> lock(e->mu);
     {
-        const int frc = search_batch_fused(e, d, npat, patterns, kopt, hits, cap, offsets);
+        const std::vector<long long> &S = d->fill_starts;
+        const long long a0 = f0 < f1 ? S[(size_t)f0] : 0;
+        const long long a1 = f0 < f1 ? (f1 < (long long)S.size() ? S[(size_t)f1] : d->n + 1) : 0;
+        const int frc = search_batch_fused(e, d, npat, patterns, kopt, a0, a1, hits, cap, offsets);
         if (frc != 1) return frc;
     }
     // general batches (errors allowed, any plan type): groups of patterns through the request pipeline
@@ -3154,7 +3164,7 @@ int pm_search_batch(pm_engine *e, pm_dataset *d, int npat, const char *const *pa
     for (int i0 = 0; i0 < npat; i0 += group) {
         const int g = std::min(group, npat - i0);
         const bool room = hits && total <= cap && !overflow;
-        int rc = pm_search_request(e, d, g, patterns + i0, kopt, room ? hits + total : nullptr, room ? cap - total : 0, off.data());
+        int rc = search_request_range(e, d, g, patterns + i0, kopt, f0, f1, room ? hits + total : nullptr, room ? cap - total : 0, off.data());
         if (rc == PM_ERR_OVERFLOW) { overflow = true; rc = PM_OK; }
         if (rc) return rc;
         for (int q = 0; q < g; q++) offsets[i0 + q + 1] = total + off[(size_t)q + 1];
@@ -3174,6 +3184,48 @@ int pm_search_batch(pm_engine *e, pm_dataset *d, int npat, const char *const *pa
         return PM_ERR_OVERFLOW;
     }
     return PM_OK;
+}
+
+static int batch_fill_range(pm_engine *e, pm_dataset *d, int64_t pos_beg, int64_t pos_end, long long *f0, long long *f1)
+{
+    Fills fills;
+    int rc;
+    CK(cudaSetDevice(e->device));
+    (void)cudaGetLastError();
+    if ((rc = ensure_fills(e, d, &fills))) return rc;
+    const std::vector<long long> &S = d->fill_starts;
+    if (pos_end < 0) { *f0 = 0; *f1 = (long long)S.size(); }
+    else {
+        *f0 = std::lower_bound(S.begin(), S.end(), (long long)pos_beg) - S.begin();
+        *f1 = std::lower_bound(S.begin(), S.end(), (long long)pos_end) - S.begin();
+    }
+    if (d->windowed && *f1 > *f0 && (S[(size_t)*f0] < d->win_lo || d->fill_ends[(size_t)*f1 - 1] > d->win_hi)) {
+        g_err = "the buffer fills of this position range are not inside the dataset's window";
+        return PM_ERR_ARG;
+    }
+    return PM_OK;
+}
+
+int pm_search_batch(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
+                    pm_hit *hits, int64_t cap, int64_t *offsets)
+{
+    if (!e || !d || npat < 0 || !patterns || !offsets || !kopt || d->e != e) { g_err = "bad argument"; return PM_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
+    long long f0, f1;
+    int rc = batch_fill_range(e, d, 0, -1, &f0, &f1);
+    if (rc) return rc;
+    return search_batch_range(e, d, npat, patterns, kopt, f0, f1, hits, cap, offsets);
+}
+
+int pm_search_batch_fills(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
+                          int64_t pos_beg, int64_t pos_end, pm_hit *hits, int64_t cap, int64_t *offsets)
+{
+    if (!e || !d || npat < 0 || !patterns || !offsets || !kopt || d->e != e || pos_beg < 0 || pos_end < pos_beg) { g_err = "bad argument"; return PM_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
+    long long f0, f1;
+    int rc = batch_fill_range(e, d, pos_beg, pos_end, &f0, &f1);
+    if (rc) return rc;
+    return search_batch_range(e, d, npat, patterns, kopt, f0, f1, hits, cap, offsets);
 }
 
 static int candidates_impl(pm_engine *e, pm_dataset *d, const char *pattern, const char *kopt, int64_t pos_beg, int64_t pos_end,

@@ -1648,7 +1648,8 @@ __host__ __device__ __forceinline__ unsigned mh_base(int lev) { return lev == 0 
 struct HashPat { unsigned ma, mc, mg, mt, mx, lenmask, m, pid; };   // position masks per symbol; pid = index in the caller's batch
 struct HashArgs {
     const unsigned *hi, *lo, *xx;
-    long long nwords, n, ntiles;           // ntiles = block tiles of MH_WORDS words
+    long long nwords, n, ntiles;           // ntiles = block tiles of MH_WORDS words, the first one is tile0
+    long long tile0, a0, a1;               // motif starts a0 <= w < a1 only (a range of buffer fills: text-sharded batches)
     const unsigned *offs;                  // MH_BUCKETS + 1 CSR offsets by (level, q-mer code)
     const unsigned *ents;                  // entries: window offset inside the motif << 20 | index into pats
     const HashPat *pats;
@@ -1697,7 +1698,7 @@ __global__ void __launch_bounds__((MH_WARPS + 1) * 32, 4) k_scan_multi_hash(cons
                         __nanosleep(400);
                     }
                 }
-                const long long q = (blockIdx.x + it * gridDim.x) * (long long)MH_WORDS;
+                const long long q = (a.tile0 + blockIdx.x + it * gridDim.x) * (long long)MH_WORDS;
                 long long words = MH_ROW;
                 if (q + MH_WORDS + 4 > a.nwords) words = a.nwords - q + MH_FRONT;
                 const unsigned bytes = (unsigned)words * 4u;
@@ -1719,7 +1720,7 @@ __global__ void __launch_bounds__((MH_WARPS + 1) * 32, 4) k_scan_multi_hash(cons
         const int seg = (wib * 32 + lane) * MH_WPL;
         const unsigned *sp = stage_base + (size_t)s * (3 * MH_ROW) + MH_FRONT + seg - 1;
         unsigned H[MH_WPL + 2], L[MH_WPL + 2], X[MH_WPL + 2];
-        const long long q = (blockIdx.x + it * gridDim.x) * (long long)MH_WORDS;
+        const long long q = (a.tile0 + blockIdx.x + it * gridDim.x) * (long long)MH_WORDS;
 #pragma unroll
         for (int w = 0; w < MH_WPL + 2; w++) { H[w] = sp[w]; L[w] = sp[MH_ROW + w]; X[w] = sp[2 * MH_ROW + w]; }
         const int s_rel = s;                             // released after the tile has been processed (see mbar_arrive_after_loads)
@@ -1754,7 +1755,7 @@ __global__ void __launch_bounds__((MH_WARPS + 1) * 32, 4) k_scan_multi_hash(cons
                         const unsigned A = ~(hw | lw | xw), C = lw & ~hw, G = hw & lw, T = hw & ~lw;
                         const unsigned acc = (A & pa.x) | (C & pa.y) | (G & pa.z) | (T & pa.w) | (xw & pb.x);
                         const long long w = segpos + t * 32 + r - (long long)(ent >> 20);
-                        ok = (acc & pb.y) == pb.y && w >= 0 && w + (long long)pb.z <= a.n;
+                        ok = (acc & pb.y) == pb.y && w >= a.a0 && w < a.a1 && w + (long long)pb.z <= a.n;
                         key = ((unsigned long long)pb.w << 40) | ((unsigned long long)w << 4);
                     }
                     const unsigned bal = __ballot_sync(0xffffffffu, ok);

@@ -398,6 +398,32 @@ static int run_request_host(pm_engine *e, pm_dataset *d, const Request &rq, pm_h
     }
 }
 
+// anchor range of the fills f0 .. f1-1 for one compiled pattern (see search_fill_range)
+static void fill_anchor_range(const pm_dataset *d, const Compiled &c, long long f0, long long f1, long long *a0, long long *a1)
+{
+    const std::vector<long long> &S = d->fill_starts;
+    if (f0 >= f1) { *a0 = 0; *a1 = 0; return; }
+    const long long shift = c.dp.type == PM_PLAN_FWD ? 1
+                          : (c.dp.type == PM_PLAN_EXT_BEG || c.dp.type == PM_PLAN_EXT_END) ? (c.dp.type == PM_PLAN_EXT_END ? 1 : 0) - c.dp.ext_off : 0;
+    *a0 = std::max<long long>(S[f0] + shift, 0);
+    // while pm_search_stream is still uploading, the table ends at the last fill that is complete: nothing beyond it
+    // has been packed yet
+    *a1 = f1 < (long long)S.size() ? S[f1] + shift : d->fills_complete ? d->n + 1 : std::min<long long>(d->fill_ends[(size_t)f1 - 1] + 1 + shift, d->n + 1);
+}
+
+// the patterns of one request over the buffer fills f0 .. f1-1 (host-mode results); engine mutex held by the caller
+static int search_request_range(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
+                                long long f0, long long f1, pm_hit *hits, int64_t cap, int64_t *offsets)
+{
+    Request rq;
+    int rc = compile_request(npat, patterns, kopt, rq);
+    if (rc) return rc;
+    Fills fills;
+    if ((rc = ensure_fills(e, d, &fills))) return rc;
+    for (int p = 0; p < npat; p++) fill_anchor_range(d, rq.comp[p], f0, f1, &rq.a0[p], &rq.a1[p]);
+    return run_request_host(e, d, rq, hits, cap, offsets);
+}
+
 int pm_search_request(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
                       pm_hit *hits, int64_t cap, int64_t *offsets)
 {
@@ -411,19 +437,6 @@ int pm_search_request(pm_engine *e, pm_dataset *d, int npat, const char *const *
     if (d->windowed) { g_err = "windowed dataset: only pm_request_fills_device can search it"; return PM_ERR_ARG; }
     for (int p = 0; p < npat; p++) { rq.a0[p] = 0; rq.a1[p] = d->n + 1; }
     return run_request_host(e, d, rq, hits, cap, offsets);
-}
-
-// anchor range of the fills f0 .. f1-1 for one compiled pattern (see search_fill_range)
-static void fill_anchor_range(const pm_dataset *d, const Compiled &c, long long f0, long long f1, long long *a0, long long *a1)
-{
-    const std::vector<long long> &S = d->fill_starts;
-    if (f0 >= f1) { *a0 = 0; *a1 = 0; return; }
-    const long long shift = c.dp.type == PM_PLAN_FWD ? 1
-                          : (c.dp.type == PM_PLAN_EXT_BEG || c.dp.type == PM_PLAN_EXT_END) ? (c.dp.type == PM_PLAN_EXT_END ? 1 : 0) - c.dp.ext_off : 0;
-    *a0 = std::max<long long>(S[f0] + shift, 0);
-    // while pm_search_stream is still uploading, the table ends at the last fill that is complete: nothing beyond it
-    // has been packed yet
-    *a1 = f1 < (long long)S.size() ? S[f1] + shift : d->fills_complete ? d->n + 1 : std::min<long long>(d->fill_ends[(size_t)f1 - 1] + 1 + shift, d->n + 1);
 }
 
 int pm_request_fills_device(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,

@@ -1,5 +1,9 @@
 """Multi-GPU search: one process per GPU (torch.distributed), no data-path collective.
 
+Requests: DeviceShardedSearch.request_fills (buffer fills split over the ranks by position, one all-gather of the hit
+lists).  Motif batches: search_batch_text_sharded (every rank all motifs x 1/N of the file).  The first-generation
+candidate-gather path is kept below:
+
 Every rank holds the dataset and scans only its share of the file positions
 (`Engine.candidates`, i.e. pm_candidates): the reference's scan is embarrassingly parallel up
 to the point where it restarts after each reported hit, and that sequential rule is applied
@@ -52,6 +56,55 @@ def search_sharded(engine, dataset, pattern, kopt, rank, world, device=None, gro
     if rank != 0:
         return None
     return engine.resolve(dataset, pattern, kopt, merged)
+
+
+def merge_batch_shards(parts, npat):
+    """parts[r] = (hits, offsets) of rank r's position range, ranks in file order -> (hits, offsets) of the whole file:
+    motif by motif, the ranks' lists one after the other (buffer fills are independent, pm_search_batch_fills)."""
+    counts = np.stack([np.diff(np.asarray(off, dtype=np.int64)) for _, off in parts]) if parts else np.zeros((0, npat), np.int64)
+    offsets = np.zeros(npat + 1, dtype=np.int64)
+    offsets[1:] = np.cumsum(counts.sum(axis=0))
+    dtype = parts[0][0].dtype if parts else np.int64
+    out = np.empty(int(offsets[-1]), dtype=dtype)
+    at = offsets[:-1].copy()                                  # where the next rank's hits of motif p go
+    for r, (hits, off) in enumerate(parts):
+        off = np.asarray(off, dtype=np.int64)
+        c = counts[r]
+        if int(off[-1]) == 0:
+            continue
+        # destination index of every hit of this rank: its motif's write position + its index inside the motif's list
+        pid = np.repeat(np.arange(npat), c)
+        dst = at[pid] + (np.arange(int(off[-1])) - off[:-1][pid])
+        out[dst] = hits[: int(off[-1])]
+        at += c
+    return out, offsets
+
+
+def search_batch_text_sharded(engine, dataset, patterns, kopt, rank, world, group=None, gather=False, device=None):
+    """A motif batch over `world` ranks, TEXT-sharded: every rank runs ALL motifs over the buffer fills that start in its
+    position range (pm_search_batch_fills), no collective on the data path.  -> (hits, offsets, totals): this rank's hit
+    lists (file offsets; a view of the engine's page-locked buffer, valid until its next batch) and the per-motif hit
+    counts summed over the ranks (one small all-reduce).  gather=True: the lists are also merged on rank 0
+    (merge_batch_shards) and returned there instead of the local ones; elsewhere None."""
+    import torch
+    import torch.distributed as dist
+    beg, end = shard_ranges(len(dataset), world)[rank]
+    hits, off = engine.search_batch(dataset, patterns, kopt, copy=False, pos_range=(beg, end))
+    counts = torch.from_numpy(np.diff(off))
+    if world > 1:
+        if device is not None:
+            counts = counts.to(device)
+        dist.all_reduce(counts, group=group)
+        counts = counts.cpu()
+    totals = counts.numpy()
+    if not gather or world == 1:
+        return hits, off, totals
+    box = [None] * world if rank == 0 else None
+    dist.gather_object((np.array(hits, copy=True), off), box, dst=0, group=group)
+    if rank != 0:
+        return None, None, totals
+    mh, mo = merge_batch_shards(box, len(patterns))
+    return mh, mo, totals
 
 
 def assemble_from_host(host, rank, world, device, full=None, group=None):

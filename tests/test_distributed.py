@@ -18,6 +18,32 @@ def test_shard_ranges_cover_every_anchor_once():
             assert all(e >= b for b, e in r)
 
 
+def test_merge_batch_shards_is_pattern_major_in_file_order():
+    from patmatchdocker_b200._native import HIT_DTYPE
+    rng = np.random.default_rng(7)
+    npat, world, n = 37, 3, 90000
+    whole = []
+    for p in range(npat):
+        b = np.sort(rng.choice(n, size=int(rng.integers(0, 40)), replace=False))
+        whole.append(b)
+    edges = [0, 31000, 31000, n + 1]                      # the middle rank owns nothing
+    parts = []
+    for r in range(world):
+        hs, off = [], [0]
+        for p in range(npat):
+            b = whole[p][(whole[p] >= edges[r]) & (whole[p] < edges[r + 1])]
+            h = np.zeros(len(b), dtype=HIT_DTYPE)
+            h["beg"], h["end"] = b, b + 9
+            hs.append(h)
+            off.append(off[-1] + len(b))
+        parts.append((np.concatenate(hs) if hs else np.zeros(0, HIT_DTYPE), np.array(off)))
+    hits, off = D.merge_batch_shards(parts, npat)
+    assert off[-1] == sum(len(w) for w in whole)
+    for p in range(npat):
+        assert np.array_equal(hits["beg"][off[p]:off[p + 1]], whole[p])
+        assert np.array_equal(hits["end"][off[p]:off[p + 1]], whole[p] + 9)
+
+
 def _worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"

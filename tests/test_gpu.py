@@ -1196,3 +1196,42 @@ def test_engine_is_safe_to_share_between_threads(engine):
     for d in datasets:
         d.close()
     assert not errors, errors[:3]
+
+
+def test_text_sharded_batch_equals_whole_batch(engine):
+    # pm_search_batch_fills: a motif batch over the buffer fills that start in a position range.  The per-range lists of
+    # a partition of the file, merged motif by motif (distributed.merge_batch_shards), must equal pm_search_batch of the
+    # whole file and the oracle -- for the lookup kernel (>= 64 exact motifs), the dense kernel (< 64) and the general
+    # path (errors allowed: groups of motifs through the request pipeline)
+    from patmatchdocker_b200 import distributed as D
+    rng = random.Random(4242)
+    iupac = {"R": "[AG]", "Y": "[CT]", "S": "[GC]", "W": "[AT]", "M": "[AC]", "K": "[GT]", "N": ".", "B": "[CGT]"}
+
+    def motifs(count, lo, hi):
+        return ["(" + "".join(rng.choice("ACGT") if rng.random() < 0.75 else iupac[rng.choice(list(iupac))] for _ in range(rng.randint(lo, hi))) + ")"
+                for _ in range(count)]
+    g = bytearray(genome(77, 7, 700_000))
+    g[0:8] = b"ACGTACGT"
+    g = bytes(g)
+    ds = engine.load_dataset(g)
+    try:
+        for pats, kopt, bs in ((motifs(300, 6, 14) + ["(ACGTACGT)"], "0ids", 30000), (motifs(20, 5, 12), "0ids", 1600000),
+                               (motifs(40, 9, 16), "1ids", 50000), (motifs(70, 6, 12), "0ids", 700)):
+            engine.set_buffer_size(bs)
+            whole_h, whole_o = engine.search_batch(ds, pats, kopt, cap=1 << 22)
+            for world in (2, 5):
+                parts = []
+                for beg, end in D.shard_ranges(len(g), world):
+                    h, o = engine.search_batch(ds, pats, kopt, cap=1 << 22, pos_range=(beg, end))
+                    parts.append((np.array(h, copy=True), o))
+                mh, mo = D.merge_batch_shards(parts, len(pats))
+                assert np.array_equal(mo, whole_o), (kopt, bs, world)
+                assert np.array_equal(mh, whole_h), (kopt, bs, world)
+            h, o = engine.search_batch(ds, pats, kopt, pos_range=(5, 5))          # an empty range
+            assert o[-1] == 0
+            for i in rng.sample(range(len(pats)), 6):
+                want = O.search(pats[i], g, kopt, bufsize=bs, cap=1 << 22)
+                assert [(int(b), int(e)) for b, e in whole_h[whole_o[i]:whole_o[i + 1]]] == want, (pats[i], kopt, bs)
+    finally:
+        engine.set_buffer_size(1600000)
+        ds.close()
