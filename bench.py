@@ -382,7 +382,8 @@ def secondary_configs(args, torch, dist, pm, eng, dev, rank, world, big_ds, big_
                 dist.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            hits, off = eng.search_batch(ds, motifs, "0ids", cap=1 << 24, copy=False, pos_range=pos_range)
+            begins, off, base, mlen = eng.search_batch_compact(ds, motifs, "0ids", pos_range=pos_range)
+            hits = (begins, base, mlen)
             torch.cuda.synchronize()
             dt = torch.tensor([time.perf_counter() - t0], device=dev)
             if world > 1:
@@ -422,7 +423,8 @@ def secondary_configs(args, torch, dist, pm, eng, dev, rank, world, big_ds, big_
         okc = 0
         for i in (0, len(mine) // 2, len(mine) - 1):
             want = [h for h in oracle_lib.search(mine[i], prefix, "0ids", cap=1 << 22) if h[1] <= cut]
-            got = [(int(x), int(y)) for x, y in hits[off[i]:off[i + 1]] if y <= cut]
+            begins, base, mlen = hits
+            got = [(int(x) + base, int(x) + base + int(mlen[i])) for x in begins[off[i]:off[i + 1]] if int(x) + base + int(mlen[i]) <= cut]
             okc += 1 if got == want else 0
         if okc != 3:
             raise SystemExit("bench: configs[3] hit lists differ from the oracle")
@@ -432,10 +434,12 @@ def secondary_configs(args, torch, dist, pm, eng, dev, rank, world, big_ds, big_
                              "value": round(npat * genome.numel() / best / 1e9, 1), "unit": "pattern*Gbases/s", "ms_per_step": round(best * 1e3, 2),
                              "kernel": "k_scan_multi_hash (TMA ring; every text position hashed once: 8/6/4-mer code -> CSR list of motifs -> bit-parallel verification on the planes) for %d of %d motifs on this rank, k_scan_packed_multi for the rest" % (st["qgram_chunks"], len(mine)), "kernel_ms": round(kms, 3),
                              "kernel_pattern_Gbases_per_s_per_gpu": round(len(mine) * genome.numel() / world / (kms / 1e3) / 1e9, 1) if kms > 0 else None,
-                             "algorithmic_bytes": int(kb), "hits_per_step": int(tot), "d2h_bytes_per_step": int(tot) * 16, "parity": parity,
+                             "algorithmic_bytes": int(kb), "hits_per_step": int(tot), "d2h_bytes_per_step": int(tot) * 4, "parity": parity,
+                             "result_format": "compact hit lists (pm_search_batch_fills_compact): 32-bit begin per hit + one length per motif; the 16-byte rows would be %.1f GB" % (tot * 16 / 1e9),
+                             "device_ms": round(st["total_ms"], 2),
                              "sharding": "text: every rank all motifs x the buffer fills that start in its 1/%d of the file; hit lists stay on the rank that found them (each crosses its own PCIe link), per-motif totals are all-reduced" % world if world > 1 else "single GPU",
                              "motif_sharded": by_motif,
-                             "note": "lookup-bound (no HBM roofline: the planes are read once per batch of patterns); wall time includes the host-side index build, sort, chain and the D2H copy of every hit"}
+                             "note": "lookup-bound (no HBM roofline: the planes are read once per batch of patterns); wall time includes sort, chain and the D2H copy of every hit (the index of the motif list is cached by the engine after the first call)"}
     ds.close()
     del genome
     return sec

@@ -177,6 +177,15 @@ int pm_search_batch(pm_engine *e, pm_dataset *d, int npat, const char *const *pa
  * scales where sharding the motif list does not. */
 int pm_search_batch_fills(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
                           int64_t pos_beg, int64_t pos_end, pm_hit *hits, int64_t cap, int64_t *offsets);
+/* The same with COMPACT hit lists, for batches whose result is large (10 000 motifs x 600 Mb: 2.3e8 hits = 3.7 GB of
+ * pm_hit rows, more PCIe time than the search takes): begins[i] = hit begin - *base as 32 bits, motif_len[p] (npat
+ * entries, may be NULL) = positions of motif p, so hit i of motif p is [*base + begins[i], *base + begins[i] +
+ * motif_len[p]).  Only for what the fused batch path serves -- exact motifs (-k 0) without repeats on a DNA dataset,
+ * a position range below 2^32 bytes (pos_end < 0: the whole dataset) -- otherwise PM_ERR_UNSUPPORTED and the caller
+ * uses pm_search_batch_fills.  PM_ERR_OVERFLOW: offsets[npat] holds the number of hits, call again with that much room. */
+int pm_search_batch_fills_compact(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
+                                  int64_t pos_beg, int64_t pos_end, uint32_t *begins, int64_t cap, int64_t *offsets,
+                                  int64_t *base, uint16_t *motif_len);
 
 /* One PatMatch request in ONE pass (replaces BOTH nrgrep_coords runs of patmatch.py:733-735 and :739-743: the pattern
  * and its reverse complement; any number of patterns with the same -k works).  All patterns are evaluated on each

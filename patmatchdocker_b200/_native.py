@@ -92,6 +92,7 @@ def load():
     L.pm_last_hits.argtypes = [vp, vp, i64, ctypes.POINTER(i64)]
     L.pm_search_batch.argtypes = [vp, vp, ctypes.c_int, ctypes.POINTER(cp), cp, vp, i64, ctypes.POINTER(i64)]
     L.pm_search_batch_fills.argtypes = [vp, vp, ctypes.c_int, ctypes.POINTER(cp), cp, i64, i64, vp, i64, ctypes.POINTER(i64)]
+    L.pm_search_batch_fills_compact.argtypes = [vp, vp, ctypes.c_int, ctypes.POINTER(cp), cp, i64, i64, vp, i64, ctypes.POINTER(i64), ctypes.POINTER(i64), vp]
     L.pm_search_request.argtypes = [vp, vp, ctypes.c_int, ctypes.POINTER(cp), cp, vp, i64, ctypes.POINTER(i64)]
     L.pm_request_fills_device.argtypes = [vp, vp, ctypes.c_int, ctypes.POINTER(cp), cp, i64, i64, i64, vp, i64]
     L.pm_candidates.argtypes = [vp, vp, cp, cp, i64, i64, vp, i64, ctypes.POINTER(i64)]
@@ -405,6 +406,35 @@ class Engine:
         return hits[: off[-1]], off
 
     @_locked
+    def search_batch_compact(self, dataset, patterns, kopt="0ids", pos_range=None):
+        """pm_search_batch_fills_compact: batches of exact motifs with large results.  -> (begins, offsets, base, motif_len):
+        hit i of motif p (offsets[p] <= i < offsets[p+1]) is [base + begins[i], base + begins[i] + motif_len[p]); 4 bytes
+        per hit cross PCIe instead of 16.  `begins` is a view of a page-locked buffer the engine object reuses: valid
+        until the next call.  expand_compact() gives the HIT_DTYPE rows.  NativeError(PM_ERR_UNSUPPORTED) for batches the
+        fused path does not serve (errors, anchors, repeats, proteomes): use search_batch."""
+        L = load()
+        npat = len(patterns)
+        arr = (ctypes.c_char_p * npat)(*[_b(p) for p in patterns])
+        offsets = (ctypes.c_int64 * (npat + 1))()
+        base = ctypes.c_int64()
+        mlen = np.zeros(npat, dtype=np.uint16)
+        beg, end = (0, -1) if pos_range is None else (int(pos_range[0]), int(pos_range[1]))
+        while True:
+            keep = getattr(self, "_keep_c", None)
+            if keep is None:
+                _, keep = pinned_empty(1 << 20, np.dtype(np.uint32))
+                self._keep_c = keep
+            rc = L.pm_search_batch_fills_compact(self._h, dataset._h, npat, arr, _b(kopt), beg, end, ctypes.c_void_p(keep.array.ctypes.data),
+                                                 keep.array.size, offsets, ctypes.byref(base), ctypes.c_void_p(mlen.ctypes.data))
+            if rc != PM_ERR_OVERFLOW:
+                break
+            total = int(offsets[npat])
+            _, self._keep_c = pinned_empty(total + total // 8 + 4096, np.dtype(np.uint32))
+        _check(rc)
+        off = np.array(list(offsets), dtype=np.int64)
+        return self._keep_c.array[: off[-1]], off, int(base.value), mlen
+
+    @_locked
     def candidates(self, dataset, pattern, kopt, pos_beg, pos_end, cap=1 << 16):
         L = load()
         n = ctypes.c_int64()
@@ -459,3 +489,11 @@ class Engine:
 def jit_wait():
     """pm_jit_wait: blocks until the background compilations of specialised scan kernels (Engine.set_jit("auto")) are done."""
     _check(load().pm_jit_wait())
+
+
+def expand_compact(begins, offsets, base, motif_len):
+    """(begins, offsets, base, motif_len) of Engine.search_batch_compact -> the HIT_DTYPE rows of Engine.search_batch."""
+    out = np.empty(len(begins), dtype=HIT_DTYPE)
+    out["beg"] = begins.astype(np.int64) + base
+    out["end"] = out["beg"] + np.repeat(motif_len.astype(np.int64), np.diff(offsets))
+    return out

@@ -2972,8 +2972,17 @@ static int build_batch_cache(const pm_engine *e, int npat, const char *const *pa
     return 0;
 }
 
+// compact results: hit begins as 32-bit offsets from a0 (every motif of the fused path is an exact SIMPLE pattern, so a
+// hit ends m positions behind its begin): 4 instead of 16 bytes per hit cross PCIe
+__global__ void k_compact_hits(const H16 *__restrict__ hits, long long n, long long base, unsigned *__restrict__ out)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) out[j] = (unsigned)(hits[j].a - base);
+}
+
 static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
-                              long long a0, long long a1, pm_hit *hits, int64_t cap, int64_t *offsets)
+                              long long a0, long long a1, pm_hit *hits, int64_t cap, int64_t *offsets,
+                              uint32_t *compact = nullptr, uint16_t *motif_len = nullptr)
 {
     pm::Options o;
     std::string err;
@@ -3126,7 +3135,17 @@ static int search_batch_fused(pm_engine *e, pm_dataset *d, int npat, const char 
     e->stats.hits = nh;
     e->last_hits = (const pm_hit *)e->hits2.p;
     bool overflow = false;
-    if (hits && nh > 0) {
+    if (motif_len) for (int b = 0; b < npat; b++) motif_len[b] = mlen[(size_t)b];
+    if (compact && nh > 0) {
+        if (nh > cap) overflow = true;
+        else {
+            // e->hits (the unselected list) is free again: it receives the 32-bit begins
+            k_compact_hits<<<(unsigned)((nh + 255) / 256), 256, 0, e->stream>>>((const H16 *)e->hits2.p, nh, a0, (unsigned *)e->hits.p);
+            CK(cudaGetLastError());
+            e->stats.launches++;
+            CK(cudaMemcpyAsync(compact, e->hits.p, (size_t)nh * 4, cudaMemcpyDeviceToHost, e->stream));
+        }
+    } else if (hits && nh > 0) {
         if (nh > cap) overflow = true;
         else CK(cudaMemcpyAsync(hits, e->hits2.p, (size_t)nh * sizeof(pm_hit), cudaMemcpyDeviceToHost, e->stream));
     }
@@ -3215,6 +3234,25 @@ int pm_search_batch(pm_engine *e, pm_dataset *d, int npat, const char *const *pa
     int rc = batch_fill_range(e, d, 0, -1, &f0, &f1);
     if (rc) return rc;
     return search_batch_range(e, d, npat, patterns, kopt, f0, f1, hits, cap, offsets);
+}
+
+int pm_search_batch_fills_compact(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
+                                  int64_t pos_beg, int64_t pos_end, uint32_t *begins, int64_t cap, int64_t *offsets,
+                                  int64_t *base, uint16_t *motif_len)
+{
+    if (!e || !d || npat < 0 || !patterns || !offsets || !kopt || d->e != e || pos_beg < 0 || (pos_end >= 0 && pos_end < pos_beg) || !begins || !base) { g_err = "bad argument"; return PM_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
+    long long f0, f1;
+    int rc = batch_fill_range(e, d, pos_beg, pos_end, &f0, &f1);
+    if (rc) return rc;
+    const std::vector<long long> &S = d->fill_starts;
+    const long long a0 = f0 < f1 ? S[(size_t)f0] : 0;
+    const long long a1 = f0 < f1 ? (f1 < (long long)S.size() ? S[(size_t)f1] : d->n + 1) : 0;
+    if (a1 - a0 >= (1LL << 32)) { g_err = "compact hit lists: the position range must span less than 2^32 bytes"; return PM_ERR_UNSUPPORTED; }
+    *base = a0;
+    rc = search_batch_fused(e, d, npat, patterns, kopt, a0, a1, nullptr, cap, offsets, begins, motif_len);
+    if (rc == 1) { g_err = "compact hit lists: only batches of exact motifs on a DNA dataset (the fused batch path)"; return PM_ERR_UNSUPPORTED; }
+    return rc;
 }
 
 int pm_search_batch_fills(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,

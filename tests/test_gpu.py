@@ -1229,6 +1229,18 @@ def test_text_sharded_batch_equals_whole_batch(engine):
                 assert np.array_equal(mh, whole_h), (kopt, bs, world)
             h, o = engine.search_batch(ds, pats, kopt, pos_range=(5, 5))          # an empty range
             assert o[-1] == 0
+            if kopt == "0ids":
+                # compact lists (32-bit begins relative to the first fill of the range) carry the same hits
+                from patmatchdocker_b200._native import expand_compact
+                b_, o_, base_, ml_ = engine.search_batch_compact(ds, pats, kopt)
+                assert np.array_equal(o_, whole_o) and np.array_equal(expand_compact(b_, o_, base_, ml_), whole_h)
+                beg, end = D.shard_ranges(len(g), 3)[1]
+                b_, o_, base_, ml_ = engine.search_batch_compact(ds, pats, kopt, pos_range=(beg, end))
+                h, o = engine.search_batch(ds, pats, kopt, cap=1 << 22, pos_range=(beg, end))
+                assert (base_ > 0) == (o[-1] > 0) and np.array_equal(o_, o) and np.array_equal(expand_compact(b_, o_, base_, ml_), h)
+            else:
+                with pytest.raises(pm.NativeError):
+                    engine.search_batch_compact(ds, pats, kopt)
             for i in rng.sample(range(len(pats)), 6):
                 want = O.search(pats[i], g, kopt, bufsize=bs, cap=1 << 22)
                 assert [(int(b), int(e)) for b, e in whole_h[whole_o[i]:whole_o[i + 1]]] == want, (pats[i], kopt, bs)
