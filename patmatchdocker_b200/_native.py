@@ -117,6 +117,18 @@ def _b(s):
     return s if isinstance(s, bytes) else s.encode("latin-1")
 
 
+def _pattern_array(owner, patterns):
+    """char*[] of a motif list; the array of the previous call is reused when the list has not changed (a motif
+    library searched again and again: marshalling 10 000 strings costs more than a millisecond)"""
+    key = tuple(patterns)
+    cached = getattr(owner, "_pat_cache", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    arr = (ctypes.c_char_p * len(key))(*[_b(p) for p in key])
+    owner._pat_cache = (key, arr)
+    return arr
+
+
 class _Pinned:
     """numpy view of page-locked host memory from pm_host_alloc (freed with the last reference)"""
 
@@ -374,7 +386,7 @@ class Engine:
         pos_range=(beg, end): pm_search_batch_fills -- only the buffer fills that START in that position range (a
         text-sharded batch: the per-range lists of a partition of the file concatenate to the whole-file lists)."""
         L = load()
-        arr = (ctypes.c_char_p * len(patterns))(*[_b(p) for p in patterns])
+        arr = _pattern_array(self, patterns)
         offsets = (ctypes.c_int64 * (len(patterns) + 1))()
         n = ctypes.c_int64()
         hits = np.empty(cap, dtype=HIT_DTYPE)
@@ -400,7 +412,7 @@ class Engine:
                     hits = np.empty(cap, dtype=HIT_DTYPE)
                     rc = run(hits, cap)
         _check(rc)
-        off = np.array(list(offsets), dtype=np.int64)
+        off = np.frombuffer(offsets, dtype=np.int64).copy()
         if copy and hits is getattr(getattr(self, "_keep", None), "array", None):
             return hits[: off[-1]].copy(), off          # the pinned staging buffer is reused by the next call: hand out a copy
         return hits[: off[-1]], off
@@ -414,7 +426,7 @@ class Engine:
         fused path does not serve (errors, anchors, repeats, proteomes): use search_batch."""
         L = load()
         npat = len(patterns)
-        arr = (ctypes.c_char_p * npat)(*[_b(p) for p in patterns])
+        arr = _pattern_array(self, patterns)
         offsets = (ctypes.c_int64 * (npat + 1))()
         base = ctypes.c_int64()
         mlen = np.zeros(npat, dtype=np.uint16)
@@ -431,7 +443,7 @@ class Engine:
             total = int(offsets[npat])
             _, self._keep_c = pinned_empty(total + total // 8 + 4096, np.dtype(np.uint32))
         _check(rc)
-        off = np.array(list(offsets), dtype=np.int64)
+        off = np.frombuffer(offsets, dtype=np.int64).copy()
         return self._keep_c.array[: off[-1]], off, int(base.value), mlen
 
     @_locked
