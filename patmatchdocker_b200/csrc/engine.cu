@@ -2047,6 +2047,9 @@ static int launch_apx_jit(pm_engine *e, const ApxArgs &a, long long lo, long lon
             } else {
                 // auto mode: the compilation (about 0.2 s) runs beside the requests; until it is there the generic
                 // kernel answers (the caller falls back on PM_ERR_UNSUPPORTED)
+                // a process that exits while NVRTC is still working must not unload it under the compiler's feet
+                static std::once_flag at_exit_once;
+                std::call_once(at_exit_once, [] { atexit([] { (void)pm_jit_wait(); }); });
                 std::thread(jit_compile_entry, key, std::move(source)).detach();
             }
             it = g_jit_cache.find(key);
