@@ -168,15 +168,7 @@ __device__ __forceinline__ int nfa_side(const unsigned char *__restrict__ text, 
 // fill [S_k, E_k) at a time; fills are computed on the host (compute_fills) and looked up here.
 struct Fills { const long long *S, *E; int n; };
 
-__device__ __forceinline__ int fill_of(const Fills &f, long long x)      // last k with S[k] <= x
-{
-    int lo = 0, hi = f.n - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (f.S[mid] <= x) lo = mid; else hi = mid - 1;
-    }
-    return lo;
-}
+__device__ __forceinline__ int fill_of(const Fills &f, long long x) { return fill_lookup(f.S, f.n, x); }     // last k with S[k] <= x
 
 // ---------------------------------------------------------------------------------------
 // Patterns of 65..255 positions: the same anchored k-error NFA with PM_MW-word state vectors (the reference keeps

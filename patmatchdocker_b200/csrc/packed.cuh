@@ -1776,6 +1776,32 @@ __global__ void __launch_bounds__((MH_WARPS + 1) * 32, 4) k_scan_multi_hash(cons
     flush();
 }
 
+// last k with S[k] <= x in the table of buffer-fill starts (0 when x lies in front of the first one)
+__device__ __forceinline__ int fill_lookup(const long long *__restrict__ S, int n, long long x)
+{
+    int lo = 0, hi = n - 1;
+    if (n > 8) {
+        // fills are nearly equally long (each is the buffer size minus one partial line): interpolate, then close in on
+        // the answer with a few probes; whatever is left goes to the bisection below
+        const long long span = S[hi] - S[0];
+        int g = span > 0 ? (int)((double)(x - S[0]) * (double)hi / (double)span) : 0;
+        g = g < 0 ? 0 : g > hi ? hi : g;
+#pragma unroll 1
+        for (int probe = 0; probe < 3; probe++) {
+            if (S[g] > x) { hi = g - 1; g = g - 1 - probe; if (g < lo) g = lo; }
+            else if (g < hi && S[g + 1] <= x) { lo = g + 1; g = g + 1 + probe; if (g > hi) g = hi; }
+            else return g;
+            if (lo >= hi) break;
+        }
+        if (hi < lo) hi = lo;
+    }
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (S[mid] <= x) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
 // chain stage for batched exact patterns: keys sorted by (pattern, position)
 __global__ void __launch_bounds__(128) k_chain_multi(const unsigned long long *__restrict__ keys, long long nkeys,
                                                      const unsigned short *__restrict__ mlen, const long long *__restrict__ fillS,
@@ -1786,11 +1812,7 @@ __global__ void __launch_bounds__(128) k_chain_multi(const unsigned long long *_
     const long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j0 >= nkeys) return;
     const unsigned long long POSMASK = (1ULL << 36) - 1;
-    auto fill_idx = [&](long long x) -> int {
-        int lo = 0, hi = nfills - 1;
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (fillS[mid] <= x) lo = mid; else hi = mid - 1; }
-        return lo;
-    };
+    auto fill_idx = [&](long long x) -> int { return fill_lookup(fillS, nfills, x); };
     auto independent = [&](long long j) -> bool {
         if (j == 0) return true;
         const unsigned long long a = keys[j - 1], b = keys[j];

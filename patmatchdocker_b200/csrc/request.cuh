@@ -101,43 +101,56 @@ __global__ void k_cand_ends_req(const ReqPat *__restrict__ pats, const Cand *__r
 
 // one warp per 32 consecutive candidates: the lanes find the cluster heads among them, the warp resolves those clusters
 // (engine.cu: chain_cluster_warp); clusters never span patterns
+#define REQ_BLOCK_PIDS 32                // patterns whose hit counts a block adds up in shared memory before touching the header
 __global__ void __launch_bounds__(128) k_chain_req(const ReqPat *__restrict__ pats, const unsigned char *__restrict__ text, long long n,
                                                    const Cand *__restrict__ cands, unsigned long long *__restrict__ hdr, long long cap,
                                                    pm_hit *__restrict__ hits, unsigned char *__restrict__ sel, const Fills fills,
                                                    const long long *__restrict__ maxend, const long long *__restrict__ mindep_rev)
 {
+    // per-pattern hit counts: one shared-memory add per cluster, one global atomic per block and pattern.  (One global
+    // atomic per cluster -- 7e4 of them on two addresses for the bench request -- serialised in L2 and WAS the kernel:
+    // 113 us, 56 % of the stall samples on the header line; profiles/r02_verify_chain.txt)
+    __shared__ unsigned blk_cnt[REQ_BLOCK_PIDS];
+    if (threadIdx.x < REQ_BLOCK_PIDS) blk_cnt[threadIdx.x] = 0;
+    __syncthreads();
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long ncand = req_nvalid(hdr, cap);
     const long long wbase = j - (threadIdx.x & 31);
-    if (wbase >= ncand) return;                               // warp-uniform
-    bool head = false;
-    if (j < ncand) head = cand_opens_cluster(pats[key_pid((unsigned long long)cands[j].key)].pl, cands, ncand, j, fills, maxend, mindep_rev);
-    bool longc = false;
-    {
-        // short clusters: walked by the lane of their first candidate
-        int pid = 0, nsel = 0;
-        if (head) {
-            pid = key_pid((unsigned long long)cands[j].key);
-            const ReqPat &rp = pats[pid];
-            nsel = chain_cluster_thread(rp.pl, text, rp.TL, rp.TR, cands, ncand, j, hits, sel, fills, maxend, mindep_rev);
-            longc = nsel < 0;
+    auto count = [&](int pid, unsigned long long nsel) {
+        if (pid < REQ_BLOCK_PIDS) atomicAdd(&blk_cnt[pid], (unsigned)nsel);
+        else atomicAdd(hdr + REQ_HDR_FIXED + pid, nsel);
+    };
+    if (wbase < ncand) {                                      // warp-uniform
+        bool head = false;
+        if (j < ncand) head = cand_opens_cluster(pats[key_pid((unsigned long long)cands[j].key)].pl, cands, ncand, j, fills, maxend, mindep_rev);
+        bool longc = false;
+        {
+            // short clusters: walked by the lane of their first candidate
+            int pid = 0, nsel = 0;
+            if (head) {
+                pid = key_pid((unsigned long long)cands[j].key);
+                const ReqPat &rp = pats[pid];
+                nsel = chain_cluster_thread(rp.pl, text, rp.TL, rp.TR, cands, ncand, j, hits, sel, fills, maxend, mindep_rev);
+                longc = nsel < 0;
+            }
+            if (head && nsel > 0) count(pid, (unsigned long long)nsel);
         }
-        if (head && nsel > 0) atomicAdd(hdr + REQ_HDR_FIXED + pid, (unsigned long long)nsel);
+        unsigned heads = __ballot_sync(0xffffffffu, longc);
+        while (heads) {
+            const int h = __ffs(heads) - 1;
+            heads &= heads - 1;
+            const long long j0 = wbase + h;
+            const int pid = key_pid((unsigned long long)cands[j0].key);
+            const ReqPat &rp = pats[pid];
+            const unsigned long long nsel = chain_cluster_warp(rp.pl, text, rp.TL, rp.TR, cands, ncand, j0, hits, sel, fills, maxend, mindep_rev);
+            if (nsel && (threadIdx.x & 31) == 0) count(pid, nsel);
+        }
     }
-    unsigned heads = __ballot_sync(0xffffffffu, longc);
-    while (heads) {
-        const int h = __ffs(heads) - 1;
-        heads &= heads - 1;
-        const long long j0 = wbase + h;
-        const int pid = key_pid((unsigned long long)cands[j0].key);
-        const ReqPat &rp = pats[pid];
-        const unsigned long long nsel = chain_cluster_warp(rp.pl, text, rp.TL, rp.TR, cands, ncand, j0, hits, sel, fills, maxend, mindep_rev);
-        if (nsel && (threadIdx.x & 31) == 0) atomicAdd(hdr + REQ_HDR_FIXED + pid, nsel);
-    }
+    __syncthreads();
+    if (threadIdx.x < REQ_BLOCK_PIDS && blk_cnt[threadIdx.x]) atomicAdd(hdr + REQ_HDR_FIXED + threadIdx.x, (unsigned long long)blk_cnt[threadIdx.x]);
     (void)n;
 }
 
-// ---------------------------------------------------------------------------------------
 struct Request {
     std::vector<Compiled> comp;
     std::vector<long long> a0, a1;       // anchor range per pattern
