@@ -1809,8 +1809,15 @@ __global__ void __launch_bounds__(128) k_chain_multi(const unsigned long long *_
                                                      long long *__restrict__ hits /* beg,end pairs */, unsigned char *__restrict__ sel,
                                                      unsigned long long *__restrict__ per_pattern)
 {
-    const long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j0 >= nkeys) return;
+    // per-pattern counts: keys are sorted by pattern, so the 128 keys of a block belong to a handful of consecutive
+    // motifs -- counted in shared memory relative to the block's first motif, one global atomic per block and motif
+    // (one per hit, or per warp, lands on the same few L2 addresses from every SM at once)
+    __shared__ unsigned cnt[128];
+    cnt[threadIdx.x] = 0;
+    const long long jb = (long long)blockIdx.x * blockDim.x;
+    const int pid0 = jb < nkeys ? (int)(keys[jb] >> 40) : 0;
+    __syncthreads();
+    const long long j0 = jb + threadIdx.x;
     const unsigned long long POSMASK = (1ULL << 36) - 1;
     auto fill_idx = [&](long long x) -> int { return fill_lookup(fillS, nfills, x); };
     auto independent = [&](long long j) -> bool {
@@ -1821,27 +1828,32 @@ __global__ void __launch_bounds__(128) k_chain_multi(const unsigned long long *_
         if (pa + mlen[b >> 40] <= pb) return true;
         return fill_idx(pa) != fill_idx(pb);
     };
-    if (!independent(j0)) return;
-    long long pos = -1;
-    for (long long t = j0; t < nkeys; t++) {
-        if (t > j0 && independent(t)) break;
-        const unsigned long long key = keys[t];
-        const int pid = (int)(key >> 40);
-        const long long p = (long long)((key >> 4) & POSMASK);
-        const int m = mlen[pid];
-        const int f = fill_idx(p);
-        sel[t] = 0;
-        if (p + m > fillE[f]) continue;                      // the window must lie inside its buffer fill
-        if (p < pos) continue;
-        hits[2 * t] = p;
-        hits[2 * t + 1] = p + m;
-        sel[t] = 1;
-        // per-pattern counts: keys are sorted by pattern, so the lanes of a warp mostly count for the same one --
-        // one atomic per group of lanes instead of one per hit
-        {
-            const unsigned grp = __match_any_sync(__activemask(), pid);
-            if ((int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&per_pattern[pid], (unsigned long long)__popc(grp));
+    if (j0 < nkeys && independent(j0)) {
+        long long pos = -1;
+        unsigned mine = 0;                                   // hits of this cluster (one motif)
+        int pid = 0;
+        for (long long t = j0; t < nkeys; t++) {
+            if (t > j0 && independent(t)) break;
+            const unsigned long long key = keys[t];
+            pid = (int)(key >> 40);
+            const long long p = (long long)((key >> 4) & POSMASK);
+            const int m = mlen[pid];
+            const int f = fill_idx(p);
+            sel[t] = 0;
+            if (p + m > fillE[f]) continue;                      // the window must lie inside its buffer fill
+            if (p < pos) continue;
+            hits[2 * t] = p;
+            hits[2 * t + 1] = p + m;
+            sel[t] = 1;
+            mine++;
+            pos = p + m;
         }
-        pos = p + m;
+        if (mine) {
+            const int d = pid - pid0;
+            if (d >= 0 && d < 128) atomicAdd(&cnt[d], mine);
+            else atomicAdd(&per_pattern[pid], (unsigned long long)mine);
+        }
     }
+    __syncthreads();
+    if (cnt[threadIdx.x]) atomicAdd(&per_pattern[pid0 + threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
 }
