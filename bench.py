@@ -437,6 +437,7 @@ def secondary_configs(args, torch, dist, pm, eng, dev, rank, world, big_ds, big_
                              "algorithmic_bytes": int(kb), "hits_per_step": int(tot), "d2h_bytes_per_step": int(tot) * 4, "parity": parity,
                              "result_format": "compact hit lists (pm_search_batch_fills_compact): 32-bit begin per hit + one length per motif; the 16-byte rows would be %.1f GB" % (tot * 16 / 1e9),
                              "device_ms": round(st["total_ms"], 2),
+                             "stage_ms": {k: round(st[k], 2) for k in ("scan_ms", "sort_ms", "verify_ms", "chain_ms", "total_ms")},
                              "sharding": "text: every rank all motifs x the buffer fills that start in its 1/%d of the file; hit lists stay on the rank that found them (each crosses its own PCIe link), per-motif totals are all-reduced" % world if world > 1 else "single GPU",
                              "motif_sharded": by_motif,
                              "note": "lookup-bound (no HBM roofline: the planes are read once per batch of patterns); wall time includes sort, chain and the D2H copy of every hit (the index of the motif list is cached by the engine after the first call)"}
