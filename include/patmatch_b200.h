@@ -208,6 +208,13 @@ int pm_search_request(pm_engine *e, pm_dataset *d, int npat, const char *const *
 int pm_request_fills_device(pm_engine *e, pm_dataset *d, int npat, const char *const *patterns, const char *kopt,
                             int64_t pos_beg, int64_t pos_end, int64_t sort_cap, void *dev_out, int64_t out_rows);
 
+/* Multi-GPU requests, after the all-gather of the per-rank blocks pm_request_fills_device wrote: dev_all = `world` blocks
+ * of `rows` rows in rank (= file) order.  Builds, on the device and without the host looking at any count,
+ * dev_out = [the world header blocks, verbatim | pattern 0: hits of rank 0, rank 1, ... | pattern 1: ...], i.e. the
+ * per-pattern lists of the whole file, ready for one device-to-host copy.  Asynchronous on the engine's stream.  At most
+ * 64 patterns and 16 ranks (else PM_ERR_UNSUPPORTED: merge on the host). */
+int pm_merge_request_shards(pm_engine *e, const void *dev_all, int world, int64_t rows, int npat, void *dev_out, int64_t out_rows);
+
 /* Sharded search for multi-GPU runs: only candidates whose anchor position lies in
  * [pos_beg, pos_end) are produced; they are verified but NOT chained.  The caller
  * gathers the per-rank lists (already sorted) and calls pm_resolve on one rank. */

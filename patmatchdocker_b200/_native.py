@@ -73,6 +73,7 @@ def load():
     L.pm_engine_set_fused_filter.argtypes = [vp, ctypes.c_int]
     L.pm_engine_set_jit.argtypes = [vp, ctypes.c_int]
     L.pm_jit_wait.argtypes = []
+    L.pm_merge_request_shards.argtypes = [vp, vp, ctypes.c_int, i64, ctypes.c_int, vp, i64]
     L.pm_engine_set_peptide_codes.argtypes = [vp, ctypes.c_int]
     L.pm_engine_set_batch_lookup.argtypes = [vp, ctypes.c_int]
     L.pm_dataset_create_window.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, vp, ctypes.c_int64, ctypes.POINTER(vp)]
@@ -245,6 +246,11 @@ class Engine:
         arr = (ctypes.c_char_p * len(patterns))(*[_b(p) for p in patterns])
         _check(load().pm_request_fills_device(self._h, dataset._h, len(patterns), arr, _b(kopt), int(pos_beg), int(pos_end),
                                               int(sort_cap), ctypes.c_void_p(dev_ptr), int(out_rows)))
+
+    def merge_request_shards(self, all_ptr, world, rows, npat, out_ptr, out_rows):
+        """pm_merge_request_shards: asynchronous device-side merge of the all-gathered [header | hits] blocks into
+        [world headers | per-pattern lists of the whole file] at out_ptr."""
+        _check(load().pm_merge_request_shards(self._h, ctypes.c_void_p(all_ptr), int(world), int(rows), int(npat), ctypes.c_void_p(out_ptr), int(out_rows)))
 
     def close(self):
         if self._h:

@@ -480,6 +480,64 @@ int pm_request_fills_device(pm_engine *e, pm_dataset *d, int npat, const char *c
     return PM_OK;
 }
 
+// ---- merge of the all-gathered per-rank blocks (multi-GPU requests) --------------------------------------------------
+// `all` holds `world` blocks of `rows` rows, each [header rows | hits of pattern 0 | hits of pattern 1 | ...] as written
+// by pm_request_fills_device, in rank (= file) order.  The per-pattern lists of the whole file are the ranks' lists one
+// after the other: out = [the world headers, verbatim | pattern 0: rank 0, rank 1, ... | pattern 1: ...].  Everything the
+// kernel needs is in the headers it reads from device memory, so the host can enqueue the merge and the result copy
+// right behind the collective without looking at the counts first.
+#define REQ_MERGE_MAXPAT 64
+#define REQ_MERGE_MAXWORLD 16
+__global__ void __launch_bounds__(256) k_merge_request_shards(const pm_hit *__restrict__ all, int world, long long rows, int npat, int hrows,
+                                                              pm_hit *__restrict__ out, long long out_hits_cap)
+{
+    __shared__ long long s_src[REQ_MERGE_MAXWORLD][REQ_MERGE_MAXPAT + 1];    // first row (inside the rank's block) of pattern p's hits
+    __shared__ long long s_dst[REQ_MERGE_MAXWORLD][REQ_MERGE_MAXPAT];        // first output row of the rank's hits of pattern p
+    __shared__ long long s_nh[REQ_MERGE_MAXWORLD];
+    if (threadIdx.x == 0) {
+        long long at = 0;
+        for (int r = 0; r < world; r++) {
+            const unsigned long long *hdr = (const unsigned long long *)(all + (size_t)r * rows);
+            long long nh = (long long)hdr[0];
+            if (nh > rows - hrows) nh = rows - hrows;             // a block that did not fit: the host sees it in the header and retries
+            s_nh[r] = nh;
+            long long a = 0;
+            for (int p = 0; p < npat; p++) { s_src[r][p] = a; a += (long long)hdr[REQ_HDR_FIXED + p]; }
+            s_src[r][npat] = a;
+        }
+        for (int p = 0; p < npat; p++)
+            for (int r = 0; r < world; r++) { s_dst[r][p] = at; at += s_src[r][p + 1] - s_src[r][p]; }
+    }
+    __syncthreads();
+    const long long per = rows;                                    // thread index space: world x rows
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < (long long)world * per; t += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(t / per);
+        const long long i = t % per;
+        if (i < hrows) { out[(size_t)r * hrows + i] = all[(size_t)r * rows + i]; continue; }      // headers, verbatim
+        const long long h = i - hrows;
+        if (h >= s_nh[r]) continue;
+        int p = 0;
+        while (p + 1 < npat && h >= s_src[r][p + 1]) p++;
+        const long long d = s_dst[r][p] + (h - s_src[r][p]);
+        if (d < out_hits_cap) out[(size_t)world * hrows + d] = all[(size_t)r * rows + i];
+    }
+}
+
+int pm_merge_request_shards(pm_engine *e, const void *dev_all, int world, int64_t rows, int npat, void *dev_out, int64_t out_rows)
+{
+    if (!e || !dev_all || !dev_out || world < 1 || npat < 1 || rows < req_hdr_rows(npat) || out_rows < (int64_t)world * req_hdr_rows(npat)) { g_err = "bad argument"; return PM_ERR_ARG; }
+    if (npat > REQ_MERGE_MAXPAT || world > REQ_MERGE_MAXWORLD) { g_err = "merge kernel: at most 64 patterns and 16 ranks"; return PM_ERR_UNSUPPORTED; }
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
+    CK(cudaSetDevice(e->device));
+    (void)cudaGetLastError();
+    const int hrows = req_hdr_rows(npat);
+    const long long total = (long long)world * rows;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)e->sms * 8));
+    k_merge_request_shards<<<grid, 256, 0, e->stream>>>((const pm_hit *)dev_all, world, rows, npat, hrows, (pm_hit *)dev_out, out_rows - (long long)world * hrows);
+    CK(cudaGetLastError());
+    return PM_OK;
+}
+
 // host-only: the source apx_jit.cpp would hand to NVRTC for this request
 int64_t pm_jit_source(int npat, const char *const *patterns, const char *kopt, char *buf, int64_t cap)
 {

@@ -147,8 +147,9 @@ class DeviceShardedSearch:
         """One PatMatch request (all patterns, e.g. motif + reverse complement) over `world` ranks with ONE collective:
         every rank runs pm_request_fills_device on the buffer fills that start in its position range -- a single
         pass over its part of the planes, one sort / verify / chain / select, no host synchronisation -- and the
-        per-rank [header | hits] blocks are all-gathered over NVLink.  Rank 0 copies the gathered buffer to the
-        host once and returns the per-pattern hit lists (== Engine.search_request); the other ranks read only the
+        per-rank [header | hits] blocks are all-gathered over NVLink.  Rank 0 merges them into per-pattern lists on
+        the device (pm_merge_request_shards: driven by the gathered headers, no host round trip), copies headers and
+        lists to the host in one go and returns the lists (== Engine.search_request); the other ranks read only the
         header rows (to agree on a retry when some rank needed more room) and return None.  The arrays returned on
         rank 0 are views of a page-locked buffer that the next call reuses: copy them to keep them."""
         import torch.distributed as dist
@@ -158,8 +159,11 @@ class DeviceShardedSearch:
         hr = request_header_rows(npat)
         on_gpu = str(self.device) != "cpu"
         if not hasattr(self, "rq_rows"):
-            self.rq_rows, self.rq_cap, self.rq_alloc = 1 << 14, 1 << 16, 0
+            self.rq_rows, self.rq_cap, self.rq_alloc, self.rq_spec = 1 << 14, 1 << 16, 0, 1 << 14
+            self.rq_merged = self.rq_out = None
         beg, end = shard_ranges(len(dataset), self.world)[self.rank]
+        device_merge = on_gpu and self.rank == 0 and npat <= 64 and self.world <= 16
+        spec = 0
         while True:
             rows = max(self.rq_rows, hr + 16)
             if rows > self.rq_alloc:
@@ -177,11 +181,26 @@ class DeviceShardedSearch:
             else:
                 flat.copy_(mine)
             view = flat.view(self.world, rows, 2)
-            # every rank reads the header rows (a few hundred bytes): they agree on a retry and on the next sizes
-            self.rq_hdr.copy_(view[:, :hr], non_blocking=True)
-            if on_gpu:
+            if device_merge:
+                # [world headers | per-pattern lists] built on the device; headers + as many hits as the last request
+                # had (with head-room) cross PCIe before the host has seen a single count
+                need = self.world * rows
+                if self.rq_merged is None or self.rq_merged.shape[0] < need:
+                    self.rq_merged = torch.empty((need + need // 2, 2), dtype=torch.int64, device=self.device)
+                if self.rq_out is None or self.rq_out.shape[0] < need:
+                    self.rq_out = torch.empty((need + need // 2, 2), dtype=torch.int64, pin_memory=True)
+                self.engine.merge_request_shards(flat.data_ptr(), self.world, rows, npat, self.rq_merged.data_ptr(), self.rq_merged.shape[0])
+                spec = min(self.rq_spec, self.world * (rows - hr))
+                ncopy = self.world * hr + spec
+                self.rq_out[:ncopy].copy_(self.rq_merged[:ncopy], non_blocking=True)
                 torch.cuda.current_stream().synchronize()
-            hdrs = self.rq_hdr.numpy()
+                hdrs = self.rq_out[: self.world * hr].numpy().reshape(self.world, hr, 2).copy()
+            else:
+                # every rank reads the header rows (a few hundred bytes): they agree on a retry and on the next sizes
+                self.rq_hdr.copy_(view[:, :hr], non_blocking=True)
+                if on_gpu:
+                    torch.cuda.current_stream().synchronize()
+                hdrs = self.rq_hdr.numpy()
             nh = hdrs[:, 0, 0]
             ncand = hdrs[:, 0, 1]
             ok = int(ncand.max()) <= self.rq_cap and int(nh.max()) + hr <= rows
@@ -192,23 +211,31 @@ class DeviceShardedSearch:
                 break
         if self.rank != 0:
             return None
-        # rank 0: the per-pattern lists are put together ON THE DEVICE (pattern-major, ranks in file order) and cross PCIe
-        # once, exactly sized; the returned arrays are views of a pinned buffer that the next call reuses
         counts = hdrs[:, 2:hr].reshape(self.world, -1)[:, :npat]
-        offs = np.zeros((self.world, npat + 1), dtype=np.int64)
-        offs[:, 1:] = np.cumsum(counts, axis=1)
         total = int(counts.sum())
         if total == 0:
             return [np.zeros(0, dtype=HIT_DTYPE) for _ in range(npat)]
-        parts = [view[r, hr + int(offs[r, p]): hr + int(offs[r, p + 1])] for p in range(npat) for r in range(self.world)]
-        merged = torch.cat(parts)
-        if getattr(self, "rq_out", None) is None or self.rq_out.shape[0] < total:
-            self.rq_out = torch.empty((total + total // 4 + 256, 2), dtype=torch.int64, pin_memory=on_gpu)
-        hout = self.rq_out[:total]
-        hout.copy_(merged, non_blocking=True)
-        if on_gpu:
-            torch.cuda.current_stream().synchronize()
-        flat_np = hout.numpy().view(HIT_DTYPE).reshape(-1)
+        if device_merge:
+            h0 = self.world * hr
+            if total > spec:                                  # more hits than guessed: fetch the rest
+                self.rq_out[h0 + spec: h0 + total].copy_(self.rq_merged[h0 + spec: h0 + total], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            self.rq_spec = total + total // 4 + 256
+            flat_np = self.rq_out[h0: h0 + total].numpy().view(HIT_DTYPE).reshape(-1)
+        else:
+            # the per-pattern lists are put together with torch (pattern-major, ranks in file order) and cross PCIe
+            # once, exactly sized
+            offs = np.zeros((self.world, npat + 1), dtype=np.int64)
+            offs[:, 1:] = np.cumsum(counts, axis=1)
+            parts = [view[r, hr + int(offs[r, p]): hr + int(offs[r, p + 1])] for p in range(npat) for r in range(self.world)]
+            merged = torch.cat(parts)
+            if self.rq_out is None or self.rq_out.shape[0] < total:
+                self.rq_out = torch.empty((total + total // 4 + 256, 2), dtype=torch.int64, pin_memory=on_gpu)
+            hout = self.rq_out[:total]
+            hout.copy_(merged, non_blocking=True)
+            if on_gpu:
+                torch.cuda.current_stream().synchronize()
+            flat_np = hout.numpy().view(HIT_DTYPE).reshape(-1)
         out, at = [], 0
         for p in range(npat):
             c = int(counts[:, p].sum())

@@ -1247,3 +1247,45 @@ def test_text_sharded_batch_equals_whole_batch(engine):
     finally:
         engine.set_buffer_size(1600000)
         ds.close()
+
+
+def test_merge_request_shards_kernel_emulated_ranks(engine):
+    # pm_merge_request_shards: the blocks that `world` ranks would all-gather are produced here by ONE engine (one
+    # pm_request_fills_device call per position range, laid out rank after rank), merged on the device, and must give
+    # the per-pattern lists of pm_search_request; small buffer fills so that every range owns several of them
+    import torch
+    from patmatchdocker_b200 import distributed as D
+    from patmatchdocker_b200._native import request_header_rows, HIT_DTYPE
+    rng = random.Random(31337)
+    engine.use_torch_stream()
+    try:
+        for it in range(14):
+            pats, kopt, text = _request_case(rng, it)
+            if isinstance(text, str):
+                text = text.encode("latin-1")
+            engine.set_buffer_size(rng.choice([300, 700, 1600000]))
+            ds = engine.load_dataset(text)
+            want = [np.array(h, copy=True) for h in engine.search_request(ds, pats, kopt)]
+            for world in (1, 3, 8):
+                npat, hr = len(pats), request_header_rows(len(pats))
+                rows = hr + sum(len(w) for w in want) + 64
+                allb = torch.zeros((world * rows, 2), dtype=torch.int64, device="cuda")
+                for r, (beg, end) in enumerate(D.shard_ranges(len(text), world)):
+                    engine.request_fills_device(ds, pats, kopt, beg, end, 1 << 14, allb[r * rows:].data_ptr(), rows)
+                out = torch.zeros((world * rows, 2), dtype=torch.int64, device="cuda")
+                engine.merge_request_shards(allb.data_ptr(), world, rows, npat, out.data_ptr(), out.shape[0])
+                torch.cuda.synchronize()
+                o = out.cpu().numpy()
+                hdrs = o[: world * hr].reshape(world, hr, 2)
+                assert np.array_equal(hdrs, allb.cpu().numpy().reshape(world, rows, 2)[:, :hr])
+                counts = hdrs[:, 2:hr].reshape(world, -1)[:, :npat]
+                flat = o[world * hr:].copy().view(HIT_DTYPE).reshape(-1)
+                at = 0
+                for p in range(npat):
+                    c = int(counts[:, p].sum())
+                    assert np.array_equal(flat[at:at + c], want[p]), (pats, kopt, world, p)
+                    at += c
+            ds.close()
+    finally:
+        engine.set_buffer_size(1600000)
+        engine.set_stream(0)
