@@ -75,6 +75,33 @@ def _worker(rank, world, port, q):
         host = torch.from_numpy(np.random.default_rng(nbytes).integers(0, 256, nbytes, dtype=np.uint8))
         full = D.assemble_from_host(host, rank, world, "cpu")
         q.put(bool(torch.equal(full[:nbytes], host)) and full.numel() % (256 * world) == 0)
+    # text-sharded motif batch: every rank "searches" all motifs over its position range (a stand-in engine that cuts
+    # a precomputed whole-file result), the totals are all-reduced and rank 0 can ask for the merged lists
+    from patmatchdocker_b200._native import HIT_DTYPE
+    npat, nfile = 23, 50000
+    r2 = np.random.default_rng(5)
+    whole = [np.sort(r2.choice(nfile, size=int(r2.integers(0, 60)), replace=False)) for _ in range(npat)]
+
+    class FakeEngine:
+        def search_batch(self, dataset, patterns, kopt, copy=True, pos_range=None):
+            hs, off = [], [0]
+            for b in whole:
+                b = b[(b >= pos_range[0]) & (b < pos_range[1])]
+                h = np.zeros(len(b), dtype=HIT_DTYPE)
+                h["beg"], h["end"] = b, b + 8
+                hs.append(h)
+                off.append(off[-1] + len(b))
+            return np.concatenate(hs), np.array(off, dtype=np.int64)
+
+    class FakeDataset:
+        def __len__(self):
+            return nfile
+    hits, off, totals = D.search_batch_text_sharded(FakeEngine(), FakeDataset(), ["x"] * npat, "0ids", rank, world, gather=True)
+    q.put(bool(np.array_equal(totals, [len(w) for w in whole])))
+    if rank == 0:
+        q.put(all(np.array_equal(hits["beg"][off[p]:off[p + 1]], whole[p]) for p in range(npat)))
+    else:
+        q.put(hits is None)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -89,7 +116,7 @@ def test_gather_over_gloo_world_size_2():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=120) for _ in range(3 + 2 * 4)]
+    results = [q.get(timeout=120) for _ in range(3 + 2 * 4 + 2 * 2)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
