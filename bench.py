@@ -409,6 +409,30 @@ def secondary_configs(args, torch, dist, pm, eng, dev, rank, world, big_ds, big_
     best, kms, kb, st, hits, off, tot = run_batch(mine, pos_range)
     if by_motif is not None and by_motif["hits_per_step"] != tot:
         raise SystemExit("bench: configs[3] text-sharded and motif-sharded batches disagree on the number of hits")
+    # the same work pipelined: the rank's range in 8 sub-ranges alternating between two engines (own stream and scratch)
+    # driven by two host threads, so that the result copy of one sub-range overlaps the scan / sort / chain of the next
+    from patmatchdocker_b200.distributed import PipelinedBatch
+    eng2 = pm.Engine(dev.index)
+    ds2 = eng2.wrap_device(genome.data_ptr(), genome.numel())
+    pipe = PipelinedBatch([eng, eng2], [ds, ds2], parts=8)
+    pbest, pres = 1e18, None
+    for rep in range(4):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pres = pipe.search(mine, "0ids", pos_range=pos_range)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        if rep > 1:
+            pbest = min(pbest, float(dt))
+    ptot = torch.tensor([sum(int(o[-1]) for _b, o, _base, _ml in pres)], device=dev)
+    if world > 1:
+        dist.all_reduce(ptot)
+    if int(ptot) != tot:
+        raise SystemExit("bench: configs[3] pipelined batch disagrees on the number of hits")
     parity = None
     if rank == 0:
         # three sampled motifs against the oracle on a prefix of the file that ends at a buffer-fill boundary
@@ -425,13 +449,16 @@ def secondary_configs(args, torch, dist, pm, eng, dev, rank, world, big_ds, big_
             want = [h for h in oracle_lib.search(mine[i], prefix, "0ids", cap=1 << 22) if h[1] <= cut]
             begins, base, mlen = hits
             got = [(int(x) + base, int(x) + base + int(mlen[i])) for x in begins[off[i]:off[i + 1]] if int(x) + base + int(mlen[i]) <= cut]
-            okc += 1 if got == want else 0
+            gotp = [(int(x) + pb_, int(x) + pb_ + int(ml_[i])) for b_, o_, pb_, ml_ in pres for x in b_[o_[i]:o_[i + 1]] if int(x) + pb_ + int(ml_[i]) <= cut]
+            okc += 1 if got == want and gotp == want else 0
         if okc != 3:
             raise SystemExit("bench: configs[3] hit lists differ from the oracle")
-        parity = "3 sampled motifs == CPU oracle on the first %.0f Mb" % (cut / 1e6)
+        parity = "3 sampled motifs (single call and pipelined) == CPU oracle on the first %.0f Mb" % (cut / 1e6)
         ach = kb / (kms / 1e3) / 1e9 if kms > 0 else 0.0
         sec["configs[3]"] = {"workload": "%d IUPAC motifs (8-14 nt, 25%% degenerate positions) x synthetic %.0f Mb in 800 chromosomes (50 genomes x 16), exact, %d rank(s)" % (npat, genome.numel() / 1e6, world),
-                             "value": round(npat * genome.numel() / best / 1e9, 1), "unit": "pattern*Gbases/s", "ms_per_step": round(best * 1e3, 2),
+                             "value": round(npat * genome.numel() / pbest / 1e9, 1), "unit": "pattern*Gbases/s", "ms_per_step": round(pbest * 1e3, 2),
+                             "pipeline": "each rank's range in 8 sub-ranges alternating between two engines of the GPU (two streams, two host threads): result copies overlap the next sub-range's scan / sort / chain (distributed.PipelinedBatch)",
+                             "single_call": {"value": round(npat * genome.numel() / best / 1e9, 1), "ms_per_step": round(best * 1e3, 2), "note": "one pm_search_batch_fills_compact call per rank; kernel_ms / stage_ms / device_ms below are this call's"},
                              "kernel": "k_scan_multi_hash (TMA ring; every text position hashed once: 8/6/4-mer code -> CSR list of motifs -> bit-parallel verification on the planes) for %d of %d motifs on this rank, k_scan_packed_multi for the rest" % (st["qgram_chunks"], len(mine)), "kernel_ms": round(kms, 3),
                              "kernel_pattern_Gbases_per_s_per_gpu": round(len(mine) * genome.numel() / world / (kms / 1e3) / 1e9, 1) if kms > 0 else None,
                              "algorithmic_bytes": int(kb), "hits_per_step": int(tot), "d2h_bytes_per_step": int(tot) * 4, "parity": parity,
@@ -441,6 +468,8 @@ def secondary_configs(args, torch, dist, pm, eng, dev, rank, world, big_ds, big_
                              "sharding": "text: every rank all motifs x the buffer fills that start in its 1/%d of the file; hit lists stay on the rank that found them (each crosses its own PCIe link), per-motif totals are all-reduced" % world if world > 1 else "single GPU",
                              "motif_sharded": by_motif,
                              "note": "lookup-bound (no HBM roofline: the planes are read once per batch of patterns); wall time includes sort, chain and the D2H copy of every hit (the index of the motif list is cached by the engine after the first call)"}
+    ds2.close()
+    eng2.close()
     ds.close()
     del genome
     return sec

@@ -131,22 +131,35 @@ def _pattern_array(owner, patterns):
 
 
 class _Pinned:
-    """numpy view of page-locked host memory from pm_host_alloc (freed with the last reference)"""
+    """page-locked host memory from pm_host_alloc.  `.array` hands out numpy views whose base keeps this object alive, so
+    the memory is freed with the last VIEW, not with the last reference to the holder (a result array that outlives the
+    engine or buffer object it came from stays valid)."""
 
     def __init__(self, count, dtype):
-        self.nbytes = max(int(count), 1) * dtype.itemsize
+        self.count, self.dtype = max(int(count), 1), dtype
+        self.nbytes = self.count * dtype.itemsize
         self.ptr = load().pm_host_alloc(self.nbytes)
         if not self.ptr:
             raise NativeError(-1, "pm_host_alloc(%d) failed" % self.nbytes)
+
+    @property
+    def array(self):
         buf = (ctypes.c_char * self.nbytes).from_address(self.ptr)
-        self.array = np.frombuffer(buf, dtype=dtype, count=max(int(count), 1))
-        self.array_owner = buf
+        buf._owner = self                 # view -> base array -> buf -> this object (no cycle: nothing here points back)
+        return np.frombuffer(buf, dtype=self.dtype, count=self.count)
 
     def __del__(self):
         try:
             load().pm_host_free(self.ptr)
         except Exception:
             pass
+
+
+class CompactBuffer:
+    """page-locked result buffer of Engine.search_batch_compact (allocated and grown on demand)"""
+
+    def __init__(self):
+        self.pinned = None
 
 
 def pinned_empty(count, dtype):
@@ -403,6 +416,7 @@ class Engine:
             return L.pm_search_batch_fills(self._h, dataset._h, len(patterns), arr, _b(kopt), int(pos_range[0]), int(pos_range[1]),
                                            ctypes.c_void_p(buf.ctypes.data), room, offsets)
         rc = run(hits, cap)
+        from_keep = False
         if rc == PM_ERR_OVERFLOW:
             total = int(offsets[len(patterns)])
             if total > 0 and self.stats()["hits"] == total:      # fused batch: the list is still on the device
@@ -411,6 +425,7 @@ class Engine:
                     _, keep = pinned_empty(total + total // 8, HIT_DTYPE)
                     self._keep = keep
                 hits = keep.array
+                from_keep = True
                 rc = L.pm_last_hits(self._h, ctypes.c_void_p(hits.ctypes.data), total, ctypes.byref(n))
             else:                                                 # per-pattern fallback: run again with room
                 while rc == PM_ERR_OVERFLOW:
@@ -419,17 +434,19 @@ class Engine:
                     rc = run(hits, cap)
         _check(rc)
         off = np.frombuffer(offsets, dtype=np.int64).copy()
-        if copy and hits is getattr(getattr(self, "_keep", None), "array", None):
+        if copy and from_keep:
             return hits[: off[-1]].copy(), off          # the pinned staging buffer is reused by the next call: hand out a copy
         return hits[: off[-1]], off
 
     @_locked
-    def search_batch_compact(self, dataset, patterns, kopt="0ids", pos_range=None):
+    def search_batch_compact(self, dataset, patterns, kopt="0ids", pos_range=None, out=None):
         """pm_search_batch_fills_compact: batches of exact motifs with large results.  -> (begins, offsets, base, motif_len):
         hit i of motif p (offsets[p] <= i < offsets[p+1]) is [base + begins[i], base + begins[i] + motif_len[p]); 4 bytes
         per hit cross PCIe instead of 16.  `begins` is a view of a page-locked buffer the engine object reuses: valid
         until the next call.  expand_compact() gives the HIT_DTYPE rows.  NativeError(PM_ERR_UNSUPPORTED) for batches the
-        fused path does not serve (errors, anchors, repeats, proteomes): use search_batch."""
+        fused path does not serve (errors, anchors, repeats, proteomes): use search_batch.
+        out: a CompactBuffer that receives the begins instead of the engine's own buffer (it grows when too small), for
+        callers that keep several results alive (distributed.PipelinedBatch)."""
         L = load()
         npat = len(patterns)
         arr = _pattern_array(self, patterns)
@@ -437,20 +454,23 @@ class Engine:
         base = ctypes.c_int64()
         mlen = np.zeros(npat, dtype=np.uint16)
         beg, end = (0, -1) if pos_range is None else (int(pos_range[0]), int(pos_range[1]))
+        if out is None:
+            out = getattr(self, "_keep_c", None)
+            if out is None:
+                out = self._keep_c = CompactBuffer()
         while True:
-            keep = getattr(self, "_keep_c", None)
-            if keep is None:
-                _, keep = pinned_empty(1 << 20, np.dtype(np.uint32))
-                self._keep_c = keep
-            rc = L.pm_search_batch_fills_compact(self._h, dataset._h, npat, arr, _b(kopt), beg, end, ctypes.c_void_p(keep.array.ctypes.data),
-                                                 keep.array.size, offsets, ctypes.byref(base), ctypes.c_void_p(mlen.ctypes.data))
+            if out.pinned is None:
+                out.pinned = pinned_empty(1 << 20, np.dtype(np.uint32))[1]
+            a = out.pinned.array
+            rc = L.pm_search_batch_fills_compact(self._h, dataset._h, npat, arr, _b(kopt), beg, end, ctypes.c_void_p(a.ctypes.data),
+                                                 a.size, offsets, ctypes.byref(base), ctypes.c_void_p(mlen.ctypes.data))
             if rc != PM_ERR_OVERFLOW:
                 break
             total = int(offsets[npat])
-            _, self._keep_c = pinned_empty(total + total // 8 + 4096, np.dtype(np.uint32))
+            out.pinned = pinned_empty(total + total // 8 + 4096, np.dtype(np.uint32))[1]
         _check(rc)
         off = np.frombuffer(offsets, dtype=np.int64).copy()
-        return self._keep_c.array[: off[-1]], off, int(base.value), mlen
+        return out.pinned.array[: off[-1]], off, int(base.value), mlen
 
     @_locked
     def candidates(self, dataset, pattern, kopt, pos_beg, pos_end, cap=1 << 16):

@@ -107,6 +107,48 @@ def search_batch_text_sharded(engine, dataset, patterns, kopt, rank, world, grou
     return mh, mo, totals
 
 
+class PipelinedBatch:
+    """A motif batch over a position range, cut into `parts` sub-ranges that alternate between two engines of the same GPU
+    (own stream and scratch each), driven by two host threads: the result copy of one sub-range (4 bytes per hit, but
+    10^8 hits) crosses PCIe while the other engine scans, sorts and chains the next one.  Buffer fills are independent,
+    so the sub-range lists are the whole-range lists cut by position (pm_search_batch_fills_compact).
+
+    engines / datasets: two Engine objects on one device and the same file as a Dataset of each (Engine.wrap_device on
+    one device buffer shares the text; the planes are packed per engine)."""
+
+    def __init__(self, engines, datasets, parts=4):
+        from ._native import CompactBuffer
+        assert len(engines) == len(datasets) >= 1
+        self.engines, self.datasets, self.parts = engines, datasets, max(int(parts), 1)
+        self.buffers = [CompactBuffer() for _ in range(self.parts)]
+
+    def search(self, patterns, kopt="0ids", pos_range=None):
+        """-> list over the sub-ranges, in file order, of (begins, offsets, base, motif_len) as Engine.search_batch_compact
+        returns them; the arrays are views of page-locked buffers this object reuses on its next search."""
+        import threading
+        n = len(self.datasets[0])
+        beg, end = (0, n + 1) if pos_range is None else (int(pos_range[0]), int(pos_range[1]))
+        edges = [beg + (end - beg) * i // self.parts for i in range(self.parts + 1)]
+        res = [None] * self.parts
+        errors = []
+
+        def worker(t):
+            try:
+                for i in range(t, self.parts, len(self.engines)):
+                    res[i] = self.engines[t].search_batch_compact(self.datasets[t], patterns, kopt, pos_range=(edges[i], edges[i + 1]), out=self.buffers[i])
+            except Exception as ex:                          # noqa: BLE001 -- re-raised on the caller's thread
+                errors.append(ex)
+        threads = [threading.Thread(target=worker, args=(t,)) for t in range(1, len(self.engines))]
+        for th in threads:
+            th.start()
+        worker(0)
+        for th in threads:
+            th.join()
+        if errors:
+            raise errors[0]
+        return res
+
+
 def assemble_from_host(host, rank, world, device, full=None, group=None):
     """Bring a file that sits in (pinned) host memory into the memory of every rank with ONE trip over PCIe:
     rank r copies only its 1/world slice host->device, then the slices are all-gathered in place over

@@ -1289,3 +1289,42 @@ def test_merge_request_shards_kernel_emulated_ranks(engine):
     finally:
         engine.set_buffer_size(1600000)
         engine.set_stream(0)
+
+
+def test_pipelined_batch_two_engines_equals_whole_batch(engine):
+    # distributed.PipelinedBatch: sub-ranges of the file alternate between two engines of one GPU (two host threads);
+    # the sub-range lists, merged motif by motif, are the lists of the whole batch
+    import torch
+    from patmatchdocker_b200 import distributed as D
+    from patmatchdocker_b200._native import expand_compact
+    rng = random.Random(5150)
+    iupac = {"R": "[AG]", "Y": "[CT]", "S": "[GC]", "W": "[AT]", "N": "."}
+    pats = ["(" + "".join(rng.choice("ACGT") if rng.random() < 0.75 else iupac[rng.choice(list(iupac))] for _ in range(rng.randint(6, 13))) + ")"
+            for _ in range(200)]
+    g = genome(78, 5, 500_000)
+    dev = torch.from_numpy(np.frombuffer(g, dtype=np.uint8).copy()).cuda()
+    other = pm.Engine(0)
+    try:
+        for bs in (20000, 1600000):
+            engine.set_buffer_size(bs)
+            other.set_buffer_size(bs)
+            d0 = engine.wrap_device(dev.data_ptr(), dev.numel())
+            d1 = other.wrap_device(dev.data_ptr(), dev.numel())
+            whole_h, whole_o = engine.search_batch(d0, pats, "0ids", cap=1 << 22)
+            for parts in (1, 2, 5):
+                pb = D.PipelinedBatch([engine, other], [d0, d1], parts=parts)
+                for rep in range(2):                              # the second search reuses the page-locked buffers
+                    res = pb.search(pats, "0ids")
+                    shards = [(expand_compact(b, o, base, ml), o) for b, o, base, ml in res]
+                    mh, mo = D.merge_batch_shards(shards, len(pats))
+                    assert np.array_equal(mo, whole_o) and np.array_equal(mh, whole_h), (bs, parts, rep)
+            lo, hi = D.shard_ranges(len(g), 3)[1]
+            res = D.PipelinedBatch([engine, other], [d0, d1], parts=3).search(pats, "0ids", pos_range=(lo, hi))
+            mh, mo = D.merge_batch_shards([(expand_compact(b, o, base, ml), o) for b, o, base, ml in res], len(pats))
+            h, o = engine.search_batch(d0, pats, "0ids", cap=1 << 22, pos_range=(lo, hi))
+            assert np.array_equal(mo, o) and np.array_equal(mh, h), bs
+            d0.close()
+            d1.close()
+    finally:
+        engine.set_buffer_size(1600000)
+        other.close()
