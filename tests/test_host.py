@@ -30,6 +30,34 @@ def test_cabi_exports_every_declared_symbol():
     assert b"sm_100a" in lib.pm_version()
 
 
+def test_ctypes_binding_matches_the_header_prototypes():
+    # every prototype of include/patmatch_b200.h against the argtypes the ctypes binding declares: the same number of
+    # parameters, pointers where the header has pointers, 64-bit integers where it has int64_t
+    import os
+    header = open(os.path.join(os.path.dirname(_native.lib_path()), "..", "..", "include", "patmatch_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    protos = re.findall(r"\b(?:int|int64_t|void|const char \*|void \*)\s*\**\s*(pm_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;", header)
+    assert len(protos) >= 30, len(protos)
+    L = _native.load()
+    checked = 0
+    for name, params in protos:
+        fn = getattr(L, name)
+        if fn.argtypes is None:
+            continue                                        # functions the Python host never calls
+        plist = [] if params.strip() in ("", "void") else [x.strip() for x in params.split(",")]
+        assert len(plist) == len(fn.argtypes), (name, plist, fn.argtypes)
+        for text, at in zip(plist, fn.argtypes):
+            is_ptr = "*" in text
+            ptr_like = at in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(at, "contents") or getattr(at, "_type_", None) is not None and issubclass(at, ctypes._Pointer)
+            assert is_ptr == bool(ptr_like), (name, text, at)
+            if not is_ptr and "int64_t" in text:
+                assert ctypes.sizeof(at) == 8, (name, text, at)
+            if not is_ptr and re.match(r"(const\s+)?int\b", text):
+                assert ctypes.sizeof(at) == 4, (name, text, at)
+        checked += 1
+    assert checked >= 25, checked
+
+
 def test_plan_is_bit_exact_with_oracle():
     rng = random.Random(11)
     for it in range(1500):
